@@ -1,0 +1,81 @@
+"""ctypes binding of libldconv_b200.so (C ABI: include/ldconv_b200.h).
+
+The library is built in-tree by `make -C experiment_yolo_b200/csrc` (see __graft_entry__.build()).  There is NO
+fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldconv_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SILU = 0, 1
+IMPL_FFMA, IMPL_TCGEN05 = 1, 2
+FLAG_FORCE_FFMA = 1
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_f = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/ldconv_b200.h one to one
+SIGNATURES = {
+    "ldconv_version": (_i, []),
+    "ldconv_last_error": (ctypes.c_char_p, []),
+    "ldconv_device_check": (_i, []),
+    "ldconv_last_impl": (_i, []),
+    "ldconv_set_flag": (_i, [_i, _i]),
+    "ldconv_p_n": (_i, [_i, _vp]),
+    "ldconv_offset_conv_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
+    "ldconv_gather_fwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_gemm_fwd": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
+    "ldconv_bn_finalize": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "ldconv_bn_act_apply": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "ldconv_bn_act_bwd_reduce": (_i, [_vp] * 7 + [_ll, _i, _i, _i, _vp]),
+    "ldconv_bn_act_bwd_apply": (_i, [_vp] * 8 + [_ll, _i, _i, _i, _i, _vp]),
+    "ldconv_gemm_bwd_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldconv_gather_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_offset_conv_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_fused_fwd": (_i, [_vp] * 9 + [_i] * 9 + [_vp]),
+}
+
+_lib = None
+
+# successful C-ABI compute calls by entry point since the last reset (bench.py's `gpu_launches` bookkeeping): every entry
+# point below launches at least one kernel of this library per call
+call_counts: dict = {}
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library.  Raises if it has not been built: the product path has no other implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C experiment_yolo_b200/csrc` "
+                "(or __graft_entry__.build()).  experiment_yolo_b200 has no CPU / eager fallback.")
+        import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library needs it)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ldconv_last_error()
+        raise RuntimeError(f"libldconv_b200 {what} failed (code {rc}): {msg.decode() if msg else ''}")
+    call_counts[what] = call_counts.get(what, 0) + 1
+
+
+def p_n_table(N: int):
+    """conv.py:413-432 through the library (host-side helper) -> list of 2N ints, rows then columns."""
+    buf = (ctypes.c_int32 * (2 * N))()
+    check(load().ldconv_p_n(N, ctypes.cast(buf, _vp)), "ldconv_p_n")
+    return list(buf)

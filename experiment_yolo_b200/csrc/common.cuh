@@ -1,0 +1,156 @@
+// common.cuh -- shared device / host helpers of libldconv_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ldconv_b200.h"
+
+#define LDC_API extern "C" __attribute__((visibility("default")))
+
+namespace ldc {
+
+// ---- error reporting (thread-local message, negative return codes) ---------------------------------------------------
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+void set_impl(int impl);
+
+#define LDC_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) return ::ldc::fail(LDCONV_E_ARG, __VA_ARGS__); \
+    } while (0)
+
+#define LDC_CUDA(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return ::ldc::fail(LDCONV_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LDC_LAUNCH_CHECK(name)                                                                          \
+    do {                                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                                           \
+        if (e__ != cudaSuccess)                                                                         \
+            return ::ldc::fail(LDCONV_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__));  \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int out_size(int H, int s) { return (H - 1) / s + 1; }
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+int num_sms();
+
+// ---- element types ---------------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kVec = 4;  // elements per 16-byte vector
+    __device__ __forceinline__ static float to_f(float v) { return v; }
+    __device__ __forceinline__ static float from_f(float v) { return v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kVec = 8;
+    __device__ __forceinline__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ __forceinline__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 16-byte vector of T, unpacked to / packed from fp32 lanes
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    __device__ __forceinline__ static void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ static void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ __forceinline__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// ---- the sampling point: the ONE place the reference's coordinate arithmetic is restated on the device ---------------
+// conv.py:435-454 (p = (p_0 + p_n) + offset, one rounding), :375-387 (floor, +1, independent clamps, clamped p),
+// :390-393 (per-axis weights; both are 1 once p leaves [0, H-1): the reference's border doubling).
+// Uses explicit round-to-nearest intrinsics so the compiler cannot contract anything into an FMA: indices, clamped
+// coordinates and the fp32 weights are bit-exact with the reference (tests/test_gpu_parity.py).
+struct SamplePoint {
+    int r0, r1, k0, k1;
+    float pcr, pck;
+    float ar0, ar1, ak0, ak1;
+    bool in_r, in_k;  // torch.clamp backward indicator (inclusive) on the unclamped coordinate
+};
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+__device__ __forceinline__ SamplePoint make_point(int i, int j, int s, int pn_r, int pn_k, float off_r, float off_k,
+                                                  int H, int W)
+{
+    SamplePoint q;
+    const float pr = __fadd_rn((float)(i * s + pn_r), off_r);
+    const float pk = __fadd_rn((float)(j * s + pn_k), off_k);
+    const float hm = (float)(H - 1), wm = (float)(W - 1);
+    const float fr = floorf(pr), fk = floorf(pk);
+    q.r0 = (int)clampf(fr, 0.f, hm);
+    q.r1 = (int)clampf(__fadd_rn(fr, 1.f), 0.f, hm);
+    q.k0 = (int)clampf(fk, 0.f, wm);
+    q.k1 = (int)clampf(__fadd_rn(fk, 1.f), 0.f, wm);
+    q.pcr = clampf(pr, 0.f, hm);
+    q.pck = clampf(pk, 0.f, wm);
+    q.ar0 = __fadd_rn(1.f, __fsub_rn((float)q.r0, q.pcr));
+    q.ar1 = __fsub_rn(1.f, __fsub_rn((float)q.r1, q.pcr));
+    q.ak0 = __fadd_rn(1.f, __fsub_rn((float)q.k0, q.pck));
+    q.ak1 = __fsub_rn(1.f, __fsub_rn((float)q.k1, q.pck));
+    q.in_r = (pr >= 0.f) && (pr <= hm);
+    q.in_k = (pk >= 0.f) && (pk <= wm);
+    return q;
+}
+
+// reference summation order lt, rb, lb, rt (conv.py:402-405), products and sums rounded separately like the
+// reference's element-wise kernels
+__device__ __forceinline__ float bilinear(float g_lt, float g_rb, float g_lb, float g_rt, float x00, float x11,
+                                          float x01, float x10)
+{
+    float v = __fmul_rn(g_lt, x00);
+    v = __fadd_rn(v, __fmul_rn(g_rb, x11));
+    v = __fadd_rn(v, __fmul_rn(g_lb, x01));
+    v = __fadd_rn(v, __fmul_rn(g_rt, x10));
+    return v;
+}
+
+__device__ __forceinline__ float silu(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad(float z)
+{
+    const float sg = 1.f / (1.f + __expf(-z));
+    return sg * (1.f + z * (1.f - sg));
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ldc

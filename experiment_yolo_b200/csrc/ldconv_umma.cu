@@ -1,0 +1,265 @@
+// ldconv_umma.cu -- tcgen05 / TMEM / TMA GEMM of the LDConv (N,1) conv for bf16 (sm_100a).
+//
+//   pre(M,O) = operand(M,K) . wt(O,K)^T   followed by the folded-BatchNorm affine and SiLU
+//   replaces nn.Conv2d(inc, outc, (N,1), (N,1)) + BatchNorm2d + SiLU of
+//   /root/reference/ultralytics/nn/modules/conv.py:355,408
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer: 128 x 64 bf16 operand blocks and O x 64 weight blocks into a 128B-swizzled smem ring
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=O, K=16) into a double-buffered TMEM accumulator
+//   warps 2..5  epilogue: tcgen05.ld accumulator rows -> affine + SiLU -> bf16 -> 16-byte global stores
+// For the YAML's shapes (K <= 192, O <= 128) the GEMM is HBM-bound (19-77 flop/B), so what matters
+// is the number of operand bytes in flight per SM (the smem ring) rather than MMA issue rate.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ldc {
+
+using namespace umma;
+
+int col_stats_bf16(const __nv_bfloat16* pre, long long M, int O, double* sum, double* sqsum, cudaStream_t st);
+
+static constexpr int kTileM = 128;
+static constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
+static constexpr int kABytes = kTileM * kBlockK * 2;    // 16 KiB
+static constexpr int kGemmThreads = 192;
+
+static thread_local int g_force_ffma = 0;   // ldconv_set_flag(LDCONV_FLAG_FORCE_FFMA, v)
+static int g_env_force_ffma = -1;           // environment LDCONV_FORCE_FFMA=1 (debug A/B switch, wins over the flag)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major (rows, cols) tensor, box (box_rows, 64 cols), 128-byte swizzle, zero fill out of bounds
+static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows)
+{
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(LDCONV_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LDCONV_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LDCONV_OK;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                 __nv_bfloat16* __restrict__ pre, int M, int O, int ON, int num_kb, int num_tiles, int stages, int act,
+                 uint32_t tmem_cols, int vec_store)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = ON * kBlockK * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + (size_t)stages * kABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)stages * b_bytes);
+    uint64_t* empty = full + stages;
+    uint64_t* tfull = empty + stages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+                    tma_load_2d(sA + (size_t)s * kABytes, &tmA, &full[s], kb * kBlockK, tile * kTileM);
+                    tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], kb * kBlockK, 0);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(kTileM, ON);
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t tph = (it >> 1) & 1;
+                mbar_wait(&tempty[buf], tph ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ON);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                                    (uint32_t)((kb | k) != 0));
+                    }
+                    mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+                    if (kb == num_kb - 1) mma_commit(&tfull[buf]);
+                    if (++s == stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        const int lg = warp & 3;  // TMEM lane group this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t tph = (it >> 1) & 1;
+            mbar_wait(&tfull[buf], tph);
+            tc_fence_after_sync();
+            const long long m = (long long)tile * kTileM + lg * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ON);
+            for (int c0 = 0; c0 < ON; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (m < M && c0 < O) {
+                    float acc[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(v[e]);
+                    const int ncol = O - c0 < 16 ? O - c0 : 16;
+                    if (pre) {
+                        __nv_bfloat16* dst = pre + m * O + c0;
+                        if (vec_store && ncol == 16) {
+                            float lo[8], hi[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { lo[e] = acc[e]; hi[e] = acc[8 + e]; }
+                            Vec16<__nv_bfloat16>::store(dst, lo);
+                            Vec16<__nv_bfloat16>::store(dst + 8, hi);
+                        } else {
+                            for (int e = 0; e < ncol; ++e) dst[e] = __float2bfloat16_rn(acc[e]);
+                        }
+                    }
+                    if (out) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            if (e < ncol) {
+                                const float sc = scale ? scale[c0 + e] : 1.f;
+                                const float sh = shift ? shift[c0 + e] : 0.f;
+                                const float z = fmaf(acc[e], sc, sh);
+                                acc[e] = act == LDCONV_ACT_SILU ? silu(z) : z;
+                            }
+                        }
+                        __nv_bfloat16* dst = out + m * O + c0;
+                        if (vec_store && ncol == 16) {
+                            float lo[8], hi[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { lo[e] = acc[e]; hi[e] = acc[8 + e]; }
+                            Vec16<__nv_bfloat16>::store(dst, lo);
+                            Vec16<__nv_bfloat16>::store(dst + 8, hi);
+                        } else {
+                            for (int e = 0; e < ncol; ++e) dst[e] = __float2bfloat16_rn(acc[e]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int umma_gemm_supported(int M, int K, int O, int dtype, const void* a, const void* wt, const void* out, const void* pre)
+{
+    if (g_env_force_ffma < 0) {
+        const char* e = getenv("LDCONV_FORCE_FFMA");
+        g_env_force_ffma = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (g_env_force_ffma || g_force_ffma) return 0;
+    if (dtype != LDCONV_BF16) return 0;
+    if (M < 1 || K % 8 != 0 || O > 256 || O < 1) return 0;
+    if (!aligned16(a) || !aligned16(wt)) return 0;
+    (void)out; (void)pre;
+    return 1;
+}
+
+int umma_set_force_ffma(int v)
+{
+    g_force_ffma = v ? 1 : 0;
+    return LDCONV_OK;
+}
+
+int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
+                  double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
+{
+    if (stat_sum && !pre) return fail(LDCONV_E_ARG, "tcgen05 GEMM: batch statistics need the `pre` output");
+    const int ON = (O + 15) / 16 * 16;
+    const int num_kb = (K + kBlockK - 1) / kBlockK;
+    const int num_tiles = (M + kTileM - 1) / kTileM;
+    const int b_bytes = ON * kBlockK * 2;
+    int stages = (200 * 1024) / (kABytes + b_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return fail(LDCONV_E_ARG, "tcgen05 GEMM: tile does not fit shared memory (O=%d)", O);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(2 * ON)) tmem_cols <<= 1;
+    const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 4) * sizeof(uint64_t) + 16;
+
+    CUtensorMap tmA, tmB;
+    if (int e = make_map_2d(&tmA, a, M, K, kTileM)) return e;
+    if (int e = make_map_2d(&tmB, wt, O, K, ON)) return e;
+
+    LDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = num_sms();
+    if (grid > num_tiles) grid = num_tiles;
+    const int vec_store = (O % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
+    umma_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, scale, shift, (__nv_bfloat16*)out, (__nv_bfloat16*)pre, M,
+                                                       O, ON, num_kb, num_tiles, stages, act, tmem_cols, vec_store);
+    LDC_LAUNCH_CHECK("umma_gemm_kernel");
+    set_impl(LDCONV_IMPL_TCGEN05);
+    if (stat_sum) return col_stats_bf16((const __nv_bfloat16*)pre, M, O, stat_sum, stat_sqsum, st);
+    return LDCONV_OK;
+}
+
+}  // namespace ldc
+
+// ---- one-kernel inference forward (declared in include/ldconv_b200.h) ---------------------------------------------------
+LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
+                             const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
+                             int N, int s, int O, int act, int dtype, void* stream)
+{
+    (void)x; (void)w_off; (void)b_off; (void)p_n; (void)wt; (void)scale; (void)shift; (void)out; (void)off_out;
+    (void)B; (void)C; (void)H; (void)W; (void)N; (void)s; (void)O; (void)act; (void)dtype; (void)stream;
+    return ldc::fail(LDCONV_E_ARG, "ldconv_fused_fwd: this build routes inference through the three-kernel path");
+}

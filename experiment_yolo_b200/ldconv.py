@@ -1,0 +1,358 @@
+"""Drop-in `LDConv` (Linear Deformable Convolution) whose forward and backward run as sm_100a CUDA kernels.
+
+Host-side mirror of the reference module /root/reference/ultralytics/nn/modules/conv.py:350-503:
+same constructor `(inc, outc, num_param, stride=1, bias=None)`, same sub-modules and registration order
+(`conv = Sequential(Conv2d((N,1),(N,1)), BatchNorm2d, SiLU)`, `p_conv = Conv2d(3x3)`, int64 buffer `p_n`), hence the same
+`state_dict()` keys / shapes / dtypes and the same random initialisation under the same seed, and the same YAML row
+`[-1, 1, LDConv, [c2, num_param, stride]]` (nn/tasks.py:813-864).  PyTorch is used for device memory and streams only;
+every op of the path goes through the C ABI of libldconv_b200.so (include/ldconv_b200.h).  No CPU fallback: a CPU tensor
+raises RuntimeError (its text contains 'CUDA tensor', which is what the reference's stride probe at nn/tasks.py:317-321
+looks for before retrying on the GPU).
+
+Numerics contract: sampling offsets, coordinates and bilinear weights are always fp32, also for bf16
+activations -- the reference's own low-precision coordinate math is broken.  bf16 parity is defined
+against the fp32 reference evaluated on bf16-rounded inputs and parameters.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["LDConv", "install", "ldconv_function", "base_grid"]
+
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def base_grid(num_param: int) -> torch.Tensor:
+    """conv.py:413-432 (`_get_p_n`): the un-centred raster base grid as the reference's int64 (1,2N,1,1) buffer,
+    rows (H axis) first, then columns."""
+    base = round(math.sqrt(num_param))
+    rows = [i // base for i in range(num_param)]
+    cols = [i % base for i in range(num_param)]
+    return torch.tensor(rows + cols, dtype=torch.int64).view(1, 2 * num_param, 1, 1)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_input(x: torch.Tensor) -> int:
+    if not x.is_cuda:
+        raise RuntimeError(
+            "experiment_yolo_b200.LDConv runs on sm_100a only and needs a CUDA tensor "
+            f"(got a {x.device.type} tensor); there is no CPU fallback")
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"experiment_yolo_b200.LDConv supports float32 and bfloat16 activations, got {x.dtype}")
+    if x.dim() != 4:
+        raise ValueError(f"LDConv expects a (B,C,H,W) tensor, got shape {tuple(x.shape)}")
+    return _DTYPES[x.dtype]
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) logical -> dense (B,H,W,C) view; zero-copy when x is already channels_last."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+class _Prepared:
+    """Per-call operand forms of the parameters (tiny tensors; cached by the module while the parameters are unchanged)."""
+    __slots__ = ("w_off", "b_off", "wt", "wt_t", "pn", "key")
+
+
+def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepared:
+    pr = _Prepared()
+    N = c_w.shape[2]
+    O, C = c_w.shape[0], c_w.shape[1]
+    # offset conv weights: (2N,C,3,3) -> (3,3,C,2N) fp32, rounded through the activation dtype first so that the bf16
+    # path sees exactly the bf16-rounded parameters the parity oracle uses
+    pr.w_off = p_w.detach().to(dtype).float().permute(2, 3, 1, 0).contiguous()
+    pr.b_off = None if p_b is None else p_b.detach().to(dtype).float().contiguous()
+    # (N,1) conv weight (O,C,N,1) -> (O, N*C), k = n*C + c: the order the NHWC gather produces
+    pr.wt = c_w.detach().to(dtype).reshape(O, C, N).permute(0, 2, 1).reshape(O, N * C).contiguous()
+    pr.wt_t = pr.wt.t().contiguous() if need_wt_t else None
+    pr.pn = p_n.detach().reshape(-1).to(device=c_w.device, dtype=torch.int32).contiguous()
+    return pr
+
+
+class _LDConvFunction(torch.autograd.Function):
+    """Forward = offset conv -> fused grid+gather -> GEMM (+BN statistics) -> BN/SiLU; backward = the closed form of
+    SURVEY.md Appendix A.  Every step is one C-ABI call."""
+
+    @staticmethod
+    def forward(ctx, x, p_w, p_b, c_w, c_b, bn_w, bn_b, running_mean, running_var, p_n, stride, eps, momentum, training,
+                prepared):
+        L = _lib.load()
+        dt = _check_input(x)
+        st = _stream()
+        B, C, H, W = x.shape
+        O, N = c_w.shape[0], c_w.shape[2]
+        s = int(stride)
+        h, w = (H - 1) // s + 1, (W - 1) // s + 1
+        M, K = B * h * w, N * C
+        dev = x.device
+        needs_grad = any(ctx.needs_input_grad)
+        pr = prepared if prepared is not None else _prepare(p_w, p_b, c_w, p_n, x.dtype, needs_grad)
+        if needs_grad and pr.wt_t is None:
+            pr.wt_t = pr.wt.t().contiguous()
+
+        xh = _nhwc(x)
+        off = torch.empty((B, h, w, 2 * N), device=dev, dtype=torch.float32)
+        _lib.check(L.ldconv_offset_conv_fwd(_ptr(xh), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
+                   "ldconv_offset_conv_fwd")
+        operand = torch.empty((M, K), device=dev, dtype=x.dtype)
+        _lib.check(L.ldconv_gather_fwd(_ptr(xh), _ptr(off), _ptr(pr.pn), _ptr(operand), None, None, B, C, H, W, N, s, dt, st),
+                   "ldconv_gather_fwd")
+
+        gamma = None if bn_w is None else bn_w.detach().float().contiguous()
+        beta = None if bn_b is None else bn_b.detach().float().contiguous()
+        scale = torch.empty(O, device=dev, dtype=torch.float32)
+        shift = torch.empty(O, device=dev, dtype=torch.float32)
+        save_mean = torch.empty(O, device=dev, dtype=torch.float32)
+        save_invstd = torch.empty(O, device=dev, dtype=torch.float32)
+        out = torch.empty((B, h, w, O), device=dev, dtype=x.dtype)
+        batch_stats = bool(training) or running_mean is None
+        cbias = None if c_b is None else c_b.detach().float()
+        pre = None
+        if batch_stats:
+            if M <= 1:
+                # torch.nn.functional.batch_norm raises the same error for the reference module
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size {(B, O, h, w)}")
+            stats = torch.zeros((2, O), device=dev, dtype=torch.float64)
+            pre = torch.empty((M, O), device=dev, dtype=x.dtype)
+            _lib.check(L.ldconv_gemm_fwd(_ptr(operand), _ptr(pr.wt), None, None, None, _ptr(pre), _ptr(stats[0]),
+                                         _ptr(stats[1]), M, K, O, _lib.ACT_NONE, dt, st), "ldconv_gemm_fwd")
+            rm32 = rv32 = None
+            if training and running_mean is not None:
+                rm32 = running_mean if running_mean.dtype == torch.float32 else running_mean.float()
+                rv32 = running_var if running_var.dtype == torch.float32 else running_var.float()
+                if cbias is not None:      # BN sees acc + bias: only the running mean notices
+                    rm32.sub_(cbias)
+            _lib.check(L.ldconv_bn_finalize(_ptr(stats[0]), _ptr(stats[1]), M, _ptr(gamma), _ptr(beta), _ptr(rm32),
+                                            _ptr(rv32), float(eps), float(momentum), 1, _ptr(scale), _ptr(shift),
+                                            _ptr(save_mean), _ptr(save_invstd), O, st), "ldconv_bn_finalize")
+            if rm32 is not None:
+                if cbias is not None:
+                    rm32.add_(cbias)
+                if rm32 is not running_mean:
+                    running_mean.copy_(rm32)
+                    running_var.copy_(rv32)
+            _lib.check(L.ldconv_bn_act_apply(_ptr(pre), _ptr(scale), _ptr(shift), _ptr(out), M, O, _lib.ACT_SILU, dt, st),
+                       "ldconv_bn_act_apply")
+        else:
+            rm32 = running_mean.float() if (running_mean.dtype != torch.float32 or cbias is not None) else running_mean
+            if cbias is not None:
+                rm32 = rm32 - cbias
+            rv32 = running_var if running_var.dtype == torch.float32 else running_var.float()
+            _lib.check(L.ldconv_bn_finalize(None, None, 0, _ptr(gamma), _ptr(beta), _ptr(rm32), _ptr(rv32), float(eps),
+                                            0.0, 0, _ptr(scale), _ptr(shift), _ptr(save_mean), _ptr(save_invstd), O, st),
+                       "ldconv_bn_finalize")
+            if needs_grad:
+                pre = torch.empty((M, O), device=dev, dtype=x.dtype)
+            _lib.check(L.ldconv_gemm_fwd(_ptr(operand), _ptr(pr.wt), _ptr(scale), _ptr(shift), _ptr(out), _ptr(pre), None,
+                                         None, M, K, O, _lib.ACT_SILU, dt, st), "ldconv_gemm_fwd")
+        if needs_grad:
+            ctx.save_for_backward(xh, off, operand, pre, scale, shift, save_mean, save_invstd, pr.wt_t, pr.w_off, pr.pn)
+            ctx.meta = (B, C, H, W, O, N, s, dt, batch_stats, x.dtype, p_w.dtype, c_w.dtype,
+                        None if bn_w is None else bn_w.dtype, c_b is not None)
+        return out.permute(0, 3, 1, 2)   # logical NCHW, channels_last strides: downstream convs / cats run unchanged
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        L = _lib.load()
+        xh, off, operand, pre, scale, shift, save_mean, save_invstd, wt_t, w_off, pn = ctx.saved_tensors
+        B, C, H, W, O, N, s, dt, batch_stats, xdtype, pw_dtype, cw_dtype, bn_dtype, has_cbias = ctx.meta
+        st = _stream()
+        dev = xh.device
+        h, w = (H - 1) // s + 1, (W - 1) // s + 1
+        M, K = B * h * w, N * C
+        need_x = ctx.needs_input_grad[0]
+
+        go = _nhwc(grad_out.to(xdtype))
+        red = torch.zeros((2, O), device=dev, dtype=torch.float64)
+        _lib.check(L.ldconv_bn_act_bwd_reduce(_ptr(pre), _ptr(go), _ptr(scale), _ptr(shift), _ptr(save_mean),
+                                              _ptr(save_invstd), _ptr(red), M, O, _lib.ACT_SILU, dt, st),
+                   "ldconv_bn_act_bwd_reduce")
+        grad_pre = torch.empty((M, O), device=dev, dtype=xdtype)
+        _lib.check(L.ldconv_bn_act_bwd_apply(_ptr(pre), _ptr(go), _ptr(scale), _ptr(shift), _ptr(save_mean),
+                                             _ptr(save_invstd), _ptr(red), _ptr(grad_pre), M, O, _lib.ACT_SILU,
+                                             int(batch_stats), dt, st), "ldconv_bn_act_bwd_apply")
+        # weight gradient of the (N,1) conv: (O,K) fp32, k = n*C + c  ->  (O,C,N,1)
+        grad_wt = torch.zeros((O, K), device=dev, dtype=torch.float32)
+        _lib.check(L.ldconv_gemm_bwd_weight(_ptr(grad_pre), _ptr(operand), _ptr(grad_wt), M, K, O, dt, st),
+                   "ldconv_gemm_bwd_weight")
+        grad_c_w = grad_wt.view(O, N, C).permute(0, 2, 1).reshape(O, C, N, 1).to(cw_dtype)
+        # data gradient: grad_operand (M,K) = grad_pre (M,O) . W (O,K)   (same GEMM kernel, roles of K and O swapped)
+        grad_operand = torch.empty((M, K), device=dev, dtype=xdtype)
+        _lib.check(L.ldconv_gemm_fwd(_ptr(grad_pre), _ptr(wt_t), None, None, _ptr(grad_operand), None, None, None, M, O, K,
+                                     _lib.ACT_NONE, dt, st), "ldconv_gemm_fwd(data grad)")
+        grad_x32 = torch.zeros((B, H, W, C), device=dev, dtype=torch.float32) if need_x else None
+        grad_off = torch.empty((B, h, w, 2 * N), device=dev, dtype=torch.float32)
+        _lib.check(L.ldconv_gather_bwd(_ptr(grad_operand), _ptr(xh), _ptr(off), _ptr(pn), _ptr(grad_x32), _ptr(grad_off),
+                                       B, C, H, W, N, s, dt, st), "ldconv_gather_bwd")
+        grad_w_off = torch.zeros((3, 3, C, 2 * N), device=dev, dtype=torch.float32)
+        grad_b_off = torch.zeros((2 * N,), device=dev, dtype=torch.float32)
+        _lib.check(L.ldconv_offset_conv_bwd(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
+                                            _ptr(grad_b_off), B, C, H, W, N, s, dt, st), "ldconv_offset_conv_bwd")
+        grad_x = grad_x32.to(xdtype).permute(0, 3, 1, 2) if need_x else None
+        grad_p_w = grad_w_off.permute(3, 2, 0, 1).contiguous().to(pw_dtype)
+        grad_p_b = grad_b_off.to(pw_dtype)
+        grad_gamma = red[1].to(bn_dtype) if bn_dtype is not None else None
+        grad_beta = red[0].to(bn_dtype) if bn_dtype is not None else None
+        grad_c_b = grad_pre.float().sum(0).to(cw_dtype) if has_cbias else None
+        return (grad_x, grad_p_w, grad_p_b, grad_c_w, grad_c_b, grad_gamma, grad_beta, None, None, None, None, None,
+                None, None, None)
+
+
+def ldconv_function(x, p_conv_weight, p_conv_bias, conv_weight, bn_weight, bn_bias, running_mean, running_var, p_n,
+                    stride: int, eps: float = 1e-5, momentum: float = 0.1, training: bool = False, conv_bias=None,
+                    prepared=None):
+    """Functional form of the whole module (parameters in the reference's own layouts)."""
+    return _LDConvFunction.apply(x, p_conv_weight, p_conv_bias, conv_weight, conv_bias, bn_weight, bn_bias, running_mean,
+                                 running_var, p_n, stride, eps, momentum, training, prepared)
+
+
+def ldconv_fused_inference(x, prepared: _Prepared, scale, shift, C, O, N, s):
+    """One-kernel bf16 inference forward (ldconv_fused_fwd): the resampled operand never reaches HBM."""
+    L = _lib.load()
+    dt = _check_input(x)
+    B, _, H, W = x.shape
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    xh = _nhwc(x)
+    out = torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
+    _lib.check(L.ldconv_fused_fwd(_ptr(xh), _ptr(prepared.w_off), _ptr(prepared.b_off), _ptr(prepared.pn),
+                                  _ptr(prepared.wt), _ptr(scale), _ptr(shift), _ptr(out), None, B, C, H, W, N, s, O,
+                                  _lib.ACT_SILU, dt, _stream()), "ldconv_fused_fwd")
+    return out.permute(0, 3, 1, 2)
+
+
+class LDConv(nn.Module):
+    """B200-native LDConv.  Signature, children, buffer and state_dict layout: conv.py:350-359."""
+
+    # one-kernel inference path (tcgen05) when shapes allow; class-level switch so tests can A/B it
+    use_fused_inference = False
+
+    def __init__(self, inc, outc, num_param, stride=1, bias=None):
+        super().__init__()
+        self.num_param = num_param
+        self.stride = stride
+        # same construction order as the reference => same parameter values under the same torch seed
+        self.conv = nn.Sequential(
+            nn.Conv2d(inc, outc, kernel_size=(num_param, 1), stride=(num_param, 1), bias=bias),
+            nn.BatchNorm2d(outc),
+            nn.SiLU())
+        self.p_conv = nn.Conv2d(inc, 2 * num_param, kernel_size=3, padding=1, stride=stride)
+        nn.init.constant_(self.p_conv.weight, 0)      # conv.py:357
+        # conv.py:358,361-364: the reference registers a backward hook that scales nothing (it builds two generators and
+        # returns None), so gradients are NOT multiplied by 0.1; reproduced by not registering anything.
+        self.register_buffer("p_n", base_grid(num_param))
+        self._prep_cache = None
+
+    # ---- parameter-derived operand cache (not part of the state; dropped on pickle / deepcopy) --------------------------
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_prep_cache"] = None
+        return state
+
+    def _prepared(self, dtype: torch.dtype, need_wt_t: bool):
+        conv, pconv = self.conv[0], self.p_conv
+        key = (dtype, conv.weight.data_ptr(), conv.weight._version, pconv.weight.data_ptr(), pconv.weight._version,
+               None if pconv.bias is None else (pconv.bias.data_ptr(), pconv.bias._version), self.p_n._version,
+               conv.weight.device)
+        c = self._prep_cache
+        if c is None or c.key != key:
+            c = _prepare(pconv.weight, pconv.bias, conv.weight, self.p_n, dtype, need_wt_t)
+            c.key = key
+            self._prep_cache = c
+        elif need_wt_t and c.wt_t is None:
+            c.wt_t = c.wt.t().contiguous()
+        return c
+
+    def _fused_ok(self, x) -> bool:
+        if not (self.use_fused_inference and x.dtype == torch.bfloat16):
+            return False
+        C, O, N = x.shape[1], self.conv[0].out_channels, self.num_param
+        bn = self.conv[1]
+        return (bn.running_mean is not None and self.conv[0].bias is None and C % 8 == 0 and O % 16 == 0 and O <= 256
+                and N * C <= 512)
+
+    def forward(self, x):
+        _check_input(x)
+        conv, bn = self.conv[0], self.conv[1]
+        training = self.training
+        momentum = bn.momentum
+        if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:  # cumulative moving average, as torch.nn.modules.batchnorm._BatchNorm.forward
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        if momentum is None:
+            momentum = 0.0
+        grad_mode = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters(recurse=True)))
+        prepared = self._prepared(x.dtype, grad_mode)
+        if not training and not grad_mode and self._fused_ok(x):
+            scale, shift = _folded_bn(bn, x.device)
+            return ldconv_fused_inference(x, prepared, scale, shift, x.shape[1], conv.out_channels, self.num_param,
+                                          int(self.stride))
+        return _LDConvFunction.apply(x, self.p_conv.weight, self.p_conv.bias, conv.weight, conv.bias, bn.weight, bn.bias,
+                                     bn.running_mean, bn.running_var, self.p_n, int(self.stride), bn.eps, momentum,
+                                     training, prepared)
+
+
+def _folded_bn(bn: nn.BatchNorm2d, device):
+    """Eval-mode BatchNorm folded to per-channel scale/shift through the C ABI (eps read from the module)."""
+    L = _lib.load()
+    O = bn.num_features
+    scale = torch.empty(O, device=device, dtype=torch.float32)
+    shift = torch.empty(O, device=device, dtype=torch.float32)
+    gamma = None if bn.weight is None else bn.weight.detach().float().contiguous()
+    beta = None if bn.bias is None else bn.bias.detach().float().contiguous()
+    rm, rv = bn.running_mean.float(), bn.running_var.float()
+    _lib.check(L.ldconv_bn_finalize(None, None, 0, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), float(bn.eps), 0.0, 0,
+                                    _ptr(scale), _ptr(shift), None, None, O, _stream()), "ldconv_bn_finalize")
+    return scale, shift
+
+
+# ---- the reference's plugin hook -------------------------------------------------------------------------------------------
+_REF_MODULES = ("ultralytics.nn.modules.conv", "ultralytics.nn.modules", "ultralytics.nn.modules.block",
+                "ultralytics.nn.tasks")
+
+
+def install(verbose: bool = False):
+    """Rebind the name `LDConv` in the four reference modules that hold it (conv.py:28, modules/__init__.py:62,
+    modules/block.py:9, nn/tasks.py:11) so that `parse_model` (nn/tasks.py:813, `globals()[m]`) instantiates this class
+    for every `LDConv` YAML row and `Bottleneck_LDConv` / `C2f_LDConv` (block.py:611-677) pick it up too.
+    Returns the list of modules patched; a no-op (empty list) when ultralytics is not importable."""
+    import importlib
+    patched = []
+    for name in _REF_MODULES:
+        try:
+            mod = importlib.import_module(name)
+        except Exception:  # ultralytics absent (the GPU box): nothing to patch
+            continue
+        if hasattr(mod, "LDConv"):
+            setattr(mod, "LDConv", LDConv)
+            patched.append(name)
+    if verbose:
+        print(f"experiment_yolo_b200.install(): LDConv rebound in {patched}")
+    return patched
+
+
+def convert(model: nn.Module) -> nn.Module:
+    """In-place conversion of an already-built reference model: every module whose class is named `LDConv` and has the
+    reference's children gets this class (parameters, buffers and state_dict untouched)."""
+    for m in model.modules():
+        if type(m).__name__ == "LDConv" and not isinstance(m, LDConv) and hasattr(m, "p_conv") and hasattr(m, "p_n"):
+            m.__class__ = LDConv
+            m._prep_cache = None
+            # the reference's no-op backward hook wraps p_conv in BackwardHookFunction nodes; drop it
+            m.p_conv._backward_hooks.clear()
+    return model

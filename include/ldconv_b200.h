@@ -1,0 +1,145 @@
+/*
+ * ldconv_b200.h -- C ABI of libldconv_b200.so: the B200 (sm_100a) implementation of DEAL-YOLO's LDConv hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native code on this path: everything
+ * below replaces eager-PyTorch lines of /root/reference/ultralytics/nn/modules/conv.py:350-503 (class LDConv), and
+ * each entry point cites the lines it replaces.  The host-side nn.Module that keeps the reference's Python surface
+ * (constructor, state_dict, YAML hook) lives in experiment_yolo_b200/ldconv.py and binds these symbols with ctypes;
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, ints, and a cudaStream_t passed as void*; no torch types, no C++ types.
+ *   - every call is asynchronous on `stream`, never synchronises the host, allocates no device memory, keeps no
+ *     state between calls (deepcopy / pickle of the Python module stay trivial) and is CUDA-graph capturable.
+ *   - return value: 0 on success, a negative LDCONV_E_* code otherwise; ldconv_last_error() returns a thread-local
+ *     message.  There is no CPU fallback: on a machine without an sm_100 device every compute call fails loudly.
+ *   - activations are NHWC ("channels_last"): x (B,H,W,C); dtype LDCONV_F32 or LDCONV_BF16 selects the element type of
+ *     x / operand / weights of the (N,1) conv / outputs.  Sampling offsets, coordinates, bilinear weights, BatchNorm
+ *     statistics and all accumulators are ALWAYS fp32 (fp64 for the cross-CTA statistics): the reference's own
+ *     low-precision coordinate math is broken and is deliberately not reproduced.
+ *   - h = (H-1)/s + 1, w = (W-1)/s + 1 (3x3, pad 1, stride s offset conv, conv.py:356); M = B*h*w; K = N*C.
+ *   - offsets are (B,h,w,2N) fp32: channels [0,N) are ROW (H axis) offsets, [N,2N) COLUMN (W axis) offsets
+ *     (conv.py:370, 463-467).
+ *   - the resampled operand is (M, K) row-major with k = n*C + c.  The reference's (N,1)-conv weight (O,C,N,1)
+ *     (conv.py:355) must therefore be passed permuted to (O, N, C) -> (O, K); the Python module does that.
+ */
+#ifndef LDCONV_B200_H
+#define LDCONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDCONV_ABI_VERSION 1
+
+#define LDCONV_F32 0
+#define LDCONV_BF16 1
+
+#define LDCONV_ACT_NONE 0
+#define LDCONV_ACT_SILU 1
+
+#define LDCONV_OK 0
+#define LDCONV_E_ARG (-1)      /* bad shape / null pointer / unsupported value */
+#define LDCONV_E_ALIGN (-2)    /* pointer not aligned for the vectorised path */
+#define LDCONV_E_CUDA (-3)     /* a CUDA runtime / launch error; message holds cudaGetErrorString */
+#define LDCONV_E_DEVICE (-4)   /* current device is not sm_100 (no fallback exists) */
+
+/* Which implementation ldconv_gemm_fwd / ldconv_fused_fwd picked for the last call on this thread (for tests and for
+ * bench.py's gpu_launches bookkeeping): 1 = CUDA-core FFMA tile kernel, 2 = tcgen05/TMEM kernel. */
+#define LDCONV_IMPL_FFMA 1
+#define LDCONV_IMPL_TCGEN05 2
+
+int ldconv_version(void);
+const char* ldconv_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, LDCONV_E_DEVICE otherwise. */
+int ldconv_device_check(void);
+int ldconv_last_impl(void);
+/* Debug / A-B switches (thread-local).  LDCONV_FLAG_FORCE_FFMA = 1 routes bf16 GEMMs to the CUDA-core kernel too, so a
+ * test can compare the two implementations; it is not a fallback (both are sm_100a CUDA). */
+#define LDCONV_FLAG_FORCE_FFMA 1
+int ldconv_set_flag(int flag, int value);
+
+/* conv.py:413-432 (_get_p_n): writes the 2N int32 base-grid table (rows then columns).  Host-side helper, no GPU. */
+int ldconv_p_n(int N, int32_t* out_host);
+
+/* conv.py:356,368  offset = p_conv(x): 3x3 / pad 1 / stride s, C -> 2N, + bias.
+ *   x    (B,H,W,C) dtype        w (3,3,C,2N) fp32 (the reference's (2N,C,3,3) permuted)      bias (2N) fp32 or NULL
+ *   off  (B,h,w,2N) fp32 */
+int ldconv_offset_conv_fwd(const void* x, const float* w, const float* bias, float* off,
+                           int B, int C, int H, int W, int N, int s, int dtype, void* stream);
+
+/* conv.py:369-407 + 413-503: sampling grid p = p_0 + p_n + offset, floor / independent clamps, four corner indices,
+ * four bilinear weights, the four gathers, the bilinear sum and the 'b c h w n -> b c (h n) w' rearrange, fused.
+ *   x (B,H,W,C) dtype; off (B,h,w,2N) fp32; p_n (2N) int32 device table
+ *   operand (M, N*C) dtype
+ *   dbg_idx   (M,N,4) int32 {r0,r1,k0,k1} or NULL;   dbg_coord (M,N,2) fp32 {clamped row, clamped col} or NULL
+ * Indices and coordinates are bit-exact with the reference given the same `off`; the fp32 operand is bit-exact too
+ * (same operation order, no FMA contraction), the bf16 operand is that value rounded to nearest-even. */
+int ldconv_gather_fwd(const void* x, const float* off, const int32_t* p_n, void* operand, int32_t* dbg_idx,
+                      float* dbg_coord, int B, int C, int H, int W, int N, int s, int dtype, void* stream);
+
+/* conv.py:355,408: the (N,1)/(N,1) conv is the GEMM pre(M,O) = operand(M,K) . wt(O,K)^T, followed by the
+ * per-channel affine (folded BatchNorm) and SiLU of the Sequential tail.
+ *   a (M,K) dtype, wt (O,K) dtype
+ *   out (M,O) dtype or NULL: act(acc*scale[o] + shift[o])   (scale/shift fp32 (O); NULL = identity)
+ *   pre (M,O) dtype or NULL: the raw accumulator (training: saved for backward)
+ *   stat_sum / stat_sqsum (O) fp64 or NULL: += sum_m acc, sum_m acc^2 (caller zero-initialises; BatchNorm batch stats)
+ * Also used for the data gradient of that conv (a = grad_pre (M,O'), wt = W^T). */
+int ldconv_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
+                    double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, int dtype, void* stream);
+
+/* torch.nn.BatchNorm2d bookkeeping of conv.py:355 (eps / momentum come from the module, never hard-coded).
+ * training != 0: mean/var from stat_sum/stat_sqsum over `count` rows; running <- (1-momentum)*running +
+ *   momentum*(mean, unbiased var) (running_* may be NULL); training == 0: mean/var = running_*.
+ * Writes scale = gamma*invstd, shift = beta - mean*scale, save_mean, save_invstd (all (O) fp32). */
+int ldconv_bn_finalize(const double* stat_sum, const double* stat_sqsum, long long count, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                       int training, float* scale, float* shift, float* save_mean, float* save_invstd, int O,
+                       void* stream);
+
+/* out = act(pre*scale + shift), (M,O) dtype -> (M,O) dtype: second pass of the training forward. */
+int ldconv_bn_act_apply(const void* pre, const float* scale, const float* shift, void* out, long long M, int O,
+                        int act, int dtype, void* stream);
+
+/* Backward of act(BN(pre)), pass 1: red[0:O] += sum_m dz, red[O:2O] += sum_m dz*xhat   (fp64, caller zero-inits)
+ * with z = pre*scale+shift, dz = grad_out * act'(z), xhat = (pre - mean)*invstd.  red[0:O] is grad beta, red[O:2O] is
+ * grad gamma. */
+int ldconv_bn_act_bwd_reduce(const void* pre, const void* grad_out, const float* scale, const float* shift,
+                             const float* mean, const float* invstd, double* red, long long M, int O, int act,
+                             int dtype, void* stream);
+/* pass 2: grad_pre = scale * (dz - [training] (red0 + xhat*red1)/M)   (M,O) dtype */
+int ldconv_bn_act_bwd_apply(const void* pre, const void* grad_out, const float* scale, const float* shift,
+                            const float* mean, const float* invstd, const double* red, void* grad_pre, long long M,
+                            int O, int act, int training, int dtype, void* stream);
+
+/* Weight gradient of the (N,1) conv: grad_wt (O,K) fp32 += grad_pre(M,O)^T . operand(M,K)  (caller zero-inits). */
+int ldconv_gemm_bwd_weight(const void* grad_pre, const void* operand, float* grad_wt, int M, int K, int O, int dtype,
+                           void* stream);
+
+/* Backward of the bilinear resampling (autograd of conv.py:386-405; closed form: SURVEY.md Appendix A).
+ *   grad_operand (M, N*C) dtype;  x, off, p_n as in ldconv_gather_fwd
+ *   grad_x   (B,H,W,C) fp32, ACCUMULATED with atomics (caller zero-inits): the four scatter_add_ of autograd;
+ *            NULL when the input needs no gradient (the image, layer 0)
+ *   grad_off (B,h,w,2N) fp32, written: clamp-backward indicator * sum_c (...) */
+int ldconv_gather_bwd(const void* grad_operand, const void* x, const float* off, const int32_t* p_n, float* grad_x,
+                      float* grad_off, int B, int C, int H, int W, int N, int s, int dtype, void* stream);
+
+/* Backward of the offset conv (conv.py:356): grad_x (B,H,W,C) fp32 += conv_transpose(grad_off, w);
+ * grad_w (3,3,C,2N) fp32 += ..., grad_b (2N) fp32 += ...  (caller zero-inits grad_w / grad_b; either may be NULL). */
+int ldconv_offset_conv_bwd(const float* grad_off, const void* x, const float* w, float* grad_x, float* grad_w,
+                           float* grad_b, int B, int C, int H, int W, int N, int s, int dtype, void* stream);
+
+/* Inference forward of the whole module in ONE kernel (bf16): offset conv + grid + gather into shared memory in the
+ * tcgen05 operand layout + UMMA with TMEM accumulators + folded BatchNorm + SiLU epilogue; the resampled operand
+ * never touches HBM.  x (B,H,W,C) bf16, wt (O,K) bf16, out (B,h,w,O) bf16.  off_out (B,h,w,2N) fp32 may be NULL. */
+int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
+                     const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
+                     int N, int s, int O, int act, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDCONV_B200_H */

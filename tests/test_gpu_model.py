@@ -1,0 +1,59 @@
+"""GPU: the DEAL-YOLO-LD benchmark graph with the CUDA LDConv against the golden output of the reference DetectionModel
+(tests/golden/model_deal_yolo_ld.npz, minted by oracle/gen_model_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from experiment_yolo_b200 import dealyolo
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _load():
+    z = np.load(os.path.join(_golden.GOLDEN_DIR, "model_deal_yolo_ld.npz"))
+    model = dealyolo.DealYolo(nc=6)
+    model.load_state_dict(dealyolo.seeded_state(model, seed=0), strict=True)
+    return z, model
+
+
+def test_full_model_fp32_matches_reference_output():
+    """BASELINE config 1 (shrunk spatially): new module on the GPU vs the reference on the CPU, fp32, TF32 off."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z, model = _load()
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        y, feats = model(torch.from_numpy(z["x"]).to(DEV))
+    y = y.cpu().numpy()
+    ref = z["y"]
+    # boxes are in pixels (up to ~128), class scores in [0,1]
+    assert np.abs(y[:, 4:] - ref[:, 4:]).max() <= 1e-4
+    assert np.abs(y[:, :4] - ref[:, :4]).max() <= 2e-3
+    assert np.abs(feats[0].cpu().numpy() - z["feat0"]).max() <= 1e-3
+
+
+def test_full_model_bf16_channels_last_close_to_reference_output():
+    z, model = _load()
+    model = model.to(DEV).bfloat16().eval().to(memory_format=torch.channels_last)
+    x = torch.from_numpy(z["x"]).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y, _ = model(x)
+    y = y.float().cpu().numpy()
+    ref = z["y"]
+    rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+    assert rel <= 5e-2, rel      # 27 bf16 layers deep; the LDConv layers alone are held to 1e-2 in test_gpu_parity.py
+
+
+def test_full_model_train_mode_backward_runs():
+    z, model = _load()
+    model = model.to(DEV).train()
+    x = torch.rand(2, 3, 64, 64, device=DEV)
+    outs = model(x)
+    loss = sum(o.float().square().mean() for o in outs)
+    loss.backward()
+    g = [p.grad for n, p in model.named_parameters() if "p_conv" in n or ".conv.0." in n]
+    assert all(t is not None and bool(torch.isfinite(t).all()) for t in g)

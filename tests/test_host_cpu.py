@@ -1,0 +1,141 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/ldconv_b200.h declares,
+and the Python module keeps the reference's surface (conv.py:350-359: constructor, children, buffer, state_dict)."""
+import copy
+import ctypes
+import os
+import pickle
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import experiment_yolo_b200 as E
+from experiment_yolo_b200 import _lib, ldconv
+from oracle import oracle
+from tests import _golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ldconv_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ldconv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 17
+    lib = ctypes.CDLL(_lib.LIB_PATH) if "torch" in sys.modules else None
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ldconv_b200.h but not exported by libldconv_b200.so"
+    assert sorted(_lib.SIGNATURES) == names, "the ctypes table must mirror the header one to one"
+
+
+def test_version_and_error_plumbing_without_gpu():
+    L = _lib.load()
+    assert L.ldconv_version() == 1
+    # no compute: only argument validation, which happens before any CUDA call
+    rc = L.ldconv_gather_fwd(None, None, None, None, None, None, 1, 8, 4, 4, 3, 1, 0, None)
+    assert rc == -1 and b"null pointer" in L.ldconv_last_error()
+    rc = L.ldconv_offset_conv_fwd(None, None, None, None, 1, 8, 4, 4, 99, 1, 0, None)
+    assert rc == -1 and b"num_param" in L.ldconv_last_error()
+    rc = L.ldconv_gemm_fwd(None, None, None, None, None, None, None, None, 4, 8, 8, 1, 7, None)
+    assert rc == -1 and b"dtype" in L.ldconv_last_error()
+
+
+@pytest.mark.parametrize("N", range(1, 17))
+def test_p_n_helper_matches_oracle(N):
+    want = oracle.p_n(N).reshape(-1).tolist()
+    assert _lib.p_n_table(N) == want
+    assert ldconv.base_grid(N).reshape(-1).tolist() == want
+    assert ldconv.base_grid(N).dtype == torch.int64 and tuple(ldconv.base_grid(N).shape) == (1, 2 * N, 1, 1)
+
+
+@pytest.mark.parametrize("name", _golden.case_names())
+def test_state_dict_layout_matches_reference(name):
+    """Keys, order, shapes and dtypes of state_dict() equal the reference module's."""
+    z, prm, m = _golden.load(name)
+    mod = E.LDConv(m["inc"], m["outc"], m["N"], m["s"])
+    sd = mod.state_dict()
+    ref_keys = ["p_n", "conv.0.weight", "conv.1.weight", "conv.1.bias", "conv.1.running_mean", "conv.1.running_var",
+                "conv.1.num_batches_tracked", "p_conv.weight", "p_conv.bias"]
+    assert list(sd.keys()) == ref_keys
+    for k in ref_keys:
+        g = z["param_" + k.replace(".", "_")]
+        assert tuple(sd[k].shape) == tuple(g.shape), k
+        assert str(sd[k].dtype).replace("torch.", "") == str(g.dtype), k
+    assert torch.equal(sd["p_n"], torch.from_numpy(z["param_p_n"]))
+    assert float(sd["p_conv.weight"].abs().max()) == 0.0          # conv.py:357
+    assert mod.conv[0].bias is None                                # conv.py:351,355
+    assert mod.num_param == m["N"] and mod.stride == m["s"]
+
+
+def test_same_seed_same_initialisation_as_reference_order():
+    """Construction order matches conv.py:355-357, so the RNG stream is consumed identically: conv weight, then p_conv
+    (whose weight is then zeroed, bias kept)."""
+    torch.manual_seed(7)
+    a = E.LDConv(6, 10, 5, 2)
+    torch.manual_seed(7)
+    conv = torch.nn.Conv2d(6, 10, kernel_size=(5, 1), stride=(5, 1), bias=None)
+    pconv = torch.nn.Conv2d(6, 10, kernel_size=3, padding=1, stride=2)
+    assert torch.equal(a.conv[0].weight, conv.weight)
+    assert torch.equal(a.p_conv.bias, pconv.bias)
+
+
+def test_cpu_tensor_raises_the_error_the_reference_probe_expects():
+    """nn/tasks.py:317-321 retries on the GPU when the RuntimeError text contains 'CUDA tensor'."""
+    mod = E.LDConv(4, 8, 3, 2)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        mod(torch.zeros(2, 4, 8, 8))
+
+
+def test_deepcopy_pickle_and_dtype_casts_keep_the_state():
+    mod = E.LDConv(4, 8, 3, 1)
+    mod2 = copy.deepcopy(mod)
+    assert list(mod2.state_dict()) == list(mod.state_dict())
+    mod3 = pickle.loads(pickle.dumps(mod))
+    assert torch.equal(mod3.conv[0].weight, mod.conv[0].weight)
+    half = copy.deepcopy(mod).bfloat16()
+    assert half.p_n.dtype == torch.int64 and half.conv[0].weight.dtype == torch.bfloat16
+    mod.load_state_dict(mod2.state_dict(), strict=True)
+
+
+def test_yaml_hook_install_rebinds_the_four_reference_modules(monkeypatch):
+    """parse_model resolves the YAML name through module globals (nn/tasks.py:813); install() rebinds `LDConv` in the four
+    modules that hold it.  ultralytics itself is absent here and on the GPU box, so the package tree is faked."""
+    class RefLDConv(torch.nn.Module):
+        pass
+    names = ["ultralytics", "ultralytics.nn", "ultralytics.nn.modules", "ultralytics.nn.modules.conv",
+             "ultralytics.nn.modules.block", "ultralytics.nn.tasks"]
+    for n in names:
+        mod = types.ModuleType(n)
+        mod.__path__ = []
+        monkeypatch.setitem(sys.modules, n, mod)
+    for n in ldconv._REF_MODULES:
+        sys.modules[n].LDConv = RefLDConv
+    patched = E.install()
+    assert sorted(patched) == sorted(ldconv._REF_MODULES)
+    for n in ldconv._REF_MODULES:
+        assert sys.modules[n].LDConv is E.LDConv
+    # the YAML row [-1, 1, LDConv, [c2, num_param, stride]] -> m(*[c1, c2, num_param, stride])  (nn/tasks.py:864,1046)
+    layer = sys.modules["ultralytics.nn.tasks"].LDConv(*[16, 32, 3, 2])
+    assert isinstance(layer, E.LDConv) and layer.p_conv.stride == (2, 2)
+
+
+def test_convert_swaps_class_in_place():
+    class LDConv(torch.nn.Module):          # stands in for the reference class (same name, same children)
+        def __init__(self):
+            super().__init__()
+            src = E.LDConv(4, 8, 3, 2)
+            self.num_param, self.stride = 3, 2
+            self.conv, self.p_conv = src.conv, src.p_conv
+            self.register_buffer("p_n", src.p_n.clone())
+    holder = torch.nn.Sequential(LDConv())
+    keys = list(holder.state_dict())
+    ldconv.convert(holder)
+    assert isinstance(holder[0], E.LDConv) and list(holder.state_dict()) == keys
