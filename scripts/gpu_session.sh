@@ -11,6 +11,10 @@ echo "=== pytest -m gpu, LDCONV_FORCE_FFMA=1 ==="
 LDCONV_FORCE_FFMA=1 timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > $OUT/pytest_ffma_$TAG.log 2>&1
 echo "exit $?"; tail -5 $OUT/pytest_ffma_$TAG.log
 
+echo "=== tcgen05 GEMM tests alone (a trap here must not poison the other tests) ==="
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "gemm_bf16" --timeout 300 > $OUT/pytest_umma_$TAG.log 2>&1
+echo "exit $?"; tail -25 $OUT/pytest_umma_$TAG.log
+
 echo "=== pytest -m gpu (tcgen05 enabled) ==="
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 > $OUT/pytest_$TAG.log 2>&1
 echo "exit $?"; tail -15 $OUT/pytest_$TAG.log
@@ -33,8 +37,9 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_r
 echo "exit $?"; tail -c 600 $OUT/bench_ref_$TAG.json
 
 if [ $BRC -eq 0 ]; then
-  echo "=== ncu launch list ==="
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv \
+  echo "=== ncu launch list (same command run plain first) ==="
+  timeout 600 python bench.py --steps 2 --warmup 3 > $OUT/plain_$TAG.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 3 > $OUT/ncu_launch_$TAG.log 2>&1
   echo "exit $?"; tail -2 $OUT/ncu_launch_$TAG.log
 fi
