@@ -209,7 +209,7 @@ def run_gpu_arm(args):
     torch.backends.cudnn.benchmark = True
     model = dealyolo.DealYolo(nc=NC)
     model.load_state_dict(dealyolo.seeded_state(model, 0))
-    model = model.to(dev).bfloat16().eval().to(memory_format=torch.channels_last)
+    model = dealyolo.channels_last_(model.to(dev).bfloat16().eval())
 
     B = PER_GPU_BATCH
     g = torch.Generator(device=dev).manual_seed(1000 + rank)

@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_SILU = 0, 1
 IMPL_FFMA, IMPL_TCGEN05 = 1, 2
 FLAG_FORCE_FFMA = 1
+FLAG_GATHER_DIRECT = 2
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -28,6 +29,7 @@ SIGNATURES = {
     "ldconv_device_check": (_i, []),
     "ldconv_last_impl": (_i, []),
     "ldconv_set_flag": (_i, [_i, _i]),
+    "ldconv_set_gather_miss_counter": (_i, [_vp]),
     "ldconv_p_n": (_i, [_i, _vp]),
     "ldconv_offset_conv_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "ldconv_gather_fwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),

@@ -747,13 +747,22 @@ LDC_API int ldconv_version(void) { return LDCONV_ABI_VERSION; }
 LDC_API const char* ldconv_last_error(void) { return ldc::err_buf(); }
 LDC_API int ldconv_last_impl(void) { return ldc::g_impl; }
 
-namespace ldc { int umma_set_force_ffma(int v); }
+namespace ldc {
+int umma_set_force_ffma(int v);
+int gather_set_direct(int v);
+int gather_set_miss_counter(void* p);
+int gather_fwd_tiled(const void* x, const float* off, const int* pn, void* operand, int* dbg_idx, float* dbg_coord, int B,
+                     int C, int H, int W, int N, int s, int dtype, cudaStream_t st);
+}
 
 LDC_API int ldconv_set_flag(int flag, int value)
 {
     if (flag == LDCONV_FLAG_FORCE_FFMA) return ldc::umma_set_force_ffma(value);
+    if (flag == LDCONV_FLAG_GATHER_DIRECT) return ldc::gather_set_direct(value);
     return fail(LDCONV_E_ARG, "ldconv_set_flag: unknown flag %d", flag);
 }
+
+LDC_API int ldconv_set_gather_miss_counter(void* device_u64) { return ldc::gather_set_miss_counter(device_u64); }
 
 LDC_API int ldconv_device_check(void)
 {
@@ -801,6 +810,10 @@ LDC_API int ldconv_gather_fwd(const void* x, const float* off, const int32_t* p_
     if (dbg_idx && !aligned16(dbg_idx)) return fail(LDCONV_E_ALIGN, "ldconv_gather_fwd: dbg_idx must be 16-byte aligned");
     if (B == 0) return LDCONV_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // TMA-staged tile kernel when the shape is eligible (C*elem % 16 == 0), else the direct-load kernel below
+        const int rc = gather_fwd_tiled(x, off, p_n, operand, dbg_idx, dbg_coord, B, C, H, W, N, s, dtype, st);
+        if (rc <= 0) return rc;
+    }
     if (dtype == LDCONV_F32)
         return launch_gather_fwd<float>((const float*)x, off, p_n, (float*)operand, dbg_idx, dbg_coord, B, C, H, W, N, s, st);
     return launch_gather_fwd<__nv_bfloat16>((const __nv_bfloat16*)x, off, p_n, (__nv_bfloat16*)operand, dbg_idx,

@@ -12,6 +12,7 @@
 // is the number of operand bytes in flight per SM (the smem ring) rather than MMA issue rate.
 #include "common.cuh"
 #include "umma.cuh"
+#include "tmap.cuh"
 
 namespace ldc {
 
@@ -27,39 +28,13 @@ static constexpr int kGemmThreads = 192;
 static thread_local int g_force_ffma = 0;   // ldconv_set_flag(LDCONV_FLAG_FORCE_FFMA, v)
 static int g_env_force_ffma = -1;           // environment LDCONV_FORCE_FFMA=1 (debug A/B switch, wins over the flag)
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 // 2-D bf16 row-major (rows, cols) tensor, box (box_rows, 64 cols), 128-byte swizzle, zero fill out of bounds
 static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows)
 {
-    EncodeTiledFn enc = get_encode_fn();
-    if (!enc) return fail(LDCONV_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(LDCONV_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return LDCONV_OK;
+    return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)

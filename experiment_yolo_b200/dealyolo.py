@@ -275,6 +275,16 @@ class DealYolo(nn.Module):
         return [m for m in self.model if type(m).__name__.startswith("LDConv")]
 
 
+def channels_last_(model: nn.Module) -> nn.Module:
+    """Put every 4-D parameter in torch.channels_last (NHWC) so cuDNN keeps activations NHWC end to end and LDConv gets
+    its dense-NHWC inputs zero-copy.  (nn.Module.to(memory_format=...) also touches the 5-D Conv3d weight of ScalSeq and
+    raises, so the conversion is done per parameter.)"""
+    for p in model.parameters():
+        if p.dim() == 4:
+            p.data = p.data.contiguous(memory_format=torch.channels_last)
+    return model
+
+
 def seeded_state(model: nn.Module, seed: int = 0, p_conv_sigma: float = 0.05):
     """Deterministic synthetic weights that do not depend on module construction order: every floating tensor of the
     state_dict, in key order, is drawn from one CPU generator (BatchNorm statistics / scales kept positive, LDConv

@@ -60,7 +60,13 @@ int ldconv_last_impl(void);
 /* Debug / A-B switches (thread-local).  LDCONV_FLAG_FORCE_FFMA = 1 routes bf16 GEMMs to the CUDA-core kernel too, so a
  * test can compare the two implementations; it is not a fallback (both are sm_100a CUDA). */
 #define LDCONV_FLAG_FORCE_FFMA 1
+/* LDCONV_FLAG_GATHER_DIRECT = 1 makes ldconv_gather_fwd use the direct-load kernel instead of the TMA-staged tile kernel
+ * (same arithmetic, same results; A/B for profiles). */
+#define LDCONV_FLAG_GATHER_DIRECT 2
 int ldconv_set_flag(int flag, int value);
+/* Optional device counter (uint64) that the TMA-tiled gather increments by the number of samples whose corners fell
+ * outside the staged tile + halo and were served from L2 instead (halo miss rate); NULL disables it.  Thread-local. */
+int ldconv_set_gather_miss_counter(void* device_u64);
 
 /* conv.py:413-432 (_get_p_n): writes the 2N int32 base-grid table (rows then columns).  Host-side helper, no GPU. */
 int ldconv_p_n(int N, int32_t* out_host);

@@ -38,7 +38,7 @@ def test_full_model_fp32_matches_reference_output():
 
 def test_full_model_bf16_channels_last_close_to_reference_output():
     z, model = _load()
-    model = model.to(DEV).bfloat16().eval().to(memory_format=torch.channels_last)
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
     x = torch.from_numpy(z["x"]).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
     with torch.no_grad():
         y, _ = model(x)

@@ -153,6 +153,49 @@ def test_gather_full_size_properties():
     assert float((lhs - rhs).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("C,N,s,H,W,B,sigma", [(16, 3, 2, 64, 80, 2, 0.5), (16, 3, 2, 64, 80, 2, 6.0), (64, 1, 1, 40, 40, 2, 1.0),
+                                               (128, 1, 1, 24, 40, 1, 3.0), (64, 3, 2, 40, 40, 2, 2.0), (32, 9, 1, 20, 28, 1, 1.5),
+                                               (256, 9, 2, 20, 20, 1, 1.0), (8, 5, 2, 37, 53, 2, 20.0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gather_tma_tile_kernel_equals_direct_kernel(C, N, s, H, W, B, sigma, dtype):
+    """The TMA-staged tile kernel and the direct-load kernel share the arithmetic; whatever the halo hit rate (small and
+    huge offsets), operand / indices / coordinates are identical bit for bit, and the miss counter counts exactly the
+    samples whose four corners are not all inside tile + halo."""
+    L = _lib.load()
+    rng = np.random.default_rng(C + N + s)
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    x = torch.from_numpy(rng.standard_normal((B, H, W, C), dtype=np.float32)).to(DEV).to(dtype)
+    off = torch.from_numpy((rng.standard_normal((B, h, w, 2 * N)) * sigma).astype(np.float32)).to(DEV)
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    dt = _lib.F32 if dtype == torch.float32 else _lib.BF16
+    M = B * h * w
+    res = []
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    for direct in (1, 0):
+        operand = torch.empty((M, N * C), device=DEV, dtype=dtype)
+        idx = torch.empty((M, N, 4), device=DEV, dtype=torch.int32)
+        coord = torch.empty((M, N, 2), device=DEV, dtype=torch.float32)
+        _lib.check(L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, direct))
+        _lib.check(L.ldconv_set_gather_miss_counter(None if direct else counter.data_ptr()))
+        try:
+            _lib.check(L.ldconv_gather_fwd(_ptr(x), _ptr(off), _ptr(pn), _ptr(operand), _ptr(idx), _ptr(coord), B, C, H, W, N,
+                                           s, dt, _stream()), "gather")
+            torch.cuda.synchronize()
+        finally:
+            L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, 0)
+            L.ldconv_set_gather_miss_counter(None)
+        res.append((operand, idx, coord))
+    assert torch.equal(res[0][0].view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                       res[1][0].view(torch.int16 if dtype == torch.bfloat16 else torch.int32))
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    misses = int(counter.item())
+    assert 0 <= misses <= M * N
+    if sigma <= 0.5:
+        assert misses == 0          # |offset| stays far below the 2-pixel halo
+    if sigma >= 6.0:
+        assert misses > 0           # offsets of many pixels must take the L2 path
+
+
 # ------------------------------------------------------------------------------------------------------ offset conv ----
 @pytest.mark.parametrize("name", CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
