@@ -41,6 +41,7 @@ SIGNATURES = {
     "ldconv_gemm_bwd_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ldconv_gather_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_offset_conv_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_fused_supported": (_i, [_i] * 8),
     "ldconv_fused_fwd": (_i, [_vp] * 9 + [_i] * 9 + [_vp]),
 }
 

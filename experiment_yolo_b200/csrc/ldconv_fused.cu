@@ -1,0 +1,198 @@
+// ldconv_fused.cu -- whole-module inference kernels (sm_100a): the resampled operand never reaches HBM.
+//
+// Replaces, in ONE launch, /root/reference/ultralytics/nn/modules/conv.py:366-410 for eval mode: offset conv (:368),
+// sampling grid / clamps / bilinear weights (:369-393), four gathers + bilinear sum + rearrange (:396-407) and the
+// (N,1) conv + folded BatchNorm + SiLU (:355,408).  Two kernels behind the one C-ABI entry point ldconv_fused_fwd:
+//
+//   * small-C kernel (C <= 4; the first layer, 3 -> 16 channels: 23 % of the model's gather bytes and far too narrow for
+//     128-bit NHWC vectors or for an MMA): one thread per output pixel on CUDA cores, x read through L1.
+//   * tcgen05 kernel (C % 16 == 0, K = N*C <= 512, O % 16 == 0, O <= 256), see below.
+#include "common.cuh"
+#include "tmap.cuh"
+#include "umma.cuh"
+
+namespace ldc {
+
+using namespace umma;
+
+// =====================================================================================================================
+// small-C kernel: thread = output pixel.  K = N*C <= 36 samples stay in registers, W (O x K) and the offset-conv weights
+// sit in shared memory as fp32.
+// =====================================================================================================================
+template <typename T, int C, int NMAX>
+__global__ void __launch_bounds__(128)
+smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, const float* __restrict__ b_off,
+                    const int* __restrict__ pn, const T* __restrict__ wt, const float* __restrict__ scale,
+                    const float* __restrict__ shift, T* __restrict__ out, float* __restrict__ off_out, int B, int H, int W,
+                    int h, int w, int N, int s, int O, int act)
+{
+    extern __shared__ __align__(16) float smem_f[];
+    const int O2 = 2 * N, K = N * C;
+    float* s_woff = smem_f;                      // [9][C][O2]
+    float* s_wt = s_woff + 9 * C * O2;           // [K][O]  (transposed: broadcast reads of consecutive o)
+    float* s_sc = s_wt + K * O;                  // [O] scale, [O] shift
+    for (int t = threadIdx.x; t < 9 * C * O2; t += blockDim.x) s_woff[t] = w_off[t];
+    for (int t = threadIdx.x; t < K * O; t += blockDim.x) {
+        const int k = t / O, o = t % O;
+        s_wt[t] = Elem<T>::to_f(wt[(size_t)o * K + k]);
+    }
+    for (int t = threadIdx.x; t < O; t += blockDim.x) {
+        s_sc[t] = scale ? scale[t] : 1.f;
+        s_sc[O + t] = shift ? shift[t] : 0.f;
+    }
+    __syncthreads();
+
+    const long long M = (long long)B * h * w;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int j = (int)(m % w);
+    const int i = (int)((m / w) % h);
+    const int b = (int)(m / ((long long)w * h));
+    const T* xb = x + (size_t)b * H * W * C;
+
+    // ---- offset conv (conv.py:368): 3x3 / pad 1 / stride s, fp32 accumulation ------------------------------------------
+    float offv[2 * NMAX];
+#pragma unroll
+    for (int o = 0; o < 2 * NMAX; ++o) offv[o] = (o < O2 && b_off) ? b_off[o] : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int r = i * s + tap / 3 - 1, k = j * s + tap % 3 - 1;
+        if (r < 0 || r >= H || k < 0 || k >= W) continue;
+        const T* xp = xb + ((size_t)r * W + k) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float xv = Elem<T>::to_f(xp[c]);
+            const float* wp = s_woff + (tap * C + c) * O2;
+#pragma unroll
+            for (int o = 0; o < 2 * NMAX; ++o)
+                if (o < O2) offv[o] = fmaf(xv, wp[o], offv[o]);
+        }
+    }
+    if (off_out) {
+        float* op = off_out + (size_t)m * O2;
+#pragma unroll
+        for (int o = 0; o < 2 * NMAX; ++o)
+            if (o < O2) op[o] = offv[o];
+    }
+
+    // ---- sampling + (N,1) conv, one sample at a time (conv.py:369-408) ----------------------------------------------------
+    constexpr int OMAX = 32;
+    float acc[OMAX];
+#pragma unroll
+    for (int o = 0; o < OMAX; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+        if (n >= N) break;
+        const SamplePoint q = make_point(i, j, s, pn[n], pn[N + n], offv[n], offv[N + n], H, W);
+        const float g_lt = __fmul_rn(q.ar0, q.ak0), g_rb = __fmul_rn(q.ar1, q.ak1);
+        const float g_lb = __fmul_rn(q.ar0, q.ak1), g_rt = __fmul_rn(q.ar1, q.ak0);
+        const T* p00 = xb + ((size_t)q.r0 * W + q.k0) * C;
+        const T* p11 = xb + ((size_t)q.r1 * W + q.k1) * C;
+        const T* p01 = xb + ((size_t)q.r0 * W + q.k1) * C;
+        const T* p10 = xb + ((size_t)q.r1 * W + q.k0) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float v = bilinear(g_lt, g_rb, g_lb, g_rt, Elem<T>::to_f(p00[c]), Elem<T>::to_f(p11[c]), Elem<T>::to_f(p01[c]),
+                               Elem<T>::to_f(p10[c]));
+            v = Elem<T>::to_f(Elem<T>::from_f(v));       // the operand is rounded to the activation dtype, as in the 3-kernel path
+            const float4* wrow = reinterpret_cast<const float4*>(s_wt + (n * C + c) * O);
+#pragma unroll
+            for (int o4 = 0; o4 < OMAX / 4; ++o4) {
+                if (o4 * 4 < O) {
+                    const float4 wv = wrow[o4];
+                    acc[o4 * 4 + 0] = fmaf(v, wv.x, acc[o4 * 4 + 0]);
+                    acc[o4 * 4 + 1] = fmaf(v, wv.y, acc[o4 * 4 + 1]);
+                    acc[o4 * 4 + 2] = fmaf(v, wv.z, acc[o4 * 4 + 2]);
+                    acc[o4 * 4 + 3] = fmaf(v, wv.w, acc[o4 * 4 + 3]);
+                }
+            }
+        }
+    }
+    // ---- folded BatchNorm + SiLU, 16-byte stores ----------------------------------------------------------------------
+    T* dst = out + (size_t)m * O;
+    constexpr int V = Vec16<T>::N;
+#pragma unroll
+    for (int o0 = 0; o0 < OMAX; o0 += V) {
+        if (o0 < O) {
+            float y[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float z = fmaf(acc[o0 + e], s_sc[o0 + e], s_sc[O + o0 + e]);
+                y[e] = act == LDCONV_ACT_SILU ? silu(z) : z;
+            }
+            Vec16<T>::store(dst + o0, y);
+        }
+    }
+}
+
+template <typename T, int C>
+static int launch_smallc(const T* x, const float* w_off, const float* b_off, const int* pn, const T* wt, const float* scale,
+                         const float* shift, T* out, float* off_out, int B, int H, int W, int N, int s, int O, int act,
+                         cudaStream_t st)
+{
+    const int h = out_size(H, s), w = out_size(W, s);
+    const long long M = (long long)B * h * w;
+    const size_t smem = (size_t)(9 * C * 2 * N + N * C * O + 2 * O) * sizeof(float);
+    auto kern = smallc_fused_kernel<T, C, 9>;
+    kern<<<cdiv(M, 128), 128, smem, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, B, H, W, h, w, N, s, O, act);
+    LDC_LAUNCH_CHECK("smallc_fused_kernel");
+    set_impl(LDCONV_IMPL_FFMA);
+    return LDCONV_OK;
+}
+
+template <typename T>
+static int dispatch_smallc(const void* x, const float* w_off, const float* b_off, const int* pn, const void* wt,
+                           const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
+                           int N, int s, int O, int act, cudaStream_t st)
+{
+    const T* xx = (const T*)x;
+    const T* ww = (const T*)wt;
+    T* oo = (T*)out;
+    switch (C) {
+        case 1: return launch_smallc<T, 1>(xx, w_off, b_off, pn, ww, scale, shift, oo, off_out, B, H, W, N, s, O, act, st);
+        case 2: return launch_smallc<T, 2>(xx, w_off, b_off, pn, ww, scale, shift, oo, off_out, B, H, W, N, s, O, act, st);
+        case 3: return launch_smallc<T, 3>(xx, w_off, b_off, pn, ww, scale, shift, oo, off_out, B, H, W, N, s, O, act, st);
+        case 4: return launch_smallc<T, 4>(xx, w_off, b_off, pn, ww, scale, shift, oo, off_out, B, H, W, N, s, O, act, st);
+        default: return fail(LDCONV_E_ARG, "small-C fused kernel: C=%d", C);
+    }
+}
+
+int umma_fused_supported(int B, int C, int H, int W, int N, int s, int O, int dtype);
+int umma_fused_fwd(const void* x, const float* w_off, const float* b_off, const int* pn, const void* wt,
+                   const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W, int N,
+                   int s, int O, int act, cudaStream_t st);
+
+}  // namespace ldc
+
+using namespace ldc;
+
+LDC_API int ldconv_fused_supported(int B, int C, int H, int W, int N, int s, int O, int dtype)
+{
+    if (B < 0 || C < 1 || H < 1 || W < 1 || N < 1 || s < 1 || O < 1) return 0;
+    if (dtype != LDCONV_F32 && dtype != LDCONV_BF16) return 0;
+    const int V = dtype == LDCONV_BF16 ? 8 : 4;
+    if (C <= 4 && N <= 9 && O <= 32 && O % V == 0) return 1;
+    return umma_fused_supported(B, C, H, W, N, s, O, dtype);
+}
+
+LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
+                             const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
+                             int N, int s, int O, int act, int dtype, void* stream)
+{
+    LDC_REQUIRE(x && w_off && p_n && wt && out, "ldconv_fused_fwd: null pointer");
+    LDC_REQUIRE(act == LDCONV_ACT_NONE || act == LDCONV_ACT_SILU, "ldconv_fused_fwd: unknown activation %d", act);
+    if (!ldconv_fused_supported(B, C, H, W, N, s, O, dtype))
+        return fail(LDCONV_E_ARG,
+                    "ldconv_fused_fwd: shape C=%d num_param=%d O=%d dtype=%d is outside the fused kernels' range "
+                    "(query ldconv_fused_supported and use the offset_conv / gather / gemm entry points)", C, N, O, dtype);
+    if (B == 0) return LDCONV_OK;
+    LDC_REQUIRE(aligned16(out), "ldconv_fused_fwd: out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 4) {
+        if (dtype == LDCONV_BF16)
+            return dispatch_smallc<__nv_bfloat16>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O,
+                                                  act, st);
+        return dispatch_smallc<float>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
+    }
+    return umma_fused_fwd(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
+}

@@ -227,14 +227,13 @@ int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float
     return LDCONV_OK;
 }
 
-}  // namespace ldc
-
-// ---- one-kernel inference forward (declared in include/ldconv_b200.h) ---------------------------------------------------
-LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
-                             const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
-                             int N, int s, int O, int act, int dtype, void* stream)
+// FUSED_KERNEL_BEGIN
+int umma_fused_supported(int, int, int, int, int, int, int, int) { return 0; }
+int umma_fused_fwd(const void*, const float*, const float*, const int*, const void*, const float*, const float*, void*,
+                   float*, int, int, int, int, int, int, int, int, cudaStream_t)
 {
-    (void)x; (void)w_off; (void)b_off; (void)p_n; (void)wt; (void)scale; (void)shift; (void)out; (void)off_out;
-    (void)B; (void)C; (void)H; (void)W; (void)N; (void)s; (void)O; (void)act; (void)dtype; (void)stream;
-    return ldc::fail(LDCONV_E_ARG, "ldconv_fused_fwd: this build routes inference through the three-kernel path");
+    return fail(LDCONV_E_ARG, "tcgen05 fused kernel not built");
 }
+// FUSED_KERNEL_END
+
+}  // namespace ldc

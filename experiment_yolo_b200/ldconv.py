@@ -238,7 +238,7 @@ class LDConv(nn.Module):
     """B200-native LDConv.  Signature, children, buffer and state_dict layout: conv.py:350-359."""
 
     # one-kernel inference path (tcgen05) when shapes allow; class-level switch so tests can A/B it
-    use_fused_inference = False
+    use_fused_inference = True
 
     def __init__(self, inc, outc, num_param, stride=1, bias=None):
         super().__init__()
@@ -277,12 +277,14 @@ class LDConv(nn.Module):
         return c
 
     def _fused_ok(self, x) -> bool:
-        if not (self.use_fused_inference and x.dtype == torch.bfloat16):
+        if not self.use_fused_inference:
             return False
-        C, O, N = x.shape[1], self.conv[0].out_channels, self.num_param
         bn = self.conv[1]
-        return (bn.running_mean is not None and self.conv[0].bias is None and C % 8 == 0 and O % 16 == 0 and O <= 256
-                and N * C <= 512)
+        if bn.running_mean is None or self.conv[0].bias is not None:
+            return False
+        B, C, H, W = x.shape
+        return bool(_lib.load().ldconv_fused_supported(B, C, H, W, self.num_param, int(self.stride),
+                                                       self.conv[0].out_channels, _DTYPES[x.dtype]))
 
     def forward(self, x):
         _check_input(x)

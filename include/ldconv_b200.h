@@ -138,9 +138,13 @@ int ldconv_gather_bwd(const void* grad_operand, const void* x, const float* off,
 int ldconv_offset_conv_bwd(const float* grad_off, const void* x, const float* w, float* grad_x, float* grad_w,
                            float* grad_b, int B, int C, int H, int W, int N, int s, int dtype, void* stream);
 
-/* Inference forward of the whole module in ONE kernel (bf16): offset conv + grid + gather into shared memory in the
- * tcgen05 operand layout + UMMA with TMEM accumulators + folded BatchNorm + SiLU epilogue; the resampled operand
- * never touches HBM.  x (B,H,W,C) bf16, wt (O,K) bf16, out (B,h,w,O) bf16.  off_out (B,h,w,2N) fp32 may be NULL. */
+/* Inference forward of the whole module (conv.py:366-410, eval mode) in ONE kernel; the resampled operand never touches
+ * HBM.  Two kernels behind it: C <= 4 (the first layer) runs one thread per output pixel on CUDA cores; C % 16 == 0 with
+ * bf16 runs offset conv + grid + gather into shared memory in the tcgen05 operand layout + UMMA with TMEM accumulators +
+ * folded BatchNorm + SiLU epilogue.  x (B,H,W,C), wt (O,K), out (B,h,w,O) all `dtype`; w_off (3,3,C,2N) / b_off fp32;
+ * off_out (B,h,w,2N) fp32 may be NULL.  ldconv_fused_supported returns 1 when a shape is covered (else use the
+ * offset_conv / gather / gemm entry points; ldconv_fused_fwd returns LDCONV_E_ARG). */
+int ldconv_fused_supported(int B, int C, int H, int W, int N, int s, int O, int dtype);
 int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
                      const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
                      int N, int s, int O, int act, int dtype, void* stream);

@@ -279,11 +279,17 @@ def _module_from_golden(z, prm, m, dtype=torch.float32):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_module_eval_forward_fp32(name):
+@pytest.mark.parametrize("fused", [False, True])
+def test_module_eval_forward_fp32(name, fused):
     z, prm, m = _golden.load(name)
     mod = _module_from_golden(z, prm, m).eval()
-    with torch.no_grad():
-        y = mod(_t(z["x"]))
+    old = E.LDConv.use_fused_inference
+    E.LDConv.use_fused_inference = fused
+    try:
+        with torch.no_grad():
+            y = mod(_t(z["x"]))
+    finally:
+        E.LDConv.use_fused_inference = old
     assert tuple(y.shape) == tuple(z["out_eval"].shape)
     if name.endswith("_far"):
         # offsets of ~8 px on a 10x14 image put many samples on the p = H-1 discontinuity ("hard parts"):
@@ -341,7 +347,7 @@ def _oracle_on_bf16_rounded(z, prm, training):
 
 
 @pytest.mark.parametrize("name", [c for c in CASES if not c.endswith("_far")])
-@pytest.mark.parametrize("fused", [False])
+@pytest.mark.parametrize("fused", [False, True])
 def test_module_eval_forward_bf16(name, fused):
     """bf16 contract: compare with the fp32 reference algorithm on bf16-rounded x / parameters."""
     z, prm, m = _golden.load(name)
