@@ -28,9 +28,9 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
 {
     extern __shared__ __align__(16) float smem_f[];
     const int O2 = 2 * N, K = N * C;
-    float* s_woff = smem_f;                      // [9][C][O2]
-    float* s_wt = s_woff + 9 * C * O2;           // [K][O]  (transposed: broadcast reads of consecutive o)
-    float* s_sc = s_wt + K * O;                  // [O] scale, [O] shift
+    float* s_woff = smem_f;                                  // [9][C][O2]
+    float* s_wt = s_woff + ((9 * C * O2 + 3) & ~3);          // [K][O]  (transposed; 16-byte aligned rows: O % 4 == 0)
+    float* s_sc = s_wt + K * O;                              // [O] scale, [O] shift
     for (int t = threadIdx.x; t < 9 * C * O2; t += blockDim.x) s_woff[t] = w_off[t];
     for (int t = threadIdx.x; t < K * O; t += blockDim.x) {
         const int k = t / O, o = t % O;
@@ -132,7 +132,7 @@ static int launch_smallc(const T* x, const float* w_off, const float* b_off, con
 {
     const int h = out_size(H, s), w = out_size(W, s);
     const long long M = (long long)B * h * w;
-    const size_t smem = (size_t)(9 * C * 2 * N + N * C * O + 2 * O) * sizeof(float);
+    const size_t smem = (size_t)(((9 * C * 2 * N + 3) & ~3) + N * C * O + 2 * O) * sizeof(float);
     auto kern = smallc_fused_kernel<T, C, 9>;
     kern<<<cdiv(M, 128), 128, smem, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, B, H, W, h, w, N, s, O, act);
     LDC_LAUNCH_CHECK("smallc_fused_kernel");

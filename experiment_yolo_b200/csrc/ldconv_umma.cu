@@ -227,13 +227,4 @@ int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float
     return LDCONV_OK;
 }
 
-// FUSED_KERNEL_BEGIN
-int umma_fused_supported(int, int, int, int, int, int, int, int) { return 0; }
-int umma_fused_fwd(const void*, const float*, const float*, const int*, const void*, const float*, const float*, void*,
-                   float*, int, int, int, int, int, int, int, int, cudaStream_t)
-{
-    return fail(LDCONV_E_ARG, "tcgen05 fused kernel not built");
-}
-// FUSED_KERNEL_END
-
 }  // namespace ldc
