@@ -99,6 +99,14 @@ def main():
                 break
         L.ldconv_set_flag(_lib.FLAG_FORCE_FFMA, 0)
 
+        if L.ldconv_fused_supported(B, C, H, W, N, s, O, dt):
+            bytes_f = e * B * C * H * W + e * M * O
+            ms = timed(lambda: _lib.check(L.ldconv_fused_fwd(x.data_ptr(), w_off.data_ptr(), b_off.data_ptr(), pn.data_ptr(),
+                                                             wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
+                                                             None, B, C, H, W, N, s, O, _lib.ACT_SILU, dt, st)), args.iters, flush)
+            rec("fused_fwd", "tcgen05" if L.ldconv_last_impl() == _lib.IMPL_TCGEN05 else "smallc", ms, bytes_f,
+                2.0 * M * K * O + 2.0 * M * 9 * C * 2 * N)
+
         if args.bwd:
             gop = torch.randn((M, K), device=dev, generator=g).to(dtype)
             grad_x = torch.zeros((B, H, W, C), device=dev)

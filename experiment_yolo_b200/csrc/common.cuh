@@ -140,6 +140,14 @@ __device__ __forceinline__ float bilinear(float g_lt, float g_rb, float g_lb, fl
 }
 
 __device__ __forceinline__ float silu(float z) { return z / (1.f + __expf(-z)); }
+// bf16 epilogues: silu(z) = z * sigmoid(z) = 0.5 z (1 + tanh(z/2)); one MUFU op, relative error ~2^-11 (below bf16's 2^-9)
+__device__ __forceinline__ float silu_fast(float z)
+{
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    const float hz = 0.5f * z;
+    return fmaf(hz, t, hz);
+}
 __device__ __forceinline__ float silu_grad(float z)
 {
     const float sg = 1.f / (1.f + __expf(-z));

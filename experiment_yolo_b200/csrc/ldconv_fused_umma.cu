@@ -25,7 +25,7 @@ using namespace umma;
 struct FusedGeom {
     int TH, TW, THin, TWin, halo, tiles_h, tiles_w;
     int num_kb, ON, ON2, Q, PP;             // K blocks of 64, O padded to 16, 2N padded to 4, channel split, pixels/thread
-    uint32_t ofs_b, ofs_x, ofs_woff, ofs_part, ofs_bar;   // byte offsets inside the 1024-aligned dynamic smem
+    uint32_t ofs_b, ofs_x, ofs_woff, ofs_part, ofs_aff, ofs_bar;   // byte offsets inside the 1024-aligned dynamic smem
     uint32_t tmem_cols;
 };
 
@@ -47,6 +47,7 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     T* sX = reinterpret_cast<T*>(smem + g.ofs_x);                  // [THin][TWin][C]
     float* sWoff = reinterpret_cast<float*>(smem + g.ofs_woff);    // [9][C][ON2]
     float* sPart = reinterpret_cast<float*>(smem + g.ofs_part);    // [Q][128][ON2]
+    float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);    // [ON] (scale, shift) of the folded BatchNorm
     uint64_t* bar_x = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
     uint64_t* bar_w = bar_x + 1;
     uint64_t* bar_mma = bar_x + 2;
@@ -85,6 +86,8 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int o = t % ON2, tc = t / ON2;
         sWoff[t] = o < O2 ? w_off[(size_t)tc * O2 + o] : 0.f;
     }
+    for (int o = tid; o < g.ON; o += kFusedThreads)
+        sAff[o] = make_float2((scale && o < O) ? scale[o] : 1.f, (shift && o < O) ? shift[o] : 0.f);
     __syncthreads();
     mbar_wait(bar_x, 0);
 
@@ -235,11 +238,11 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 float lo[8], hi[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float z0 = fmaf(__uint_as_float(v[e]), scale ? scale[c0 + e] : 1.f, shift ? shift[c0 + e] : 0.f);
-                    const float z1 =
-                        fmaf(__uint_as_float(v[8 + e]), scale ? scale[c0 + 8 + e] : 1.f, shift ? shift[c0 + 8 + e] : 0.f);
-                    lo[e] = act == LDCONV_ACT_SILU ? silu(z0) : z0;
-                    hi[e] = act == LDCONV_ACT_SILU ? silu(z1) : z1;
+                    const float2 a0 = sAff[c0 + e], a1 = sAff[c0 + 8 + e];
+                    const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
+                    const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
+                    lo[e] = act == LDCONV_ACT_SILU ? silu_fast(z0) : z0;
+                    hi[e] = act == LDCONV_ACT_SILU ? silu_fast(z1) : z1;
                 }
                 T* dst = out + m * O + c0;
                 Vec16<T>::store(dst, lo);
@@ -277,6 +280,7 @@ static int fused_geometry(int C, int N, int s, int O, int max_pn_r, int max_pn_k
         ofs = (ofs + 15) & ~15u;
         g.ofs_woff = ofs; ofs += 9u * C * g.ON2 * 4;
         g.ofs_part = ofs; ofs += (uint32_t)g.Q * 128 * g.ON2 * 4;
+        g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8;
         ofs = (ofs + 7) & ~7u;
         g.ofs_bar = ofs; ofs += 32;
         *smem = ofs + 1024;

@@ -23,7 +23,7 @@ int col_stats_bf16(const __nv_bfloat16* pre, long long M, int O, double* sum, do
 static constexpr int kTileM = 128;
 static constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
 static constexpr int kABytes = kTileM * kBlockK * 2;    // 16 KiB
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmThreads = 320;          // TMA warp, MMA warp, 8 epilogue warps
 
 static thread_local int g_force_ffma = 0;   // ldconv_set_flag(LDCONV_FLAG_FORCE_FFMA, v)
 static int g_env_force_ffma = -1;           // environment LDCONV_FORCE_FFMA=1 (debug A/B switch, wins over the flag)
@@ -37,7 +37,7 @@ static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long 
     return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, int M, int O, int ON, int num_kb, int num_tiles, int stages, int act,
@@ -53,6 +53,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = empty + stages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float2* s_affine = reinterpret_cast<float2*>(tmem_slot + 4);     // [ON] (scale, shift)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -61,10 +62,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    for (int o = threadIdx.x; o < ON; o += blockDim.x)
+        s_affine[o] = make_float2((scale && o < O) ? scale[o] : 1.f, (shift && o < O) ? shift[o] : 0.f);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -113,7 +116,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        const int lg = warp & 3;  // TMEM lane group this warp may access
+        const int lg = warp & 3;              // TMEM lane group this warp may access
+        const int half = (warp - 2) >> 2;     // warps 2..5 take the first half of the column chunks, 6..9 the second
+        const int chunks = ON / 16;
+        const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2, ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -122,46 +128,47 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after_sync();
             const long long m = (long long)tile * kTileM + lg * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ON);
-            for (int c0 = 0; c0 < ON; c0 += 16) {
+            for (int ch = ch_begin; ch < ch_end; ++ch) {
+                const int c0 = ch * 16;
                 uint32_t v[16];
                 tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
                 tmem_ld_wait();
                 if (m < M && c0 < O) {
-                    float acc[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(v[e]);
-                    const int ncol = O - c0 < 16 ? O - c0 : 16;
+                    const bool full16 = vec_store && (c0 + 16 <= O);
                     if (pre) {
                         __nv_bfloat16* dst = pre + m * O + c0;
-                        if (vec_store && ncol == 16) {
+                        if (full16) {
                             float lo[8], hi[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) { lo[e] = acc[e]; hi[e] = acc[8 + e]; }
+                            for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(v[e]); hi[e] = __uint_as_float(v[8 + e]); }
                             Vec16<__nv_bfloat16>::store(dst, lo);
                             Vec16<__nv_bfloat16>::store(dst + 8, hi);
                         } else {
-                            for (int e = 0; e < ncol; ++e) dst[e] = __float2bfloat16_rn(acc[e]);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (c0 + e < O) dst[e] = __float2bfloat16_rn(__uint_as_float(v[e]));
                         }
                     }
                     if (out) {
+                        float lo[8], hi[8];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            if (e < ncol) {
-                                const float sc = scale ? scale[c0 + e] : 1.f;
-                                const float sh = shift ? shift[c0 + e] : 0.f;
-                                const float z = fmaf(acc[e], sc, sh);
-                                acc[e] = act == LDCONV_ACT_SILU ? silu(z) : z;
-                            }
+                        for (int e = 0; e < 8; ++e) {
+                            const float2 a0 = s_affine[c0 + e], a1 = s_affine[c0 + 8 + e];
+                            const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
+                            const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
+                            lo[e] = act == LDCONV_ACT_SILU ? silu_fast(z0) : z0;
+                            hi[e] = act == LDCONV_ACT_SILU ? silu_fast(z1) : z1;
                         }
                         __nv_bfloat16* dst = out + m * O + c0;
-                        if (vec_store && ncol == 16) {
-                            float lo[8], hi[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) { lo[e] = acc[e]; hi[e] = acc[8 + e]; }
+                        if (full16) {
                             Vec16<__nv_bfloat16>::store(dst, lo);
                             Vec16<__nv_bfloat16>::store(dst + 8, hi);
                         } else {
-                            for (int e = 0; e < ncol; ++e) dst[e] = __float2bfloat16_rn(acc[e]);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                if (c0 + e < O) dst[e] = __float2bfloat16_rn(lo[e]);
+                                if (c0 + 8 + e < O) dst[8 + e] = __float2bfloat16_rn(hi[e]);
+                            }
                         }
                     }
                 }
@@ -204,19 +211,23 @@ int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float
     const int num_kb = (K + kBlockK - 1) / kBlockK;
     const int num_tiles = (M + kTileM - 1) / kTileM;
     const int b_bytes = ON * kBlockK * 2;
-    int stages = (200 * 1024) / (kABytes + b_bytes);
+    // two CTAs per SM when both accumulator pairs fit TMEM (2 x 2 x ON <= 512 columns): ~100 KB of smem ring each;
+    // one CTA with the whole ~200 KB otherwise
+    const bool two_per_sm = 4 * ON <= 512;
+    int stages = ((two_per_sm ? 100 : 200) * 1024) / (kABytes + b_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(LDCONV_E_ARG, "tcgen05 GEMM: tile does not fit shared memory (O=%d)", O);
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(2 * ON)) tmem_cols <<= 1;
-    const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 4) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 4) * sizeof(uint64_t) + 16 +
+                        (size_t)ON * sizeof(float2);
 
     CUtensorMap tmA, tmB;
     if (int e = make_map_2d(&tmA, a, M, K, kTileM)) return e;
     if (int e = make_map_2d(&tmB, wt, O, K, ON)) return e;
 
     LDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = num_sms();
+    int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > num_tiles) grid = num_tiles;
     const int vec_store = (O % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
     umma_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, scale, shift, (__nv_bfloat16*)out, (__nv_bfloat16*)pre, M,

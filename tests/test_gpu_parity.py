@@ -378,6 +378,50 @@ def test_module_train_bf16(name):
     assert _rel(mod.p_conv.weight.grad.float().cpu().numpy(), g["p_conv.weight"]) <= 5e-2
 
 
+# ------------------------------------------------------------------------------------------- one-kernel inference ----
+@pytest.mark.parametrize("C,O,N,s,H,W,B,sigma", [
+    (16, 32, 3, 2, 64, 80, 2, 0.05), (16, 32, 3, 2, 37, 53, 2, 0.3), (32, 64, 3, 2, 40, 40, 2, 0.05), (64, 128, 3, 2, 24, 40, 2, 0.05),
+    (128, 64, 1, 1, 20, 20, 2, 0.05), (64, 64, 1, 1, 40, 24, 1, 0.1), (64, 32, 1, 1, 17, 19, 2, 0.05), (32, 32, 1, 1, 48, 48, 1, 0.05),
+    (64, 64, 3, 2, 40, 40, 2, 0.5), (32, 48, 5, 1, 20, 28, 1, 0.05), (16, 16, 9, 2, 33, 47, 2, 0.05), (48, 32, 2, 1, 16, 16, 2, 0.05),
+    (3, 16, 3, 2, 64, 96, 2, 0.05), (4, 8, 5, 1, 21, 17, 2, 0.2), (1, 16, 9, 2, 30, 30, 1, 0.3)])
+def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s, H, W, B, sigma):
+    """ldconv_fused_fwd (small-C CUDA-core kernel / tcgen05 kernel) against (a) the offset_conv -> gather -> gemm path on
+    the same inputs and (b) the fp32 oracle on bf16-rounded tensors (rel-L2 <= 1e-2).  sigma scales p_conv.weight: large
+    values push samples outside the staged halo (L2 path) and outside the image (clamp quirk)."""
+    L = _lib.load()
+    assert L.ldconv_fused_supported(B, C, H, W, N, s, O, _lib.BF16) == 1
+    torch.manual_seed(C * 7 + O + N)
+    mod = E.LDConv(C, O, N, s)
+    with torch.no_grad():
+        mod.p_conv.weight.normal_(0, sigma)
+        mod.conv[1].running_mean.normal_(0, 0.3)
+        mod.conv[1].running_var.uniform_(0.5, 1.5)
+        mod.conv[1].weight.uniform_(0.5, 1.5)
+        mod.conv[1].bias.normal_(0, 0.2)
+    mod.conv[1].eps = 1e-3
+    x = torch.randn(B, C, H, W)
+    rnd = lambda t: t.detach().bfloat16().float().numpy()
+    prm = oracle.LDConvParams(rnd(mod.p_conv.weight), rnd(mod.p_conv.bias), rnd(mod.conv[0].weight), rnd(mod.conv[1].weight),
+                              rnd(mod.conv[1].bias), rnd(mod.conv[1].running_mean), rnd(mod.conv[1].running_var), N, s, 1e-3, 0.1)
+    f = oracle.forward(rnd(x), prm, training=False)
+    dmod = mod.to(DEV).bfloat16().eval()
+    xd = x.to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    outs = {}
+    for fused in (True, False):
+        E.LDConv.use_fused_inference = fused
+        try:
+            _lib.call_counts.clear()
+            with torch.no_grad():
+                outs[fused] = dmod(xd).float().cpu().numpy()
+            assert ("ldconv_fused_fwd" in _lib.call_counts) == fused
+        finally:
+            E.LDConv.use_fused_inference = True
+    assert _rel(outs[True], f["out"]) <= 1e-2
+    assert _rel(outs[True], outs[False]) <= 6e-3
+    if sigma <= 0.1:
+        assert np.abs(outs[True] - outs[False]).max() <= 0.05 * max(1.0, np.abs(outs[False]).max())
+
+
 # ------------------------------------------------------------------------------------- larger seeded cases vs oracle ----
 @pytest.mark.parametrize("C,O,N,s,H,W,B", [(16, 32, 3, 2, 40, 40, 2), (64, 64, 1, 1, 20, 20, 2), (32, 32, 5, 1, 16, 24, 2),
                                            (128, 64, 1, 1, 10, 10, 2), (3, 16, 3, 2, 64, 64, 2), (64, 128, 3, 2, 20, 20, 2)])
