@@ -79,6 +79,13 @@ def main():
                                                                off_out.data_ptr(), B, C, H, W, N, s, dt, st)), args.iters, flush)
         rec("offset_conv_fwd", "ffma", ms, bytes_off, 2.0 * M * 9 * C * 2 * N)
 
+        if L.ldconv_offset_conv_tc_supported(C, N, s, dt):
+            w_tc = w_off.permute(3, 0, 1, 2).reshape(2 * N, 9 * C).to(dtype).contiguous()
+            ms = timed(lambda: _lib.check(L.ldconv_offset_conv_tc_fwd(x.data_ptr(), w_tc.data_ptr(), b_off.data_ptr(),
+                                                                      off_out.data_ptr(), B, C, H, W, N, s, dt, st)),
+                       args.iters, flush)
+            rec("offset_conv_fwd", "tcgen05", ms, bytes_off, 2.0 * M * 9 * C * 2 * N)
+
         bytes_g = e * B * C * H * W + 4 * B * 2 * N * h * w + e * M * K
         for variant, direct in (("tma_tile", 0), ("direct", 1)):
             L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, direct)

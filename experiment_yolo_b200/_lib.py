@@ -32,6 +32,8 @@ SIGNATURES = {
     "ldconv_set_gather_miss_counter": (_i, [_vp]),
     "ldconv_p_n": (_i, [_i, _vp]),
     "ldconv_offset_conv_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
+    "ldconv_offset_conv_tc_supported": (_i, [_i] * 4),
+    "ldconv_offset_conv_tc_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "ldconv_gather_fwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_gemm_fwd": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
     "ldconv_bn_finalize": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -41,6 +43,8 @@ SIGNATURES = {
     "ldconv_gemm_bwd_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ldconv_gather_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_offset_conv_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_conv3x3_supported": (_i, [_i] * 4),
+    "ldconv_conv3x3_bn_act_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 8 + [_vp]),
     "ldconv_fused_supported": (_i, [_i] * 8),
     "ldconv_fused_fwd": (_i, [_vp] * 9 + [_i] * 9 + [_vp]),
 }

@@ -1,0 +1,366 @@
+// ldconv_conv3x3_umma.cu -- 3x3 / pad 1 / stride s convolution as a tcgen05 implicit GEMM (bf16, NHWC, sm_100a).
+//
+// Two users on the LDConv path and one next to it:
+//   * the offset conv of LDConv, offset = p_conv(x) (/root/reference/ultralytics/nn/modules/conv.py:356,368):
+//     C -> 2N outputs, fp32 result + bias (mode OFFSETS).  On CUDA cores this conv was the slowest kernel of the path
+//     (4-15 TFLOP/s, profiles/r1_layers_*.jsonl); as an MMA with N = 16 it is an HBM-bound read of x.
+//   * Conv2d(3x3, no bias) + BatchNorm2d + SiLU blocks around LDConv (`Conv`, nn/modules/conv.py:41-59, inside
+//     Bottleneck / C2f / Detect), with the folded BatchNorm affine, SiLU and an optional residual
+//     add in the epilogue (mode CONV_BN_ACT); input and output may be channel slices of wider NHWC buffers (pixel
+//     strides ldx / ldo), which is what removes the torch.cat copies of C2f.
+//
+// GEMM view: D(128 pixels, Cout) = A(128, 9*Cin) . W(Cout, 9*Cin)^T with k = tap*Cin + c.  Persistent warp-specialised CTA:
+//   warp 0     TMA: the input tile + 1-pixel halo of the NEXT tile (4-D box, zero fill outside the image = conv padding)
+//              into a double-buffered staging area; weight K-blocks (resident when small, else streamed with the ring)
+//   warp 1     one elected thread issues tcgen05.mma (M=128, N=Cout padded to 16, K=16) per K-block, TMEM accumulators x2
+//   warps 2-9  im2col: copy 16-byte channel chunks from the staged tile into a ring of K-major SWIZZLE_128B operand blocks
+//              (shared -> shared, no HBM traffic), then the epilogue of the previous tile (tcgen05.ld -> affine/act -> store)
+#include "common.cuh"
+#include "tmap.cuh"
+#include "umma.cuh"
+
+namespace ldc {
+
+using namespace umma;
+
+static constexpr int kConvThreads = 320;
+static constexpr int kConvTileH = 8, kConvTileW = 16;
+
+enum { CONV_MODE_BN_ACT = 0, CONV_MODE_OFFSETS = 1 };
+
+struct ConvGeom {
+    int Cin, Cout, ON, H, W, h, w, s, B;
+    int THin, TWin, tiles_h, tiles_w, num_tiles;
+    int K, num_kb, stages, b_resident;
+    int ldo, ldr;                                   // pixel strides (elements) of out / residual
+    uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_bar; // smem byte offsets (1024-aligned base)
+    uint32_t x_bytes, b_bytes, tmem_cols;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const __nv_bfloat16* __restrict__ residual, void* __restrict__ out_v, int act, ConvGeom g)
+{
+    using T = __nv_bfloat16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sI = smem + g.ofs_i;        // [stages][128 rows][128 B]  im2col ring, SWIZZLE_128B
+    uint8_t* sB = smem + g.ofs_b;        // resident: [num_kb][ON][128 B]; streamed: [stages][ON][128 B]
+    uint8_t* sX = smem + g.ofs_x;        // [2][THin][TWin][Cin]
+    float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
+    uint64_t* x_empty = x_full + 2;
+    uint64_t* t_full = x_empty + 2;
+    uint64_t* t_empty = t_full + 2;
+    uint64_t* w_full = t_empty + 2;
+    uint64_t* i_full = w_full + 1;
+    uint64_t* i_empty = i_full + g.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(i_empty + g.stages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i_full_count = 8 + (g.b_resident ? 0 : 1);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&x_full[i], 1);
+            mbar_init(&x_empty[i], 8);
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], 8);
+        }
+        mbar_init(w_full, 1);
+        for (int i = 0; i < g.stages; ++i) {
+            mbar_init(&i_full[i], i_full_count);
+            mbar_init(&i_empty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    for (int o = threadIdx.x; o < g.ON; o += blockDim.x)
+        sAff[o] = make_float2((scale && o < g.Cout) ? scale[o] : 1.f, (shift && o < g.Cout) ? shift[o] : 0.f);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = g.tiles_h * g.tiles_w;
+
+    if (warp == 0) {
+        // =========================================== TMA producer ===========================================================
+        if (lane == 0) {
+            if (g.b_resident) {
+                mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes);
+                for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(sB + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+            }
+            auto issue_x = [&](int tile, int it) {
+                const int buf = it & 1;
+                mbar_wait(&x_empty[buf], ((it >> 1) & 1) ^ 1);
+                const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
+                mbar_arrive_expect_tx(&x_full[buf], g.x_bytes);
+                tma_load_4d(sX + (size_t)buf * g.x_bytes, &tmX, &x_full[buf], 0, tj * kConvTileW * g.s - 1,
+                            ti * kConvTileH * g.s - 1, b);
+            };
+            int it = 0, st = 0;
+            uint32_t ph = 0;
+            if ((int)blockIdx.x < g.num_tiles) issue_x(blockIdx.x, 0);
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+                const int next = tile + gridDim.x;
+                if (next < g.num_tiles) issue_x(next, it + 1);
+                if (!g.b_resident) {
+                    for (int kb = 0; kb < g.num_kb; ++kb) {
+                        mbar_wait(&i_empty[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&i_full[st], g.b_bytes);
+                        tma_load_2d(sB + (size_t)st * g.b_bytes, &tmW, &i_full[st], kb * 64, 0);
+                        if (++st == g.stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================== MMA issuer =============================================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, g.ON);
+            if (g.b_resident) mbar_wait(w_full, 0);
+            int it = 0, st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(&i_full[st], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(sI + (size_t)st * 16384);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)(g.b_resident ? kb : st) * g.b_bytes);
+                    const int ksteps = min(4, (g.K - kb * 64) / 16);
+                    for (int k = 0; k < ksteps; ++k)
+                        mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                                    (uint32_t)((kb | k) != 0));
+                    mma_commit(&i_empty[st]);
+                    if (kb == g.num_kb - 1) mma_commit(&t_full[buf]);
+                    if (++st == g.stages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // =========================================== im2col workers + epilogue ================================================
+        const int ww = warp - 2;                       // 0..7
+        const int lg = warp & 3, half = ww >> 2;
+        const int chunks16 = g.ON / 16;
+        const int ch_begin = half == 0 ? 0 : (chunks16 + 1) / 2, ch_end = half == 0 ? (chunks16 + 1) / 2 : chunks16;
+
+        auto epilogue = [&](int tile, int it) {
+            const int buf = it & 1;
+            mbar_wait(&t_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
+            const int p = lg * 32 + lane;
+            const int i = ti * kConvTileH + p / kConvTileW, j = tj * kConvTileW + p % kConvTileW;
+            const bool valid = i < g.h && j < g.w;
+            const size_t m = ((size_t)b * g.h + i) * g.w + j;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * g.ON);
+            for (int ch = ch_begin; ch < ch_end; ++ch) {
+                const int c0 = ch * 16;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (!valid || c0 >= g.Cout) continue;
+                if (MODE == CONV_MODE_OFFSETS) {
+                    float* dst = reinterpret_cast<float*>(out_v) + m * g.ldo + c0;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + e < g.Cout) dst[e] = __uint_as_float(v[e]) + sAff[c0 + e].y;
+                } else {
+                    float lo[8], hi[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 a0 = sAff[c0 + e], a1 = sAff[c0 + 8 + e];
+                        const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
+                        const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
+                        lo[e] = act == LDCONV_ACT_SILU ? silu_fast(z0) : z0;
+                        hi[e] = act == LDCONV_ACT_SILU ? silu_fast(z1) : z1;
+                    }
+                    if (residual) {
+                        float r0[8], r1[8];
+                        Vec16<T>::load(residual + m * g.ldr + c0, r0);
+                        Vec16<T>::load(residual + m * g.ldr + c0 + 8, r1);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { lo[e] += r0[e]; hi[e] += r1[e]; }
+                    }
+                    T* dst = reinterpret_cast<T*>(out_v) + m * g.ldo + c0;
+                    Vec16<T>::store(dst, lo);
+                    Vec16<T>::store(dst + 8, hi);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        };
+
+        int it = 0, st = 0, prev_tile = -1;
+        uint32_t ph = 0;
+        const int chunk = lane & 7;                    // 16-byte chunk inside the 128-byte K-block row
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+            const int xbuf = it & 1;
+            mbar_wait(&x_full[xbuf], (it >> 1) & 1);
+            const T* xt = reinterpret_cast<const T*>(sX + (size_t)xbuf * g.x_bytes);
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&i_empty[st], ph ^ 1);
+                uint8_t* dstI = sI + (size_t)st * 16384;
+                const int kk = kb * 64 + chunk * 8;    // first k of this thread's chunk
+                if (kk < g.K) {
+                    const int tap = kk / g.Cin, c0 = kk % g.Cin;
+                    const int tofs = ((tap / 3) * g.TWin + (tap % 3)) * g.Cin + c0;
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; ++r4) {
+                        const int p = (r4 * 8 + ww) * 4 + (lane >> 3);
+                        const int pi = p / kConvTileW, pj = p % kConvTileW;
+                        const uint4 val =
+                            *reinterpret_cast<const uint4*>(xt + (pi * g.s * g.TWin + pj * g.s) * g.Cin + tofs);
+                        *reinterpret_cast<uint4*>(dstI + sw128_offset((uint32_t)p, (uint32_t)chunk)) = val;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&i_full[st]);
+                if (++st == g.stages) { st = 0; ph ^= 1; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_empty[xbuf]);
+            if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+            prev_tile = tile;
+        }
+        if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+int conv3x3_umma_supported(int Cin, int Cout, int s, int mode)
+{
+    if (Cin % 16 != 0 || Cin > 256 || Cout < 1 || Cout > 256) return 0;
+    if (mode == CONV_MODE_BN_ACT && Cout % 16 != 0) return 0;
+    if (s < 1 || s > 2) return 0;
+    return 1;
+}
+
+// x: (B,H,W,*) bf16 with pixel stride ldx (channel slice of a wider NHWC buffer allowed; ldx % 8 == 0)
+// wt: (Cout, 9*Cin) bf16, k = tap*Cin + c
+int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, const float* shift, const void* residual,
+                 int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout, int s, int act, int mode,
+                 cudaStream_t st)
+{
+    if (!conv3x3_umma_supported(Cin, Cout, s, mode)) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: unsupported shape");
+    if (!aligned16(x) || !aligned16(wt) || (ldx % 8) != 0)
+        return fail(LDCONV_E_ALIGN, "conv3x3 tcgen05: x / wt must be 16-byte aligned and ldx a multiple of 8");
+    if (mode == CONV_MODE_BN_ACT && (!aligned16(out) || (ldo % 8) != 0 || (residual && (!aligned16(residual) || ldr % 8))))
+        return fail(LDCONV_E_ALIGN, "conv3x3 tcgen05: out / residual must be 16-byte aligned with strides multiple of 8");
+    ConvGeom g;
+    g.Cin = Cin; g.Cout = Cout; g.ON = (Cout + 15) / 16 * 16; g.H = H; g.W = W; g.s = s; g.B = B;
+    g.h = out_size(H, s); g.w = out_size(W, s);
+    g.THin = (kConvTileH - 1) * s + 3;
+    g.TWin = (kConvTileW - 1) * s + 3;
+    g.tiles_h = (g.h + kConvTileH - 1) / kConvTileH;
+    g.tiles_w = (g.w + kConvTileW - 1) / kConvTileW;
+    const long long nt = (long long)B * g.tiles_h * g.tiles_w;
+    if (nt > 0x7fffffffll) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: too many tiles");
+    g.num_tiles = (int)nt;
+    g.K = 9 * Cin;
+    g.num_kb = (g.K + 63) / 64;
+    g.b_bytes = (uint32_t)g.ON * 128;
+    g.x_bytes = (uint32_t)g.THin * g.TWin * Cin * 2;
+    g.x_bytes = (g.x_bytes + 127) & ~127u;
+    g.ldo = ldo; g.ldr = ldr;
+    g.b_resident = (size_t)g.num_kb * g.b_bytes <= 72 * 1024;
+    const size_t fixed = 2 * (size_t)g.x_bytes + (size_t)g.ON * 8 + 256 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
+    const size_t per_stage = 16384 + (g.b_resident ? 0 : g.b_bytes);
+    int stages = (int)((220 * 1024 - (long long)fixed) / (long long)per_stage);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
+    g.stages = stages;
+    uint32_t ofs = 0;
+    g.ofs_i = ofs; ofs += (uint32_t)stages * 16384;
+    g.ofs_b = ofs; ofs += (uint32_t)(g.b_resident ? g.num_kb : stages) * g.b_bytes;
+    ofs = (ofs + 127) & ~127u;
+    g.ofs_x = ofs; ofs += 2 * g.x_bytes;
+    g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8;
+    ofs = (ofs + 7) & ~7u;
+    g.ofs_bar = ofs; ofs += (uint32_t)(9 + 2 * stages) * 8 + 16;
+    const size_t smem = ofs + 1024;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < (uint32_t)(2 * g.ON)) g.tmem_cols <<= 1;
+
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
+        cuuint32_t box[4] = {(cuuint32_t)Cin, (cuuint32_t)g.TWin, (cuuint32_t)g.THin, 1};
+        if (int e = encode_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return e;
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)g.K, (cuuint64_t)Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)g.K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)g.ON};
+        if (int e = encode_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return e;
+    }
+    int grid = num_sms();
+    if (grid > g.num_tiles) grid = g.num_tiles;
+    if (mode == CONV_MODE_OFFSETS) {
+        auto kern = conv3x3_umma_kernel<CONV_MODE_OFFSETS>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kConvThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+    } else {
+        auto kern = conv3x3_umma_kernel<CONV_MODE_BN_ACT>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kConvThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+    }
+    LDC_LAUNCH_CHECK("conv3x3_umma_kernel");
+    set_impl(LDCONV_IMPL_TCGEN05);
+    return LDCONV_OK;
+}
+
+}  // namespace ldc
+
+using namespace ldc;
+
+// C ABI -----------------------------------------------------------------------------------------------------------------
+LDC_API int ldconv_conv3x3_supported(int Cin, int Cout, int stride, int dtype)
+{
+    return dtype == LDCONV_BF16 ? conv3x3_umma_supported(Cin, Cout, stride, CONV_MODE_BN_ACT) : 0;
+}
+
+LDC_API int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                                      const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W,
+                                      int Cout, int stride, int act, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_conv3x3_bn_act_fwd: bf16 only (the fp32 path keeps the framework conv)");
+    LDC_REQUIRE(x && wt && out && B >= 0 && H >= 1 && W >= 1, "ldconv_conv3x3_bn_act_fwd: bad arguments");
+    LDC_REQUIRE(ldx >= Cin && ldo >= Cout, "ldconv_conv3x3_bn_act_fwd: pixel strides smaller than the channel counts");
+    if (B == 0) return LDCONV_OK;
+    return conv3x3_umma(x, ldx, wt, scale, shift, residual, ldr, out, ldo, B, Cin, H, W, Cout, stride, act, CONV_MODE_BN_ACT,
+                        (cudaStream_t)stream);
+}
+
+LDC_API int ldconv_offset_conv_tc_supported(int C, int N, int stride, int dtype)
+{
+    return dtype == LDCONV_BF16 && N >= 1 && N <= 16 ? conv3x3_umma_supported(C, 2 * N, stride, CONV_MODE_OFFSETS) : 0;
+}
+
+LDC_API int ldconv_offset_conv_tc_fwd(const void* x, const void* w_bf16, const float* bias, float* off, int B, int C, int H,
+                                      int W, int N, int stride, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_offset_conv_tc_fwd: bf16 only");
+    LDC_REQUIRE(x && w_bf16 && off && B >= 0, "ldconv_offset_conv_tc_fwd: bad arguments");
+    if (B == 0) return LDCONV_OK;
+    // bias rides in the `shift` slot of the epilogue affine (scale unused in this mode)
+    return conv3x3_umma(x, C, w_bf16, nullptr, bias, nullptr, 0, off, 2 * N, B, C, H, W, 2 * N, stride, LDCONV_ACT_NONE,
+                        CONV_MODE_OFFSETS, (cudaStream_t)stream);
+}

@@ -64,7 +64,7 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 
 class _Prepared:
     """Per-call operand forms of the parameters (tiny tensors; cached by the module while the parameters are unchanged)."""
-    __slots__ = ("w_off", "b_off", "wt", "wt_t", "pn", "key")
+    __slots__ = ("w_off", "b_off", "w_off_tc", "wt", "wt_t", "pn", "key")
 
 
 def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepared:
@@ -75,6 +75,9 @@ def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepar
     # path sees exactly the bf16-rounded parameters the parity oracle uses
     pr.w_off = p_w.detach().to(dtype).float().permute(2, 3, 1, 0).contiguous()
     pr.b_off = None if p_b is None else p_b.detach().to(dtype).float().contiguous()
+    # tensor-core offset conv (bf16): (2N,C,3,3) -> (2N, 3,3,C) -> (2N, 9C), k = tap*C + c
+    pr.w_off_tc = (p_w.detach().to(dtype).permute(0, 2, 3, 1).reshape(2 * N, 9 * C).contiguous()
+                   if dtype == torch.bfloat16 else None)
     # (N,1) conv weight (O,C,N,1) -> (O, N*C), k = n*C + c: the order the NHWC gather produces
     pr.wt = c_w.detach().to(dtype).reshape(O, C, N).permute(0, 2, 1).reshape(O, N * C).contiguous()
     pr.wt_t = pr.wt.t().contiguous() if need_wt_t else None
@@ -105,8 +108,12 @@ class _LDConvFunction(torch.autograd.Function):
 
         xh = _nhwc(x)
         off = torch.empty((B, h, w, 2 * N), device=dev, dtype=torch.float32)
-        _lib.check(L.ldconv_offset_conv_fwd(_ptr(xh), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
-                   "ldconv_offset_conv_fwd")
+        if pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
+            _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(xh), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt,
+                                                   st), "ldconv_offset_conv_tc_fwd")
+        else:
+            _lib.check(L.ldconv_offset_conv_fwd(_ptr(xh), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
+                       "ldconv_offset_conv_fwd")
         operand = torch.empty((M, K), device=dev, dtype=x.dtype)
         _lib.check(L.ldconv_gather_fwd(_ptr(xh), _ptr(off), _ptr(pr.pn), _ptr(operand), None, None, B, C, H, W, N, s, dt, st),
                    "ldconv_gather_fwd")

@@ -77,6 +77,14 @@ int ldconv_p_n(int N, int32_t* out_host);
 int ldconv_offset_conv_fwd(const void* x, const float* w, const float* bias, float* off,
                            int B, int C, int H, int W, int N, int s, int dtype, void* stream);
 
+/* The same offset conv on the tensor cores (bf16 x, C % 16 == 0): im2col in shared memory from a TMA-staged tile +
+ * tcgen05.mma with N = 16/32, fp32 accumulation in TMEM.  w_bf16 is (2N, 9*C) bf16 with k = (ky*3+kx)*C + c (the
+ * reference's (2N,C,3,3) permuted to (2N,3,3,C)); bias (2N) fp32 or NULL; off (B,h,w,2N) fp32.
+ * ldconv_offset_conv_tc_supported returns 1 when the shape is covered. */
+int ldconv_offset_conv_tc_supported(int C, int N, int stride, int dtype);
+int ldconv_offset_conv_tc_fwd(const void* x, const void* w_bf16, const float* bias, float* off,
+                              int B, int C, int H, int W, int N, int stride, int dtype, void* stream);
+
 /* conv.py:369-407 + 413-503: sampling grid p = p_0 + p_n + offset, floor / independent clamps, four corner indices,
  * four bilinear weights, the four gathers, the bilinear sum and the 'b c h w n -> b c (h n) w' rearrange, fused.
  *   x (B,H,W,C) dtype; off (B,h,w,2N) fp32; p_n (2N) int32 device table
@@ -148,6 +156,18 @@ int ldconv_fused_supported(int B, int C, int H, int W, int N, int s, int O, int 
 int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
                      const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
                      int N, int s, int O, int act, int dtype, void* stream);
+
+/* ---- neighbours of LDConv in the DEAL-YOLO graph, same kernels, same ABI conventions ------------
+ * `Conv` = Conv2d(k, no bias) + BatchNorm2d + SiLU (nn/modules/conv.py:41-59) with the BatchNorm folded to scale/shift.
+ * x / out / residual may be channel slices of wider NHWC buffers: ld* are PIXEL strides in elements (multiples of 8), so
+ * C2f / SPPF (nn/modules/block.py:151-232) can write their branches straight into the concatenated buffer (no torch.cat).
+ * 3x3: x (B,H,W,Cin|ldx) bf16, wt (Cout, 9*Cin) bf16 with k = (ky*3+kx)*Cin + c, out (B,h,w,Cout|ldo) bf16,
+ *      out = act(conv*scale+shift) (+ residual).  Cin % 16 == 0, Cout % 16 == 0, stride 1 or 2, pad 1.
+ * 1x1: rows = B*H*W pixels; out(rows, Cout|ldo) = act(x(rows, Cin|ldx) . wt(Cout,Cin)^T * scale + shift) (+ residual). */
+int ldconv_conv3x3_supported(int Cin, int Cout, int stride, int dtype);
+int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                              const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout,
+                              int stride, int act, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

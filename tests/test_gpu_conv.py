@@ -1,0 +1,95 @@
+"""GPU: the tcgen05 3x3 implicit-GEMM convolution -- as LDConv's offset conv (conv.py:356,368) and as the
+Conv2d + folded BatchNorm + SiLU block next to it (nn/modules/conv.py:41-59) -- against fp32 references on bf16-rounded
+operands (fp32 accumulation on both sides: products of bf16 values are exact in fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from experiment_yolo_b200 import _lib
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 3, 2, 37, 41, 2), (64, 1, 1, 20, 20, 2), (128, 1, 1, 17, 33, 1),
+                                         (64, 3, 2, 24, 24, 2), (32, 5, 1, 16, 48, 1), (16, 9, 2, 33, 19, 2), (256, 9, 1, 12, 12, 1),
+                                         (48, 2, 1, 9, 9, 3), (32, 1, 1, 160, 160, 2)])
+def test_offset_conv_tensor_core_vs_oracle(C, N, s, H, W, B):
+    L = _lib.load()
+    assert L.ldconv_offset_conv_tc_supported(C, N, s, _lib.BF16) == 1
+    g = torch.Generator().manual_seed(C + N)
+    x = torch.randn(B, C, H, W, generator=g).bfloat16()
+    w = (torch.randn(2 * N, C, 3, 3, generator=g) * 0.1).bfloat16()
+    b = torch.randn(2 * N, generator=g)
+    want = oracle.offset_conv(x.float().numpy(), w.float().numpy(), b.numpy(), N, s)            # (B,2N,h,w)
+    h, wo = (H - 1) // s + 1, (W - 1) // s + 1
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wd = w.permute(0, 2, 3, 1).reshape(2 * N, 9 * C).contiguous().to(DEV)
+    bd = b.to(DEV)
+    off = torch.full((B, h, wo, 2 * N), float("nan"), device=DEV)
+    _lib.check(L.ldconv_offset_conv_tc_fwd(_p(xd), _p(wd), _p(bd), _p(off), B, C, H, W, N, s, _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    got = off.cpu().numpy().transpose(0, 3, 1, 2)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("Cin,Cout,s,H,W,B,res", [(16, 16, 1, 40, 40, 2, True), (32, 32, 1, 37, 21, 2, True), (64, 64, 1, 20, 20, 2, False),
+                                                  (32, 64, 1, 24, 40, 1, False), (128, 64, 1, 17, 17, 2, False), (64, 32, 2, 40, 40, 1, False),
+                                                  (16, 48, 1, 8, 8, 3, False), (64, 64, 1, 80, 80, 2, True), (256, 128, 1, 10, 12, 1, False)])
+def test_conv3x3_bn_silu_vs_torch(Cin, Cout, s, H, W, B, res):
+    L = _lib.load()
+    assert L.ldconv_conv3x3_supported(Cin, Cout, s, _lib.BF16) == 1
+    g = torch.Generator(device=DEV).manual_seed(Cin * 3 + Cout)
+    x = torch.randn((B, Cin, H, W), device=DEV, generator=g).bfloat16()
+    w = (torch.randn((Cout, Cin, 3, 3), device=DEV, generator=g) * (1.0 / (3 * Cin ** 0.5))).bfloat16()
+    scale = torch.rand(Cout, device=DEV, generator=g) + 0.5
+    shift = torch.randn(Cout, device=DEV, generator=g) * 0.2
+    torch.backends.cudnn.allow_tf32 = False
+    z = F.conv2d(x.float(), w.float(), None, s, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    ref = F.silu(z)
+    h, wo = ref.shape[2:]
+    r = torch.randn((B, h, wo, Cout), device=DEV, generator=g).bfloat16() if res else None
+    if res:
+        ref = ref + r.permute(0, 3, 1, 2).float()
+    xd = x.permute(0, 2, 3, 1).contiguous()
+    wd = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.full((B, h, wo, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.ldconv_conv3x3_bn_act_fwd(_p(xd), Cin, _p(wd), _p(scale), _p(shift), _p(r), Cout, _p(out), Cout, B, Cin, H, W,
+                                           Cout, s, _lib.ACT_SILU, _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).float()
+    assert bool(torch.isfinite(got).all())
+    rel = float((got - ref).norm() / ref.norm())
+    assert rel <= 6e-3, rel
+
+
+def test_conv3x3_channel_slices_in_and_out():
+    """Input and output as channel slices of wider NHWC buffers (what makes C2f concat-free)."""
+    L = _lib.load()
+    B, H, W, Cin, Cout, ldx, ldo = 2, 24, 24, 32, 32, 96, 128
+    g = torch.Generator(device=DEV).manual_seed(3)
+    xbuf = torch.randn((B, H, W, ldx), device=DEV, generator=g).bfloat16()
+    obuf = torch.zeros((B, H, W, ldo), device=DEV, dtype=torch.bfloat16)
+    w = (torch.randn((Cout, Cin, 3, 3), device=DEV, generator=g) * 0.06).bfloat16()
+    xs = xbuf[..., 32:64]
+    ref = F.silu(F.conv2d(xs.permute(0, 3, 1, 2).float(), w.float(), None, 1, 1))
+    wd = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    xptr = xbuf.data_ptr() + 32 * 2
+    optr = obuf.data_ptr() + 64 * 2
+    _lib.check(L.ldconv_conv3x3_bn_act_fwd(xptr, ldx, _p(wd), None, None, None, 0, optr, ldo, B, Cin, H, W, Cout, 1,
+                                           _lib.ACT_SILU, _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    got = obuf[..., 64:96].permute(0, 3, 1, 2).float()
+    assert float((got - ref).norm() / ref.norm()) <= 6e-3
+    assert float(obuf[..., :64].abs().max()) == 0.0 and float(obuf[..., 96:].abs().max()) == 0.0
