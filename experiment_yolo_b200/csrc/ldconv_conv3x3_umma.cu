@@ -34,7 +34,7 @@ struct ConvGeom {
     int K, num_kb, stages, b_resident;
     int ldo, ldr;                                   // pixel strides (elements) of out / residual
     uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_bar; // smem byte offsets (1024-aligned base)
-    uint32_t x_bytes, b_bytes, tmem_cols;
+    uint32_t x_bytes, x_tx_bytes, b_bytes, tmem_cols;   // x_bytes: 128-aligned buffer pitch; x_tx_bytes: exact TMA box bytes
 };
 
 template <int MODE>
@@ -99,7 +99,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(&x_empty[buf], ((it >> 1) & 1) ^ 1);
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
-                mbar_arrive_expect_tx(&x_full[buf], g.x_bytes);
+                mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
                 tma_load_4d(sX + (size_t)buf * g.x_bytes, &tmX, &x_full[buf], 0, tj * kConvTileW * g.s - 1,
                             ti * kConvTileH * g.s - 1, b);
             };
@@ -274,8 +274,8 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     g.K = 9 * Cin;
     g.num_kb = (g.K + 63) / 64;
     g.b_bytes = (uint32_t)g.ON * 128;
-    g.x_bytes = (uint32_t)g.THin * g.TWin * Cin * 2;
-    g.x_bytes = (g.x_bytes + 127) & ~127u;
+    g.x_tx_bytes = (uint32_t)g.THin * g.TWin * Cin * 2;
+    g.x_bytes = (g.x_tx_bytes + 127) & ~127u;
     g.ldo = ldo; g.ldr = ldr;
     g.b_resident = (size_t)g.num_kb * g.b_bytes <= 72 * 1024;
     const size_t fixed = 2 * (size_t)g.x_bytes + (size_t)g.ON * 8 + 256 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
