@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldconv_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_SILU = 0, 1
+ACT_NONE, ACT_SILU, ACT_LEAKY01 = 0, 1, 2
 IMPL_FFMA, IMPL_TCGEN05 = 1, 2
 FLAG_FORCE_FFMA = 1
 FLAG_GATHER_DIRECT = 2
@@ -43,6 +43,7 @@ SIGNATURES = {
     "ldconv_gemm_bwd_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ldconv_gather_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_offset_conv_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_conv1x1_bn_act_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp]),
     "ldconv_conv3x3_supported": (_i, [_i] * 4),
     "ldconv_conv3x3_bn_act_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 8 + [_vp]),
     "ldconv_fused_supported": (_i, [_i] * 8),

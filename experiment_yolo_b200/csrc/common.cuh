@@ -148,6 +148,13 @@ __device__ __forceinline__ float silu_fast(float z)
     const float hz = 0.5f * z;
     return fmaf(hz, t, hz);
 }
+// activation selector of the bf16 epilogues (LDCONV_ACT_*)
+__device__ __forceinline__ float apply_act_fast(float z, int act)
+{
+    if (act == LDCONV_ACT_SILU) return silu_fast(z);
+    if (act == LDCONV_ACT_LEAKY01) return z > 0.f ? z : 0.1f * z;
+    return z;
+}
 __device__ __forceinline__ float silu_grad(float z)
 {
     const float sg = 1.f / (1.f + __expf(-z));

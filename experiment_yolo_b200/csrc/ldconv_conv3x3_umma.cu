@@ -25,13 +25,14 @@ using namespace umma;
 
 static constexpr int kConvThreads = 320;
 static constexpr int kConvTileH = 8, kConvTileW = 16;
+static constexpr int kMaxXBufs = 8;     // input tiles in flight per CTA: HBM latency x bandwidth needs ~40+ KB per SM
 
 enum { CONV_MODE_BN_ACT = 0, CONV_MODE_OFFSETS = 1 };
 
 struct ConvGeom {
     int Cin, Cout, ON, H, W, h, w, s, B;
     int THin, TWin, tiles_h, tiles_w, num_tiles;
-    int K, num_kb, stages, b_resident;
+    int K, num_kb, stages, b_resident, xbufs;       // xbufs: 2 = next tile prefetched while this one is consumed
     int ldo, ldr;                                   // pixel strides (elements) of out / residual
     uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_bar; // smem byte offsets (1024-aligned base)
     uint32_t x_bytes, x_tx_bytes, b_bytes, tmem_cols;   // x_bytes: 128-aligned buffer pitch; x_tx_bytes: exact TMA box bytes
@@ -50,9 +51,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint8_t* sB = smem + g.ofs_b;        // resident: [num_kb][ON][128 B]; streamed: [stages][ON][128 B]
     uint8_t* sX = smem + g.ofs_x;        // [2][THin][TWin][Cin]
     float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);
-    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
-    uint64_t* x_empty = x_full + 2;
-    uint64_t* t_full = x_empty + 2;
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);      // [kMaxXBufs]
+    uint64_t* x_empty = x_full + kMaxXBufs;
+    uint64_t* t_full = x_empty + kMaxXBufs;
     uint64_t* t_empty = t_full + 2;
     uint64_t* w_full = t_empty + 2;
     uint64_t* i_full = w_full + 1;
@@ -65,9 +66,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxXBufs; ++i) {
             mbar_init(&x_full[i], 1);
             mbar_init(&x_empty[i], 8);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&t_full[i], 1);
             mbar_init(&t_empty[i], 8);
         }
@@ -95,20 +98,26 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(sB + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
             }
             auto issue_x = [&](int tile, int it) {
-                const int buf = it & 1;
-                mbar_wait(&x_empty[buf], ((it >> 1) & 1) ^ 1);
+                const int buf = it % g.xbufs;
+                mbar_wait(&x_empty[buf], ((it / g.xbufs) & 1) ^ 1);
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
                 mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
                 tma_load_4d(sX + (size_t)buf * g.x_bytes, &tmX, &x_full[buf], 0, tj * kConvTileW * g.s - 1,
                             ti * kConvTileH * g.s - 1, b);
             };
-            int it = 0, st = 0;
+            int it = 0, st = 0, issued = 0;
             uint32_t ph = 0;
-            if ((int)blockIdx.x < g.num_tiles) issue_x(blockIdx.x, 0);
+            int next_tile = blockIdx.x;
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-                const int next = tile + gridDim.x;
-                if (next < g.num_tiles) issue_x(next, it + 1);
+                // keep xbufs input tiles in flight: tile `it` itself plus xbufs-1 ahead (a slot frees when the workers have
+                // finished the copies of the tile that used it, which never depends on this tile's weight blocks)
+                const int ahead = g.xbufs > 1 ? g.xbufs : 1;
+                while (issued < it + ahead && next_tile < g.num_tiles && (g.xbufs > 1 || issued <= it)) {
+                    issue_x(next_tile, issued);
+                    next_tile += gridDim.x;
+                    ++issued;
+                }
                 if (!g.b_resident) {
                     for (int kb = 0; kb < g.num_kb; ++kb) {
                         mbar_wait(&i_empty[st], ph ^ 1);
@@ -182,8 +191,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         const float2 a0 = sAff[c0 + e], a1 = sAff[c0 + 8 + e];
                         const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
                         const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
-                        lo[e] = act == LDCONV_ACT_SILU ? silu_fast(z0) : z0;
-                        hi[e] = act == LDCONV_ACT_SILU ? silu_fast(z1) : z1;
+                        lo[e] = apply_act_fast(z0, act);
+                        hi[e] = apply_act_fast(z1, act);
                     }
                     if (residual) {
                         float r0[8], r1[8];
@@ -206,8 +215,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         uint32_t ph = 0;
         const int chunk = lane & 7;                    // 16-byte chunk inside the 128-byte K-block row
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-            const int xbuf = it & 1;
-            mbar_wait(&x_full[xbuf], (it >> 1) & 1);
+            const int xbuf = it % g.xbufs;
+            mbar_wait(&x_full[xbuf], (it / g.xbufs) & 1);
             const T* xt = reinterpret_cast<const T*>(sX + (size_t)xbuf * g.x_bytes);
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 mbar_wait(&i_empty[st], ph ^ 1);
@@ -277,10 +286,22 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     g.x_tx_bytes = (uint32_t)g.THin * g.TWin * Cin * 2;
     g.x_bytes = (g.x_tx_bytes + 127) & ~127u;
     g.ldo = ldo; g.ldr = ldr;
-    g.b_resident = (size_t)g.num_kb * g.b_bytes <= 72 * 1024;
-    const size_t fixed = 2 * (size_t)g.x_bytes + (size_t)g.ON * 8 + 256 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
+    // shared memory plan: >= 3 ring stages first, then as many input tiles in flight as fit (up to kMaxXBufs)
+    g.b_resident = (size_t)g.num_kb * g.b_bytes <= 48u * 1024;
     const size_t per_stage = 16384 + (g.b_resident ? 0 : g.b_bytes);
-    int stages = (int)((220 * 1024 - (long long)fixed) / (long long)per_stage);
+    const size_t base = (size_t)g.ON * 8 + 512 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
+    const long long budget = 220 * 1024 - (long long)base;
+    int stages = 3;
+    long long xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes;
+    if (xb < 1) { stages = 2; xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes; }
+    if (xb < 1) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
+    // enough tiles in flight for ~64 KB per SM, no more
+    long long want = (64 * 1024 + g.x_bytes - 1) / g.x_bytes + 1;
+    if (want < 2) want = 2;
+    if (xb > want) xb = want;
+    if (xb > kMaxXBufs) xb = kMaxXBufs;
+    g.xbufs = (int)xb;
+    stages = (int)((budget - (long long)g.xbufs * g.x_bytes) / (long long)per_stage);
     if (stages > 6) stages = 6;
     if (stages < 2) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     g.stages = stages;
@@ -288,10 +309,10 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     g.ofs_i = ofs; ofs += (uint32_t)stages * 16384;
     g.ofs_b = ofs; ofs += (uint32_t)(g.b_resident ? g.num_kb : stages) * g.b_bytes;
     ofs = (ofs + 127) & ~127u;
-    g.ofs_x = ofs; ofs += 2 * g.x_bytes;
+    g.ofs_x = ofs; ofs += (uint32_t)g.xbufs * g.x_bytes;
     g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8;
     ofs = (ofs + 7) & ~7u;
-    g.ofs_bar = ofs; ofs += (uint32_t)(9 + 2 * stages) * 8 + 16;
+    g.ofs_bar = ofs; ofs += (uint32_t)(2 * kMaxXBufs + 5 + 2 * stages) * 8 + 16;
     const size_t smem = ofs + 1024;
     g.tmem_cols = 32;
     while (g.tmem_cols < (uint32_t)(2 * g.ON)) g.tmem_cols <<= 1;

@@ -241,8 +241,8 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     const float2 a0 = sAff[c0 + e], a1 = sAff[c0 + 8 + e];
                     const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
                     const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
-                    lo[e] = act == LDCONV_ACT_SILU ? silu_fast(z0) : z0;
-                    hi[e] = act == LDCONV_ACT_SILU ? silu_fast(z1) : z1;
+                    lo[e] = apply_act_fast(z0, act);
+                    hi[e] = apply_act_fast(z1, act);
                 }
                 T* dst = out + m * O + c0;
                 Vec16<T>::store(dst, lo);

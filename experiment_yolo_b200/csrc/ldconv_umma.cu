@@ -29,10 +29,10 @@ static thread_local int g_force_ffma = 0;   // ldconv_set_flag(LDCONV_FLAG_FORCE
 static int g_env_force_ffma = -1;           // environment LDCONV_FORCE_FFMA=1 (debug A/B switch, wins over the flag)
 
 // 2-D bf16 row-major (rows, cols) tensor, box (box_rows, 64 cols), 128-byte swizzle, zero fill out of bounds
-static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows)
+static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, long long ld)
 {
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
     return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -40,8 +40,8 @@ static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long 
 __global__ void __launch_bounds__(kGemmThreads, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-                 __nv_bfloat16* __restrict__ pre, int M, int O, int ON, int num_kb, int num_tiles, int stages, int act,
-                 uint32_t tmem_cols, int vec_store)
+                 __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
+                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -136,7 +136,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < M && c0 < O) {
                     const bool full16 = vec_store && (c0 + 16 <= O);
                     if (pre) {
-                        __nv_bfloat16* dst = pre + m * O + c0;
+                        __nv_bfloat16* dst = pre + m * ldo + c0;
                         if (full16) {
                             float lo[8], hi[8];
 #pragma unroll
@@ -156,10 +156,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const float2 a0 = s_affine[c0 + e], a1 = s_affine[c0 + 8 + e];
                             const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
                             const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
-                            lo[e] = act == LDCONV_ACT_SILU ? silu_fast(z0) : z0;
-                            hi[e] = act == LDCONV_ACT_SILU ? silu_fast(z1) : z1;
+                            lo[e] = apply_act_fast(z0, act);
+                            hi[e] = apply_act_fast(z1, act);
                         }
-                        __nv_bfloat16* dst = out + m * O + c0;
+                        if (residual) {
+                            const __nv_bfloat16* rp = residual + m * ldr + c0;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                if (c0 + e < O) lo[e] += __bfloat162float(rp[e]);
+                                if (c0 + 8 + e < O) hi[e] += __bfloat162float(rp[8 + e]);
+                            }
+                        }
+                        __nv_bfloat16* dst = out + m * ldo + c0;
                         if (full16) {
                             Vec16<__nv_bfloat16>::store(dst, lo);
                             Vec16<__nv_bfloat16>::store(dst + 8, hi);
@@ -203,8 +211,19 @@ int umma_set_force_ffma(int v)
     return LDCONV_OK;
 }
 
+int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale, const float* shift, void* out, void* pre,
+                     const void* residual, int ldr, int ldo, double* stat_sum, double* stat_sqsum, int M, int K, int O, int act,
+                     cudaStream_t st);
+
 int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                   double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
+{
+    return umma_gemm_fwd_ld(a, K, wt, scale, shift, out, pre, nullptr, 0, O, stat_sum, stat_sqsum, M, K, O, act, st);
+}
+
+int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale, const float* shift, void* out, void* pre,
+                     const void* residual, int ldr, int ldo, double* stat_sum, double* stat_sqsum, int M, int K, int O, int act,
+                     cudaStream_t st)
 {
     if (stat_sum && !pre) return fail(LDCONV_E_ARG, "tcgen05 GEMM: batch statistics need the `pre` output");
     const int ON = (O + 15) / 16 * 16;
@@ -223,19 +242,43 @@ int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float
                         (size_t)ON * sizeof(float2);
 
     CUtensorMap tmA, tmB;
-    if (int e = make_map_2d(&tmA, a, M, K, kTileM)) return e;
-    if (int e = make_map_2d(&tmB, wt, O, K, ON)) return e;
+    if (int e = make_map_2d(&tmA, a, M, K, kTileM, lda)) return e;
+    if (int e = make_map_2d(&tmB, wt, O, K, ON, K)) return e;
 
     LDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > num_tiles) grid = num_tiles;
-    const int vec_store = (O % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
-    umma_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, scale, shift, (__nv_bfloat16*)out, (__nv_bfloat16*)pre, M,
-                                                       O, ON, num_kb, num_tiles, stages, act, tmem_cols, vec_store);
+    const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
+    umma_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, scale, shift, (__nv_bfloat16*)out, (__nv_bfloat16*)pre,
+                                                       (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages,
+                                                       act, tmem_cols, vec_store, ldo, ldr);
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
-    if (stat_sum) return col_stats_bf16((const __nv_bfloat16*)pre, M, O, stat_sum, stat_sqsum, st);
+    if (stat_sum) {
+        if (ldo != O) return fail(LDCONV_E_ARG, "tcgen05 GEMM: batch statistics need a dense `pre`");
+        return col_stats_bf16((const __nv_bfloat16*)pre, M, O, stat_sum, stat_sqsum, st);
+    }
     return LDCONV_OK;
 }
 
 }  // namespace ldc
+
+using namespace ldc;
+
+// 1x1 `Conv` block (Conv2d(1x1, no bias) + folded BatchNorm + activation, nn/modules/conv.py:41-59) = the same GEMM with
+// pixel strides: x and out may be channel slices of wider NHWC buffers.
+LDC_API int ldconv_conv1x1_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                                      const void* residual, int ldr, void* out, int ldo, long long rows, int Cin, int Cout,
+                                      int act, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_conv1x1_bn_act_fwd: bf16 only (the fp32 path keeps the framework conv)");
+    LDC_REQUIRE(x && wt && out && rows >= 0 && rows < (1ll << 31), "ldconv_conv1x1_bn_act_fwd: bad arguments");
+    LDC_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo >= Cout && Cout <= 256,
+                "ldconv_conv1x1_bn_act_fwd: needs Cin %% 8 == 0, ldx %% 8 == 0, Cout <= 256 (got Cin=%d ldx=%d Cout=%d)", Cin, ldx,
+                Cout);
+    LDC_REQUIRE(aligned16(x) && aligned16(wt), "ldconv_conv1x1_bn_act_fwd: x / wt must be 16-byte aligned");
+    if (rows == 0) return LDCONV_OK;
+    return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, out, nullptr, residual, ldr, ldo, nullptr, nullptr, (int)rows, Cin, Cout,
+                            act, (cudaStream_t)stream);
+}
+

@@ -40,6 +40,7 @@ extern "C" {
 
 #define LDCONV_ACT_NONE 0
 #define LDCONV_ACT_SILU 1
+#define LDCONV_ACT_LEAKY01 2   /* LeakyReLU(0.1): ScalSeq (nn/extra_modules/block.py:3424); tcgen05 epilogues only */
 
 #define LDCONV_OK 0
 #define LDCONV_E_ARG (-1)      /* bad shape / null pointer / unsupported value */
@@ -164,6 +165,9 @@ int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, cons
  * 3x3: x (B,H,W,Cin|ldx) bf16, wt (Cout, 9*Cin) bf16 with k = (ky*3+kx)*Cin + c, out (B,h,w,Cout|ldo) bf16,
  *      out = act(conv*scale+shift) (+ residual).  Cin % 16 == 0, Cout % 16 == 0, stride 1 or 2, pad 1.
  * 1x1: rows = B*H*W pixels; out(rows, Cout|ldo) = act(x(rows, Cin|ldx) . wt(Cout,Cin)^T * scale + shift) (+ residual). */
+int ldconv_conv1x1_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                              const void* residual, int ldr, void* out, int ldo, long long rows, int Cin, int Cout, int act,
+                              int dtype, void* stream);
 int ldconv_conv3x3_supported(int Cin, int Cout, int stride, int dtype);
 int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                               const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout,
