@@ -34,7 +34,7 @@ struct ConvGeom {
     int THin, TWin, tiles_h, tiles_w, num_tiles;
     int K, num_kb, stages, b_resident, xbufs;       // xbufs: 2 = next tile prefetched while this one is consumed
     int ldo, ldr;                                   // pixel strides (elements) of out / residual
-    uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_bar; // smem byte offsets (1024-aligned base)
+    uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_tofs, ofs_bar; // smem byte offsets (1024-aligned base)
     uint32_t x_bytes, x_tx_bytes, b_bytes, tmem_cols;   // x_bytes: 128-aligned buffer pitch; x_tx_bytes: exact TMA box bytes
 };
 
@@ -51,6 +51,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint8_t* sB = smem + g.ofs_b;        // resident: [num_kb][ON][128 B]; streamed: [stages][ON][128 B]
     uint8_t* sX = smem + g.ofs_x;        // [2][THin][TWin][Cin]
     float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);
+    int* sTofs = reinterpret_cast<int*>(smem + g.ofs_tofs);   // [num_kb*8] element offset of each 16-byte K chunk's tap, -1 past K
     uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);      // [kMaxXBufs]
     uint64_t* x_empty = x_full + kMaxXBufs;
     uint64_t* t_full = x_empty + kMaxXBufs;
@@ -84,6 +85,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
     for (int o = threadIdx.x; o < g.ON; o += blockDim.x)
         sAff[o] = make_float2((scale && o < g.Cout) ? scale[o] : 1.f, (shift && o < g.Cout) ? shift[o] : 0.f);
+    for (int t = threadIdx.x; t < g.num_kb * 8; t += blockDim.x) {
+        const int kk = t * 8;
+        const int tap = kk / g.Cin, c0 = kk % g.Cin;
+        sTofs[t] = kk < g.K ? ((tap / 3) * g.TWin + (tap % 3)) * g.Cin + c0 : -1;
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -214,6 +220,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         int it = 0, st = 0, prev_tile = -1;
         uint32_t ph = 0;
         const int chunk = lane & 7;                    // 16-byte chunk inside the 128-byte K-block row
+        // per-thread constants of the im2col copy: 4 rows (pixels) of the 128-row block, source offset inside the staged
+        // tile and swizzled destination offset inside the K-block
+        int src_row[4];
+        uint32_t dst_off[4];
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+            const int p = (r4 * 8 + ww) * 4 + (lane >> 3);
+            src_row[r4] = ((p / kConvTileW) * g.s * g.TWin + (p % kConvTileW) * g.s) * g.Cin;
+            dst_off[r4] = sw128_offset((uint32_t)p, (uint32_t)chunk);
+        }
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const int xbuf = it % g.xbufs;
             mbar_wait(&x_full[xbuf], (it / g.xbufs) & 1);
@@ -221,18 +237,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 mbar_wait(&i_empty[st], ph ^ 1);
                 uint8_t* dstI = sI + (size_t)st * 16384;
-                const int kk = kb * 64 + chunk * 8;    // first k of this thread's chunk
-                if (kk < g.K) {
-                    const int tap = kk / g.Cin, c0 = kk % g.Cin;
-                    const int tofs = ((tap / 3) * g.TWin + (tap % 3)) * g.Cin + c0;
+                const int tofs = sTofs[kb * 8 + chunk];
+                if (tofs >= 0) {
+                    uint4 val[4];
 #pragma unroll
-                    for (int r4 = 0; r4 < 4; ++r4) {
-                        const int p = (r4 * 8 + ww) * 4 + (lane >> 3);
-                        const int pi = p / kConvTileW, pj = p % kConvTileW;
-                        const uint4 val =
-                            *reinterpret_cast<const uint4*>(xt + (pi * g.s * g.TWin + pj * g.s) * g.Cin + tofs);
-                        *reinterpret_cast<uint4*>(dstI + sw128_offset((uint32_t)p, (uint32_t)chunk)) = val;
-                    }
+                    for (int r4 = 0; r4 < 4; ++r4) val[r4] = *reinterpret_cast<const uint4*>(xt + src_row[r4] + tofs);
+#pragma unroll
+                    for (int r4 = 0; r4 < 4; ++r4) *reinterpret_cast<uint4*>(dstI + dst_off[r4]) = val[r4];
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -289,7 +300,7 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     // shared memory plan: >= 3 ring stages first, then as many input tiles in flight as fit (up to kMaxXBufs)
     g.b_resident = (size_t)g.num_kb * g.b_bytes <= 48u * 1024;
     const size_t per_stage = 16384 + (g.b_resident ? 0 : g.b_bytes);
-    const size_t base = (size_t)g.ON * 8 + 512 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
+    const size_t base = (size_t)g.ON * 8 + (size_t)g.num_kb * 32 + 512 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
     const long long budget = 220 * 1024 - (long long)base;
     int stages = 3;
     long long xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes;
@@ -311,6 +322,7 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     ofs = (ofs + 127) & ~127u;
     g.ofs_x = ofs; ofs += (uint32_t)g.xbufs * g.x_bytes;
     g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8;
+    g.ofs_tofs = ofs; ofs += (uint32_t)g.num_kb * 8 * 4;
     ofs = (ofs + 7) & ~7u;
     g.ofs_bar = ofs; ofs += (uint32_t)(2 * kMaxXBufs + 5 + 2 * stages) * 8 + 16;
     const size_t smem = ofs + 1024;
