@@ -29,11 +29,24 @@ static constexpr int kMaxXBufs = 8;     // input tiles in flight per CTA: HBM la
 
 enum { CONV_MODE_BN_ACT = 0, CONV_MODE_OFFSETS = 1 };
 
+// debug timeline (LDCONV_DBG bit 32): three roles of CTA 0 record (tag, clock64) pairs for tile iterations 8..11 into
+// shared memory (cheap), dumped to g_trace at kernel end
+static constexpr int kTraceN = 96;
+__device__ long long g_trace[3 * kTraceN * 2];
+__device__ int g_trace_n[3];
+struct Tracer {
+    long long* buf; int n; bool on;
+    __device__ __forceinline__ void operator()(int it, int tag) {
+        if (on && it >= 8 && it < 12 && n < kTraceN) { buf[2 * n] = tag; buf[2 * n + 1] = clock64(); ++n; }
+    }
+};
+
 struct ConvGeom {
     int Cin, Cout, ON, H, W, h, w, s, B;
     int THin, TWin, tiles_h, tiles_w, num_tiles;
     int K, num_kb, stages, b_resident, xbufs;       // xbufs: 2 = next tile prefetched while this one is consumed
     int ldo, ldr;                                   // pixel strides (elements) of out / residual
+    int dbg;                                        // LDCONV_DBG experiment bits (0 in production)
     uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_tofs, ofs_bar; // smem byte offsets (1024-aligned base)
     uint32_t x_bytes, x_tx_bytes, b_bytes, tmem_cols;   // x_bytes: 128-aligned buffer pitch; x_tx_bytes: exact TMA box bytes
 };
@@ -63,6 +76,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i_full_count = 8 + (g.b_resident ? 0 : 1);
+    __shared__ long long s_trace[3 * kTraceN * 2];
+    const bool tracing = (g.dbg & 32) && blockIdx.x == 0 && lane == 0 && warp < 3;
+    Tracer tr{s_trace + (warp < 3 ? warp : 0) * kTraceN * 2, 0, tracing};
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmX);
@@ -108,6 +124,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(&x_empty[buf], ((it / g.xbufs) & 1) ^ 1);
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
+                tr(it, 100000 + it * 100);
                 mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
                 tma_load_4d(sX + (size_t)buf * g.x_bytes, &tmX, &x_full[buf], 0, tj * kConvTileW * g.s - 1,
                             ti * kConvTileH * g.s - 1, b);
@@ -148,15 +165,17 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
                 for (int kb = 0; kb < g.num_kb; ++kb) {
                     mbar_wait(&i_full[st], ph);
+                    tr(it, 200000 + it * 100 + kb);
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(sI + (size_t)st * 16384);
                     const uint32_t b_addr = smem_u32(sB + (size_t)(g.b_resident ? kb : st) * g.b_bytes);
                     const int ksteps = min(4, (g.K - kb * 64) / 16);
-                    for (int k = 0; k < ksteps; ++k)
+                    for (int k = 0; k < ((g.dbg & 4) ? 0 : ksteps); ++k)
                         mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
                                     (uint32_t)((kb | k) != 0));
                     mma_commit(&i_empty[st]);
                     if (kb == g.num_kb - 1) mma_commit(&t_full[buf]);
+                    tr(it, 300000 + it * 100 + kb);
                     if (++st == g.stages) { st = 0; ph ^= 1; }
                 }
             }
@@ -232,27 +251,38 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const int xbuf = it % g.xbufs;
+            tr(it, 600000 + it * 100);
             mbar_wait(&x_full[xbuf], (it / g.xbufs) & 1);
+            tr(it, 700000 + it * 100);
             const T* xt = reinterpret_cast<const T*>(sX + (size_t)xbuf * g.x_bytes);
             for (int kb = 0; kb < g.num_kb; ++kb) {
-                mbar_wait(&i_empty[st], ph ^ 1);
+                if (g.dbg & 16) {
+                    if (lane == 0) mbar_wait(&i_empty[st], ph ^ 1);
+                    __syncwarp();
+                } else {
+                    mbar_wait(&i_empty[st], ph ^ 1);
+                }
+                tr(it, 400000 + it * 100 + kb);
                 uint8_t* dstI = sI + (size_t)st * 16384;
                 const int tofs = sTofs[kb * 8 + chunk];
-                if (tofs >= 0) {
+                if (tofs >= 0 && !(g.dbg & 2)) {
                     uint4 val[4];
 #pragma unroll
                     for (int r4 = 0; r4 < 4; ++r4) val[r4] = *reinterpret_cast<const uint4*>(xt + src_row[r4] + tofs);
 #pragma unroll
                     for (int r4 = 0; r4 < 4; ++r4) *reinterpret_cast<uint4*>(dstI + dst_off[r4]) = val[r4];
                 }
-                fence_proxy_async_smem();
+                if (!(g.dbg & 1)) fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&i_full[st]);
+                tr(it, 500000 + it * 100 + kb);
                 if (++st == g.stages) { st = 0; ph ^= 1; }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[xbuf]);
+            tr(it, 800000 + it * 100);
             if (prev_tile >= 0) epilogue(prev_tile, it - 1);
+            tr(it, 900000 + it * 100);
             prev_tile = tile;
         }
         if (prev_tile >= 0) epilogue(prev_tile, it - 1);
@@ -260,6 +290,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+    if (tracing) {
+        for (int i = 0; i < 2 * tr.n; ++i) g_trace[warp * kTraceN * 2 + i] = tr.buf[i];
+        g_trace_n[warp] = tr.n;
+    }
 }
 
 int conv3x3_umma_supported(int Cin, int Cout, int s, int mode)
@@ -297,6 +331,7 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     g.x_tx_bytes = (uint32_t)g.THin * g.TWin * Cin * 2;
     g.x_bytes = (g.x_tx_bytes + 127) & ~127u;
     g.ldo = ldo; g.ldr = ldr;
+    { const char* e = getenv("LDCONV_DBG"); g.dbg = e ? atoi(e) : 0; }
     // shared memory plan: >= 3 ring stages first, then as many input tiles in flight as fit (up to kMaxXBufs)
     g.b_resident = (size_t)g.num_kb * g.b_bytes <= 48u * 1024;
     const size_t per_stage = 16384 + (g.b_resident ? 0 : g.b_bytes);
@@ -314,6 +349,7 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     g.xbufs = (int)xb;
     stages = (int)((budget - (long long)g.xbufs * g.x_bytes) / (long long)per_stage);
     if (stages > 6) stages = 6;
+    if (g.dbg & 8) stages = 2;
     if (stages < 2) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     g.stages = stages;
     uint32_t ofs = 0;
@@ -396,4 +432,19 @@ LDC_API int ldconv_offset_conv_tc_fwd(const void* x, const void* w_bf16, const f
     // bias rides in the `shift` slot of the epilogue affine (scale unused in this mode)
     return conv3x3_umma(x, C, w_bf16, nullptr, bias, nullptr, 0, off, 2 * N, B, C, H, W, 2 * N, stride, LDCONV_ACT_NONE,
                         CONV_MODE_OFFSETS, (cudaStream_t)stream);
+}
+
+LDC_API int ldconv_debug_trace(long long* host_out, int max_pairs)
+{
+    int n[3] = {0, 0, 0};
+    long long all[3 * ldc::kTraceN * 2];
+    cudaMemcpyFromSymbol(n, ldc::g_trace_n, sizeof(n));
+    cudaMemcpyFromSymbol(all, ldc::g_trace, sizeof(all));
+    int k = 0;
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < n[r] && k < max_pairs; ++i, ++k) {
+            host_out[2 * k] = all[(r * ldc::kTraceN + i) * 2];
+            host_out[2 * k + 1] = all[(r * ldc::kTraceN + i) * 2 + 1];
+        }
+    return k;
 }

@@ -721,6 +721,59 @@ static int dispatch_offset_conv_bwd(const float* goff, const T* x, const float* 
     }
 }
 
+// =====================================================================================================================
+// Detect head decode (reference nn/modules/head.py:55-77 + DFL nn/modules/block.py:37-56 + dist2bbox utils/tal.py:309-319):
+// per anchor, softmax-expectation over the reg_max bins of each of the 4 sides, distances -> xywh box around the
+// cell-centre anchor, times the level stride; class logits -> sigmoid.  One thread per anchor, fp32 math.
+// =====================================================================================================================
+template <int REG>
+__global__ void __launch_bounds__(128)
+detect_decode_kernel(const __nv_bfloat16* __restrict__ box, const __nv_bfloat16* __restrict__ cls,
+                     __nv_bfloat16* __restrict__ y, int B, int H, int W, int nc, float stride, int a0, int total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_img = (long long)H * W;
+    if (t >= (long long)B * per_img) return;
+    const int b = (int)(t / per_img);
+    const int a = (int)(t % per_img);
+    const float ax = (float)(a % W) + 0.5f, ay = (float)(a / W) + 0.5f;
+    const __nv_bfloat16* bp = box + t * (4 * REG);
+    float d[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        float v[REG];
+#pragma unroll
+        for (int k0 = 0; k0 < REG; k0 += 8) {
+            float tmp[8];
+            Vec16<__nv_bfloat16>::load(bp + side * REG + k0, tmp);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k0 + e] = tmp[e];
+        }
+        float mx = v[0];
+#pragma unroll
+        for (int k = 1; k < REG; ++k) mx = fmaxf(mx, v[k]);
+        float den = 0.f, num = 0.f;
+#pragma unroll
+        for (int k = 0; k < REG; ++k) {
+            const float e = __expf(v[k] - mx);
+            den += e;
+            num = fmaf(e, (float)k, num);
+        }
+        d[side] = num / den;
+    }
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    __nv_bfloat16* yp = y + (size_t)b * (4 + nc) * total + a0 + a;
+    yp[0] = __float2bfloat16_rn(0.5f * (x1 + x2) * stride);
+    yp[(size_t)total] = __float2bfloat16_rn(0.5f * (y1 + y2) * stride);
+    yp[2 * (size_t)total] = __float2bfloat16_rn((x2 - x1) * stride);
+    yp[3 * (size_t)total] = __float2bfloat16_rn((y2 - y1) * stride);
+    const __nv_bfloat16* cp = cls + t * nc;
+    for (int c = 0; c < nc; ++c) {
+        const float z = __bfloat162float(cp[c]);
+        yp[(size_t)(4 + c) * total] = __float2bfloat16_rn(1.f / (1.f + __expf(-z)));
+    }
+}
+
 static int check_dims(const char* fn, int B, int C, int H, int W, int N, int s)
 {
     if (B < 0 || C < 1 || H < 1 || W < 1 || N < 1 || N > 16 || s < 1)
@@ -995,3 +1048,20 @@ LDC_API int ldconv_offset_conv_bwd(const float* grad_off, const void* x, const f
     return dispatch_offset_conv_bwd<__nv_bfloat16>(grad_off, (const __nv_bfloat16*)x, w, grad_x, grad_w, grad_b, B, C, H,
                                                    W, N, s, st);
 }
+
+LDC_API int ldconv_detect_decode(const void* box, const void* cls, void* y, int B, int H, int W, int nc, int reg_max,
+                                 float stride, int anchor_offset, int total_anchors, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_detect_decode: bf16 only");
+    LDC_REQUIRE(box && cls && y && B >= 0 && H >= 1 && W >= 1 && nc >= 1, "ldconv_detect_decode: bad arguments");
+    LDC_REQUIRE(reg_max == 16, "ldconv_detect_decode: reg_max %d not supported (16)", reg_max);
+    LDC_REQUIRE(aligned16(box), "ldconv_detect_decode: box must be 16-byte aligned");
+    LDC_REQUIRE(anchor_offset >= 0 && anchor_offset + H * W <= total_anchors, "ldconv_detect_decode: anchor range");
+    if (B == 0) return LDCONV_OK;
+    const long long n = (long long)B * H * W;
+    detect_decode_kernel<16><<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)box, (const __nv_bfloat16*)cls, (__nv_bfloat16*)y, B, H, W, nc, stride, anchor_offset, total_anchors);
+    LDC_LAUNCH_CHECK("detect_decode_kernel");
+    return LDCONV_OK;
+}
+

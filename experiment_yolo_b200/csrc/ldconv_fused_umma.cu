@@ -27,9 +27,13 @@ struct FusedGeom {
     int num_kb, ON, ON2, Q, PP;             // K blocks of 64, O padded to 16, 2N padded to 4, channel split, pixels/thread
     uint32_t ofs_b, ofs_x, ofs_woff, ofs_part, ofs_aff, ofs_bar;   // byte offsets inside the 1024-aligned dynamic smem
     uint32_t tmem_cols;
+    int dbg;
 };
 
 static constexpr int kFusedThreads = 256;
+
+// debug phase timeline (LDCONV_DBG bit 64): thread 0 of one mid-grid CTA records clock64 after each phase
+__device__ long long g_fused_trace[16];
 
 template <int ON2>
 __global__ void __launch_bounds__(kFusedThreads)
@@ -62,6 +66,9 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int O2 = 2 * N, K = N * C;
     const int b_bytes = g.ON * 128;
 
+    const bool tracing = g.dbg && tid == 0 && blockIdx.x == gridDim.x / 2;
+    long long tr[10];
+    if (tracing) tr[0] = clock64();
     // ---- phase 0: barriers, TMEM, TMA issue, offset-conv weights -------------------------------------------------------
     if (tid == 0) {
         tma_prefetch_desc(&tmX);
@@ -76,6 +83,7 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    if (tracing) tr[1] = clock64();
     if (tid == 0) {
         mbar_arrive_expect_tx(bar_x, (uint32_t)((size_t)g.THin * g.TWin * C * sizeof(T)));
         tma_load_4d(sX, &tmX, bar_x, 0, k_org, r_org, b);
@@ -89,7 +97,9 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (int o = tid; o < g.ON; o += kFusedThreads)
         sAff[o] = make_float2((scale && o < O) ? scale[o] : 1.f, (shift && o < O) ? shift[o] : 0.f);
     __syncthreads();
+    if (tracing) tr[2] = clock64();
     mbar_wait(bar_x, 0);
+    if (tracing) tr[3] = clock64();
 
     // ---- phase 2: offset conv.  thread = (pixel group pg, channel slice q); PP pixels per thread share weight loads -------
     {
@@ -148,6 +158,7 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
     }
     __syncthreads();
+    if (tracing) tr[4] = clock64();
 
     // ---- phase 3: grid + gather + bilinear -> swizzled operand tile -----------------------------------------------------------
     {
@@ -201,6 +212,7 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     fence_proxy_async_smem();      // generic-proxy writes of the operand tile -> visible to the tensor core (async proxy)
     __syncthreads();
+    if (tracing) tr[5] = clock64();
 
     // ---- phase 4: MMA ----------------------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -215,11 +227,13 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         make_desc_k_sw128(b_addr + kb * b_bytes + kk * 32), idesc, (uint32_t)(st != 0));
         }
         mma_commit(bar_mma);
+        if (tracing) tr[6] = clock64();
     }
 
     // ---- phase 5: epilogue --------------------------------------------------------------------------------------------------
     mbar_wait(bar_mma, 0);
     tc_fence_after_sync();
+    if (tracing) tr[7] = clock64();
     {
         const int lg = warp & 3, half = warp >> 2;
         const int p = lg * 32 + lane;
@@ -252,6 +266,10 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (tracing) {
+        tr[8] = clock64();
+        for (int i = 0; i < 9; ++i) g_fused_trace[i] = tr[i];
+    }
     if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
@@ -292,6 +310,7 @@ static int fused_geometry(int C, int N, int s, int O, int max_pn_r, int max_pn_k
     g.tiles_w = (w + g.TW - 1) / g.TW;
     g.tmem_cols = 32;
     while (g.tmem_cols < (uint32_t)g.ON) g.tmem_cols <<= 1;
+    { const char* e = getenv("LDCONV_DBG"); g.dbg = e ? (atoi(e) & 64) : 0; }
     *out = g;
     return 1;
 }
@@ -387,3 +406,10 @@ int umma_fused_fwd(const void* x, const float* w_off, const float* b_off, const 
 }
 
 }  // namespace ldc
+
+LDC_API int ldconv_debug_fused_trace(long long* host_out)
+{
+    cudaMemcpyFromSymbol(host_out, ldc::g_fused_trace, sizeof(long long) * 9);
+    return 9;
+}
+

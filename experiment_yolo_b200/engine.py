@@ -1,0 +1,251 @@
+"""Fused bf16 inference executor for the DEAL-YOLO-LD graph (SURVEY.md 8f "next" rows, widened after the LDConv path).
+
+`FusedDealYolo(model)` takes an eval-mode `dealyolo.DealYolo` on a B200 and runs the same graph with the library's kernels
+instead of the eager torch modules around LDConv:
+
+  * every `Conv` block (Conv2d no-bias + BatchNorm2d + SiLU, reference nn/modules/conv.py:41-59) is ONE kernel: the
+    BatchNorm is folded to a per-channel scale/shift (what the reference's own `model.fuse()` does for these blocks,
+    nn/tasks.py:168-195) and applied with the SiLU in the epilogue of the tcgen05 GEMM (1x1) or of the tcgen05 implicit-GEMM
+    3x3 kernel;
+  * C2f / SPPF (nn/modules/block.py:151-232) write their branches straight into the concatenated NHWC buffer through the
+    kernels' pixel-stride arguments, so the `chunk` / `torch.cat` copies disappear; Bottleneck's residual add rides in the
+    3x3 kernel's epilogue;
+  * ScalSeq (nn/extra_modules/block.py:3414-3443): Conv3d(1x1x1)+BatchNorm3d+LeakyReLU(0.1) is point-wise per level, so it is
+    evaluated at each level's NATIVE resolution (nearest up-sampling commutes with point-wise ops) as a folded 1x1 GEMM with a
+    LeakyReLU epilogue; only the final max over the three levels runs at P2 resolution;
+  * Detect (nn/modules/head.py:43-93): the 3x3 / 1x1 convs through the same kernels, and the DFL softmax-expectation +
+    dist2bbox + stride scaling + class sigmoid of all three levels in one decode kernel;
+  * LDConv layers call the module's own inference path (fused tcgen05 / small-C kernel, or offset-conv -> gather -> GEMM).
+
+Activations are dense NHWC bf16 tensors (or channel slices of them).  No CPU / eager fallback for the fused ops: a missing
+library or an unsupported device raises.  Numerics: bf16 storage, fp32 accumulation; tests/test_gpu_model.py compares with
+the golden output of the reference DetectionModel.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, dealyolo
+from .ldconv import LDConv
+
+_ACT = {"none": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "leaky": _lib.ACT_LEAKY01}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _nhwc_geometry(t: torch.Tensor):
+    """(B,H,W,C) tensor whose channels are contiguous and whose pixels are `ld` elements apart (a dense NHWC tensor or a
+    channel slice of one)."""
+    B, H, W, C = t.shape
+    ld = t.stride(2)
+    assert t.stride(3) == 1 and t.stride(1) == W * ld and t.stride(0) == H * W * ld, "not an NHWC (slice) tensor"
+    return B, H, W, C, ld
+
+
+class _Folded:
+    """Conv weight in the kernels' (Cout, K) bf16 layout + folded per-channel affine (fp32)."""
+    __slots__ = ("w", "scale", "shift", "k", "stride", "cin", "cout")
+
+    def __init__(self, conv: nn.Conv2d, bn=None, extra_bias=None):
+        w = conv.weight.detach()
+        self.cout, self.cin = w.shape[0], w.shape[1]
+        self.k = w.shape[2] if w.dim() >= 4 else 1
+        self.stride = conv.stride[0] if isinstance(conv.stride, tuple) else conv.stride
+        if w.dim() == 5:                       # Conv3d(1,1,1)
+            w = w.reshape(self.cout, self.cin, 1, 1)
+            self.k = 1
+        if self.k == 1:
+            self.w = w.reshape(self.cout, self.cin).to(torch.bfloat16).contiguous()
+        else:
+            self.w = w.permute(0, 2, 3, 1).reshape(self.cout, self.k * self.k * self.cin).to(torch.bfloat16).contiguous()
+        dev = w.device
+        bias = conv.bias.detach().float() if conv.bias is not None else torch.zeros(self.cout, device=dev)
+        if bn is not None:
+            inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+            g = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(inv)
+            b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(inv)
+            self.scale = (g * inv).contiguous()
+            self.shift = (b + (bias - bn.running_mean.detach().float()) * g * inv).contiguous()
+        else:
+            self.scale = torch.ones(self.cout, device=dev)
+            self.shift = bias.contiguous()
+
+
+def conv1x1(x: torch.Tensor, p: _Folded, out: torch.Tensor, act: str = "silu", residual=None):
+    B, H, W, C, ldx = _nhwc_geometry(x)
+    _, _, _, O, ldo = _nhwc_geometry(out)
+    assert C == p.cin and O == p.cout
+    ldr = _nhwc_geometry(residual)[4] if residual is not None else 0
+    _lib.check(_lib.load().ldconv_conv1x1_bn_act_fwd(
+        x.data_ptr(), ldx, p.w.data_ptr(), p.scale.data_ptr(), p.shift.data_ptr(),
+        None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, B * H * W, C, O, _ACT[act], _lib.BF16,
+        _stream()), "ldconv_conv1x1_bn_act_fwd")
+    return out
+
+
+def conv3x3(x: torch.Tensor, p: _Folded, out: torch.Tensor, act: str = "silu", residual=None):
+    B, H, W, C, ldx = _nhwc_geometry(x)
+    _, h, w, O, ldo = _nhwc_geometry(out)
+    assert C == p.cin and O == p.cout and h == (H - 1) // p.stride + 1 and w == (W - 1) // p.stride + 1
+    ldr = _nhwc_geometry(residual)[4] if residual is not None else 0
+    _lib.check(_lib.load().ldconv_conv3x3_bn_act_fwd(
+        x.data_ptr(), ldx, p.w.data_ptr(), p.scale.data_ptr(), p.shift.data_ptr(),
+        None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, B, C, H, W, O, p.stride, _ACT[act],
+        _lib.BF16, _stream()), "ldconv_conv3x3_bn_act_fwd")
+    return out
+
+
+def _new(like: torch.Tensor, B, H, W, C):
+    return torch.empty((B, H, W, C), device=like.device, dtype=torch.bfloat16)
+
+
+class _C2f:
+    def __init__(self, m: dealyolo.C2f):
+        self.c = m.c
+        self.n = len(m.m)
+        self.cv1 = _Folded(m.cv1.conv, m.cv1.bn)
+        self.cv2 = _Folded(m.cv2.conv, m.cv2.bn)
+        self.blocks = [(_Folded(b.cv1.conv, b.cv1.bn), _Folded(b.cv2.conv, b.cv2.bn), b.add) for b in m.m]
+
+    def __call__(self, x):
+        B, H, W, _ = x.shape
+        c, n = self.c, self.n
+        cat = _new(x, B, H, W, (2 + n) * c)
+        conv1x1(x, self.cv1, cat[..., : 2 * c])
+        tmp = _new(x, B, H, W, c)
+        for i, (p1, p2, add) in enumerate(self.blocks):
+            src = cat[..., (1 + i) * c: (2 + i) * c]
+            conv3x3(src, p1, tmp)
+            conv3x3(tmp, p2, cat[..., (2 + i) * c: (3 + i) * c], residual=src if add else None)
+        return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout))
+
+
+class _SPPF:
+    def __init__(self, m: dealyolo.SPPF):
+        self.cv1 = _Folded(m.cv1.conv, m.cv1.bn)
+        self.cv2 = _Folded(m.cv2.conv, m.cv2.bn)
+        self.k = m.m.kernel_size
+
+    def __call__(self, x):
+        B, H, W, _ = x.shape
+        c = self.cv1.cout
+        cat = _new(x, B, H, W, 4 * c)
+        conv1x1(x, self.cv1, cat[..., :c])
+        for i in range(3):      # three chained k x k max-pools (torch, channels_last views of the slices; tiny 40x40 maps)
+            src = cat[..., i * c: (i + 1) * c].permute(0, 3, 1, 2)
+            cat[..., (i + 1) * c: (i + 2) * c].copy_(F.max_pool2d(src, self.k, 1, self.k // 2).permute(0, 2, 3, 1))
+        return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout))
+
+
+def _upsample2(x, factor=2):
+    """nearest up-sampling of an NHWC tensor (torch kernel on the channels_last view)."""
+    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=factor, mode="nearest").permute(0, 2, 3, 1)
+
+
+class _ScalSeq:
+    def __init__(self, m: dealyolo.ScalSeq):
+        self.conv0 = _Folded(m.conv0.conv, m.conv0.bn) if hasattr(m, "conv0") else None
+        self.conv1 = _Folded(m.conv1.conv, m.conv1.bn)
+        self.conv2 = _Folded(m.conv2.conv, m.conv2.bn)
+        self.mix = _Folded(m.conv3d, m.bn)          # Conv3d(1x1x1) + BatchNorm3d, point-wise per level
+
+    def __call__(self, xs):
+        fine, mid, coarse = xs
+        ch = self.mix.cout
+        if self.conv0 is not None:
+            fine = conv1x1(fine, self.conv0, _new(fine, *fine.shape[:3], ch))
+        mid = conv1x1(mid, self.conv1, _new(mid, *mid.shape[:3], ch))
+        coarse = conv1x1(coarse, self.conv2, _new(coarse, *coarse.shape[:3], ch))
+        z = [conv1x1(t, self.mix, _new(t, *t.shape[:3], ch), act="leaky") for t in (fine, mid, coarse)]
+        H, W = fine.shape[1:3]
+        up1 = F.interpolate(z[1].permute(0, 3, 1, 2), size=(H, W), mode="nearest").permute(0, 2, 3, 1)
+        up2 = F.interpolate(z[2].permute(0, 3, 1, 2), size=(H, W), mode="nearest").permute(0, 2, 3, 1)
+        return torch.maximum(torch.maximum(z[0], up1), up2)      # MaxPool3d((3,1,1)) over the stacked depth axis
+
+
+class _Detect:
+    def __init__(self, m: dealyolo.Detect):
+        self.nc, self.reg_max, self.no = m.nc, m.reg_max, m.no
+        self.stride = [float(s) for s in m.stride]
+        self.box = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv2]
+        self.cls = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv3]
+
+    def __call__(self, xs):
+        L = _lib.load()
+        B = xs[0].shape[0]
+        total = sum(x.shape[1] * x.shape[2] for x in xs)
+        y = torch.empty((B, 4 + self.nc, total), device=xs[0].device, dtype=torch.bfloat16)
+        feats, a0 = [], 0
+        for lvl, x in enumerate(xs):
+            _, H, W, _ = x.shape
+            b = conv3x3(x, self.box[lvl][0], _new(x, B, H, W, self.box[lvl][0].cout))
+            b = conv3x3(b, self.box[lvl][1], _new(x, B, H, W, self.box[lvl][1].cout))
+            b = conv1x1(b, self.box[lvl][2], _new(x, B, H, W, 4 * self.reg_max), act="none")
+            c = conv3x3(x, self.cls[lvl][0], _new(x, B, H, W, self.cls[lvl][0].cout))
+            c = conv3x3(c, self.cls[lvl][1], _new(x, B, H, W, self.cls[lvl][1].cout))
+            c = conv1x1(c, self.cls[lvl][2], _new(x, B, H, W, self.nc), act="none")
+            _lib.check(L.ldconv_detect_decode(b.data_ptr(), c.data_ptr(), y.data_ptr(), B, H, W, self.nc, self.reg_max,
+                                              self.stride[lvl], a0, total, _lib.BF16, _stream()), "ldconv_detect_decode")
+            feats.append((b, c))
+            a0 += H * W
+        return y, feats
+
+
+class FusedDealYolo:
+    """Inference executor: `y, feats = FusedDealYolo(model)(images)` with `images` (B,3,H,W) bf16 (any memory format).
+    `y` is the decoded (B, 4+nc, anchors) tensor of the reference's Detect head in eval mode."""
+
+    def __init__(self, model: dealyolo.DealYolo):
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("FusedDealYolo needs the model on a CUDA device (sm_100a); there is no CPU path")
+        _lib.check(_lib.load().ldconv_device_check(), "ldconv_device_check")
+        if model.training:
+            raise RuntimeError("FusedDealYolo is an inference executor: call model.eval() first")
+        self.model = model
+        self.layers = []
+        for layer in model.model:
+            if isinstance(layer, LDConv):
+                op = ("ldconv", layer)
+            elif isinstance(layer, dealyolo.C2f):
+                op = ("fn", _C2f(layer))
+            elif isinstance(layer, dealyolo.SPPF):
+                op = ("fn", _SPPF(layer))
+            elif isinstance(layer, dealyolo.ScalSeq):
+                op = ("fn", _ScalSeq(layer))
+            elif isinstance(layer, dealyolo.Detect):
+                op = ("fn", _Detect(layer))
+            elif isinstance(layer, dealyolo.Concat):
+                op = ("cat", None)
+            elif isinstance(layer, dealyolo.Add):
+                op = ("add", None)
+            elif isinstance(layer, nn.Upsample):
+                op = ("up", int(layer.scale_factor))
+            else:
+                raise NotImplementedError(f"FusedDealYolo: no fused executor for {type(layer).__name__}")
+            self.layers.append((op, layer.f, layer.i))
+        self.save = set(model.save)
+
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor):
+        x = images.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()       # NHWC; zero-copy for channels_last input
+        saved = []
+        for (kind, arg), f, i in self.layers:
+            if f != -1:
+                x = saved[f] if isinstance(f, int) else [x if j == -1 else saved[j] for j in f]
+            if kind == "ldconv":
+                x = arg(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)          # module API is logical NCHW; views only
+            elif kind == "fn":
+                x = arg(x)
+            elif kind == "cat":
+                x = torch.cat(x, dim=3)
+            elif kind == "add":
+                x = x[0] + x[1]
+            elif kind == "up":
+                x = _upsample2(x, arg)
+            saved.append(x if i in self.save else None)
+        return x

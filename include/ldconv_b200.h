@@ -173,6 +173,12 @@ int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const floa
                               const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout,
                               int stride, int act, int dtype, void* stream);
 
+/* Detect head decode of one pyramid level (nn/modules/head.py:55-77, DFL nn/modules/block.py:37-56, dist2bbox
+ * utils/tal.py:309-319): box (B,H,W,4*reg_max) bf16 logits, cls (B,H,W,nc) bf16 logits ->
+ * y (B, 4+nc, total_anchors) bf16 at columns [anchor_offset, anchor_offset + H*W): xywh * stride, sigmoid(cls). */
+int ldconv_detect_decode(const void* box, const void* cls, void* y, int B, int H, int W, int nc, int reg_max, float stride,
+                         int anchor_offset, int total_anchors, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,3 +57,46 @@ def test_full_model_train_mode_backward_runs():
     loss.backward()
     g = [p.grad for n, p in model.named_parameters() if "p_conv" in n or ".conv.0." in n]
     assert all(t is not None and bool(torch.isfinite(t).all()) for t in g)
+
+
+def test_fused_engine_matches_reference_output_and_eager_graph():
+    """engine.FusedDealYolo (Conv/C2f/SPPF/ScalSeq/Detect through the library's kernels, concat-free) against the golden output
+    of the reference DetectionModel and against the eager bf16 graph."""
+    from experiment_yolo_b200 import engine
+    z, model = _load()
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
+    x = torch.from_numpy(z["x"]).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    eng = engine.FusedDealYolo(model)
+    y, _ = eng(x)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        y_eager, _ = model(x)
+    y, y_eager, ref = y.float().cpu().numpy(), y_eager.float().cpu().numpy(), z["y"]
+    assert y.shape == ref.shape
+    assert np.isfinite(y).all()
+    assert np.linalg.norm(y - ref) / np.linalg.norm(ref) <= 5e-2
+    assert np.linalg.norm(y - y_eager) / np.linalg.norm(y_eager) <= 5e-2
+    # class scores are probabilities: compare them separately from the pixel-valued boxes
+    assert np.abs(y[:, 4:] - ref[:, 4:]).max() <= 0.05
+
+
+def test_fused_engine_batch_and_graph_capture():
+    from experiment_yolo_b200 import engine
+    z, model = _load()
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
+    eng = engine.FusedDealYolo(model)
+    x = torch.rand(4, 3, 128, 160, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    y0, _ = eng(x)
+    y0 = y0.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        eng(x)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y1, _ = eng(x)
+    g.replay()
+    torch.cuda.synchronize()
+    assert tuple(y0.shape) == (4, 10, 32 * 40 + 16 * 20 + 8 * 10)
+    assert torch.equal(y0, y1)
