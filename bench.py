@@ -8,7 +8,7 @@ A step = one full forward of DEAL-YOLO-LD (cfg/deal-yolo-ld-p2.yaml = the refere
 parameters, random-init seeded weights) over one synthetic batch of 64 bf16 640x640 images per GPU, inference mode,
 channels_last; the batch is sharded over ranks with no collective (every LDConv sample depends on its own image only).
   value     images/s with the batch already resident in HBM (CUDA-graph replay of the forward), max over ranks
-  e2e       images/s through the public call `DealYolo.forward` with HOST buffers: every step copies its uint8 batch from
+  e2e       images/s through the public call `engine.FusedDealYolo(model)(images)` with HOST buffers: every step copies its uint8 batch from
             pinned host memory, normalises on the device, runs the forward and reads the detections back to the host
   roofline  the LDConv gather kernels of one step (10 launches): algorithmic bytes / CUDA-event time
   cpu_baseline / --impl reference: the eager CPU port of the reference path (oracle/ldconv_torch_port.py inside the same
@@ -123,8 +123,8 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(n_gpus: int):
-    return {"workload": "DEAL-YOLO-LD (yolov8-LD-P2 graph, 10 LDConv + SSFF, nc=6) full forward, 640x640, inference",
+def workload_config(n_gpus: int, engine: str = "fused"):
+    return {"engine": engine, "workload": "DEAL-YOLO-LD (yolov8-LD-P2 graph, 10 LDConv + SSFF, nc=6) full forward, 640x640, inference",
             "global_batch": PER_GPU_BATCH * n_gpus, "per_gpu_batch": PER_GPU_BATCH, "imgsz": IMG,
             "layout": "channels_last", "parallelism": f"batch-sharded x{n_gpus}, no collective",
             "l2_policy": "inputs_exceed_l2 (157 MB bf16 batch, two alternating input buffers; activations of one step are GBs)",
@@ -187,7 +187,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from experiment_yolo_b200 import _lib, dealyolo
+    from experiment_yolo_b200 import _lib, dealyolo, engine
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,6 +210,9 @@ def run_gpu_arm(args):
     model = dealyolo.DealYolo(nc=NC)
     model.load_state_dict(dealyolo.seeded_state(model, 0))
     model = dealyolo.channels_last_(model.to(dev).bfloat16().eval())
+    # the public inference call: the fused executor (every Conv / C2f / SPPF / ScalSeq / Detect block and every LDConv through
+    # the library's kernels); --engine eager runs the plain torch graph around the CUDA LDConv instead
+    run = engine.FusedDealYolo(model) if args.engine == "fused" else model
 
     B = PER_GPU_BATCH
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -223,13 +226,13 @@ def run_gpu_arm(args):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
-                model(static_x)
+                run(static_x)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         _lib.call_counts.clear()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            static_y, _ = model(static_x)
+            static_y, _ = run(static_x)
         launches_per_step = sum(_lib.call_counts.values())
 
         def step(i):
@@ -266,7 +269,7 @@ def run_gpu_arm(args):
         def e2e_step(i):
             xu = host_u8[i & 1].to(dev, non_blocking=True)
             xb = (xu.to(torch.bfloat16) * (1.0 / 255.0)).contiguous(memory_format=torch.channels_last)
-            y, _ = model(xb)
+            y, _ = run(xb)
             host_out.copy_(y, non_blocking=True)
 
         for i in range(max(3, args.warmup)):
@@ -294,7 +297,7 @@ def run_gpu_arm(args):
         line = {"metric": "images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(world),
+                "config": workload_config(world, args.engine),
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "input": "uint8 NCHW batch in pinned host memory, normalised on device",
                         "result": "decoded detections (B,10,33600) bf16 copied to pinned host memory"},
@@ -317,6 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--engine", default="fused", choices=["fused", "eager"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
