@@ -1,0 +1,148 @@
+// ldconv_graph_ops.cu -- the small HBM-bound glue ops between the conv blocks of the DEAL-YOLO-LD graph (bf16, NHWC,
+// sm_100a), each a single 128-bit-vectorised pass that can read / write channel slices of wider NHWC buffers (pixel
+// strides ld*), so no torch.cat / torch.stack copy is needed around them:
+//   * nearest up-sampling (nn.Upsample rows of yolov8-LD-P2.yaml:26,33) straight into the concat buffer;
+//   * SSFF tail (reference nn/extra_modules/block.py:3432-3443 + Add :3479-3484): max over the three pyramid levels (the
+//     two coarser ones read through nearest up-sampling index arithmetic instead of being materialised) + the residual add;
+//   * the three chained 5x5 max-pools of SPPF (nn/modules/block.py:166-171) = 5x5, 9x9, 13x13 maxima of the same input,
+//     computed together.
+#include "common.cuh"
+
+namespace ldc {
+
+using T = __nv_bfloat16;
+
+__global__ void __launch_bounds__(256)
+upsample_nearest_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int H, int W, int CV, int f,
+                        long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    const long long pix = t / CV;
+    const int Wo = W * f, Ho = H * f;
+    const int j = (int)(pix % Wo);
+    const int i = (int)((pix / Wo) % Ho);
+    const long long b = pix / ((long long)Wo * Ho);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((b * H + i / f) * W + j / f) * ldx + cv * 8);
+    *reinterpret_cast<uint4*>(out + pix * ldo + cv * 8) = v;
+}
+
+__global__ void __launch_bounds__(256)
+scalseq_tail_kernel(const T* __restrict__ z0, const T* __restrict__ z1, const T* __restrict__ z2, const T* __restrict__ add,
+                    int ld_add, T* __restrict__ out, int ldo, int H, int W, int H1, int W1, int H2, int W2, int CV,
+                    long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    const long long pix = t / CV;
+    const int j = (int)(pix % W);
+    const int i = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    const int C = CV * 8;
+    // torch nearest: src = floor(dst * in / out)
+    const int i1 = (int)(((long long)i * H1) / H), j1 = (int)(((long long)j * W1) / W);
+    const int i2 = (int)(((long long)i * H2) / H), j2 = (int)(((long long)j * W2) / W);
+    float a[8], b1[8], c2[8];
+    Vec16<T>::load(z0 + pix * C + cv * 8, a);
+    Vec16<T>::load(z1 + ((b * H1 + i1) * W1 + j1) * C + cv * 8, b1);
+    Vec16<T>::load(z2 + ((b * H2 + i2) * W2 + j2) * C + cv * 8, c2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = fmaxf(fmaxf(a[e], b1[e]), c2[e]);
+    if (add) {
+        float r[8];
+        Vec16<T>::load(add + pix * ld_add + cv * 8, r);
+        // the reference adds two bf16 tensors: round the max first (it is already a bf16 value), then add and round once
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += r[e];
+    }
+    Vec16<T>::store(out + pix * ldo + cv * 8, a);
+}
+
+__global__ void __launch_bounds__(256)
+sppf_pools_kernel(const T* __restrict__ x, T* __restrict__ o1, T* __restrict__ o2, T* __restrict__ o3, int ld, int H, int W,
+                  int CV, int r, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    const long long pix = t / CV;
+    const int j = (int)(pix % W);
+    const int i = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    float m1[8], m2[8], m3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m1[e] = m2[e] = m3[e] = -INFINITY;
+    for (int di = -3 * r; di <= 3 * r; ++di) {
+        const int ii = i + di;
+        if (ii < 0 || ii >= H) continue;
+        const int ai = di < 0 ? -di : di;
+        for (int dj = -3 * r; dj <= 3 * r; ++dj) {
+            const int jj = j + dj;
+            if (jj < 0 || jj >= W) continue;
+            const int aj = dj < 0 ? -dj : dj;
+            const int ring = ai > aj ? ai : aj;
+            float v[8];
+            Vec16<T>::load(x + ((b * H + ii) * W + jj) * ld + cv * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                m3[e] = fmaxf(m3[e], v[e]);
+                if (ring <= 2 * r) m2[e] = fmaxf(m2[e], v[e]);
+                if (ring <= r) m1[e] = fmaxf(m1[e], v[e]);
+            }
+        }
+    }
+    Vec16<T>::store(o1 + pix * ld + cv * 8, m1);
+    Vec16<T>::store(o2 + pix * ld + cv * 8, m2);
+    Vec16<T>::store(o3 + pix * ld + cv * 8, m3);
+}
+
+}  // namespace ldc
+
+using namespace ldc;
+
+LDC_API int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, int H, int W, int C, int factor,
+                                    int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_upsample_nearest: bf16 only");
+    LDC_REQUIRE(x && out && C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && factor >= 1 && aligned16(x) && aligned16(out),
+                "ldconv_upsample_nearest: needs C, ldx, ldo multiples of 8 and 16-byte aligned pointers");
+    const long long total = (long long)B * H * factor * W * factor * (C / 8);
+    if (total == 0) return LDCONV_OK;
+    upsample_nearest_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, ldo, H, W, C / 8,
+                                                                               factor, total);
+    LDC_LAUNCH_CHECK("upsample_nearest_kernel");
+    return LDCONV_OK;
+}
+
+LDC_API int ldconv_scalseq_tail(const void* z0, const void* z1, const void* z2, const void* addend, int ld_add, void* out,
+                                int ldo, int B, int H, int W, int H1, int W1, int H2, int W2, int C, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_scalseq_tail: bf16 only");
+    LDC_REQUIRE(z0 && z1 && z2 && out && C % 8 == 0 && ldo % 8 == 0 && (!addend || ld_add % 8 == 0),
+                "ldconv_scalseq_tail: bad arguments");
+    LDC_REQUIRE(aligned16(z0) && aligned16(z1) && aligned16(z2) && aligned16(out) && (!addend || aligned16(addend)),
+                "ldconv_scalseq_tail: pointers must be 16-byte aligned");
+    const long long total = (long long)B * H * W * (C / 8);
+    if (total == 0) return LDCONV_OK;
+    scalseq_tail_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)z0, (const T*)z1, (const T*)z2,
+                                                                           (const T*)addend, ld_add, (T*)out, ldo, H, W, H1,
+                                                                           W1, H2, W2, C / 8, total);
+    LDC_LAUNCH_CHECK("scalseq_tail_kernel");
+    return LDCONV_OK;
+}
+
+LDC_API int ldconv_sppf_pools(const void* x, void* o1, void* o2, void* o3, int ld, int B, int H, int W, int C, int k,
+                              int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_sppf_pools: bf16 only");
+    LDC_REQUIRE(x && o1 && o2 && o3 && C % 8 == 0 && ld % 8 == 0 && k >= 1 && (k & 1), "ldconv_sppf_pools: bad arguments");
+    LDC_REQUIRE(aligned16(x) && aligned16(o1) && aligned16(o2) && aligned16(o3), "ldconv_sppf_pools: alignment");
+    const long long total = (long long)B * H * W * (C / 8);
+    if (total == 0) return LDCONV_OK;
+    sppf_pools_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)o1, (T*)o2, (T*)o3, ld, H, W, C / 8,
+                                                                         k / 2, total);
+    LDC_LAUNCH_CHECK("sppf_pools_kernel");
+    return LDCONV_OK;
+}

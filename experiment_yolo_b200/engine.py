@@ -135,15 +135,19 @@ class _SPPF:
         c = self.cv1.cout
         cat = _new(x, B, H, W, 4 * c)
         conv1x1(x, self.cv1, cat[..., :c])
-        for i in range(3):      # three chained k x k max-pools (torch, channels_last views of the slices; tiny 40x40 maps)
-            src = cat[..., i * c: (i + 1) * c].permute(0, 3, 1, 2)
-            cat[..., (i + 1) * c: (i + 2) * c].copy_(F.max_pool2d(src, self.k, 1, self.k // 2).permute(0, 2, 3, 1))
+        _lib.check(_lib.load().ldconv_sppf_pools(cat.data_ptr(), cat[..., c:].data_ptr(), cat[..., 2 * c:].data_ptr(),
+                                                 cat[..., 3 * c:].data_ptr(), 4 * c, B, H, W, c, self.k, _lib.BF16, _stream()),
+                   "ldconv_sppf_pools")
         return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout))
 
 
-def _upsample2(x, factor=2):
-    """nearest up-sampling of an NHWC tensor (torch kernel on the channels_last view)."""
-    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=factor, mode="nearest").permute(0, 2, 3, 1)
+def upsample_into(x: torch.Tensor, out: torch.Tensor, factor: int):
+    """nearest up-sampling of an NHWC tensor (slice) straight into an NHWC tensor (slice)."""
+    B, H, W, C, ldx = _nhwc_geometry(x)
+    ldo = _nhwc_geometry(out)[4]
+    _lib.check(_lib.load().ldconv_upsample_nearest(x.data_ptr(), ldx, out.data_ptr(), ldo, B, H, W, C, factor, _lib.BF16,
+                                                   _stream()), "ldconv_upsample_nearest")
+    return out
 
 
 class _ScalSeq:
@@ -153,7 +157,7 @@ class _ScalSeq:
         self.conv2 = _Folded(m.conv2.conv, m.conv2.bn)
         self.mix = _Folded(m.conv3d, m.bn)          # Conv3d(1x1x1) + BatchNorm3d, point-wise per level
 
-    def __call__(self, xs):
+    def __call__(self, xs, addend=None):
         fine, mid, coarse = xs
         ch = self.mix.cout
         if self.conv0 is not None:
@@ -161,10 +165,14 @@ class _ScalSeq:
         mid = conv1x1(mid, self.conv1, _new(mid, *mid.shape[:3], ch))
         coarse = conv1x1(coarse, self.conv2, _new(coarse, *coarse.shape[:3], ch))
         z = [conv1x1(t, self.mix, _new(t, *t.shape[:3], ch), act="leaky") for t in (fine, mid, coarse)]
-        H, W = fine.shape[1:3]
-        up1 = F.interpolate(z[1].permute(0, 3, 1, 2), size=(H, W), mode="nearest").permute(0, 2, 3, 1)
-        up2 = F.interpolate(z[2].permute(0, 3, 1, 2), size=(H, W), mode="nearest").permute(0, 2, 3, 1)
-        return torch.maximum(torch.maximum(z[0], up1), up2)      # MaxPool3d((3,1,1)) over the stacked depth axis
+        B, H, W, _ = fine.shape
+        out = _new(fine, B, H, W, ch)
+        # MaxPool3d((3,1,1)) over the stacked depth axis (+ the following Add layer when it consumes this output)
+        _lib.check(_lib.load().ldconv_scalseq_tail(
+            z[0].data_ptr(), z[1].data_ptr(), z[2].data_ptr(), None if addend is None else addend.data_ptr(),
+            0 if addend is None else _nhwc_geometry(addend)[4], out.data_ptr(), ch, B, H, W, z[1].shape[1], z[1].shape[2],
+            z[2].shape[1], z[2].shape[2], ch, _lib.BF16, _stream()), "ldconv_scalseq_tail")
+        return out
 
 
 class _Detect:
@@ -193,6 +201,14 @@ class _Detect:
             feats.append((b, c))
             a0 += H * W
         return y, feats
+
+
+class _Deferred:
+    """an nn.Upsample output that has not been materialised yet"""
+    __slots__ = ("src", "factor")
+
+    def __init__(self, src, factor):
+        self.src, self.factor = src, factor
 
 
 class FusedDealYolo:
@@ -229,6 +245,30 @@ class FusedDealYolo:
                 raise NotImplementedError(f"FusedDealYolo: no fused executor for {type(layer).__name__}")
             self.layers.append((op, layer.f, layer.i))
         self.save = set(model.save)
+        # ScalSeq -> Add (yolov8-LD-P2.yaml rows 24, 25): the Add's other operand is folded into the ScalSeq tail kernel
+        for n, ((kind, arg), f, i) in enumerate(self.layers[:-1]):
+            (k2, _), f2, _ = self.layers[n + 1]
+            if kind == "fn" and isinstance(arg, _ScalSeq) and k2 == "add" and isinstance(f2, list) and -1 in f2 and len(f2) == 2:
+                other = [j for j in f2 if j != -1][0]
+                self.layers[n] = (("scalseq_add", (arg, other)), f, i)
+                self.layers[n + 1] = (("identity", None), -1, self.layers[n + 1][2])
+
+    @staticmethod
+    def _concat(xs):
+        """channel concat of NHWC tensors; deferred up-samplings are written straight into their slice"""
+        ref = next(t for t in xs if isinstance(t, torch.Tensor))
+        B = ref.shape[0]
+        H, W = (ref.shape[1], ref.shape[2])
+        chans = [t.src.shape[3] if isinstance(t, _Deferred) else t.shape[3] for t in xs]
+        out = _new(ref, B, H, W, sum(chans))
+        c0 = 0
+        for t, c in zip(xs, chans):
+            if isinstance(t, _Deferred):
+                upsample_into(t.src, out[..., c0:c0 + c], t.factor)
+            else:
+                out[..., c0:c0 + c].copy_(t)
+            c0 += c
+        return out
 
     @torch.no_grad()
     def __call__(self, images: torch.Tensor):
@@ -239,13 +279,17 @@ class FusedDealYolo:
                 x = saved[f] if isinstance(f, int) else [x if j == -1 else saved[j] for j in f]
             if kind == "ldconv":
                 x = arg(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)          # module API is logical NCHW; views only
+            elif kind == "scalseq_add":     # ScalSeq whose only consumer is the next Add layer: one tail kernel does both
+                x = arg[0](x, addend=saved[arg[1]])
             elif kind == "fn":
                 x = arg(x)
             elif kind == "cat":
-                x = torch.cat(x, dim=3)
+                x = self._concat(x)
             elif kind == "add":
                 x = x[0] + x[1]
             elif kind == "up":
-                x = _upsample2(x, arg)
+                x = _Deferred(x, arg)        # materialised by the consumer (Concat writes it straight into its buffer)
+            elif kind == "identity":
+                pass
             saved.append(x if i in self.save else None)
         return x

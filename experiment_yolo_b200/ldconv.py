@@ -246,6 +246,10 @@ class LDConv(nn.Module):
 
     # one-kernel inference path (tcgen05) when shapes allow; class-level switch so tests can A/B it
     use_fused_inference = True
+    # the tcgen05 one-kernel path (C % 16 == 0) is correct but, until its offset-conv phase moves to the tensor cores, slower
+    # than offset-conv(tcgen05) -> gather -> GEMM(tcgen05) on the YAML's shapes (profiles/r1_layers_*.jsonl); the small-C
+    # one-kernel path (layer 0) is always used
+    fused_tcgen05 = False
 
     def __init__(self, inc, outc, num_param, stride=1, bias=None):
         super().__init__()
@@ -290,6 +294,8 @@ class LDConv(nn.Module):
         if bn.running_mean is None or self.conv[0].bias is not None:
             return False
         B, C, H, W = x.shape
+        if C > 4 and not self.fused_tcgen05:
+            return False
         return bool(_lib.load().ldconv_fused_supported(B, C, H, W, self.num_param, int(self.stride),
                                                        self.conv[0].out_channels, _DTYPES[x.dtype]))
 

@@ -179,6 +179,17 @@ int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const floa
 int ldconv_detect_decode(const void* box, const void* cls, void* y, int B, int H, int W, int nc, int reg_max, float stride,
                          int anchor_offset, int total_anchors, int dtype, void* stream);
 
+/* Glue ops of the graph (bf16 NHWC, channel-slice aware through the pixel strides ld*):
+ * nearest up-sampling by an integer factor (yolov8-LD-P2.yaml:26,33); the SSFF tail = max over the three pyramid levels,
+ * coarser levels indexed like torch's nearest interpolation, + optional residual (nn/extra_modules/block.py:3432-3443,
+ * :3479-3484); SPPF's three chained k x k max-pools (nn/modules/block.py:166-171) as the k, 2k-1, 3k-2 window maxima. */
+int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, int H, int W, int C, int factor, int dtype,
+                            void* stream);
+int ldconv_scalseq_tail(const void* z0, const void* z1, const void* z2, const void* addend, int ld_add, void* out, int ldo,
+                        int B, int H, int W, int H1, int W1, int H2, int W2, int C, int dtype, void* stream);
+int ldconv_sppf_pools(const void* x, void* o1, void* o2, void* o3, int ld, int B, int H, int W, int C, int k, int dtype,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -409,6 +409,7 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
     outs = {}
     for fused in (True, False):
         E.LDConv.use_fused_inference = fused
+        E.LDConv.fused_tcgen05 = True
         try:
             _lib.call_counts.clear()
             with torch.no_grad():
@@ -416,6 +417,7 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
             assert ("ldconv_fused_fwd" in _lib.call_counts) == fused
         finally:
             E.LDConv.use_fused_inference = True
+            E.LDConv.fused_tcgen05 = False
     assert _rel(outs[True], f["out"]) <= 1e-2
     assert _rel(outs[True], outs[False]) <= 6e-3
     if sigma <= 0.1:
