@@ -49,6 +49,7 @@ SIGNATURES = {
     "ldconv_detect_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "ldconv_upsample_nearest": (_i, [_vp, _i, _vp, _i] + [_i] * 6 + [_vp]),
     "ldconv_scalseq_tail": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 9 + [_vp]),
+    "ldconv_image_u8_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     "ldconv_sppf_pools": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "ldconv_fused_supported": (_i, [_i] * 8),
     "ldconv_fused_fwd": (_i, [_vp] * 9 + [_i] * 9 + [_vp]),

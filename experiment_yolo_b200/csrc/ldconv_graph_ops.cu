@@ -98,9 +98,35 @@ sppf_pools_kernel(const T* __restrict__ x, T* __restrict__ o1, T* __restrict__ o
     Vec16<T>::store(o3 + pix * ld + cv * 8, m3);
 }
 
+// uint8 NCHW image batch (what the reference's predictor uploads, engine/predictor.py:120-131) -> bf16 NHWC in [0,1]:
+// the `im.half(); im /= 255` of the reference plus the layout change, one pass.
+__global__ void __launch_bounds__(256)
+image_u8_to_nhwc_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int C, long long hw, float scale, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long b = t / hw, p = t % hw;
+    const uint8_t* src = x + b * C * hw + p;
+    T* dst = out + t * C;
+    for (int c = 0; c < C; ++c) dst[c] = __float2bfloat16_rn((float)src[(long long)c * hw] * scale);
+}
+
 }  // namespace ldc
 
 using namespace ldc;
+
+LDC_API int ldconv_image_u8_to_nhwc(const void* x_u8, void* out, int B, int C, int H, int W, float scale, int dtype,
+                                    void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_image_u8_to_nhwc: bf16 only");
+    LDC_REQUIRE(x_u8 && out && C >= 1 && C <= 16, "ldconv_image_u8_to_nhwc: bad arguments");
+    const long long total = (long long)B * H * W;
+    if (total == 0) return LDCONV_OK;
+    image_u8_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x_u8, (T*)out, C,
+                                                                               (long long)H * W, scale, total);
+    LDC_LAUNCH_CHECK("image_u8_to_nhwc_kernel");
+    return LDCONV_OK;
+}
 
 LDC_API int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, int H, int W, int C, int factor,
                                     int dtype, void* stream)

@@ -272,7 +272,13 @@ class FusedDealYolo:
 
     @torch.no_grad()
     def __call__(self, images: torch.Tensor):
-        x = images.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()       # NHWC; zero-copy for channels_last input
+        if images.dtype == torch.uint8:       # raw (B,C,H,W) uint8 batch: normalise + NHWC in one kernel
+            B, C, H, W = images.shape
+            x = torch.empty((B, H, W, C), device=images.device, dtype=torch.bfloat16)
+            _lib.check(_lib.load().ldconv_image_u8_to_nhwc(images.contiguous().data_ptr(), x.data_ptr(), B, C, H, W, 1.0 / 255.0,
+                                                           _lib.BF16, _stream()), "ldconv_image_u8_to_nhwc")
+        else:
+            x = images.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()   # NHWC; zero-copy for channels_last input
         saved = []
         for (kind, arg), f, i in self.layers:
             if f != -1:
@@ -293,3 +299,81 @@ class FusedDealYolo:
                 pass
             saved.append(x if i in self.save else None)
         return x
+
+
+class PipelinedPredictor:
+    """The end-to-end inference call on HOST buffers: `submit(u8_batch_in_pinned_memory)` / `result()`.
+
+    Mirrors what the reference's predictor does per batch (upload uint8 images, normalise on the device, forward, read
+    detections back; engine/predictor.py:120-140,266-300) with the B200-side plumbing around the fused executor: the whole
+    forward (uint8 -> bf16 NHWC conversion included) is captured once per input slot in a CUDA graph, and two slots are
+    rotated so that the upload of batch i+1 and the download of batch i-1 overlap the compute of batch i on separate
+    streams.  Results come back in submission order."""
+
+    def __init__(self, model: dealyolo.DealYolo, batch: int, imgsz: int, channels: int = 3, slots: int = 2):
+        self.exec = FusedDealYolo(model)
+        dev = next(model.parameters()).device
+        self.dev, self.slots = dev, slots
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.u8 = [torch.zeros((batch, channels, imgsz, imgsz), device=dev, dtype=torch.uint8) for _ in range(slots)]
+        self.graphs, self.y_dev, self.y_host = [], [], []
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.exec(self.u8[0])
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for k in range(slots):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y, _ = self.exec(self.u8[k])
+            self.graphs.append(g)
+            self.y_dev.append(y)
+            self.y_host.append(torch.empty(tuple(y.shape), dtype=y.dtype).pin_memory())
+        self.ev_in = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(slots)]
+        self.ev_out = [torch.cuda.Event() for _ in range(slots)]
+        self.n_submitted = 0
+        self.n_returned = 0
+        self.h2d_bytes = self.u8[0].numel()
+        self.d2h_bytes = self.y_host[0].numel() * self.y_host[0].element_size()
+
+    def submit(self, host_u8: torch.Tensor):
+        """host_u8: (B,C,H,W) uint8 in pinned host memory.  Asynchronous."""
+        k = self.n_submitted % self.slots
+        comp = torch.cuda.current_stream(self.dev)
+        if self.n_submitted >= self.slots:
+            self.s_in.wait_event(self.ev_comp[k])        # slot's previous batch has been consumed by its graph
+        else:
+            self.s_in.wait_stream(comp)
+        with torch.cuda.stream(self.s_in):
+            self.u8[k].copy_(host_u8, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        comp.wait_event(self.ev_in[k])
+        if self.n_submitted >= self.slots:
+            comp.wait_event(self.ev_out[k])              # slot's previous result has left the device buffer
+        self.graphs[k].replay()
+        self.ev_comp[k].record(comp)
+        self.s_out.wait_event(self.ev_comp[k])
+        with torch.cuda.stream(self.s_out):
+            self.y_host[k].copy_(self.y_dev[k], non_blocking=True)
+            self.ev_out[k].record(self.s_out)
+        self.n_submitted += 1
+
+    def result(self) -> torch.Tensor:
+        """Blocks until the oldest outstanding batch's detections are in host memory and returns them (a pinned buffer that
+        is reused `slots` submissions later)."""
+        assert self.n_returned < self.n_submitted, "no outstanding batch"
+        k = self.n_returned % self.slots
+        self.ev_out[k].synchronize()
+        self.n_returned += 1
+        return self.y_host[k]
+
+    def drain_to(self, stream=None):
+        """make `stream` (default: current) wait for every outstanding download (for device-side timing)"""
+        stream = stream or torch.cuda.current_stream(self.dev)
+        for k in range(min(self.slots, self.n_submitted)):
+            stream.wait_event(self.ev_out[k])
+

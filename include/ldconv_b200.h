@@ -187,6 +187,9 @@ int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, i
                             void* stream);
 int ldconv_scalseq_tail(const void* z0, const void* z1, const void* z2, const void* addend, int ld_add, void* out, int ldo,
                         int B, int H, int W, int H1, int W1, int H2, int W2, int C, int dtype, void* stream);
+/* uint8 NCHW image batch -> `scale`-normalised bf16 NHWC (the predictor's `im.half(); im /= 255`, engine/predictor.py:120-131,
+ * plus the layout change), one pass. */
+int ldconv_image_u8_to_nhwc(const void* x_u8, void* out, int B, int C, int H, int W, float scale, int dtype, void* stream);
 int ldconv_sppf_pools(const void* x, void* o1, void* o2, void* o3, int ld, int B, int H, int W, int C, int k, int dtype,
                       void* stream);
 

@@ -100,3 +100,27 @@ def test_fused_engine_batch_and_graph_capture():
     torch.cuda.synchronize()
     assert tuple(y0.shape) == (4, 10, 32 * 40 + 16 * 20 + 8 * 10)
     assert torch.equal(y0, y1)
+
+
+def test_pipelined_predictor_host_buffers_round_trip():
+    """engine.PipelinedPredictor: uint8 host batches in, detections in host memory out, in submission order, equal to the
+    synchronous executor on the same images."""
+    from experiment_yolo_b200 import engine
+    z, model = _load()
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
+    pred = engine.PipelinedPredictor(model, batch=2, imgsz=96)
+    g = torch.Generator().manual_seed(9)
+    batches = [torch.randint(0, 256, (2, 3, 96, 96), dtype=torch.uint8, generator=g).pin_memory() for _ in range(5)]
+    outs = []
+    for i, b in enumerate(batches):
+        pred.submit(b)
+        if i >= 1:
+            outs.append(pred.result().clone())
+    outs.append(pred.result().clone())
+    eng = engine.FusedDealYolo(model)
+    for b, o in zip(batches, outs):
+        y, _ = eng(b.to(DEV))
+        assert torch.equal(y.cpu(), o)
+    # the uint8 path equals the float path on the normalised images
+    y_f, _ = eng((batches[0].to(DEV).float() / 255.0).bfloat16())
+    assert float((y_f.float().cpu() - outs[0].float()).abs().max()) <= 0.5
