@@ -75,7 +75,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(i_empty + g.stages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i_full_count = 8 + (g.b_resident ? 0 : 1);
+    const int i_full_count = 1 + (g.b_resident ? 0 : 1);      // the one worker warp that fills the block (+ TMA of B)
     __shared__ long long s_trace[3 * kTraceN * 2];
     const bool tracing = (g.dbg & 32) && blockIdx.x == 0 && lane == 0 && warp < 3;
     Tracer tr{s_trace + (warp < 3 ? warp : 0) * kTraceN * 2, 0, tracing};
@@ -236,50 +236,53 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             if (lane == 0) mbar_arrive(&t_empty[buf]);
         };
 
-        int it = 0, st = 0, prev_tile = -1;
-        uint32_t ph = 0;
+        // K-block q (counted across tiles: q = it*num_kb + kb) is filled by warp q % 8 alone: 128 rows x 8 chunks = 32
+        // (row, chunk) pairs per lane.  The eight warps therefore work on eight different ring stages at once and no
+        // per-block rendezvous between them is needed; the MMA thread consumes the blocks in order.
+        int it = 0, prev_tile = -1;
         const int chunk = lane & 7;                    // 16-byte chunk inside the 128-byte K-block row
-        // per-thread constants of the im2col copy: 4 rows (pixels) of the 128-row block, source offset inside the staged
-        // tile and swizzled destination offset inside the K-block
-        int src_row[4];
-        uint32_t dst_off[4];
-#pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
-            const int p = (r4 * 8 + ww) * 4 + (lane >> 3);
-            src_row[r4] = ((p / kConvTileW) * g.s * g.TWin + (p % kConvTileW) * g.s) * g.Cin;
-            dst_off[r4] = sw128_offset((uint32_t)p, (uint32_t)chunk);
-        }
+        const int row0 = lane >> 3;                    // rows row0 + 4*r, r = 0..31
+        long long q_next = ww;                         // next K-block sequence number owned by this warp
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-            const int xbuf = it % g.xbufs;
-            tr(it, 600000 + it * 100);
-            mbar_wait(&x_full[xbuf], (it / g.xbufs) & 1);
-            tr(it, 700000 + it * 100);
-            const T* xt = reinterpret_cast<const T*>(sX + (size_t)xbuf * g.x_bytes);
-            for (int kb = 0; kb < g.num_kb; ++kb) {
-                if (g.dbg & 16) {
-                    if (lane == 0) mbar_wait(&i_empty[st], ph ^ 1);
-                    __syncwarp();
-                } else {
+            const long long q_end = (long long)(it + 1) * g.num_kb;
+            if (q_next < q_end) {
+                const int xbuf = it % g.xbufs;
+                mbar_wait(&x_full[xbuf], (it / g.xbufs) & 1);
+                tr(it, 700000 + it * 100);
+                const T* xt = reinterpret_cast<const T*>(sX + (size_t)xbuf * g.x_bytes);
+                for (; q_next < q_end; q_next += 8) {
+                    const int kb = (int)(q_next - (long long)it * g.num_kb);
+                    const int st = (int)(q_next % g.stages);
+                    const uint32_t ph = (uint32_t)((q_next / g.stages) & 1);
                     mbar_wait(&i_empty[st], ph ^ 1);
-                }
-                tr(it, 400000 + it * 100 + kb);
-                uint8_t* dstI = sI + (size_t)st * 16384;
-                const int tofs = sTofs[kb * 8 + chunk];
-                if (tofs >= 0 && !(g.dbg & 2)) {
-                    uint4 val[4];
+                    tr(it, 400000 + it * 100 + kb);
+                    uint8_t* dstI = sI + (size_t)st * 16384;
+                    const int tofs = sTofs[kb * 8 + chunk];
+                    if (tofs >= 0 && !(g.dbg & 2)) {
+#pragma unroll 4
+                        for (int r8 = 0; r8 < 32; r8 += 8) {
+                            uint4 val[8];
 #pragma unroll
-                    for (int r4 = 0; r4 < 4; ++r4) val[r4] = *reinterpret_cast<const uint4*>(xt + src_row[r4] + tofs);
+                            for (int u = 0; u < 8; ++u) {
+                                const int p = row0 + 4 * (r8 + u);
+                                val[u] = *reinterpret_cast<const uint4*>(
+                                    xt + ((p / kConvTileW) * g.s * g.TWin + (p % kConvTileW) * g.s) * g.Cin + tofs);
+                            }
 #pragma unroll
-                    for (int r4 = 0; r4 < 4; ++r4) *reinterpret_cast<uint4*>(dstI + dst_off[r4]) = val[r4];
+                            for (int u = 0; u < 8; ++u) {
+                                const int p = row0 + 4 * (r8 + u);
+                                *reinterpret_cast<uint4*>(dstI + sw128_offset((uint32_t)p, (uint32_t)chunk)) = val[u];
+                            }
+                        }
+                    }
+                    if (!(g.dbg & 1)) fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&i_full[st]);
+                    tr(it, 500000 + it * 100 + kb);
                 }
-                if (!(g.dbg & 1)) fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&i_full[st]);
-                tr(it, 500000 + it * 100 + kb);
-                if (++st == g.stages) { st = 0; ph ^= 1; }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&x_empty[xbuf]);
+            if (lane == 0) mbar_arrive(&x_empty[it % g.xbufs]);
             tr(it, 800000 + it * 100);
             if (prev_tile >= 0) epilogue(prev_tile, it - 1);
             tr(it, 900000 + it * 100);
@@ -337,8 +340,9 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     const size_t per_stage = 16384 + (g.b_resident ? 0 : g.b_bytes);
     const size_t base = (size_t)g.ON * 8 + (size_t)g.num_kb * 32 + 512 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
     const long long budget = 220 * 1024 - (long long)base;
-    int stages = 3;
+    int stages = 6;
     long long xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes;
+    if (xb < 2) { stages = 3; xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes; }
     if (xb < 1) { stages = 2; xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes; }
     if (xb < 1) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     // enough tiles in flight for ~64 KB per SM, no more
@@ -348,7 +352,7 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     if (xb > kMaxXBufs) xb = kMaxXBufs;
     g.xbufs = (int)xb;
     stages = (int)((budget - (long long)g.xbufs * g.x_bytes) / (long long)per_stage);
-    if (stages > 6) stages = 6;
+    if (stages > 8) stages = 8;
     if (g.dbg & 8) stages = 2;
     if (stages < 2) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     g.stages = stages;
