@@ -44,7 +44,7 @@ struct Tracer {
 struct ConvGeom {
     int Cin, Cout, ON, H, W, h, w, s, B;
     int THin, TWin, tiles_h, tiles_w, num_tiles;
-    int K, num_kb, stages, b_resident, xbufs;       // xbufs: 2 = next tile prefetched while this one is consumed
+    int K, num_kb, stages, b_resident, xbufs, nfill; // nfill = min(8, stages) warps fill K-blocks (see worker loop)       // xbufs: 2 = next tile prefetched while this one is consumed
     int ldo, ldr;                                   // pixel strides (elements) of out / residual
     int dbg;                                        // LDCONV_DBG experiment bits (0 in production)
     uint32_t ofs_i, ofs_b, ofs_x, ofs_aff, ofs_tofs, ofs_bar; // smem byte offsets (1024-aligned base)
@@ -242,7 +242,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         int it = 0, prev_tile = -1;
         const int chunk = lane & 7;                    // 16-byte chunk inside the 128-byte K-block row
         const int row0 = lane >> 3;                    // rows row0 + 4*r, r = 0..31
-        long long q_next = ww;                         // next K-block sequence number owned by this warp
+        // Only nfill = min(8, stages) warps fill blocks (block q belongs to warp q % nfill): with nfill <= stages a warp's
+        // previous block (q - nfill) is at most one ring revolution behind q, so when it waits for "use u-1 of the stage
+        // consumed" use u-2 is already known consumed and the one-bit phase parity cannot alias.
+        long long q_next = ww < g.nfill ? ww : (1ll << 62);
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const long long q_end = (long long)(it + 1) * g.num_kb;
             if (q_next < q_end) {
@@ -250,7 +253,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(&x_full[xbuf], (it / g.xbufs) & 1);
                 tr(it, 700000 + it * 100);
                 const T* xt = reinterpret_cast<const T*>(sX + (size_t)xbuf * g.x_bytes);
-                for (; q_next < q_end; q_next += 8) {
+                for (; q_next < q_end; q_next += g.nfill) {
                     const int kb = (int)(q_next - (long long)it * g.num_kb);
                     const int st = (int)(q_next % g.stages);
                     const uint32_t ph = (uint32_t)((q_next / g.stages) & 1);
@@ -356,6 +359,7 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     if (g.dbg & 8) stages = 2;
     if (stages < 2) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     g.stages = stages;
+    g.nfill = stages < 8 ? stages : 8;
     uint32_t ofs = 0;
     g.ofs_i = ofs; ofs += (uint32_t)stages * 16384;
     g.ofs_b = ofs; ofs += (uint32_t)(g.b_resident ? g.num_kb : stages) * g.b_bytes;
