@@ -153,9 +153,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
     } else if (warp == 1) {
         // =========================================== MMA issuer =============================================================
+        // One thread.  Its instruction stream is the serial resource of the kernel (a tcgen05.mma of M=128, N<=64, K=16 costs
+        // ~50 cycles back to back but ~140+ after an idle gap, benchmarks/ubench), so K-blocks are consumed in batches of up
+        // to kBatch: wait for all of them, issue every MMA back to back from precomputed descriptors, then release the stages.
         if (lane == 0) {
+            constexpr int kBatch = 4;
             const uint32_t idesc = make_idesc_bf16(128, g.ON);
             if (g.b_resident) mbar_wait(w_full, 0);
+            const uint64_t descA0 = make_desc_k_sw128(smem_u32(sI));     // + stage * (16384 >> 4)
+            const uint64_t descB0 = make_desc_k_sw128(smem_u32(sB));     // + block * (b_bytes >> 4)
+            const uint64_t b_step = (uint64_t)(g.b_bytes >> 4);
             int it = 0, st = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
@@ -163,21 +170,37 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
-                for (int kb = 0; kb < g.num_kb; ++kb) {
-                    mbar_wait(&i_full[st], ph);
-                    tr(it, 200000 + it * 100 + kb);
+                for (int kb0 = 0; kb0 < g.num_kb; kb0 += kBatch) {
+                    const int nb = min(kBatch, g.num_kb - kb0);
+                    {   // wait for the whole batch
+                        int s2 = st;
+                        uint32_t p2 = ph;
+                        for (int j = 0; j < nb; ++j) {
+                            mbar_wait(&i_full[s2], p2);
+                            if (++s2 == g.stages) { s2 = 0; p2 ^= 1; }
+                        }
+                    }
+                    tr(it, 200000 + it * 100 + kb0);
                     tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(sI + (size_t)st * 16384);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)(g.b_resident ? kb : st) * g.b_bytes);
-                    const int ksteps = min(4, (g.K - kb * 64) / 16);
-                    for (int k = 0; k < ((g.dbg & 4) ? 0 : ksteps); ++k)
-                        mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
-                                    (uint32_t)((kb | k) != 0));
-                    mma_commit(&i_empty[st]);
-                    if (kb == g.num_kb - 1) mma_commit(&t_full[buf]);
-                    tr(it, 300000 + it * 100 + kb);
-                    if (++st == g.stages) { st = 0; ph ^= 1; }
+                    {   // issue
+                        int s2 = st;
+                        for (int j = 0; j < nb; ++j) {
+                            const int kb = kb0 + j;
+                            const uint64_t da = descA0 + (uint64_t)s2 * 1024u;
+                            const uint64_t db = descB0 + (uint64_t)(g.b_resident ? kb : s2) * b_step;
+                            const int ksteps = (g.dbg & 4) ? 0 : min(4, (g.K - kb * 64) / 16);
+                            for (int k = 0; k < ksteps; ++k)
+                                mma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                            if (++s2 == g.stages) s2 = 0;
+                        }
+                    }
+                    for (int j = 0; j < nb; ++j) {   // release the stages (each commit covers all MMAs issued so far)
+                        mma_commit(&i_empty[st]);
+                        if (++st == g.stages) { st = 0; ph ^= 1; }
+                    }
+                    tr(it, 300000 + it * 100 + kb0);
                 }
+                mma_commit(&t_full[buf]);
             }
         }
     } else {
