@@ -157,7 +157,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // ~50 cycles back to back but ~140+ after an idle gap, benchmarks/ubench), so K-blocks are consumed in batches of up
         // to kBatch: wait for all of them, issue every MMA back to back from precomputed descriptors, then release the stages.
         if (lane == 0) {
-            constexpr int kBatch = 4;
+            // a batch never exceeds half the ring, so the fill warps always have free stages while a batch is in flight
+            const int batch = max(1, min(4, g.stages / 2));
             const uint32_t idesc = make_idesc_bf16(128, g.ON);
             if (g.b_resident) mbar_wait(w_full, 0);
             const uint64_t descA0 = make_desc_k_sw128(smem_u32(sI));     // + stage * (16384 >> 4)
@@ -170,8 +171,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
-                for (int kb0 = 0; kb0 < g.num_kb; kb0 += kBatch) {
-                    const int nb = min(kBatch, g.num_kb - kb0);
+                for (int kb0 = 0; kb0 < g.num_kb; kb0 += batch) {
+                    const int nb = min(batch, g.num_kb - kb0);
                     {   // wait for the whole batch
                         int s2 = st;
                         uint32_t p2 = ph;
