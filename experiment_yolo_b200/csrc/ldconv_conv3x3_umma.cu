@@ -430,6 +430,12 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
 
 }  // namespace ldc
 
+namespace ldc {
+int conv3x3_zc_supported(int Cin, int Cout, int s, int mode);
+int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const float* shift, const void* residual,
+               int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout, int act, int mode, cudaStream_t st);
+}
+
 using namespace ldc;
 
 // C ABI -----------------------------------------------------------------------------------------------------------------
@@ -446,6 +452,9 @@ LDC_API int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, co
     LDC_REQUIRE(x && wt && out && B >= 0 && H >= 1 && W >= 1, "ldconv_conv3x3_bn_act_fwd: bad arguments");
     LDC_REQUIRE(ldx >= Cin && ldo >= Cout, "ldconv_conv3x3_bn_act_fwd: pixel strides smaller than the channel counts");
     if (B == 0) return LDCONV_OK;
+    if (conv3x3_zc_supported(Cin, Cout, stride, CONV_MODE_BN_ACT))      // stride 1: zero-copy operand from the staged tile
+        return conv3x3_zc(x, ldx, wt, scale, shift, residual, ldr, out, ldo, B, Cin, H, W, Cout, act, CONV_MODE_BN_ACT,
+                          (cudaStream_t)stream);
     return conv3x3_umma(x, ldx, wt, scale, shift, residual, ldr, out, ldo, B, Cin, H, W, Cout, stride, act, CONV_MODE_BN_ACT,
                         (cudaStream_t)stream);
 }
@@ -462,6 +471,9 @@ LDC_API int ldconv_offset_conv_tc_fwd(const void* x, const void* w_bf16, const f
     LDC_REQUIRE(x && w_bf16 && off && B >= 0, "ldconv_offset_conv_tc_fwd: bad arguments");
     if (B == 0) return LDCONV_OK;
     // bias rides in the `shift` slot of the epilogue affine (scale unused in this mode)
+    if (conv3x3_zc_supported(C, 2 * N, stride, CONV_MODE_OFFSETS))
+        return conv3x3_zc(x, C, w_bf16, nullptr, bias, nullptr, 0, off, 2 * N, B, C, H, W, 2 * N, LDCONV_ACT_NONE,
+                          CONV_MODE_OFFSETS, (cudaStream_t)stream);
     return conv3x3_umma(x, C, w_bf16, nullptr, bias, nullptr, 0, off, 2 * N, B, C, H, W, 2 * N, stride, LDCONV_ACT_NONE,
                         CONV_MODE_OFFSETS, (cudaStream_t)stream);
 }

@@ -1,0 +1,298 @@
+// ldconv_conv3x3_zc.cu -- stride-1 3x3 / pad 1 convolution as a ZERO-COPY tcgen05 implicit GEMM (bf16, NHWC, sm_100a).
+//
+// Same job as ldconv_conv3x3_umma.cu (LDConv's offset conv, /root/reference/ultralytics/nn/modules/conv.py:356,368, for
+// its stride-1 layers, and the Conv2d+BatchNorm2d+SiLU 3x3 blocks around LDConv, nn/modules/conv.py:41-59), without the
+// shared->shared im2col copy, whose shared-memory traffic (and the MMA operand fetches competing with it) bounded that
+// kernel at ~0.5 TB/s (profiles/r1_conv3x3_timeline.txt).
+//
+// Trick: the TMA-staged input tile is already a valid tcgen05 A operand for every filter tap.  The tile is stored
+// [row][col][channel-block] with one pixel = one swizzle row (128 B for 64 channels, 64 B for 32, 32 B for 16), the output
+// tile is 8 pixels wide x 16 rows, so an MMA row group (8 rows of the 128 x K operand) is 8 consecutive pixels of one
+// staged row and the 16 groups are one staged row apart: a K-major descriptor with start = tile + ((dy*TWs + dx) pixels),
+// stride-byte-offset = one staged row, the tile's swizzle mode, and (for starts that are not aligned to the swizzle
+// pattern) the matrix-base-offset field.  Nine taps x Cin/16 MMAs accumulate the whole convolution in TMEM.
+//
+//   warp 0     TMA: input tiles (+1 pixel halo, zero fill = padding) into a ring; the weights once (resident)
+//   warp 1     one thread issues the MMAs of a tile back to back; tcgen05.commit frees the tile slot and publishes the accumulator
+//   warps 2-9  epilogue: tcgen05.ld -> folded BatchNorm / bias -> activation (-> + residual) -> 16-byte stores
+#include "common.cuh"
+#include "tmap.cuh"
+#include "umma.cuh"
+
+namespace ldc {
+
+using namespace umma;
+
+static constexpr int kZcThreads = 320;
+static constexpr int kZcTileH = 16, kZcTileW = 8, kZcTHs = 18, kZcTWs = 10;
+static constexpr int kZcMaxX = 8;
+
+enum { ZC_MODE_BN_ACT = 0, ZC_MODE_OFFSETS = 1 };
+
+struct ZcGeom {
+    int Cin, Cout, ON, H, W, B;
+    int tiles_h, tiles_w, num_tiles;
+    int pb;                 // bytes of one pixel row in the staged tile (= channel block * 2): 32, 64 or 128
+    int halves;             // channel blocks per pixel (Cin / (pb/2)): 1, or 2 for Cin = 128
+    int layout;             // UMMA layout type of the staged tile: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+    int num_kb, xbufs, ldo, ldr, base_mode;
+    uint32_t ofs_b, ofs_x, ofs_aff, ofs_bar, x_bytes, x_tx_bytes, b_bytes, tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t zc_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout, uint32_t base_off)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7) << 49;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kZcThreads, 1)
+conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const float* __restrict__ scale, const float* __restrict__ shift,
+                  const __nv_bfloat16* __restrict__ residual, void* __restrict__ out_v, int act, ZcGeom g)
+{
+    using T = __nv_bfloat16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sX = smem + g.ofs_x;        // [xbufs][halves][18][10][pb]  (each half 1024-aligned)
+    uint8_t* sB = smem + g.ofs_b;        // [num_kb][ON][128 B] SWIZZLE_128B
+    float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
+    uint64_t* x_empty = x_full + kZcMaxX;
+    uint64_t* t_full = x_empty + kZcMaxX;
+    uint64_t* t_empty = t_full + 2;
+    uint64_t* w_full = t_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < kZcMaxX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    for (int o = threadIdx.x; o < g.ON; o += blockDim.x)
+        sAff[o] = make_float2((scale && o < g.Cout) ? scale[o] : 1.f, (shift && o < g.Cout) ? shift[o] : 0.f);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = g.tiles_h * g.tiles_w;
+    const uint32_t half_bytes = g.x_bytes / (uint32_t)g.halves;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes);
+            for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(sB + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it % g.xbufs;
+                mbar_wait(&x_empty[buf], ((it / g.xbufs) & 1) ^ 1);
+                const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+                const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
+                mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
+                for (int hf = 0; hf < g.halves; ++hf)
+                    tma_load_4d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], hf * (g.pb / 2),
+                                tj * kZcTileW - 1, ti * kZcTileH - 1, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, g.ON);
+            mbar_wait(w_full, 0);
+            const uint32_t sbo = (uint32_t)(kZcTWs * g.pb);
+            const uint32_t b_base = smem_u32(sB);
+            const int ks_per_half = g.pb / 32;            // 16-element K steps per pixel row
+            int it = 0;
+            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1, xb = it % g.xbufs;
+                mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&x_full[xb], (it / g.xbufs) & 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
+                const uint32_t x_base = smem_u32(sX + (size_t)xb * g.x_bytes);
+                uint32_t first = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t tap_ofs = (uint32_t)(((tap / 3) * kZcTWs + (tap % 3)) * g.pb);
+                    for (int hf = 0; hf < g.halves; ++hf) {
+                        const uint32_t a0 = x_base + (uint32_t)hf * half_bytes + tap_ofs;
+                        const uint32_t boff = g.base_mode ? ((a0 >> 7) & 7u) : 0u;
+                        const int k0 = tap * g.Cin + hf * (g.pb / 2);      // first K index of this (tap, half)
+                        for (int ks = 0; ks < ks_per_half; ++ks) {
+                            const int k = k0 + ks * 16;
+                            const uint32_t b_addr = b_base + (uint32_t)(k >> 6) * g.b_bytes + (uint32_t)((k & 63) * 2);
+                            mma_bf16_ss(d_tmem, zc_desc(a0 + ks * 32, sbo, (uint32_t)g.layout, boff),
+                                        make_desc_k_sw128(b_addr), idesc, first);
+                            first = 1;
+                        }
+                    }
+                }
+                mma_commit(&x_empty[xb]);     // the tile slot is free once these MMAs have read it
+                mma_commit(&t_full[buf]);
+            }
+        }
+    } else {
+        const int ww = warp - 2;
+        const int lg = warp & 3, half = ww >> 2;
+        const int chunks16 = g.ON / 16;
+        const int ch_begin = half == 0 ? 0 : (chunks16 + 1) / 2, ch_end = half == 0 ? (chunks16 + 1) / 2 : chunks16;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&t_full[buf], (it >> 1) & 1);
+            tc_fence_after_sync();
+            const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
+            const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
+            const int p = lg * 32 + lane;
+            const int i = ti * kZcTileH + p / kZcTileW, j = tj * kZcTileW + p % kZcTileW;
+            const bool valid = i < g.H && j < g.W;
+            const size_t m = ((size_t)b * g.H + i) * g.W + j;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * g.ON);
+            for (int ch = ch_begin; ch < ch_end; ++ch) {
+                const int c0 = ch * 16;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (!valid || c0 >= g.Cout) continue;
+                if (MODE == ZC_MODE_OFFSETS) {
+                    float* dst = reinterpret_cast<float*>(out_v) + m * g.ldo + c0;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c0 + e < g.Cout) dst[e] = __uint_as_float(v[e]) + sAff[c0 + e].y;
+                } else {
+                    float lo[8], hi[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 a0 = sAff[c0 + e], a1 = sAff[c0 + 8 + e];
+                        lo[e] = apply_act_fast(fmaf(__uint_as_float(v[e]), a0.x, a0.y), act);
+                        hi[e] = apply_act_fast(fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y), act);
+                    }
+                    if (residual) {
+                        float r0[8], r1[8];
+                        Vec16<T>::load(residual + m * g.ldr + c0, r0);
+                        Vec16<T>::load(residual + m * g.ldr + c0 + 8, r1);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { lo[e] += r0[e]; hi[e] += r1[e]; }
+                    }
+                    T* dst = reinterpret_cast<T*>(out_v) + m * g.ldo + c0;
+                    Vec16<T>::store(dst, lo);
+                    Vec16<T>::store(dst + 8, hi);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+static int zc_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_CONV_ZC"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
+int conv3x3_zc_supported(int Cin, int Cout, int s, int mode)
+{
+    if (!zc_enabled() || s != 1) return 0;
+    if (Cin != 16 && Cin != 32 && Cin != 64 && Cin != 128) return 0;
+    if (Cout < 1 || Cout > 256) return 0;
+    if (mode == ZC_MODE_BN_ACT && Cout % 16 != 0) return 0;
+    const int ON = (Cout + 15) / 16 * 16;
+    const size_t wbytes = (size_t)((9 * Cin + 63) / 64) * ON * 128;
+    const size_t xbytes = (size_t)kZcTHs * kZcTWs * Cin * 2 + 2048;
+    return wbytes + 2 * xbytes + 4096 <= 220 * 1024;
+}
+
+int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const float* shift, const void* residual,
+               int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout, int act, int mode, cudaStream_t st)
+{
+    if (!aligned16(x) || !aligned16(wt) || (ldx % 8) != 0)
+        return fail(LDCONV_E_ALIGN, "conv3x3 zero-copy: x / wt must be 16-byte aligned and ldx a multiple of 8");
+    if (mode == ZC_MODE_BN_ACT && (!aligned16(out) || (ldo % 8) != 0 || (residual && (!aligned16(residual) || ldr % 8))))
+        return fail(LDCONV_E_ALIGN, "conv3x3 zero-copy: out / residual must be 16-byte aligned with strides multiple of 8");
+    ZcGeom g;
+    g.Cin = Cin; g.Cout = Cout; g.ON = (Cout + 15) / 16 * 16; g.H = H; g.W = W; g.B = B;
+    g.tiles_h = (H + kZcTileH - 1) / kZcTileH;
+    g.tiles_w = (W + kZcTileW - 1) / kZcTileW;
+    const long long nt = (long long)B * g.tiles_h * g.tiles_w;
+    if (nt > 0x7fffffffll) return fail(LDCONV_E_ARG, "conv3x3 zero-copy: too many tiles");
+    g.num_tiles = (int)nt;
+    const int cb = Cin >= 64 ? 64 : Cin;        // channel block = one swizzle row
+    g.pb = cb * 2;
+    g.halves = Cin / cb;
+    g.layout = g.pb == 128 ? 2 : (g.pb == 64 ? 4 : 6);
+    g.num_kb = (9 * Cin + 63) / 64;
+    g.b_bytes = (uint32_t)g.ON * 128;
+    const uint32_t half_tx = (uint32_t)kZcTHs * kZcTWs * g.pb;
+    const uint32_t half_pitch = (half_tx + 1023) & ~1023u;
+    g.x_tx_bytes = half_tx * g.halves;
+    g.x_bytes = half_pitch * g.halves;
+    g.ldo = ldo; g.ldr = ldr;
+    { const char* e = getenv("LDCONV_ZC_BASE"); g.base_mode = e ? atoi(e) : 1; }
+    const size_t wbytes = (size_t)g.num_kb * g.b_bytes;
+    long long xb = ((long long)220 * 1024 - (long long)wbytes - 4096) / (long long)g.x_bytes;
+    long long want = (96 * 1024 + g.x_bytes - 1) / g.x_bytes;
+    if (want < 2) want = 2;
+    if (xb > want) xb = want;
+    if (xb > kZcMaxX) xb = kZcMaxX;
+    if (xb < 2) return fail(LDCONV_E_ARG, "conv3x3 zero-copy: does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
+    g.xbufs = (int)xb;
+    uint32_t ofs = 0;
+    g.ofs_x = ofs; ofs += (uint32_t)g.xbufs * g.x_bytes;
+    g.ofs_b = ofs; ofs += (uint32_t)wbytes;
+    g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8;
+    ofs = (ofs + 7) & ~7u;
+    g.ofs_bar = ofs; ofs += (uint32_t)(2 * kZcMaxX + 5) * 8 + 16;
+    const size_t smem = ofs + 1024;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < (uint32_t)(2 * g.ON)) g.tmem_cols <<= 1;
+
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
+        cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)kZcTWs, (cuuint32_t)kZcTHs, 1};
+        const CUtensorMapSwizzle sw = g.pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : (g.pb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        if (int e = encode_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, gdim, gstr, box, sw)) return e;
+    }
+    {
+        const int K = 9 * Cin;
+        cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)g.ON};
+        if (int e = encode_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return e;
+    }
+    int grid = num_sms();
+    if (grid > g.num_tiles) grid = g.num_tiles;
+    if (mode == ZC_MODE_OFFSETS) {
+        auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+    } else {
+        auto kern = conv3x3_zc_kernel<ZC_MODE_BN_ACT>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+    }
+    LDC_LAUNCH_CHECK("conv3x3_zc_kernel");
+    set_impl(LDCONV_IMPL_TCGEN05);
+    return LDCONV_OK;
+}
+
+}  // namespace ldc
