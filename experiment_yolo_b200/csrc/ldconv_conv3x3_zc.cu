@@ -243,7 +243,9 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     g.x_tx_bytes = half_tx * g.halves;
     g.x_bytes = half_pitch * g.halves;
     g.ldo = ldo; g.ldr = ldr;
-    { const char* e = getenv("LDCONV_ZC_BASE"); g.base_mode = e ? atoi(e) : 0;   // measured: the swizzle XOR uses absolute smem address bits, base offset stays 0 }
+    // measured on B200: the swizzle XOR uses absolute shared-memory address bits, so the descriptor's matrix-base-offset
+    // stays 0 even for starts that are not aligned to the swizzle pattern (LDCONV_ZC_BASE=1 is the experiment that fails)
+    { const char* e = getenv("LDCONV_ZC_BASE"); g.base_mode = e ? atoi(e) : 0; }
     const size_t wbytes = (size_t)g.num_kb * g.b_bytes;
     long long xb = ((long long)220 * 1024 - (long long)wbytes - 4096) / (long long)g.x_bytes;
     long long want = (96 * 1024 + g.x_bytes - 1) / g.x_bytes;
