@@ -11,7 +11,7 @@ w = (torch.randn((2 * N, 9 * C), device=dev) * 0.05).bfloat16()
 b = torch.zeros(2 * N, device=dev)
 off = torch.empty((B, H, W, 2 * N), device=dev)
 st = torch.cuda.current_stream().cuda_stream
-fn = ctypes.CDLL(_lib.LIB_PATH).ldconv_debug_trace
+fn = ctypes.CDLL(_lib.LIB_PATH).ldconv_debug_trace_zc
 buf = (ctypes.c_longlong * 8192)()
 for rep in range(2):
     _lib.check(L.ldconv_offset_conv_tc_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), off.data_ptr(), B, C, H, W, N, s, 1, st))
@@ -19,8 +19,8 @@ for rep in range(2):
     n = fn(buf, 4096)
 ev = sorted(((buf[2 * i + 1], buf[2 * i]) for i in range(n)))
 t0 = ev[0][0]
-names = {1: "TMA issue", 2: "MMA got i_full", 3: "MMA committed", 4: "WRK got i_empty", 5: "WRK arrived i_full", 6: "WRK wait x_full",
-         7: "WRK got x_full", 8: "WRK copies done", 9: "WRK epilogue done"}
+names = {1: "TMA issue", 2: "MMA operands ready", 3: "MMA issued+committed", 4: "EPI wait t_full", 5: "EPI got t_full",
+         6: "MMA wait t_empty", 7: "MMA got t_empty", 8: "WRK copies done", 9: "EPI done"}
 for t, tag in ev:
     role, rest = divmod(tag, 100000)
     it, kb = divmod(rest, 100)

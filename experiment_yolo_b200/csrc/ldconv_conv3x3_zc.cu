@@ -29,13 +29,24 @@ static constexpr int kZcMaxX = 8;
 
 enum { ZC_MODE_BN_ACT = 0, ZC_MODE_OFFSETS = 1 };
 
+// debug timeline (LDCONV_DBG bit 32), same format as ldconv_conv3x3_umma.cu: warps 0..2 of CTA 0, tile iterations 8..11
+static constexpr int kZcTraceN = 96;
+__device__ long long g_zc_trace[3 * kZcTraceN * 2];
+__device__ int g_zc_trace_n[3];
+struct ZcTracer {
+    long long* buf; int n; bool on;
+    __device__ __forceinline__ void operator()(int it, int tag) {
+        if (on && it >= 8 && it < 12 && n < kZcTraceN) { buf[2 * n] = tag; buf[2 * n + 1] = clock64(); ++n; }
+    }
+};
+
 struct ZcGeom {
     int Cin, Cout, ON, H, W, B;
     int tiles_h, tiles_w, num_tiles;
     int pb;                 // bytes of one pixel row in the staged tile (= channel block * 2): 32, 64 or 128
     int halves;             // channel blocks per pixel (Cin / (pb/2)): 1, or 2 for Cin = 128
     int layout;             // UMMA layout type of the staged tile: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
-    int num_kb, xbufs, ldo, ldr, base_mode;
+    int num_kb, xbufs, ldo, ldr, base_mode, dbg;
     uint32_t ofs_b, ofs_x, ofs_aff, ofs_bar, x_bytes, x_tx_bytes, b_bytes, tmem_cols;
 };
 
@@ -51,8 +62,8 @@ __device__ __forceinline__ uint64_t zc_desc(uint32_t addr, uint32_t sbo_bytes, u
     return d;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kZcThreads, 1)
+template <int MODE, int CIN>
+__global__ void __launch_bounds__(kZcThreads, 2)
 conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const float* __restrict__ scale, const float* __restrict__ shift,
                   const __nv_bfloat16* __restrict__ residual, void* __restrict__ out_v, int act, ZcGeom g)
@@ -71,6 +82,9 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ long long s_trace[3 * kZcTraceN * 2];
+    const bool tracing = (g.dbg & 32) && blockIdx.x == 0 && lane == 0 && warp < 3;
+    ZcTracer tr{s_trace + (warp < 3 ? warp : 0) * kZcTraceN * 2, 0, tracing};
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -99,6 +113,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 mbar_wait(&x_empty[buf], ((it / g.xbufs) & 1) ^ 1);
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
+                tr(it, 100000 + it * 100);
                 mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
                 for (int hf = 0; hf < g.halves; ++hf)
                     tma_load_4d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], hf * (g.pb / 2),
@@ -107,38 +122,50 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
+            // The single issuing thread is the serial resource of this kernel (profiles/r1_conv3x3_timeline.txt: ~230 cycles
+            // per MMA when the descriptors are rebuilt with run-time arithmetic), so everything that depends only on the
+            // channel count is a compile-time constant and the 9 * CIN/16 MMAs of a tile are fully unrolled: per MMA one add
+            // for the A descriptor (tile base + constant) and one for the B descriptor.
+            constexpr int PB = CIN >= 64 ? 128 : CIN * 2;          // bytes per pixel row
+            constexpr int HALVES = CIN >= 64 ? CIN / 64 : 1;
+            constexpr int KS = PB / 32;                            // K steps of 16 per pixel row
+            constexpr uint32_t LAYOUT = PB == 128 ? 2u : (PB == 64 ? 4u : 6u);
             const uint32_t idesc = make_idesc_bf16(128, g.ON);
             mbar_wait(w_full, 0);
-            const uint32_t sbo = (uint32_t)(kZcTWs * g.pb);
-            const uint32_t b_base = smem_u32(sB);
-            const int ks_per_half = g.pb / 32;            // 16-element K steps per pixel row
+            const uint64_t descA_hi = zc_desc(0, (uint32_t)(kZcTWs * PB), LAYOUT, 0) & ~0x3fffull;
+            const uint64_t descB0 = make_desc_k_sw128(smem_u32(sB));
+            const uint32_t b16 = g.b_bytes >> 4;
+            const uint32_t x0 = smem_u32(sX) >> 4;
+            const uint32_t xstep = g.x_bytes >> 4, hstep = half_bytes >> 4;
             int it = 0;
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1, xb = it % g.xbufs;
+                tr(it, 600000 + it * 100);
                 mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
+                tr(it, 700000 + it * 100);
                 mbar_wait(&x_full[xb], (it / g.xbufs) & 1);
+                tr(it, 200000 + it * 100);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
-                const uint32_t x_base = smem_u32(sX + (size_t)xb * g.x_bytes);
-                uint32_t first = 0;
-#pragma unroll 1
+                const uint64_t descA = descA_hi | (uint64_t)(x0 + (uint32_t)xb * xstep);
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t tap_ofs = (uint32_t)(((tap / 3) * kZcTWs + (tap % 3)) * g.pb);
-                    for (int hf = 0; hf < g.halves; ++hf) {
-                        const uint32_t a0 = x_base + (uint32_t)hf * half_bytes + tap_ofs;
-                        const uint32_t boff = g.base_mode ? ((a0 >> 7) & 7u) : 0u;
-                        const int k0 = tap * g.Cin + hf * (g.pb / 2);      // first K index of this (tap, half)
-                        for (int ks = 0; ks < ks_per_half; ++ks) {
-                            const int k = k0 + ks * 16;
-                            const uint32_t b_addr = b_base + (uint32_t)(k >> 6) * g.b_bytes + (uint32_t)((k & 63) * 2);
-                            mma_bf16_ss(d_tmem, zc_desc(a0 + ks * 32, sbo, (uint32_t)g.layout, boff),
-                                        make_desc_k_sw128(b_addr), idesc, first);
-                            first = 1;
+#pragma unroll
+                    for (int hf = 0; hf < HALVES; ++hf) {
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            constexpr int dummy = 0; (void)dummy;
+                            const uint32_t a_delta = (uint32_t)((((tap / 3) * kZcTWs + (tap % 3)) * PB + ks * 32) >> 4);
+                            const int k = tap * CIN + hf * (PB / 2) + ks * 16;
+                            const uint32_t b_delta = (uint32_t)(k >> 6) * b16 + (uint32_t)(((k & 63) * 2) >> 4);
+                            mma_bf16_ss(d_tmem, descA + (uint64_t)(a_delta + (uint32_t)hf * hstep), descB0 + (uint64_t)b_delta, idesc,
+                                        (uint32_t)((tap | hf | ks) != 0));
                         }
                     }
                 }
                 mma_commit(&x_empty[xb]);     // the tile slot is free once these MMAs have read it
                 mma_commit(&t_full[buf]);
+                tr(it, 300000 + it * 100);
             }
         }
     } else {
@@ -149,7 +176,9 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         int it = 0;
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
+            tr(it, 400000 + it * 100);
             mbar_wait(&t_full[buf], (it >> 1) & 1);
+            tr(it, 500000 + it * 100);
             tc_fence_after_sync();
             const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
             const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
@@ -192,11 +221,16 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
+            tr(it, 900000 + it * 100);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+    if (tracing) {
+        for (int i = 0; i < 2 * tr.n; ++i) g_zc_trace[warp * kZcTraceN * 2 + i] = tr.buf[i];
+        g_zc_trace_n[warp] = tr.n;
+    }
 }
 
 static int zc_enabled()
@@ -246,9 +280,12 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     // measured on B200: the swizzle XOR uses absolute shared-memory address bits, so the descriptor's matrix-base-offset
     // stays 0 even for starts that are not aligned to the swizzle pattern (LDCONV_ZC_BASE=1 is the experiment that fails)
     { const char* e = getenv("LDCONV_ZC_BASE"); g.base_mode = e ? atoi(e) : 0; }
+    { const char* e = getenv("LDCONV_DBG"); g.dbg = e ? atoi(e) : 0; }
     const size_t wbytes = (size_t)g.num_kb * g.b_bytes;
-    long long xb = ((long long)220 * 1024 - (long long)wbytes - 4096) / (long long)g.x_bytes;
-    long long want = (96 * 1024 + g.x_bytes - 1) / g.x_bytes;
+    // two CTAs (two MMA issuers) per SM when the weights + a useful tile ring fit in half the shared memory
+    const bool two = wbytes + 3 * (size_t)g.x_bytes + 4096 <= 104 * 1024 && 4 * g.ON <= 512;
+    long long xb = ((long long)(two ? 104 : 220) * 1024 - (long long)wbytes - 4096) / (long long)g.x_bytes;
+    long long want = ((two ? 64 : 96) * 1024 + g.x_bytes - 1) / g.x_bytes;
     if (want < 2) want = 2;
     if (xb > want) xb = want;
     if (xb > kZcMaxX) xb = kZcMaxX;
@@ -281,20 +318,43 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
         if (int e = encode_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B))
             return e;
     }
-    int grid = num_sms();
+    int grid = num_sms() * (two ? 2 : 1);
     if (grid > g.num_tiles) grid = g.num_tiles;
-    if (mode == ZC_MODE_OFFSETS) {
-        auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS>;
-        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
-    } else {
-        auto kern = conv3x3_zc_kernel<ZC_MODE_BN_ACT>;
-        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+#define LDC_ZC_LAUNCH(MODE_, CIN_)                                                                                     \
+    do {                                                                                                               \
+        auto kern = conv3x3_zc_kernel<MODE_, CIN_>;                                                                    \
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);     \
+    } while (0)
+#define LDC_ZC_CIN(MODE_)                                                                                              \
+    switch (Cin) {                                                                                                     \
+        case 16: LDC_ZC_LAUNCH(MODE_, 16); break;                                                                      \
+        case 32: LDC_ZC_LAUNCH(MODE_, 32); break;                                                                      \
+        case 64: LDC_ZC_LAUNCH(MODE_, 64); break;                                                                      \
+        default: LDC_ZC_LAUNCH(MODE_, 128); break;                                                                     \
     }
+    if (mode == ZC_MODE_OFFSETS) { LDC_ZC_CIN(ZC_MODE_OFFSETS) } else { LDC_ZC_CIN(ZC_MODE_BN_ACT) }
+#undef LDC_ZC_CIN
+#undef LDC_ZC_LAUNCH
     LDC_LAUNCH_CHECK("conv3x3_zc_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     return LDCONV_OK;
 }
 
 }  // namespace ldc
+
+LDC_API int ldconv_debug_trace_zc(long long* host_out, int max_pairs)
+{
+    int n[3] = {0, 0, 0};
+    long long all[3 * ldc::kZcTraceN * 2];
+    cudaMemcpyFromSymbol(n, ldc::g_zc_trace_n, sizeof(n));
+    cudaMemcpyFromSymbol(all, ldc::g_zc_trace, sizeof(all));
+    int k = 0;
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < n[r] && k < max_pairs; ++i, ++k) {
+            host_out[2 * k] = all[(r * ldc::kZcTraceN + i) * 2];
+            host_out[2 * k + 1] = all[(r * ldc::kZcTraceN + i) * 2 + 1];
+        }
+    return k;
+}
+
