@@ -290,7 +290,8 @@ static int launch_smallc(const T* x, const float* w_off, const float* b_off, con
     const int O2P = (2 * N + 3) & ~3;
     const size_t smem = (size_t)(((THin * TWin * C + 3) & ~3) + 9 * C * O2P + N * C * O + 2 * O) * sizeof(float);
     const long long ctas = (long long)B * tiles_h * tiles_w;
-    if (smem <= 96 * 1024 && ctas <= 0x7fffffffll) {
+    static const int use_tiled = getenv("LDCONV_SMALLC_TILED") ? atoi(getenv("LDCONV_SMALLC_TILED")) : 0;   // measured slower (1448 vs 1124 us on layer 0)
+    if (use_tiled && smem <= 96 * 1024 && ctas <= 0x7fffffffll) {
         auto kern = smallc_tiled_kernel<T, C, 9>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)ctas, 256, smem, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, H, W, h, w, N, s, O, act, THin,

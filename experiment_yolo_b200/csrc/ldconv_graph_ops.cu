@@ -98,6 +98,65 @@ sppf_pools_kernel(const T* __restrict__ x, T* __restrict__ o1, T* __restrict__ o
     Vec16<T>::store(o3 + pix * ld + cv * 8, m3);
 }
 
+// SPPF pools, one CTA per (image, 8-channel vector): the plane is staged in shared memory, a horizontal pass produces
+// the 5/9/13-wide row maxima, a vertical pass the window maxima (40 loads per output instead of 169).
+__global__ void __launch_bounds__(256)
+sppf_pools_smem_kernel(const T* __restrict__ x, T* __restrict__ o1, T* __restrict__ o2, T* __restrict__ o3, int ld, int H, int W,
+                       int CV, int r)
+{
+    extern __shared__ uint4 s_pl[];            // [4][H*W]: input, h(r), h(2r), h(3r)
+    const int cv = blockIdx.x % CV;
+    const long long b = blockIdx.x / CV;
+    const int HW = H * W;
+    const T* xb = x + b * HW * ld + cv * 8;
+    for (int t = threadIdx.x; t < HW; t += blockDim.x) s_pl[t] = *reinterpret_cast<const uint4*>(xb + (long long)t * ld);
+    __syncthreads();
+    auto vmax = [](uint4 a, uint4 b2) {
+        uint4 o;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b2);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) po[e] = __hmax2(pa[e], pb[e]);
+        return o;
+    };
+    for (int t = threadIdx.x; t < HW; t += blockDim.x) {
+        const int i = t / W, j = t % W;
+        uint4 m = s_pl[t];
+        uint4 m1 = m, m2 = m, m3 = m;
+        for (int d = 1; d <= 3 * r; ++d) {
+            if (j - d >= 0) m = vmax(m, s_pl[i * W + j - d]);
+            if (j + d < W) m = vmax(m, s_pl[i * W + j + d]);
+            if (d == r) m1 = m;
+            if (d == 2 * r) m2 = m;
+        }
+        m3 = m;
+        s_pl[HW + t] = m1; s_pl[2 * HW + t] = m2; s_pl[3 * HW + t] = m3;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < HW; t += blockDim.x) {
+        const int i = t / W, j = t % W;
+        uint4 a = s_pl[HW + t], b2 = s_pl[2 * HW + t], c = s_pl[3 * HW + t];
+        for (int d = 1; d <= 3 * r; ++d) {
+            const int up = i - d, dn = i + d;
+            if (d <= r) {
+                if (up >= 0) a = vmax(a, s_pl[HW + up * W + j]);
+                if (dn < H) a = vmax(a, s_pl[HW + dn * W + j]);
+            }
+            if (d <= 2 * r) {
+                if (up >= 0) b2 = vmax(b2, s_pl[2 * HW + up * W + j]);
+                if (dn < H) b2 = vmax(b2, s_pl[2 * HW + dn * W + j]);
+            }
+            if (up >= 0) c = vmax(c, s_pl[3 * HW + up * W + j]);
+            if (dn < H) c = vmax(c, s_pl[3 * HW + dn * W + j]);
+        }
+        const long long o = (b * HW + t) * ld + cv * 8;
+        *reinterpret_cast<uint4*>(o1 + o) = a;
+        *reinterpret_cast<uint4*>(o2 + o) = b2;
+        *reinterpret_cast<uint4*>(o3 + o) = c;
+    }
+}
+
 // uint8 NCHW image batch (what the reference's predictor uploads, engine/predictor.py:120-131) -> bf16 NHWC in [0,1]:
 // the `im.half(); im /= 255` of the reference plus the layout change, one pass.
 __global__ void __launch_bounds__(256)
@@ -167,6 +226,14 @@ LDC_API int ldconv_sppf_pools(const void* x, void* o1, void* o2, void* o3, int l
     LDC_REQUIRE(aligned16(x) && aligned16(o1) && aligned16(o2) && aligned16(o3), "ldconv_sppf_pools: alignment");
     const long long total = (long long)B * H * W * (C / 8);
     if (total == 0) return LDCONV_OK;
+    const size_t plane = (size_t)4 * H * W * 16;
+    if (plane <= 200 * 1024 && (long long)B * (C / 8) <= 0x7fffffffll) {
+        LDC_CUDA(cudaFuncSetAttribute(sppf_pools_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane));
+        sppf_pools_smem_kernel<<<(unsigned)(B * (C / 8)), 256, plane, (cudaStream_t)stream>>>((const T*)x, (T*)o1, (T*)o2, (T*)o3,
+                                                                                              ld, H, W, C / 8, k / 2);
+        LDC_LAUNCH_CHECK("sppf_pools_smem_kernel");
+        return LDCONV_OK;
+    }
     sppf_pools_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)o1, (T*)o2, (T*)o3, ld, H, W, C / 8,
                                                                          k / 2, total);
     LDC_LAUNCH_CHECK("sppf_pools_kernel");

@@ -28,7 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, dealyolo
-from .ldconv import LDConv
+from .ldconv import LDConv, infer_nhwc
 
 _ACT = {"none": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "leaky": _lib.ACT_LEAKY01}
 
@@ -245,6 +245,38 @@ class FusedDealYolo:
                 raise NotImplementedError(f"FusedDealYolo: no fused executor for {type(layer).__name__}")
             self.layers.append((op, layer.f, layer.i))
         self.save = set(model.save)
+        # LDConv whose ONLY consumer is a Concat writes its output straight into that Concat's buffer
+        self.cat_plan = {}
+        consumers = {}
+        for (kind, arg), f, i in self.layers:
+            for j in ([f] if isinstance(f, int) else f):
+                consumers.setdefault((i + j) if j < 0 else j, []).append(i)
+        chan_out = {}
+        for (kind, arg), f, i in self.layers:
+            if kind == "ldconv":
+                chan_out[i] = arg.conv[0].out_channels
+        for (kind, arg), f, i in self.layers:
+            if kind != "cat":
+                continue
+            srcs = [(i + j) if j < 0 else j for j in f]
+            widths = []
+            for sidx in srcs:
+                k2, a2 = self.layers[sidx][0]
+                if k2 == "ldconv":
+                    widths.append(a2.conv[0].out_channels)
+                elif k2 == "up":
+                    up_src = self.layers[sidx][1]
+                    up_src = (sidx + up_src) if up_src < 0 else up_src
+                    widths.append(self._out_channels(up_src))
+                else:
+                    widths.append(self._out_channels(sidx))
+            if any(wd is None for wd in widths):
+                continue
+            c0 = 0
+            for sidx, wd in zip(srcs, widths):
+                if self.layers[sidx][0][0] == "ldconv" and consumers.get(sidx) == [i] and c0 % 8 == 0:
+                    self.cat_plan[sidx] = (i, c0, sum(widths))
+                c0 += wd
         # ScalSeq -> Add (yolov8-LD-P2.yaml rows 24, 25): the Add's other operand is folded into the ScalSeq tail kernel
         for n, ((kind, arg), f, i) in enumerate(self.layers[:-1]):
             (k2, _), f2, _ = self.layers[n + 1]
@@ -253,20 +285,36 @@ class FusedDealYolo:
                 self.layers[n] = (("scalseq_add", (arg, other)), f, i)
                 self.layers[n + 1] = (("identity", None), -1, self.layers[n + 1][2])
 
+    def _out_channels(self, idx):
+        kind, arg = self.layers[idx][0]
+        if kind == "ldconv":
+            return arg.conv[0].out_channels
+        if kind == "fn" and hasattr(arg, "cv2"):
+            return arg.cv2.cout
+        if kind in ("fn", "scalseq_add") :
+            a = arg[0] if kind == "scalseq_add" else arg
+            return a.mix.cout if hasattr(a, "mix") else None
+        if kind == "up":
+            f = self.layers[idx][1]
+            return self._out_channels((idx + f) if f < 0 else f)
+        return None
+
     @staticmethod
-    def _concat(xs):
-        """channel concat of NHWC tensors; deferred up-samplings are written straight into their slice"""
+    def _concat(xs, buf=None):
+        """channel concat of NHWC tensors; deferred up-samplings are written straight into their slice, inputs that already
+        live in `buf` (producers that wrote into the concat buffer) are skipped"""
         ref = next(t for t in xs if isinstance(t, torch.Tensor))
         B = ref.shape[0]
         H, W = (ref.shape[1], ref.shape[2])
         chans = [t.src.shape[3] if isinstance(t, _Deferred) else t.shape[3] for t in xs]
-        out = _new(ref, B, H, W, sum(chans))
+        out = buf if buf is not None else _new(ref, B, H, W, sum(chans))
         c0 = 0
         for t, c in zip(xs, chans):
+            dst = out[..., c0:c0 + c]
             if isinstance(t, _Deferred):
-                upsample_into(t.src, out[..., c0:c0 + c], t.factor)
-            else:
-                out[..., c0:c0 + c].copy_(t)
+                upsample_into(t.src, dst, t.factor)
+            elif t.data_ptr() != dst.data_ptr():
+                dst.copy_(t)
             c0 += c
         return out
 
@@ -280,17 +328,30 @@ class FusedDealYolo:
         else:
             x = images.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()   # NHWC; zero-copy for channels_last input
         saved = []
+        cat_bufs = {}
         for (kind, arg), f, i in self.layers:
             if f != -1:
                 x = saved[f] if isinstance(f, int) else [x if j == -1 else saved[j] for j in f]
             if kind == "ldconv":
-                x = arg(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)          # module API is logical NCHW; views only
+                plan = self.cat_plan.get(i)
+                if plan is None:
+                    x = infer_nhwc(arg, x)
+                else:       # the only consumer is a Concat: write straight into its buffer
+                    cat_i, c0, ctot = plan
+                    B, H, W, _ = x.shape
+                    s_ = int(arg.stride)
+                    h, w = (H - 1) // s_ + 1, (W - 1) // s_ + 1
+                    buf = cat_bufs.get(cat_i)
+                    if buf is None:
+                        buf = cat_bufs[cat_i] = _new(x, B, h, w, ctot)
+                    O = arg.conv[0].out_channels
+                    x = infer_nhwc(arg, x, out=buf[..., c0:c0 + O])
             elif kind == "scalseq_add":     # ScalSeq whose only consumer is the next Add layer: one tail kernel does both
                 x = arg[0](x, addend=saved[arg[1]])
             elif kind == "fn":
                 x = arg(x)
             elif kind == "cat":
-                x = self._concat(x)
+                x = self._concat(x, cat_bufs.pop(i, None))
             elif kind == "add":
                 x = x[0] + x[1]
             elif kind == "up":

@@ -313,17 +313,78 @@ class LDConv(nn.Module):
         grad_mode = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters(recurse=True)))
         prepared = self._prepared(x.dtype, grad_mode)
-        if not training and not grad_mode and self._fused_ok(x):
-            scale, shift = _folded_bn(bn, x.device)
-            return ldconv_fused_inference(x, prepared, scale, shift, x.shape[1], conv.out_channels, self.num_param,
-                                          int(self.stride))
+        if not training and not grad_mode and bn.running_mean is not None and conv.bias is None:
+            return infer_nhwc(self, _nhwc(x)).permute(0, 3, 1, 2)      # lean inference path (cached BN fold)
         return _LDConvFunction.apply(x, self.p_conv.weight, self.p_conv.bias, conv.weight, conv.bias, bn.weight, bn.bias,
                                      bn.running_mean, bn.running_var, self.p_n, int(self.stride), bn.eps, momentum,
                                      training, prepared)
 
 
+_FOLD_CACHE_ATTR = "_ldc_fold_cache"
+
+
+def infer_nhwc(mod: "LDConv", x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Inference forward on a dense NHWC tensor (B,H,W,C) -> NHWC (B,h,w,O); `out` may be a channel slice of a wider NHWC
+    buffer (the concat buffer of the consumer), which the GEMM epilogue then writes directly.  One-kernel path for the
+    shapes `_fused_ok` selects, else offset conv (tensor cores when eligible) -> TMA-tiled gather -> tcgen05 GEMM."""
+    L = _lib.load()
+    dt = _DTYPES[x.dtype]
+    conv, bn = mod.conv[0], mod.conv[1]
+    B, H, W, C = x.shape
+    N, s, O = mod.num_param, int(mod.stride), conv.out_channels
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    st = _stream()
+    pr = mod._prepared(x.dtype, False)
+    scale, shift = _folded_bn(bn, x.device)
+    dense = out is None or (out.stride(2) == O and out.is_contiguous())
+    if dense and mod._fused_ok(x.permute(0, 3, 1, 2)):
+        if out is None:
+            out = torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
+        _lib.check(L.ldconv_fused_fwd(_ptr(x), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(pr.pn), _ptr(pr.wt), _ptr(scale),
+                                      _ptr(shift), _ptr(out), None, B, C, H, W, N, s, O, _lib.ACT_SILU, dt, st),
+                   "ldconv_fused_fwd")
+        return out
+    M, K = B * h * w, N * C
+    off = torch.empty((B, h, w, 2 * N), device=x.device, dtype=torch.float32)
+    if pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
+        _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(x), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
+                   "ldconv_offset_conv_tc_fwd")
+    else:
+        _lib.check(L.ldconv_offset_conv_fwd(_ptr(x), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
+                   "ldconv_offset_conv_fwd")
+    operand = torch.empty((M, K), device=x.device, dtype=x.dtype)
+    _lib.check(L.ldconv_gather_fwd(_ptr(x), _ptr(off), _ptr(pr.pn), _ptr(operand), None, None, B, C, H, W, N, s, dt, st),
+               "ldconv_gather_fwd")
+    if out is None:
+        out = torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
+    ldo = out.stride(2)
+    if dt == _lib.BF16 and K % 8 == 0 and O <= 256:
+        _lib.check(L.ldconv_conv1x1_bn_act_fwd(_ptr(operand), K, _ptr(pr.wt), _ptr(scale), _ptr(shift), None, 0, _ptr(out), ldo,
+                                               M, K, O, _lib.ACT_SILU, dt, st), "ldconv_conv1x1_bn_act_fwd")
+    else:
+        tmp = out if ldo == O else torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
+        _lib.check(L.ldconv_gemm_fwd(_ptr(operand), _ptr(pr.wt), _ptr(scale), _ptr(shift), _ptr(tmp), None, None, None, M, K, O,
+                                     _lib.ACT_SILU, dt, st), "ldconv_gemm_fwd")
+        if tmp is not out:
+            out.copy_(tmp)
+    return out
+
+
 def _folded_bn(bn: nn.BatchNorm2d, device):
-    """Eval-mode BatchNorm folded to per-channel scale/shift through the C ABI (eps read from the module)."""
+    """Eval-mode BatchNorm folded to per-channel scale/shift through the C ABI (eps read from the module).  Cached on the
+    BatchNorm module while its parameters / statistics / eps are unchanged (the fold is five tiny launches otherwise)."""
+    key = (bn.eps, bn.running_mean.data_ptr(), bn.running_mean._version, bn.running_var._version,
+           None if bn.weight is None else (bn.weight.data_ptr(), bn.weight._version),
+           None if bn.bias is None else bn.bias._version, str(device))
+    cached = bn.__dict__.get(_FOLD_CACHE_ATTR)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    scale, shift = _fold_bn_uncached(bn, device)
+    bn.__dict__[_FOLD_CACHE_ATTR] = (key, scale, shift)
+    return scale, shift
+
+
+def _fold_bn_uncached(bn: nn.BatchNorm2d, device):
     L = _lib.load()
     O = bn.num_features
     scale = torch.empty(O, device=device, dtype=torch.float32)
