@@ -19,13 +19,19 @@ using namespace umma;
 // small-C kernel: thread = output pixel.  K = N*C <= 36 samples stay in registers, W (O x K) and the offset-conv weights
 // sit in shared memory as fp32.
 // =====================================================================================================================
-template <typename T, int C, int NMAX>
+// NFIX / OFIX: num_param and outc as compile-time constants (0 = run-time values N_rt / O_rt).  The model's first layer
+// (N=3, O=16) gets the exact instantiation: with run-time bounds the unrolled loops executed ~3600 mostly predicated-off
+// instructions per pixel and missed the instruction cache (profiles/r1_ncu_smallc_before.csv).
+template <typename T, int C, int NMAX, int NFIX, int OFIX>
 __global__ void __launch_bounds__(128)
 smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, const float* __restrict__ b_off,
                     const int* __restrict__ pn, const T* __restrict__ wt, const float* __restrict__ scale,
                     const float* __restrict__ shift, T* __restrict__ out, float* __restrict__ off_out, int B, int H, int W,
-                    int h, int w, int N, int s, int O, int act)
+                    int h, int w, int N_rt, int s, int O_rt, int act)
 {
+    const int N = NFIX ? NFIX : N_rt;
+    const int O = OFIX ? OFIX : O_rt;
+    constexpr int NLOOP = NFIX ? NFIX : NMAX;
     extern __shared__ __align__(16) float smem_f[];
     const int O2 = 2 * N, K = N * C;
     float* s_woff = smem_f;                                  // [9][C][O2]
@@ -51,9 +57,9 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
     const T* xb = x + (size_t)b * H * W * C;
 
     // ---- offset conv (conv.py:368): 3x3 / pad 1 / stride s, fp32 accumulation ------------------------------------------
-    float offv[2 * NMAX];
+    float offv[2 * NLOOP];
 #pragma unroll
-    for (int o = 0; o < 2 * NMAX; ++o) offv[o] = (o < O2 && b_off) ? b_off[o] : 0.f;
+    for (int o = 0; o < 2 * NLOOP; ++o) offv[o] = (o < O2 && b_off) ? b_off[o] : 0.f;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         const int r = i * s + tap / 3 - 1, k = j * s + tap % 3 - 1;
@@ -64,24 +70,24 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
             const float xv = Elem<T>::to_f(xp[c]);
             const float* wp = s_woff + (tap * C + c) * O2;
 #pragma unroll
-            for (int o = 0; o < 2 * NMAX; ++o)
+            for (int o = 0; o < 2 * NLOOP; ++o)
                 if (o < O2) offv[o] = fmaf(xv, wp[o], offv[o]);
         }
     }
     if (off_out) {
         float* op = off_out + (size_t)m * O2;
 #pragma unroll
-        for (int o = 0; o < 2 * NMAX; ++o)
+        for (int o = 0; o < 2 * NLOOP; ++o)
             if (o < O2) op[o] = offv[o];
     }
 
     // ---- sampling + (N,1) conv, one sample at a time (conv.py:369-408) ----------------------------------------------------
-    constexpr int OMAX = 32;
+    constexpr int OMAX = OFIX ? OFIX : 32;
     float acc[OMAX];
 #pragma unroll
     for (int o = 0; o < OMAX; ++o) acc[o] = 0.f;
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n) {
+    for (int n = 0; n < NLOOP; ++n) {
         if (n >= N) break;
         const SamplePoint q = make_point(i, j, s, pn[n], pn[N + n], offv[n], offv[N + n], H, W);
         const float g_lt = __fmul_rn(q.ar0, q.ak0), g_rb = __fmul_rn(q.ar1, q.ak1);
@@ -300,8 +306,13 @@ static int launch_smallc(const T* x, const float* w_off, const float* b_off, con
     } else {
         const long long M = (long long)B * h * w;
         const size_t smem1 = (size_t)(((9 * C * 2 * N + 3) & ~3) + N * C * O + 2 * O) * sizeof(float);
-        auto kern = smallc_fused_kernel<T, C, 9>;
-        kern<<<cdiv(M, 128), 128, smem1, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, B, H, W, h, w, N, s, O, act);
+        if (N == 3 && O == 16) {
+            auto kern = smallc_fused_kernel<T, C, 9, 3, 16>;
+            kern<<<cdiv(M, 128), 128, smem1, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, B, H, W, h, w, N, s, O, act);
+        } else {
+            auto kern = smallc_fused_kernel<T, C, 9, 0, 0>;
+            kern<<<cdiv(M, 128), 128, smem1, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, B, H, W, h, w, N, s, O, act);
+        }
         LDC_LAUNCH_CHECK("smallc_fused_kernel");
     }
     set_impl(LDCONV_IMPL_FFMA);
