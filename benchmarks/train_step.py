@@ -1,0 +1,86 @@
+"""BASELINE.json config 4: DEAL-YOLO-LD training step on synthetic 640x640 batches, random-init weights, bf16 autocast,
+per-GPU BatchNorm statistics, ONE flat gradient all-reduce over NCCL per step (experiment_yolo_b200/dist.py), SGD with
+nesterov momentum (lr 0.01, momentum 0.937: reference engine/trainer.py:1164, cfg/default.yaml:90-92).
+The loss is a dense surrogate on the raw head maps (dist.surrogate_detection_loss): the reference's TAL + WIoU + NWD loss
+is a "next" row and cannot travel to the GPU box.
+    python benchmarks/train_step.py [--batch 128] [--steps 10]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 benchmarks/train_step.py --batch 128
+(--batch is the GLOBAL batch, split evenly over ranks.)
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from experiment_yolo_b200 import _lib, dealyolo  # noqa: E402
+from experiment_yolo_b200 import dist as xdist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--img", type=int, default=640)
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    model = dealyolo.DealYolo(nc=6)
+    model.load_state_dict(dealyolo.seeded_state(model, 0))
+    model = dealyolo.channels_last_(model.to(dev)).train()
+    lo, hi = xdist.shard_bounds(args.batch, rank, world)
+    B = hi - lo
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = torch.rand((B, 3, args.img, args.img), device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+    targets = [torch.zeros((B, 70, args.img // s, args.img // s), device=dev) for s in (4, 8, 16)]
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.01, momentum=0.937, nesterov=True)
+    red = xdist.FlatGradAllReduce(model.parameters())
+
+    def step():
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+            opt.zero_grad(set_to_none=True)
+            outs = model(x)
+        loss = xdist.surrogate_detection_loss(outs, targets)
+        loss.backward()
+        red()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.call_counts.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        print(json.dumps({"metric": "train_images_per_sec", "value": round(args.batch / ms * 1e3, 1), "ms_per_step": round(ms, 3),
+                          "n_gpus": world, "global_batch": args.batch, "per_gpu_batch": B, "dtype": "bf16 autocast (fp32 master weights)",
+                          "loss": "dense surrogate (not the reference WIoU+NWD loss)", "final_loss": float(loss),
+                          "grad_allreduce": f"one flat fp32 buffer, {red.numel} values" + (" over NCCL" if world > 1 else " (single rank: none)"),
+                          "ldconv_calls_per_step": {k: v // args.steps for k, v in sorted(_lib.call_counts.items())}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
