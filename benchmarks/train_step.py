@@ -74,7 +74,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "train_images_per_sec", "value": round(args.batch / ms * 1e3, 1), "ms_per_step": round(ms, 3),
                           "n_gpus": world, "global_batch": args.batch, "per_gpu_batch": B, "dtype": "bf16 autocast (fp32 master weights)",
-                          "loss": "dense surrogate (not the reference WIoU+NWD loss)", "final_loss": float(loss),
+                          "loss": "dense surrogate (not the reference WIoU+NWD loss)", "final_loss": float(loss.detach()),
                           "grad_allreduce": f"one flat fp32 buffer, {red.numel} values" + (" over NCCL" if world > 1 else " (single rank: none)"),
                           "ldconv_calls_per_step": {k: v // args.steps for k, v in sorted(_lib.call_counts.items())}}), flush=True)
     if world > 1:

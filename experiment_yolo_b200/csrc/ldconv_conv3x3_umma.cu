@@ -326,12 +326,41 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
 }
 
+// shared-memory plan of the im2col kernel; returns 0 when the shape does not fit
+static int conv3x3_smem_plan(int Cin, int Cout, int s, int* xbufs_out, int* stages_out, int* b_resident_out)
+{
+    const int ON = (Cout + 15) / 16 * 16;
+    const int THin = (kConvTileH - 1) * s + 3, TWin = (kConvTileW - 1) * s + 3;
+    const int num_kb = (9 * Cin + 63) / 64;
+    const uint32_t b_bytes = (uint32_t)ON * 128;
+    const uint32_t x_bytes = ((uint32_t)THin * TWin * Cin * 2 + 127) & ~127u;
+    const int b_resident = (size_t)num_kb * b_bytes <= 48u * 1024;
+    const size_t per_stage = 16384 + (b_resident ? 0 : b_bytes);
+    const size_t base = (size_t)ON * 8 + (size_t)num_kb * 32 + 512 + 1024 + (b_resident ? (size_t)num_kb * b_bytes : 0);
+    const long long budget = 220 * 1024 - (long long)base;
+    int stages = 6;
+    long long xb = (budget - (long long)stages * (long long)per_stage) / (long long)x_bytes;
+    if (xb < 2) { stages = 3; xb = (budget - (long long)stages * (long long)per_stage) / (long long)x_bytes; }
+    if (xb < 1) { stages = 2; xb = (budget - (long long)stages * (long long)per_stage) / (long long)x_bytes; }
+    if (xb < 1) return 0;
+    long long want = (64 * 1024 + x_bytes - 1) / x_bytes + 1;
+    if (want < 2) want = 2;
+    if (xb > want) xb = want;
+    if (xb > kMaxXBufs) xb = kMaxXBufs;
+    stages = (int)((budget - xb * (long long)x_bytes) / (long long)per_stage);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return 0;
+    *xbufs_out = (int)xb; *stages_out = stages; *b_resident_out = b_resident;
+    return 1;
+}
+
 int conv3x3_umma_supported(int Cin, int Cout, int s, int mode)
 {
     if (Cin % 16 != 0 || Cin > 256 || Cout < 1 || Cout > 256) return 0;
     if (mode == CONV_MODE_BN_ACT && Cout % 16 != 0) return 0;
     if (s < 1 || s > 2) return 0;
-    return 1;
+    int xb, st, br;
+    return conv3x3_smem_plan(Cin, Cout, s, &xb, &st, &br);
 }
 
 // x: (B,H,W,*) bf16 with pixel stride ldx (channel slice of a wider NHWC buffer allowed; ldx % 8 == 0)
@@ -362,23 +391,9 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     g.x_bytes = (g.x_tx_bytes + 127) & ~127u;
     g.ldo = ldo; g.ldr = ldr;
     { const char* e = getenv("LDCONV_DBG"); g.dbg = e ? atoi(e) : 0; }
-    // shared memory plan: >= 3 ring stages first, then as many input tiles in flight as fit (up to kMaxXBufs)
-    g.b_resident = (size_t)g.num_kb * g.b_bytes <= 48u * 1024;
-    const size_t per_stage = 16384 + (g.b_resident ? 0 : g.b_bytes);
-    const size_t base = (size_t)g.ON * 8 + (size_t)g.num_kb * 32 + 512 + 1024 + (g.b_resident ? (size_t)g.num_kb * g.b_bytes : 0);
-    const long long budget = 220 * 1024 - (long long)base;
-    int stages = 6;
-    long long xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes;
-    if (xb < 2) { stages = 3; xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes; }
-    if (xb < 1) { stages = 2; xb = (budget - (long long)stages * (long long)per_stage) / (long long)g.x_bytes; }
-    if (xb < 1) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
-    // enough tiles in flight for ~64 KB per SM, no more
-    long long want = (64 * 1024 + g.x_bytes - 1) / g.x_bytes + 1;
-    if (want < 2) want = 2;
-    if (xb > want) xb = want;
-    if (xb > kMaxXBufs) xb = kMaxXBufs;
-    g.xbufs = (int)xb;
-    stages = (int)((budget - (long long)g.xbufs * g.x_bytes) / (long long)per_stage);
+    int stages = 0;
+    if (!conv3x3_smem_plan(Cin, Cout, s, &g.xbufs, &stages, &g.b_resident))
+        return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     if (stages > 8) stages = 8;
     if (g.dbg & 8) stages = 2;
     if (stages < 2) return fail(LDCONV_E_ARG, "conv3x3 tcgen05: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
