@@ -13,6 +13,8 @@
 namespace ldc {
 
 int umma_gemm_supported(int M, int K, int O, int dtype, const void* a, const void* wt, const void* out, const void* pre);
+int wgrad_umma_supported(int M, int K, int O, const void* g, const void* a);
+int wgrad_umma(const void* g, const void* a, float* dW, int M, int K, int O, cudaStream_t st);
 int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                   double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st);
 
@@ -276,6 +278,11 @@ LDC_API int ldconv_gemm_bwd_weight(const void* grad_pre, const void* operand, fl
     LDC_REQUIRE(grad_pre && operand && grad_wt && M >= 0 && K >= 1 && O >= 1, "ldconv_gemm_bwd_weight: bad arguments");
     if (M == 0) return LDCONV_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LDCONV_BF16 && wgrad_umma_supported(M, K, O, grad_pre, operand)) {      // tensor-core reduction over M
+        set_impl(LDCONV_IMPL_TCGEN05);
+        return wgrad_umma(grad_pre, operand, grad_wt, M, K, O, st);
+    }
+    set_impl(LDCONV_IMPL_FFMA);
     if (dtype == LDCONV_F32) return gemm_tn_t<float>((const float*)grad_pre, (const float*)operand, grad_wt, M, K, O, st);
     return gemm_tn_t<__nv_bfloat16>((const __nv_bfloat16*)grad_pre, (const __nv_bfloat16*)operand, grad_wt, M, K, O, st);
 }

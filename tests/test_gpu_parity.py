@@ -269,6 +269,27 @@ def test_gemm_bf16(M, K, O, force_ffma):
     assert _rel(st[1].cpu().numpy(), (ref_pre ** 2).sum(0).cpu().numpy()) <= 5e-3
 
 
+@pytest.mark.parametrize("M,K,O", [(5000, 48, 32), (128 * 64 + 17, 96, 64), (300, 192, 128), (20000, 16, 16), (7777, 2304, 128),
+                                   (4096, 576, 64), (1000, 40, 24)])
+def test_weight_gradient_tensor_core_reduction(M, K, O):
+    """dWt(O,K) = grad_pre(M,O)^T . operand(M,K): the tcgen05 MN-major reduction against an fp64 reference (and the
+    CUDA-core kernel for fp32 inputs)."""
+    L = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(M + K)
+    gp = torch.randn((M, O), device=DEV, generator=g).bfloat16()
+    a = torch.randn((M, K), device=DEV, generator=g).bfloat16()
+    dw = torch.zeros((O, K), device=DEV)
+    _lib.check(L.ldconv_gemm_bwd_weight(_ptr(gp), _ptr(a), _ptr(dw), M, K, O, _lib.BF16, _stream()), "wgrad")
+    assert L.ldconv_last_impl() == _lib.IMPL_TCGEN05
+    torch.cuda.synchronize()
+    ref = gp.double().t() @ a.double()
+    assert _rel(dw.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
+    dw32 = torch.zeros((O, K), device=DEV)
+    _lib.check(L.ldconv_gemm_bwd_weight(_ptr(gp.float()), _ptr(a.float()), _ptr(dw32), M, K, O, _lib.F32, _stream()), "wgrad32")
+    assert L.ldconv_last_impl() == _lib.IMPL_FFMA
+    assert _rel(dw32.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ whole module, fp32 ----
 def _module_from_golden(z, prm, m, dtype=torch.float32):
     mod = E.LDConv(m["inc"], m["outc"], m["N"], m["s"])
