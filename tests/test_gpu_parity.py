@@ -285,7 +285,8 @@ def test_weight_gradient_tensor_core_reduction(M, K, O):
     ref = gp.double().t() @ a.double()
     assert _rel(dw.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
     dw32 = torch.zeros((O, K), device=DEV)
-    _lib.check(L.ldconv_gemm_bwd_weight(_ptr(gp.float()), _ptr(a.float()), _ptr(dw32), M, K, O, _lib.F32, _stream()), "wgrad32")
+    gp32, a32 = gp.float(), a.float()      # keep the temporaries alive: the call only sees raw pointers
+    _lib.check(L.ldconv_gemm_bwd_weight(_ptr(gp32), _ptr(a32), _ptr(dw32), M, K, O, _lib.F32, _stream()), "wgrad32")
     assert L.ldconv_last_impl() == _lib.IMPL_FFMA
     assert _rel(dw32.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
 
