@@ -67,6 +67,12 @@ template <> struct Vec16<float> {
     __device__ __forceinline__ static void store(float* p, const float (&v)[4]) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+    __device__ __forceinline__ static void unpack(const uint4& t, float (&v)[4]) {
+        v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+    }
+    __device__ __forceinline__ static uint4 pack(const float (&v)[4]) {
+        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    }
 };
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int N = 8;
@@ -78,6 +84,23 @@ template <> struct Vec16<__nv_bfloat16> {
             v[2 * i] = __uint_as_float(w[i] << 16);
             v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
         }
+    }
+    __device__ __forceinline__ static void unpack(const uint4& t, float (&v)[8]) {
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ __forceinline__ static uint4 pack(const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
     }
     __device__ __forceinline__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
         uint32_t w[4];

@@ -21,10 +21,33 @@ namespace ldc {
 
 using namespace umma;
 
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 struct TileGeom {
     int TH, TW, THin, TWin, halo, tiles_h, tiles_w;
+    int tw_shift;            // TW = 1 << tw_shift
+    int cv_shift;            // CV = 1 << cv_shift, or -1 when CV is not a power of two
+    unsigned inv_n;          // ceil(2^16 / N): sample / N for sample < 4096
+    unsigned inv_row;        // ceil(2^32 / (TW*N*CV)): item / row_items
 };
 
+// Two phases per CTA (the kernel was issue-bound when every (sample, channel vector) item redid the coordinate arithmetic
+// and its integer divisions -- profiles/r1_ncu_gather_L1_v1.csv: 432 instructions per item, issue slots 79 % busy):
+//   phase 1  one thread per SAMPLE (pixel, n) of the tile: make_point once, the four corner positions as 16-byte-vector
+//            offsets (into the staged tile, or into the image when a corner lies outside tile + halo) and the four bilinear
+//            weights go to shared memory.  Runs while the TMA load of the tile is in flight.
+//   phase 2  one thread per ITEM (sample, 16-byte channel vector): two broadcast record loads, four 16-byte corner loads,
+//            the bilinear sum, one 16-byte store.  Items of one tile row are a contiguous run of the operand, so the item
+//            index maps linearly onto the output address.
 template <typename T>
 __global__ void __launch_bounds__(256)
 gather_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmX, const T* __restrict__ x, const float* __restrict__ off,
@@ -35,7 +58,13 @@ gather_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmX, const T* __rest
     constexpr int V = Vec16<T>::N;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    T* tile = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int CV = C / V;
+    const int samples = g.TH * g.TW * N;
+    const size_t tile_bytes = ((size_t)g.THin * g.TWin * C * sizeof(T) + 15) & ~(size_t)15;
+    const uint32_t tile_s = smem_u32(sm);                                  // explicit shared-space addresses: LDS / STS
+    const uint32_t rec_o = tile_s + (uint32_t)tile_bytes;                   // int4 per sample: corner offsets
+    const uint32_t rec_g = rec_o + (uint32_t)samples * 16u;                 // float4 per sample: bilinear weights
 
     const int tj = blockIdx.x % g.tiles_w;
     const int ti = (blockIdx.x / g.tiles_w) % g.tiles_h;
@@ -46,66 +75,81 @@ gather_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmX, const T* __rest
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(&bar, (uint32_t)((size_t)g.THin * g.TWin * C * sizeof(T)));
-        tma_load_4d(tile, &tmX, &bar, 0, k_org, r_org, b);
+        tma_load_4d(sm, &tmX, &bar, 0, k_org, r_org, b);
     }
 
-    const int CV = C / V;
-    const int items = g.TH * g.TW * N * CV;
+    // ---- phase 1: sampling points of the tile ------------------------------------------------------------------------
     const int r_end = r_org + g.THin, k_end = k_org + g.TWin;
-    const T* xb = x + (size_t)b * H * W * C;
     unsigned misses = 0;
-    bool waited = false;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int cv = it % CV;
-        const int n = (it / CV) % N;
-        const int p = it / (CV * N);
-        const int i = i0 + p / g.TW, j = j0 + p % g.TW;
-        if (i >= h || j >= w) continue;
+    for (int sidx = threadIdx.x; sidx < samples; sidx += blockDim.x) {
+        const int p = (int)(((unsigned)sidx * g.inv_n) >> 16);
+        const int n = sidx - p * N;
+        const int i = i0 + (p >> g.tw_shift), j = j0 + (p & (g.TW - 1));
+        if (i >= h || j >= w) {
+            sts128(rec_o + sidx * 16, 0xffffffffu, 0, 0, 0);
+            continue;
+        }
         const long long m = ((long long)b * h + i) * w + j;
         const float* op = off + (size_t)m * 2 * N;
         const SamplePoint q = make_point(i, j, s, pn[n], pn[N + n], op[n], op[N + n], H, W);
-        if (cv == 0) {
-            const long long sn = m * N + n;
-            if (dbg_idx) *reinterpret_cast<int4*>(dbg_idx + (size_t)sn * 4) = make_int4(q.r0, q.r1, q.k0, q.k1);
-            if (dbg_coord) {
-                dbg_coord[(size_t)sn * 2 + 0] = q.pcr;
-                dbg_coord[(size_t)sn * 2 + 1] = q.pck;
-            }
+        const long long sn = m * N + n;
+        if (dbg_idx) *reinterpret_cast<int4*>(dbg_idx + (size_t)sn * 4) = make_int4(q.r0, q.r1, q.k0, q.k1);
+        if (dbg_coord) {
+            dbg_coord[(size_t)sn * 2 + 0] = q.pcr;
+            dbg_coord[(size_t)sn * 2 + 1] = q.pck;
         }
-        const float g_lt = __fmul_rn(q.ar0, q.ak0), g_rb = __fmul_rn(q.ar1, q.ak1);
-        const float g_lb = __fmul_rn(q.ar0, q.ak1), g_rt = __fmul_rn(q.ar1, q.ak0);
+        sts128(rec_g + sidx * 16, __float_as_uint(__fmul_rn(q.ar0, q.ak0)), __float_as_uint(__fmul_rn(q.ar1, q.ak1)),
+               __float_as_uint(__fmul_rn(q.ar0, q.ak1)), __float_as_uint(__fmul_rn(q.ar1, q.ak0)));
         const bool inside = q.r0 >= r_org && q.r1 < r_end && q.k0 >= k_org && q.k1 < k_end;
-        float x00[V], x11[V], x01[V], x10[V], r[V];
         if (inside) {
-            if (!waited) {       // first use of the staged tile: wait for the TMA bytes to land
-                mbar_wait(&bar, 0);
-                waited = true;
-            }
-            const T* t0 = tile + (size_t)cv * V;
             const int ra = (q.r0 - r_org) * g.TWin, rb = (q.r1 - r_org) * g.TWin;
             const int ka = q.k0 - k_org, kb = q.k1 - k_org;
-            Vec16<T>::load(t0 + (size_t)(ra + ka) * C, x00);
-            Vec16<T>::load(t0 + (size_t)(rb + kb) * C, x11);
-            Vec16<T>::load(t0 + (size_t)(ra + kb) * C, x01);
-            Vec16<T>::load(t0 + (size_t)(rb + ka) * C, x10);
-        } else {
-            const T* g0 = xb + (size_t)cv * V;
-            Vec16<T>::load(g0 + ((size_t)q.r0 * W + q.k0) * C, x00);
-            Vec16<T>::load(g0 + ((size_t)q.r1 * W + q.k1) * C, x11);
-            Vec16<T>::load(g0 + ((size_t)q.r0 * W + q.k1) * C, x01);
-            Vec16<T>::load(g0 + ((size_t)q.r1 * W + q.k0) * C, x10);
-            if (cv == 0) ++misses;
+            sts128(rec_o + sidx * 16, (uint32_t)((ra + ka) * CV), (uint32_t)((rb + kb) * CV), (uint32_t)((ra + kb) * CV),
+                   (uint32_t)((rb + ka) * CV));
+        } else {   // served from global memory (L2): offsets relative to the image, bit 31 of .x marks it
+            const int ra = q.r0 * W, rb = q.r1 * W;
+            sts128(rec_o + sidx * 16, (uint32_t)((ra + q.k0) * CV) | 0x80000000u, (uint32_t)((rb + q.k1) * CV),
+                   (uint32_t)((ra + q.k1) * CV), (uint32_t)((rb + q.k0) * CV));
+            ++misses;
         }
-#pragma unroll
-        for (int v = 0; v < V; ++v) r[v] = bilinear(g_lt, g_rb, g_lb, g_rt, x00[v], x11[v], x01[v], x10[v]);
-        Vec16<T>::store(operand + (size_t)m * N * C + (size_t)n * C + (size_t)cv * V, r);
     }
-    // the TMA write must have completed before the CTA's shared memory is released
-    if (!waited) mbar_wait(&bar, 0);
+    __syncthreads();
+    mbar_wait(&bar, 0);      // the staged tile has landed (also: the TMA write completes before the CTA's smem is released)
+
+    // ---- phase 2: bilinear resampling, one 16-byte channel vector per item ----------------------------------------------
+    const int row_items = g.TW * N * CV;
+    const int items = g.TH * row_items;
+    const uint4* xb4 = reinterpret_cast<const uint4*>(x + (size_t)b * H * W * C);
+    // operand row of tile pixel (0,0) in 16-byte vectors; a tile row is a contiguous run of row_items vectors, consecutive
+    // tile rows are w*N*CV vectors apart
+    uint4* out4 = reinterpret_cast<uint4*>(operand) + (((long long)b * h + i0) * w + j0) * (long long)(N * CV);
+    const long long row_stride = (long long)w * N * CV;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int sidx = g.cv_shift >= 0 ? (it >> g.cv_shift) : it / CV;
+        const int cv = it - sidx * CV;
+        const uint4 o = lds128(rec_o + sidx * 16);
+        if (o.x == 0xffffffffu) continue;
+        const uint4 gq = lds128(rec_g + sidx * 16);
+        const float4 gw = make_float4(__uint_as_float(gq.x), __uint_as_float(gq.y), __uint_as_float(gq.z), __uint_as_float(gq.w));
+        uint4 q00, q11, q01, q10;
+        if ((int)o.x >= 0) {
+            const uint32_t t0 = tile_s + (uint32_t)cv * 16u;
+            q00 = lds128(t0 + o.x * 16u); q11 = lds128(t0 + o.y * 16u); q01 = lds128(t0 + o.z * 16u); q10 = lds128(t0 + o.w * 16u);
+        } else {
+            const uint4* g0 = xb4 + cv;
+            q00 = __ldg(g0 + (o.x & 0x7fffffffu)); q11 = __ldg(g0 + o.y); q01 = __ldg(g0 + o.z); q10 = __ldg(g0 + o.w);
+        }
+        float x00[V], x11[V], x01[V], x10[V], r[V];
+        Vec16<T>::unpack(q00, x00);
+        Vec16<T>::unpack(q11, x11);
+        Vec16<T>::unpack(q01, x01);
+        Vec16<T>::unpack(q10, x10);
+#pragma unroll
+        for (int v = 0; v < V; ++v) r[v] = bilinear(gw.x, gw.y, gw.z, gw.w, x00[v], x11[v], x01[v], x10[v]);
+        const int pi = (int)__umulhi((unsigned)it, g.inv_row);
+        out4[(long long)pi * row_stride + (it - pi * row_items)] = Vec16<T>::pack(r);
+    }
     if (miss_counter) {
         misses = (unsigned)__reduce_add_sync(0xffffffffu, misses);
         if ((threadIdx.x & 31) == 0 && misses) atomicAdd(miss_counter, (unsigned long long)misses);
@@ -131,12 +175,25 @@ static int gather_tiled_t(const T* x, const float* off, const int* pn, T* operan
         return (size_t)((t.TH - 1) * s + 2 + max_pn_r + 2 * t.halo) * ((t.TW - 1) * s + 2 + max_pn_k + 2 * t.halo) * C *
                sizeof(T);
     };
+    auto rec_bytes = [&](const TileGeom& t) { return (size_t)t.TH * t.TW * N * 32; };
     while (smem_of(g) > 64 * 1024 && g.TH * g.TW > 16) {
         if (g.TW > g.TH) g.TW /= 2; else g.TH /= 2;
     }
     g.THin = (g.TH - 1) * s + 2 + max_pn_r + 2 * g.halo;
     g.TWin = (g.TW - 1) * s + 2 + max_pn_k + 2 * g.halo;
-    if (g.THin > 256 || g.TWin > 256 || smem_of(g) > 200 * 1024) return 1;   // not eligible: caller uses the direct kernel
+    if (g.THin > 256 || g.TWin > 256 || smem_of(g) + rec_bytes(g) > 200 * 1024) return 1;   // not eligible: direct kernel
+    constexpr int V = Vec16<T>::N;
+    const int CV = C / V;
+    g.tw_shift = 0;
+    while ((1 << g.tw_shift) < g.TW) ++g.tw_shift;
+    g.cv_shift = -1;
+    for (int sh = 0; sh < 16; ++sh)
+        if ((1 << sh) == CV) g.cv_shift = sh;
+    g.inv_n = (65536u + (unsigned)N - 1) / (unsigned)N;
+    const unsigned row_items = (unsigned)(g.TW * N * CV);
+    g.inv_row = (unsigned)((0x100000000ull + row_items - 1) / row_items);
+    // the image-relative corner offsets of phase 1 are 31-bit counts of 16-byte vectors
+    if ((long long)H * W * CV >= 0x7fffffffll) return 1;
     g.tiles_h = (h + g.TH - 1) / g.TH;
     g.tiles_w = (w + g.TW - 1) / g.TW;
     const long long ctas = (long long)B * g.tiles_h * g.tiles_w;
@@ -149,7 +206,7 @@ static int gather_tiled_t(const T* x, const float* off, const int* pn, T* operan
     const CUtensorMapDataType dt = sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if (int e = encode_map(&tm, dt, 4, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
 
-    const size_t smem = smem_of(g) + 128;
+    const size_t smem = smem_of(g) + 16 + rec_bytes(g) + 128;
     auto kern = gather_fwd_tiled_kernel<T>;
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)ctas, 256, smem, st>>>(tm, x, off, pn, operand, dbg_idx, dbg_coord, g_miss_counter, C, H, W, h, w, N, s,
