@@ -37,11 +37,74 @@ static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long 
     return encode_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+// Epilogue of one 16-column chunk of one accumulator row: raw accumulator -> `pre`, affine + activation (+ residual) -> `out`.
+// aff_s = shared-space address of the (scale, shift) pair of column c0 (explicit LDS: the generic loads this replaces were
+// the top stall of the kernel, profiles/r1_ncu_gemm_L1_v2.txt).
+__device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
+                                                    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
+                                                    const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store)
+{
+    const bool full16 = vec_store && (c0 + 16 <= O);
+    if (pre) {
+        __nv_bfloat16* dst = pre + m * ldo + c0;
+        if (full16) {
+            float lo[8], hi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(v[e]); hi[e] = __uint_as_float(v[8 + e]); }
+            Vec16<__nv_bfloat16>::store(dst, lo);
+            Vec16<__nv_bfloat16>::store(dst + 8, hi);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (c0 + e < O) dst[e] = __float2bfloat16_rn(__uint_as_float(v[e]));
+        }
+    }
+    if (out) {
+        float z[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+            const float4 a = lds_f4(aff_s + (uint32_t)e * 8u);      // (scale, shift) of columns c0+e, c0+e+1
+            z[e] = apply_act_fast(fmaf(__uint_as_float(v[e]), a.x, a.y), act);
+            z[e + 1] = apply_act_fast(fmaf(__uint_as_float(v[e + 1]), a.z, a.w), act);
+        }
+        if (residual) {
+            const __nv_bfloat16* rp = residual + m * ldr + c0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (c0 + e < O) z[e] += __bfloat162float(rp[e]);
+        }
+        __nv_bfloat16* dst = out + m * ldo + c0;
+        if (full16) {
+            float lo[8], hi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { lo[e] = z[e]; hi[e] = z[8 + e]; }
+            Vec16<__nv_bfloat16>::store(dst, lo);
+            Vec16<__nv_bfloat16>::store(dst + 8, hi);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (c0 + e < O) dst[e] = __float2bfloat16_rn(z[e]);
+        }
+    }
+}
+
+// A pipeline UNIT is G consecutive 128-row tiles accumulated side by side in one TMEM buffer (G * ON columns, two buffers):
+// for the narrow outputs of the model (O = 16..64) one tile is only 1-4 column chunks, and with one tile per buffer the
+// per-tile latency chain (tfull wait -> tcgen05.ld -> wait::ld -> math -> store -> tempty arrive) bounded the kernel at
+// ~1.9 us per tile per CTA (3.2 TB/s at K=48, O=32).  With G tiles per buffer every epilogue warp has 2 tcgen05.ld in
+// flight per wait and pays the barrier round trip once per unit.
 __global__ void __launch_bounds__(kGemmThreads, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
-                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr)
+                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int G)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -57,6 +120,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int num_units = (num_tiles + G - 1) / G;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -77,13 +141,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
-                    tma_load_2d(sA + (size_t)s * kABytes, &tmA, &full[s], kb * kBlockK, tile * kTileM);
-                    tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], kb * kBlockK, 0);
-                    if (++s == stages) { s = 0; ph ^= 1; }
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int t_end = min(num_tiles, (unit + 1) * G);
+                for (int tile = unit * G; tile < t_end; ++tile) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+                        tma_load_2d(sA + (size_t)s * kABytes, &tmA, &full[s], kb * kBlockK, tile * kTileM);
+                        tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], kb * kBlockK, 0);
+                        if (++s == stages) { s = 0; ph ^= 1; }
+                    }
                 }
             }
         }
@@ -93,92 +160,67 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t tph = (it >> 1) & 1;
                 mbar_wait(&tempty[buf], tph ^ 1);
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ON);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
+                const int t_end = min(num_tiles, (unit + 1) * G);
+                uint32_t d_tmem = tmem_base + (uint32_t)(buf * G * ON);
+                for (int tile = unit * G; tile < t_end; ++tile, d_tmem += (uint32_t)ON) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after_sync();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                                        (uint32_t)((kb | k) != 0));
+                        }
+                        mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+                        if (++s == stages) { s = 0; ph ^= 1; }
                     }
-                    mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
-                    if (kb == num_kb - 1) mma_commit(&tfull[buf]);
-                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
+                mma_commit(&tfull[buf]);
             }
         }
     } else {
         const int lg = warp & 3;              // TMEM lane group this warp may access
-        const int half = (warp - 2) >> 2;     // warps 2..5 take the first half of the column chunks, 6..9 the second
-        const int chunks = ON / 16;
-        const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2, ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
+        const int half = (warp - 2) >> 2;     // warps 2..5 take the first half of the unit's column chunks, 6..9 the second
+        const int chunks = ON / 16;           // per tile
+        const int uc = G * chunks;            // per unit
+        const int ch_begin = half == 0 ? 0 : (uc + 1) / 2, ch_end = half == 0 ? (uc + 1) / 2 : uc;
+        const int g_begin = ch_begin / chunks, c_begin = ch_begin - g_begin * chunks;
+        const uint32_t aff_s = smem_u32(s_affine);
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t tph = (it >> 1) & 1;
             mbar_wait(&tfull[buf], tph);
             tc_fence_after_sync();
-            const long long m = (long long)tile * kTileM + lg * 32 + lane;
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ON);
-            for (int ch = ch_begin; ch < ch_end; ++ch) {
-                const int c0 = ch * 16;
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * G * ON);
+            const long long m_unit = (long long)unit * G * kTileM + lg * 32 + lane;
+            int g = g_begin, c = c_begin;                 // tile within the unit, chunk within the tile
+            for (int ch = ch_begin; ch < ch_end; ch += 2) {
+                const bool two = ch + 1 < ch_end;
+                uint32_t v0[16], v1[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)ch * 16u, v0);
+                if (two) tmem_ld_32x32b_x16(taddr + (uint32_t)(ch + 1) * 16u, v1);
                 tmem_ld_wait();
-                if (m < M && c0 < O) {
-                    const bool full16 = vec_store && (c0 + 16 <= O);
-                    if (pre) {
-                        __nv_bfloat16* dst = pre + m * ldo + c0;
-                        if (full16) {
-                            float lo[8], hi[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(v[e]); hi[e] = __uint_as_float(v[8 + e]); }
-                            Vec16<__nv_bfloat16>::store(dst, lo);
-                            Vec16<__nv_bfloat16>::store(dst + 8, hi);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e)
-                                if (c0 + e < O) dst[e] = __float2bfloat16_rn(__uint_as_float(v[e]));
-                        }
-                    }
-                    if (out) {
-                        float lo[8], hi[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float2 a0 = s_affine[c0 + e], a1 = s_affine[c0 + 8 + e];
-                            const float z0 = fmaf(__uint_as_float(v[e]), a0.x, a0.y);
-                            const float z1 = fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y);
-                            lo[e] = apply_act_fast(z0, act);
-                            hi[e] = apply_act_fast(z1, act);
-                        }
-                        if (residual) {
-                            const __nv_bfloat16* rp = residual + m * ldr + c0;
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                if (c0 + e < O) lo[e] += __bfloat162float(rp[e]);
-                                if (c0 + 8 + e < O) hi[e] += __bfloat162float(rp[8 + e]);
-                            }
-                        }
-                        __nv_bfloat16* dst = out + m * ldo + c0;
-                        if (full16) {
-                            Vec16<__nv_bfloat16>::store(dst, lo);
-                            Vec16<__nv_bfloat16>::store(dst + 8, hi);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                if (c0 + e < O) dst[e] = __float2bfloat16_rn(lo[e]);
-                                if (c0 + 8 + e < O) dst[8 + e] = __float2bfloat16_rn(hi[e]);
-                            }
-                        }
-                    }
+                {
+                    const long long m = m_unit + (long long)g * kTileM;
+                    if (m < M && c * 16 < O)
+                        gemm_epilogue_chunk(v0, m, c * 16, O, aff_s + (uint32_t)c * 128u, act, out, pre, residual, ldo, ldr,
+                                            vec_store != 0);
+                    if (++c == chunks) { c = 0; ++g; }
+                }
+                if (two) {
+                    const long long m = m_unit + (long long)g * kTileM;
+                    if (m < M && c * 16 < O)
+                        gemm_epilogue_chunk(v1, m, c * 16, O, aff_s + (uint32_t)c * 128u, act, out, pre, residual, ldo, ldr,
+                                            vec_store != 0);
+                    if (++c == chunks) { c = 0; ++g; }
                 }
             }
             tc_fence_before_sync();
@@ -233,11 +275,18 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     // two CTAs per SM when both accumulator pairs fit TMEM (2 x 2 x ON <= 512 columns): ~100 KB of smem ring each;
     // one CTA with the whole ~200 KB otherwise
     const bool two_per_sm = 4 * ON <= 512;
+    // tiles per accumulator buffer: as many as fit 128 TMEM columns, but keep at least ~2 units per CTA
+    int G = 128 / ON;
+    if (G < 1) G = 1;
+    while (G > 1 && (num_tiles + G - 1) / G < 2 * num_sms() * (two_per_sm ? 2 : 1)) --G;
+    static int g_env_group = -2;
+    if (g_env_group == -2) { const char* e = getenv("LDCONV_GEMM_GROUP"); g_env_group = e ? atoi(e) : -1; }
+    if (g_env_group >= 1 && g_env_group * ON <= 128) G = g_env_group;
     int stages = ((two_per_sm ? 100 : 200) * 1024) / (kABytes + b_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(LDCONV_E_ARG, "tcgen05 GEMM: tile does not fit shared memory (O=%d)", O);
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(2 * ON)) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(2 * G * ON)) tmem_cols <<= 1;
     const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 4) * sizeof(uint64_t) + 16 +
                         (size_t)ON * sizeof(float2);
 
@@ -247,11 +296,12 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
 
     LDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * (two_per_sm ? 2 : 1);
-    if (grid > num_tiles) grid = num_tiles;
+    const int num_units = (num_tiles + G - 1) / G;
+    if (grid > num_units) grid = num_units;
     const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
     umma_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, scale, shift, (__nv_bfloat16*)out, (__nv_bfloat16*)pre,
                                                        (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages,
-                                                       act, tmem_cols, vec_store, ldo, ldr);
+                                                       act, tmem_cols, vec_store, ldo, ldr, G);
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
