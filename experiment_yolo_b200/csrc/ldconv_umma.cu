@@ -275,10 +275,10 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     // two CTAs per SM when both accumulator pairs fit TMEM (2 x 2 x ON <= 512 columns): ~100 KB of smem ring each;
     // one CTA with the whole ~200 KB otherwise
     const bool two_per_sm = 4 * ON <= 512;
-    // tiles per accumulator buffer: as many as fit 128 TMEM columns, but keep at least ~2 units per CTA
-    int G = 128 / ON;
-    if (G < 1) G = 1;
-    while (G > 1 && (num_tiles + G - 1) / G < 2 * num_sms() * (two_per_sm ? 2 : 1)) --G;
+    // tiles per accumulator buffer.  Measured (profiles/r1_layers_gemm_group.txt): grouping does not move the needle -- the
+    // kernel is bound by the TMA request rate of narrow operand rows (K*2 < 128 B), not by the epilogue chain -- so the
+    // default stays 1; LDCONV_GEMM_GROUP=n selects n tiles per buffer (n * ON <= 128) for experiments.
+    int G = 1;
     static int g_env_group = -2;
     if (g_env_group == -2) { const char* e = getenv("LDCONV_GEMM_GROUP"); g_env_group = e ? atoi(e) : -1; }
     if (g_env_group >= 1 && g_env_group * ON <= 128) G = g_env_group;
