@@ -106,6 +106,13 @@ def main():
                 break
         L.ldconv_set_flag(_lib.FLAG_FORCE_FFMA, 0)
 
+        if L.ldconv_gather_gemm_supported(B, C, H, W, N, s, O, O, dt):
+            bytes_gg = e * B * C * H * W + 4 * B * 2 * N * h * w + e * M * O
+            ms = timed(lambda: _lib.check(L.ldconv_gather_gemm_fwd(x.data_ptr(), off.data_ptr(), pn.data_ptr(), wt.data_ptr(),
+                                                                   scale.data_ptr(), shift.data_ptr(), out.data_ptr(), O, B, C, H,
+                                                                   W, N, s, O, _lib.ACT_SILU, dt, st)), args.iters, flush)
+            rec("gather_gemm_fwd", "tcgen05", ms, bytes_gg, 2.0 * M * K * O)
+
         if L.ldconv_fused_supported(B, C, H, W, N, s, O, dt):
             bytes_f = e * B * C * H * W + e * M * O
             ms = timed(lambda: _lib.check(L.ldconv_fused_fwd(x.data_ptr(), w_off.data_ptr(), b_off.data_ptr(), pn.data_ptr(),

@@ -56,6 +56,9 @@ def main():
             w_tc = w_off.permute(3, 0, 1, 2).reshape(2 * N, 9 * C).to(dtype).contiguous()
             _lib.check(L.ldconv_offset_conv_tc_fwd(x.data_ptr(), w_tc.data_ptr(), b_off.data_ptr(), off.data_ptr(), B, C, H, W,
                                                    N, s, dt, st))
+        elif args.kernel == "gg":
+            _lib.check(L.ldconv_gather_gemm_fwd(x.data_ptr(), off.data_ptr(), pn.data_ptr(), wt.data_ptr(), scale.data_ptr(),
+                                                shift.data_ptr(), out.data_ptr(), O, B, C, H, W, N, s, O, _lib.ACT_SILU, dt, st))
         elif args.kernel == "fused":
             _lib.check(L.ldconv_fused_fwd(x.data_ptr(), w_off.data_ptr(), b_off.data_ptr(), pn.data_ptr(), wt.data_ptr(),
                                           scale.data_ptr(), shift.data_ptr(), out.data_ptr(), None, B, C, H, W, N, s, O,

@@ -162,6 +162,13 @@ __device__ __forceinline__ float bilinear(float g_lt, float g_rb, float g_lb, fl
     return v;
 }
 
+// same four terms with fused multiply-adds: for kernels whose operand is rounded to bf16 anyway (one fp32 ulp of difference)
+__device__ __forceinline__ float bilinear_fma(float g_lt, float g_rb, float g_lb, float g_rt, float x00, float x11,
+                                              float x01, float x10)
+{
+    return fmaf(g_rt, x10, fmaf(g_lb, x01, fmaf(g_rb, x11, g_lt * x00)));
+}
+
 __device__ __forceinline__ float silu(float z) { return z / (1.f + __expf(-z)); }
 // bf16 epilogues: silu(z) = z * sigmoid(z) = 0.5 z (1 + tanh(z/2)); one MUFU op, relative error ~2^-11 (below bf16's 2^-9)
 __device__ __forceinline__ float silu_fast(float z)

@@ -1,0 +1,485 @@
+// ldconv_gg_umma.cu -- LDConv gather + (N,1)-conv GEMM + BatchNorm + SiLU as ONE persistent tcgen05 kernel (bf16, sm_100a).
+//
+// Replaces /root/reference/ultralytics/nn/modules/conv.py:369-408 for inference: the sampling grid p_0 + p_n + offset
+// (:413-454), floor / independent clamps / corner indices / bilinear weights (:375-393), the four gathers and the bilinear
+// sum (:396-405), the 'b c h w n -> b c (h n) w' rearrange (:494-503) and Conv2d((N,1),(N,1)) + BatchNorm2d + SiLU (:355,
+// :408).  The resampled (M, N*C) operand is never written to HBM: the gather warps write it straight into the K-major
+// SWIZZLE_128B shared-memory tile that tcgen05.mma reads, so per call the kernel moves x + offsets + out instead of
+// x + offsets + 2 x operand + out (for layer 1 of yolov8-LD-P2 at batch 64: 354 MB instead of 668 MB).
+//
+// Persistent CTA of 8 warps, one 128-pixel output tile (8 x 16 or 16 x 8) per pipeline step, up to three CTAs per SM.  Every
+// warp is a worker (the resampling is issue-bound -- a B200 SM has ~5.5 thread instructions per byte of HBM traffic -- and a
+// first version with dedicated TMA / MMA / epilogue warps spent 94 us of its 170 us at layer 1 in barrier hand-offs alone,
+// profiles/r1_gg_stage_skips.txt); thread 0 issues the asynchronous work right after the block barriers:
+//   phase 1   one thread per sample (pixel, n): common.cuh::make_point (bit-exact grid / indices / weights), corner
+//             offsets + weights -> shared-memory records                                                  | barrier A
+//   phase 2   one thread per (sample, 16-byte channel vector): four 16-byte corner loads from the TMA-staged tile (L2 when
+//             a corner leaves the halo), bilinear sum, one 16-byte store into the swizzled operand tile    | barrier B
+//   thread 0  TMA of the tile that reuses this input buffer; K/16 tcgen05.mma (M = 128 pixels, N = O, fp32 accumulators in
+//             TMEM, double-buffered) + commit
+//   all       epilogue of the PREVIOUS tile while this tile's MMA runs: tcgen05.ld -> folded BatchNorm -> SiLU -> 16-byte
+//             NHWC stores (out may be a channel slice of a concat buffer)
+// The offsets come from HBM (written by the tensor-core offset conv); the next tile's offsets are prefetched into registers
+// before phase 2.
+#include "common.cuh"
+#include "tmap.cuh"
+#include "umma.cuh"
+
+namespace ldc {
+
+using namespace umma;
+
+static constexpr int kGGThreads = 256;
+
+struct GGGeom {
+    int C, CV, cv_shift, N, s, H, W, h, w, O, ON, K, num_kb, ksteps;
+    int TH, TW, tw_shift, THin, TWin, halo, tiles_h, tiles_w, num_tiles;
+    int XB, AB, ldo, act, per_sm, dbg;
+    unsigned inv_n, inv_img, inv_tw;
+    uint32_t ofs_a, ofs_b, ofs_x, ofs_rec, ofs_aff, ofs_bar, x_bytes, x_tx_bytes, a_bytes, b_bytes, rec_bytes, tmem_cols;
+};
+
+__device__ __forceinline__ uint4 gg_lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 gg_lds_f4(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void gg_sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kGGThreads, MINB)
+ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 const __nv_bfloat16* __restrict__ x, const float* __restrict__ off, const int* __restrict__ pn,
+                 const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                 const GGGeom g)
+{
+    using T = __nv_bfloat16;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment by pointer arithmetic on the shared symbol (no integer round trip): the compiler keeps the
+    // shared address space, so the C++ loads / stores below are LDS / STS that it may schedule freely between barriers
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t smem_s = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
+    uint64_t* x_full = bars;            // [2]  TMA bytes of an input tile have landed
+    uint64_t* mma_done = bars + 2;      // [2]  tcgen05.commit of the tile that used TMEM buffer / operand buffer i
+    uint64_t* w_full = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_per_img = g.tiles_h * g.tiles_w;
+    const int N = g.N, CV = g.CV;
+    const int samples = 128 * N;
+    const int items = samples * CV;
+
+    auto tile_coords = [&](int tile, int& b, int& i0, int& j0) {      // exact magic-number divisions (host-checked range)
+        b = g.inv_img ? (int)__umulhi((unsigned)tile, g.inv_img) : tile;
+        const int rem = tile - b * tiles_per_img;
+        const int ti = g.inv_tw ? (int)__umulhi((unsigned)rem, g.inv_tw) : rem;
+        i0 = ti * g.TH;
+        j0 = (rem - ti * g.tiles_w) * g.TW;
+    };
+    auto issue_x_tile = [&](int tile, int xb) {                         // thread 0 only
+        if (g.dbg & 4) { mbar_arrive(&x_full[xb]); return; }
+        int b, i0, j0;
+        tile_coords(tile, b, i0, j0);
+        mbar_arrive_expect_tx(&x_full[xb], g.x_tx_bytes);
+        tma_load_4d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, j0 * g.s - g.halo, i0 * g.s - g.halo, b);
+    };
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&mma_done[i], 1); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    for (int o = tid; o < g.ON; o += kGGThreads)
+        sAff[o] = make_float2((scale && o < g.O) ? scale[o] : 1.f, (shift && o < g.O) ? shift[o] : 0.f);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {       // weights once (resident), then the first XB input tiles of this CTA
+        mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes);
+        for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(smem + g.ofs_b + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+        for (int k = 0; k < g.XB; ++k)
+            if ((int)blockIdx.x + k * (int)gridDim.x < g.num_tiles) issue_x_tile(blockIdx.x + k * gridDim.x, k);
+    }
+
+    // this thread's first two samples (rounds of 256): the (pixel, n) decomposition is tile-independent
+    int my_p[2], my_n[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int sidx = tid + r * kGGThreads;
+        my_p[r] = (int)(((unsigned)sidx * g.inv_n) >> 16);
+        my_n[r] = sidx - my_p[r] * N;
+    }
+    const bool has0 = tid < samples, has1 = tid + kGGThreads < samples;
+    const int pn_r0 = has0 ? pn[my_n[0]] : 0, pn_k0 = has0 ? pn[N + my_n[0]] : 0;
+    const int pn_r1 = has1 ? pn[my_n[1]] : 0, pn_k1 = has1 ? pn[N + my_n[1]] : 0;
+    float2 nxt[2];       // offsets (row, col) of those samples in the NEXT tile (software prefetch across phase 2)
+    auto fetch_offsets = [&](int tile, float2 (&dst)[2]) {
+        int b, i0, j0;
+        tile_coords(tile, b, i0, j0);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            dst[r] = make_float2(0.f, 0.f);
+            if (r == 0 ? has0 : has1) {
+                const int i = i0 + (my_p[r] >> g.tw_shift), j = j0 + (my_p[r] & (g.TW - 1));
+                if (i < g.h && j < g.w) {
+                    const float* op = off + (((size_t)b * g.h + i) * g.w + j) * (size_t)(2 * N);
+                    dst[r] = make_float2(__ldg(op + my_n[r]), __ldg(op + N + my_n[r]));
+                }
+            }
+        }
+    };
+    if ((int)blockIdx.x < g.num_tiles) fetch_offsets(blockIdx.x, nxt);
+
+    // epilogue of one finished tile: this warp's TMEM lane group (warp % 4) and its half of the column chunks
+    const int lg = warp & 3, half = warp >> 2;
+    const int ep = lg * 32 + lane;
+    const int epi = ep >> g.tw_shift, epj = ep & (g.TW - 1);
+    const int chunks = g.ON / 16;
+    const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2, ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
+    auto epilogue = [&](int tile, int eit) {
+        const int tb = eit & 1;
+        mbar_wait(&mma_done[tb], (eit >> 1) & 1);
+        tc_fence_after_sync();
+        int b, i0, j0;
+        tile_coords(tile, b, i0, j0);
+        const int i = i0 + epi, j = j0 + epj;
+        const bool valid = i < g.h && j < g.w;
+        T* orow = out + (((size_t)b * g.h + i) * g.w + j) * (size_t)g.ldo;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(tb * g.ON);
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+            const int c0 = ch * 16;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (!valid || c0 >= g.O || (g.dbg & 8)) continue;
+            const float4* aff4 = reinterpret_cast<const float4*>(sAff + c0);
+            float z[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+                const float4 a = aff4[e >> 1];
+                z[e] = fmaf(__uint_as_float(v[e]), a.x, a.y);
+                z[e + 1] = fmaf(__uint_as_float(v[e + 1]), a.z, a.w);
+            }
+            if (g.act == LDCONV_ACT_SILU) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) z[e] = silu_fast(z[e]);
+            } else if (g.act == LDCONV_ACT_LEAKY01) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) z[e] = z[e] > 0.f ? z[e] : 0.1f * z[e];
+            }
+            float lo[8], hi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { lo[e] = z[e]; hi[e] = z[8 + e]; }
+            Vec16<T>::store(orow + c0, lo);
+            Vec16<T>::store(orow + c0 + 8, hi);
+        }
+        tc_fence_before_sync();       // ordered before the block barrier that precedes the next MMA into this buffer
+    };
+
+    const uint32_t idesc = make_idesc_bf16(128, g.ON);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int xb = it % g.XB, ab = it % g.AB, tb = it & 1;
+        int b, i0, j0;
+        tile_coords(tile, b, i0, j0);
+        const int r_org = i0 * g.s - g.halo, k_org = j0 * g.s - g.halo;
+        const int r_end = r_org + g.THin, k_end = k_org + g.TWin;
+        // records are double-buffered: buffer it&1 was last read in phase 2 of tile it-2, two block barriers ago
+        uint4* rec_o = reinterpret_cast<uint4*>(smem + g.ofs_rec + (size_t)(it & 1) * g.rec_bytes);
+        float4* rec_g = reinterpret_cast<float4*>(rec_o + samples);
+
+        // ---- phase 1: one record per sample --------------------------------------------------------------------------------
+        auto make_record = [&](int sidx, int p, int n, int pr_, int pk_, float o_r, float o_k, bool have_off) {
+            const int i = i0 + (p >> g.tw_shift), j = j0 + (p & (g.TW - 1));
+            if (i >= g.h || j >= g.w) {
+                rec_o[sidx] = make_uint4(0xffffffffu, 0, 0, 0);
+                return;
+            }
+            if (!have_off) {
+                const float* op = off + (((size_t)b * g.h + i) * g.w + j) * (size_t)(2 * N);
+                o_r = __ldg(op + n); o_k = __ldg(op + N + n);
+            }
+            const SamplePoint q = make_point(i, j, g.s, pr_, pk_, o_r, o_k, g.H, g.W);
+            rec_g[sidx] = make_float4(__fmul_rn(q.ar0, q.ak0), __fmul_rn(q.ar1, q.ak1), __fmul_rn(q.ar0, q.ak1),
+                                      __fmul_rn(q.ar1, q.ak0));
+            const bool inside = q.r0 >= r_org && q.r1 < r_end && q.k0 >= k_org && q.k1 < k_end;
+            if (inside) {
+                const int ra = (q.r0 - r_org) * g.TWin, rb = (q.r1 - r_org) * g.TWin;
+                const int ka = q.k0 - k_org, kb = q.k1 - k_org;
+                rec_o[sidx] = make_uint4((uint32_t)((ra + ka) * CV), (uint32_t)((rb + kb) * CV), (uint32_t)((ra + kb) * CV),
+                                         (uint32_t)((rb + ka) * CV));
+            } else {      // served from global memory (L2): image-relative offsets, bit 31 of .x marks it
+                const int ra = q.r0 * g.W, rb = q.r1 * g.W;
+                rec_o[sidx] = make_uint4((uint32_t)((ra + q.k0) * CV) | 0x80000000u, (uint32_t)((rb + q.k1) * CV),
+                                         (uint32_t)((ra + q.k1) * CV), (uint32_t)((rb + q.k0) * CV));
+            }
+        };
+        if (!(g.dbg & 2) || it == 0) {
+            if (has0) make_record(tid, my_p[0], my_n[0], pn_r0, pn_k0, nxt[0].x, nxt[0].y, true);
+            if (has1) make_record(tid + kGGThreads, my_p[1], my_n[1], pn_r1, pn_k1, nxt[1].x, nxt[1].y, true);
+            for (int sidx = tid + 2 * kGGThreads; sidx < samples; sidx += kGGThreads) {
+                const int p = (int)(((unsigned)sidx * g.inv_n) >> 16);
+                const int n = sidx - p * N;
+                make_record(sidx, p, n, pn[n], pn[N + n], 0.f, 0.f, false);
+            }
+        }
+        // prefetch the next tile's offsets; their latency hides behind phase 2
+        if (tile + (int)gridDim.x < g.num_tiles) fetch_offsets(tile + gridDim.x, nxt);
+        __syncthreads();                                   // (A) records of this tile are visible
+        mbar_wait(&x_full[xb], (it / g.XB) & 1);           // the staged input tile has landed
+        if (g.AB == 1 && it > 0) mbar_wait(&mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1);   // operand buffer free again
+
+        // ---- phase 2: bilinear resampling into the swizzled operand tile; two items per iteration, loads first ----------------
+        {
+            const uint4* tile4 = reinterpret_cast<const uint4*>(smem + g.ofs_x + (size_t)xb * g.x_bytes);
+            const uint4* ro4 = rec_o;
+            const float4* rg4 = rec_g;
+            uint8_t* a_tile = smem + g.ofs_a + (size_t)ab * g.a_bytes;
+            const uint4* xb4 = reinterpret_cast<const uint4*>(x + (size_t)b * g.H * g.W * g.C);
+            auto corners = [&](const uint4& o, int cv, uint4& q00, uint4& q11, uint4& q01, uint4& q10) {
+                if ((int)o.x >= 0) {
+                    const uint4* t0 = tile4 + cv;
+                    q00 = t0[o.x]; q11 = t0[o.y]; q01 = t0[o.z]; q10 = t0[o.w];
+                } else {
+                    const uint4* g0 = xb4 + cv;
+                    q00 = __ldg(g0 + (o.x & 0x7fffffffu)); q11 = __ldg(g0 + o.y); q01 = __ldg(g0 + o.z); q10 = __ldg(g0 + o.w);
+                }
+            };
+            auto resample = [&](const float4& gw, const uint4& q00, const uint4& q11, const uint4& q01, const uint4& q10) {
+                float x00[8], x11[8], x01[8], x10[8], r[8];
+                Vec16<T>::unpack(q00, x00);
+                Vec16<T>::unpack(q11, x11);
+                Vec16<T>::unpack(q01, x01);
+                Vec16<T>::unpack(q10, x10);
+#pragma unroll
+                for (int v = 0; v < 8; ++v) r[v] = bilinear_fma(gw.x, gw.y, gw.z, gw.w, x00[v], x11[v], x01[v], x10[v]);
+                return Vec16<T>::pack(r);
+            };
+            auto a_slot = [&](int sidx, int cv) {
+                const uint32_t p = ((unsigned)sidx * g.inv_n) >> 16;
+                const uint32_t n = (uint32_t)sidx - p * (uint32_t)N;
+                const uint32_t k8 = n * (uint32_t)CV + (uint32_t)cv;            // 16-byte chunk index along K
+                return reinterpret_cast<uint4*>(a_tile + (k8 >> 3) * 16384u + sw128_offset(p, k8 & 7u));
+            };
+            for (int ia = tid; ia < ((g.dbg & 1) ? 0 : items); ia += 2 * kGGThreads) {
+                const int ib = ia + kGGThreads;
+                const bool hb = ib < items;
+                const int sa = g.cv_shift >= 0 ? (ia >> g.cv_shift) : ia / CV;
+                const int sb = hb ? (g.cv_shift >= 0 ? (ib >> g.cv_shift) : ib / CV) : sa;
+                const int cva = ia - sa * CV, cvb = hb ? ib - sb * CV : cva;
+                const uint4 oa = ro4[sa], ob = ro4[sb];
+                const float4 ga = rg4[sa], gb = rg4[sb];
+                const bool va = oa.x != 0xffffffffu, vb = hb && ob.x != 0xffffffffu;
+                uint4 a00, a11, a01, a10, b00, b11, b01, b10;
+                a00 = a11 = a01 = a10 = b00 = b11 = b01 = b10 = make_uint4(0, 0, 0, 0);
+                if (va) corners(oa, cva, a00, a11, a01, a10);
+                if (vb) corners(ob, cvb, b00, b11, b01, b10);
+                if (va) *a_slot(sa, cva) = resample(ga, a00, a11, a01, a10);
+                if (vb) *a_slot(sb, cvb) = resample(gb, b00, b11, b01, b10);
+            }
+        }
+        fence_proxy_async_smem();      // generic-proxy stores of the operand tile -> visible to tcgen05 (async proxy)
+        __syncthreads();               // (B) operand tile complete, input tile consumed, epilogue(it-2) done by every warp
+
+        if (tid == 0) {
+            // the input buffer is free: stage the tile that will use it next
+            if (tile + g.XB * (int)gridDim.x < g.num_tiles) issue_x_tile(tile + g.XB * gridDim.x, xb);
+            if (it == 0) mbar_wait(w_full, 0);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(tb * g.ON);
+            const uint32_t a_addr = smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes;
+            const uint32_t b_addr = smem_s + g.ofs_b;
+            for (int st = 0; st < g.ksteps; ++st) {
+                const uint32_t kb = (uint32_t)st >> 2, kk = (uint32_t)st & 3;
+                mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + kb * 16384u + kk * 32u),
+                            make_desc_k_sw128(b_addr + kb * g.b_bytes + kk * 32u), idesc, (uint32_t)(st != 0));
+            }
+            mma_commit(&mma_done[tb]);
+        }
+        __syncwarp();
+        if (it > 0) epilogue(tile - (int)gridDim.x, it - 1);      // the previous tile's MMA ran during this tile's phases
+    }
+    if (it > 0) epilogue((int)blockIdx.x + (it - 1) * (int)gridDim.x, it - 1);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+static void gg_pn_extent(int N, int* max_r, int* max_k)
+{
+    int32_t table[64];
+    *max_r = *max_k = 0;
+    if (N > 16 || ldconv_p_n(N, table) != LDCONV_OK) return;
+    for (int n = 0; n < N; ++n) {
+        if (table[n] > *max_r) *max_r = table[n];
+        if (table[N + n] > *max_k) *max_k = table[N + n];
+    }
+}
+
+// Fills the geometry and the dynamic shared-memory size; returns 0 when the shape is not covered.
+static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo, int act, GGGeom* out, size_t* smem_bytes)
+{
+    if (C % 8 != 0 || C > 256 || N < 1 || N > 16 || O % 16 != 0 || O > 256 || ldo % 8 != 0 || ldo < O) return 0;
+    const int K = N * C;
+    if (K % 16 != 0 || K > 1024) return 0;
+    GGGeom g;
+    g.C = C; g.CV = C / 8; g.N = N; g.s = s; g.H = H; g.W = W; g.O = O; g.K = K; g.ldo = ldo; g.act = act;
+    g.h = out_size(H, s); g.w = out_size(W, s);
+    g.ON = (O + 15) / 16 * 16;
+    g.num_kb = (K + 63) / 64;
+    g.ksteps = K / 16;
+    g.cv_shift = -1;
+    for (int sh = 0; sh < 8; ++sh)
+        if ((1 << sh) == g.CV) g.cv_shift = sh;
+    g.inv_n = (65536u + (unsigned)N - 1) / (unsigned)N;
+    if ((long long)H * W * g.CV >= 0x7fffffffll) return 0;
+    int mr, mk;
+    gg_pn_extent(N, &mr, &mk);
+    auto waste = [&](int th, int tw) {
+        return (long long)((g.h + th - 1) / th * th) * ((g.w + tw - 1) / tw * tw) - (long long)g.h * g.w;
+    };
+    g.TH = 8; g.TW = 16;
+    if (waste(16, 8) < waste(8, 16)) { g.TH = 16; g.TW = 8; }
+    g.tw_shift = g.TW == 16 ? 4 : 3;
+    g.b_bytes = (uint32_t)g.ON * 128u;
+    g.a_bytes = (uint32_t)g.num_kb * 16384u;
+    g.rec_bytes = (uint32_t)(128 * N * 32);
+    g.tmem_cols = 32;
+    while (g.tmem_cols < (uint32_t)(2 * g.ON)) g.tmem_cols <<= 1;
+    // candidate plans (halo, input-tile buffers, operand buffers): pick the one with the most CTAs per SM (<= 3: registers),
+    // ties go to the deeper buffering / wider halo (listed first)
+    static const int cfg[5][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 2, 1}, {1, 1, 1}};
+    int best_ctas = 0;
+    GGGeom best = g;
+    size_t best_smem = 0;
+    static int env_plan = -2, env_ctas = -2;      // experiments: LDCONV_GG_PLAN=<plan index>, LDCONV_GG_CTAS=<CTAs per SM>
+    if (env_plan == -2) { const char* e = getenv("LDCONV_GG_PLAN"); env_plan = e ? atoi(e) : -1; }
+    if (env_ctas == -2) { const char* e = getenv("LDCONV_GG_CTAS"); env_ctas = e ? atoi(e) : -1; }
+    for (int ci = 0; ci < 5; ++ci) {
+        if (env_plan >= 0 && ci != env_plan) continue;
+        g.halo = cfg[ci][0]; g.XB = cfg[ci][1]; g.AB = cfg[ci][2];
+        g.THin = (g.TH - 1) * s + 2 + mr + 2 * g.halo;
+        g.TWin = (g.TW - 1) * s + 2 + mk + 2 * g.halo;
+        if (g.THin > 256 || g.TWin > 256) continue;
+        g.x_tx_bytes = (uint32_t)((size_t)g.THin * g.TWin * C * 2);
+        g.x_bytes = (g.x_tx_bytes + 127u) & ~127u;
+        uint32_t ofs = 0;
+        g.ofs_a = ofs; ofs += (uint32_t)g.AB * g.a_bytes;
+        g.ofs_b = ofs; ofs += (uint32_t)g.num_kb * g.b_bytes;
+        g.ofs_x = ofs; ofs += (uint32_t)g.XB * g.x_bytes;
+        g.ofs_rec = ofs; ofs += 2u * g.rec_bytes;
+        g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8u;
+        ofs = (ofs + 7u) & ~7u;
+        g.ofs_bar = ofs; ofs += 6u * 8u + 16u;
+        const size_t need = (size_t)ofs + 1024;
+        if (need > 225 * 1024) continue;
+        int ctas = (int)((227 * 1024) / (need + 1024));          // + the per-CTA reservation of the driver
+        if (ctas > 3) ctas = 3;
+        if (ctas > (int)(512u / g.tmem_cols)) ctas = (int)(512u / g.tmem_cols);
+        if (env_ctas >= 1 && ctas > env_ctas) ctas = env_ctas;
+        if (ctas > best_ctas) { best_ctas = ctas; best = g; best_smem = need; }
+    }
+    if (best_ctas == 0) return 0;
+    g = best;
+    g.per_sm = best_ctas;
+    g.tiles_h = (g.h + g.TH - 1) / g.TH;
+    g.tiles_w = (g.w + g.TW - 1) / g.TW;
+    const long long nt = (long long)B * g.tiles_h * g.tiles_w;
+    if (nt > 0x7fffffffll) return 0;
+    g.num_tiles = (int)nt;
+    { static int d = -1; if (d < 0) { const char* e = getenv("LDCONV_GG_DBG"); d = e ? atoi(e) : 0; } g.dbg = d; }
+    // tile / tiles_per_img and rem / tiles_w as __umulhi(x, ceil(2^32 / d)): exact while x * d < 2^32
+    const unsigned tpi = (unsigned)(g.tiles_h * g.tiles_w);
+    if (nt * tpi >= 0xffffffffll) return 0;
+    g.inv_img = tpi == 1 ? 0u : (unsigned)((0x100000000ull + tpi - 1) / tpi);
+    g.inv_tw = g.tiles_w == 1 ? 0u : (unsigned)((0x100000000ull + (unsigned)g.tiles_w - 1) / (unsigned)g.tiles_w);
+    *smem_bytes = best_smem;
+    *out = g;
+    return 1;
+}
+
+static int gg_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_GG"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
+int gather_gemm_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype)
+{
+    if (!gg_enabled() || dtype != LDCONV_BF16) return 0;
+    GGGeom g;
+    size_t smem;
+    return gg_geometry(B, C, H, W, N, s, O, ldo, LDCONV_ACT_SILU, &g, &smem);
+}
+
+int gather_gemm_fwd(const void* x, const float* off, const int* pn, const void* wt, const float* scale, const float* shift,
+                    void* out, int ldo, int B, int C, int H, int W, int N, int s, int O, int act, cudaStream_t st)
+{
+    GGGeom g;
+    size_t smem;
+    if (!gg_geometry(B, C, H, W, N, s, O, ldo, act, &g, &smem))
+        return fail(LDCONV_E_ARG, "gather+GEMM kernel: shape not covered (C=%d N=%d s=%d O=%d ldo=%d)", C, N, s, O, ldo);
+    if (!aligned16(x) || !aligned16(wt) || !aligned16(out))
+        return fail(LDCONV_E_ALIGN, "gather+GEMM kernel: x / wt / out must be 16-byte aligned");
+    CUtensorMap tmX, tmW;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)g.TWin, (cuuint32_t)g.THin, 1};
+        if (int e = encode_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)g.K, (cuuint64_t)O};
+        cuuint64_t gstr[1] = {(cuuint64_t)g.K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)g.ON};
+        if (int e = encode_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    auto kern = ldconv_gg_kernel<3>;      // <= 84 registers, no spills; a 64-register build for four CTAs per SM measured equal
+    LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = num_sms() * g.per_sm;
+    if (grid > g.num_tiles) grid = g.num_tiles;
+    kern<<<grid, kGGThreads, smem, st>>>(tmX, tmW, (const __nv_bfloat16*)x, off, pn, scale, shift, (__nv_bfloat16*)out, g);
+    LDC_LAUNCH_CHECK("ldconv_gg_kernel");
+    set_impl(LDCONV_IMPL_TCGEN05);
+    return LDCONV_OK;
+}
+
+}  // namespace ldc
+
+// Inference forward of everything after the offset conv (conv.py:369-408) in one kernel; `out` (B,h,w,O | ldo) may be a
+// channel slice of a wider NHWC buffer (ldo = its pixel stride in elements).
+LDC_API int ldconv_gather_gemm_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype)
+{
+    return ldc::gather_gemm_supported(B, C, H, W, N, s, O, ldo, dtype);
+}
+
+LDC_API int ldconv_gather_gemm_fwd(const void* x, const float* off, const int32_t* p_n, const void* wt, const float* scale,
+                                   const float* shift, void* out, int ldo, int B, int C, int H, int W, int N, int s, int O,
+                                   int act, int dtype, void* stream)
+{
+    using namespace ldc;
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_gather_gemm_fwd: bf16 only");
+    LDC_REQUIRE(x && off && p_n && wt && out, "ldconv_gather_gemm_fwd: null pointer");
+    LDC_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1 && N >= 1 && s >= 1 && O >= 1, "ldconv_gather_gemm_fwd: bad dims");
+    if (B == 0) return LDCONV_OK;
+    return gather_gemm_fwd(x, off, p_n, wt, scale, shift, out, ldo, B, C, H, W, N, s, O, act, (cudaStream_t)stream);
+}

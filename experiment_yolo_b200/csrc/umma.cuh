@@ -73,6 +73,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// Wait of a single control thread (TMA producer / MMA issuer) that shares its SM with issue-bound worker warps: sleep between
+// polls so the spin does not eat issue slots (profiles/r1_ncu_gg_L1_v1.txt: two spinning lanes executed 21 % of all
+// instructions of the kernel).  Still bounded: traps after ~4 s.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 128)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if ((++spins & 0xfff) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+
 // ---- proxies / fences -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }

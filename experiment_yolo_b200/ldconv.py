@@ -250,6 +250,8 @@ class LDConv(nn.Module):
     # than offset-conv(tcgen05) -> gather -> GEMM(tcgen05) on the YAML's shapes (profiles/r1_layers_*.jsonl); the small-C
     # one-kernel path (layer 0) is always used
     fused_tcgen05 = False
+    # inference: gather + GEMM + BN + SiLU as one persistent kernel after the tensor-core offset conv (ldconv_gather_gemm_fwd)
+    use_gather_gemm = True
 
     def __init__(self, inc, outc, num_param, stride=1, bias=None):
         super().__init__()
@@ -352,12 +354,17 @@ def infer_nhwc(mod: "LDConv", x: torch.Tensor, out: Optional[torch.Tensor] = Non
     else:
         _lib.check(L.ldconv_offset_conv_fwd(_ptr(x), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
                    "ldconv_offset_conv_fwd")
-    operand = torch.empty((M, K), device=x.device, dtype=x.dtype)
-    _lib.check(L.ldconv_gather_fwd(_ptr(x), _ptr(off), _ptr(pr.pn), _ptr(operand), None, None, B, C, H, W, N, s, dt, st),
-               "ldconv_gather_fwd")
     if out is None:
         out = torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
     ldo = out.stride(2)
+    if mod.use_gather_gemm and L.ldconv_gather_gemm_supported(B, C, H, W, N, s, O, ldo, dt):
+        # gather + GEMM + BN + SiLU in one persistent kernel: the (M, N*C) operand never reaches HBM
+        _lib.check(L.ldconv_gather_gemm_fwd(_ptr(x), _ptr(off), _ptr(pr.pn), _ptr(pr.wt), _ptr(scale), _ptr(shift), _ptr(out), ldo,
+                                            B, C, H, W, N, s, O, _lib.ACT_SILU, dt, st), "ldconv_gather_gemm_fwd")
+        return out
+    operand = torch.empty((M, K), device=x.device, dtype=x.dtype)
+    _lib.check(L.ldconv_gather_fwd(_ptr(x), _ptr(off), _ptr(pr.pn), _ptr(operand), None, None, B, C, H, W, N, s, dt, st),
+               "ldconv_gather_fwd")
     if dt == _lib.BF16 and K % 8 == 0 and O <= 256:
         _lib.check(L.ldconv_conv1x1_bn_act_fwd(_ptr(operand), K, _ptr(pr.wt), _ptr(scale), _ptr(shift), None, 0, _ptr(out), ldo,
                                                M, K, O, _lib.ACT_SILU, dt, st), "ldconv_conv1x1_bn_act_fwd")

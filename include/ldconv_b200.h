@@ -158,6 +158,18 @@ int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, cons
                      const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
                      int N, int s, int O, int act, int dtype, void* stream);
 
+/* Everything AFTER the offset conv in one persistent kernel (conv.py:369-408, eval mode, bf16): sampling grid, clamps,
+ * bilinear gather (TMA-staged tile + halo, L2 beyond it), the rearrange, the (N,1) conv as a tcgen05 GEMM whose operand tile
+ * is written by the gather warps straight into shared memory (never to HBM), folded BatchNorm + activation.
+ *   x (B,H,W,C) bf16; off (B,h,w,2N) fp32 (from ldconv_offset_conv_*); p_n (2N) int32; wt (O, N*C) bf16; scale/shift (O) fp32
+ *   out (B,h,w,O) bf16 with pixel stride ldo elements (ldo = O for a dense tensor; a channel slice of a concat buffer else)
+ * C % 8 == 0, (N*C) % 16 == 0, O % 16 == 0, O <= 256; ldconv_gather_gemm_supported returns 1 when the shape (and its
+ * shared-memory plan) is covered -- otherwise use ldconv_gather_fwd + ldconv_gemm_fwd. */
+int ldconv_gather_gemm_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype);
+int ldconv_gather_gemm_fwd(const void* x, const float* off, const int32_t* p_n, const void* wt, const float* scale,
+                           const float* shift, void* out, int ldo, int B, int C, int H, int W, int N, int s, int O, int act,
+                           int dtype, void* stream);
+
 /* ---- neighbours of LDConv in the DEAL-YOLO graph, same kernels, same ABI conventions ------------
  * `Conv` = Conv2d(k, no bias) + BatchNorm2d + SiLU (nn/modules/conv.py:41-59) with the BatchNorm folded to scale/shift.
  * x / out / residual may be channel slices of wider NHWC buffers: ld* are PIXEL strides in elements (multiples of 8), so

@@ -446,6 +446,50 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
         assert np.abs(outs[True] - outs[False]).max() <= 0.05 * max(1.0, np.abs(outs[False]).max())
 
 
+# ------------------------------------------------------------------------------- gather + GEMM in one kernel ----
+@pytest.mark.parametrize("C,O,N,s,H,W,B,sigma,pad", [
+    (16, 32, 3, 2, 64, 80, 2, 0.5, 0), (16, 32, 3, 2, 37, 53, 3, 3.0, 0), (32, 64, 3, 2, 40, 40, 2, 0.5, 64), (32, 32, 1, 1, 48, 48, 1, 0.5, 0),
+    (64, 64, 1, 1, 40, 24, 2, 1.0, 0), (64, 32, 1, 1, 17, 19, 2, 8.0, 32), (128, 64, 1, 1, 20, 20, 2, 0.5, 0), (32, 32, 3, 2, 160, 160, 9, 0.5, 0),
+    (16, 16, 1, 1, 160, 160, 4, 0.5, 0), (8, 16, 2, 1, 30, 30, 2, 0.5, 0), (32, 48, 5, 1, 20, 28, 1, 0.5, 0), (16, 32, 4, 2, 33, 47, 2, 1.0, 0)])
+def test_gather_gemm_kernel_matches_gather_then_gemm(C, O, N, s, H, W, B, sigma, pad):
+    """ldconv_gather_gemm_fwd (persistent tcgen05 kernel, operand tile written by the gather warps into shared memory) against
+    ldconv_gather_fwd + ldconv_gemm_fwd on the SAME offsets: the operand bits are identical (same make_point / bilinear code),
+    so only the accumulation order inside the tensor core may differ.  sigma = offset std in pixels (large values leave the
+    staged halo -> L2 path, and the image -> clamp quirk); pad > 0 writes into a channel slice of a wider NHWC buffer; the
+    9 x 160 x 160 case has more tiles than CTAs (persistent loop, both ring phases)."""
+    L = _lib.load()
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    M, K = B * h * w, N * C
+    ldo = O + pad
+    assert L.ldconv_gather_gemm_supported(B, C, H, W, N, s, O, ldo, _lib.BF16) == 1
+    g = torch.Generator(device=DEV).manual_seed(C * 31 + O * 7 + N + H)
+    x = torch.randn((B, H, W, C), device=DEV, generator=g).bfloat16()
+    off = torch.randn((B, h, w, 2 * N), device=DEV, generator=g) * sigma
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    wt = (torch.randn((O, K), device=DEV, generator=g) * (1.0 / K ** 0.5)).bfloat16()
+    scale = torch.rand(O, device=DEV, generator=g) + 0.5
+    shift = torch.randn(O, device=DEV, generator=g) * 0.2
+    operand = torch.empty((M, K), device=DEV, dtype=torch.bfloat16)
+    ref = torch.empty((M, O), device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.ldconv_gather_fwd(_ptr(x), _ptr(off), _ptr(pn), _ptr(operand), None, None, B, C, H, W, N, s, _lib.BF16, _stream()),
+               "ldconv_gather_fwd")
+    _lib.check(L.ldconv_gemm_fwd(_ptr(operand), _ptr(wt), _ptr(scale), _ptr(shift), _ptr(ref), None, None, None, M, K, O,
+                                 _lib.ACT_SILU, _lib.BF16, _stream()), "ldconv_gemm_fwd")
+    buf = torch.full((M, ldo), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = buf[:, pad:] if pad else buf
+    _lib.check(L.ldconv_gather_gemm_fwd(_ptr(x), _ptr(off), _ptr(pn), _ptr(wt), _ptr(scale), _ptr(shift), _ptr(out), ldo, B, C, H, W,
+                                        N, s, O, _lib.ACT_SILU, _lib.BF16, _stream()), "ldconv_gather_gemm_fwd")
+    torch.cuda.synchronize()
+    a, b = out.float().cpu().numpy(), ref.float().cpu().numpy()
+    assert _rel(a, b) <= 2e-3
+    assert np.abs(a - b).max() <= 0.02 * max(1.0, np.abs(b).max())
+    if pad:
+        assert float((buf[:, :pad].float() - 7.0).abs().max()) == 0.0      # the neighbouring channels are untouched
+    # and against an fp64 evaluation of the same GEMM on the gathered operand
+    z = (operand.double() @ wt.double().t()) * scale.double() + shift.double()
+    assert _rel(a, (z * torch.sigmoid(z)).cpu().numpy()) <= 6e-3
+
+
 # ------------------------------------------------------------------------------------- larger seeded cases vs oracle ----
 @pytest.mark.parametrize("C,O,N,s,H,W,B", [(16, 32, 3, 2, 40, 40, 2), (64, 64, 1, 1, 20, 20, 2), (32, 32, 5, 1, 16, 24, 2),
                                            (128, 64, 1, 1, 10, 10, 2), (3, 16, 3, 2, 64, 64, 2), (64, 128, 3, 2, 20, 20, 2)])
