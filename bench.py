@@ -10,7 +10,8 @@ channels_last; the batch is sharded over ranks with no collective (every LDConv 
   value     images/s with the batch already resident in HBM (CUDA-graph replay of the forward), max over ranks
   e2e       images/s through the public call `engine.FusedDealYolo(model)(images)` with HOST buffers: every step copies its uint8 batch from
             pinned host memory, normalises on the device, runs the forward and reads the detections back to the host
-  roofline  the LDConv gather kernels of one step (10 launches): algorithmic bytes / CUDA-event time
+  roofline  the LDConv gather+GEMM kernel at its largest launch of the step (and `roofline_gather`: the stand-alone gather
+            kernel): algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the eager CPU port of the reference path (oracle/ldconv_torch_port.py inside the same
             graph), all host threads, on a bounded sample (batch 8) of the same workload
 Nothing here reads /root/reference.
@@ -37,17 +38,50 @@ NC = 6
 
 # ---------------------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a thread every
+    ~2 ms (a 64-image step is ~4 ms, `nvidia-smi -lms` cannot sample that fast); nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop, self.nvml = index, [], None, False, None
+        self.sm, self.mx, self.reasons = [], 0.0, set()
+
+    def _poll_nvml(self):
+        n, h = self.nvml, self.handle
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -60,6 +94,9 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
+        self.stop = True
+        if self.nvml is not None:
+            self.t.join(timeout=1)
         if self.proc:
             self.proc.terminate()
             try:
@@ -68,7 +105,7 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons = list(self.sm), self.mx, set(self.reasons)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -80,7 +117,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------ CPU baseline
@@ -132,11 +169,17 @@ def workload_config(n_gpus: int, engine: str = "fused"):
 
 
 # --------------------------------------------------------------------------------------------------------------- GPU arm
-def ldconv_gather_roofline(model, x, peaks, iters: int):
-    """Time the gather kernel of each of the 10 LDConv layers at this step's shapes with CUDA events on the launching
-    stream, feeding it the real layer inputs; achieved = algorithmic bytes / time (SURVEY.md 8d formula)."""
+def ldconv_roofline(model, x, peaks, iters: int):
+    """Time the LDConv kernels of one step at this step's shapes with CUDA events on the launching stream, feeding them the
+    real layer inputs and offsets.  Two kernels are reported (SURVEY.md 8d formulas for the algorithmic bytes):
+      gather+GEMM  ldconv_gather_gemm_fwd, the kernel the inference step runs after the offset conv: x + offsets + out
+      gather       ldconv_gather_fwd, the stand-alone resampling kernel of the training path: x + offsets + operand
+    `roofline` (the contract's key) is the gather+GEMM kernel at its largest launch (layer 1: 16->32 channels, 3 samples,
+    stride 2, 320x320 -> 160x160, batch 64); `traffic` is that launch's dram__bytes_read + dram__bytes_write from the
+    committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)."""
     import torch
     from experiment_yolo_b200 import _lib
+    from experiment_yolo_b200.ldconv import _folded_bn
     L = _lib.load()
     feats = {}
     hooks = [m.register_forward_pre_hook(lambda mod, inp, i=m.i: feats.__setitem__(i, inp[0])) for m in model.ldconv_layers()]
@@ -145,42 +188,78 @@ def ldconv_gather_roofline(model, x, peaks, iters: int):
     for h in hooks:
         h.remove()
     st = torch.cuda.current_stream()
-    tot_bytes, tot_ms, per_layer = 0.0, 0.0, []
+
+    def timed(fn):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters + 1)]
+        for a, b in ev:
+            a.record(st)
+            fn()
+            b.record(st)
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ev[1:])
+        return ms[len(ms) // 2]
+
+    per_layer, tot = [], {"gg": [0.0, 0.0], "gather": [0.0, 0.0]}
     for m in model.ldconv_layers():
         xin = feats[m.i]
         B, C, H, W = xin.shape
-        N, s = m.num_param, int(m.stride)
+        N, s, O = m.num_param, int(m.stride), m.conv[0].out_channels
         h, w = (H - 1) // s + 1, (W - 1) // s + 1
         e = xin.element_size()
         xh = xin.permute(0, 2, 3, 1).contiguous()
         pr = m._prepared(xin.dtype, False)
+        scale, shift = _folded_bn(m.conv[1], xin.device)
         off = torch.empty((B, h, w, 2 * N), device=xin.device, dtype=torch.float32)
         dt = _lib.BF16 if xin.dtype == torch.bfloat16 else _lib.F32
         _lib.check(L.ldconv_offset_conv_fwd(xh.data_ptr(), pr.w_off.data_ptr(), pr.b_off.data_ptr(), off.data_ptr(), B, C, H,
                                             W, N, s, dt, st.cuda_stream), "ldconv_offset_conv_fwd")
+        row = {"layer": m.i, "C": C, "O": O, "N": N, "s": s, "hw": [h, w]}
         operand = torch.empty((B * h * w, N * C), device=xin.device, dtype=xin.dtype)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        for a, b in ev:
-            a.record(st)
-            _lib.check(L.ldconv_gather_fwd(xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(), operand.data_ptr(), None, None,
-                                           B, C, H, W, N, s, dt, st.cuda_stream), "ldconv_gather_fwd")
-            b.record(st)
-        torch.cuda.synchronize()
-        ms = sorted(a.elapsed_time(b) for a, b in ev)
-        ms = sum(ms[: max(1, len(ms) // 2 + 1)]) / max(1, len(ms) // 2 + 1) if len(ms) > 2 else sum(ms) / len(ms)
+        ms = timed(lambda: _lib.check(L.ldconv_gather_fwd(xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(), operand.data_ptr(),
+                                                          None, None, B, C, H, W, N, s, dt, st.cuda_stream), "ldconv_gather_fwd"))
         nbytes = e * B * C * H * W + 4 * B * 2 * N * h * w + e * B * h * w * N * C
-        tot_bytes += nbytes
-        tot_ms += ms
-        per_layer.append({"layer": m.i, "C": C, "N": N, "s": s, "hw": [h, w], "MB": round(nbytes / 1e6, 1),
-                          "us": round(ms * 1e3, 1), "GBps": round(nbytes / ms / 1e6, 1)})
-    achieved = tot_bytes / tot_ms / 1e6
+        row.update({"gather_MB": round(nbytes / 1e6, 1), "gather_us": round(ms * 1e3, 1), "gather_GBps": round(nbytes / ms / 1e6, 1)})
+        if C >= 8:          # layer 0 (C = 3) runs the one-kernel small-C path in the step, not these kernels
+            tot["gather"][0] += nbytes
+            tot["gather"][1] += ms
+        if L.ldconv_gather_gemm_supported(B, C, H, W, N, s, O, O, dt):
+            out = torch.empty((B, h, w, O), device=xin.device, dtype=xin.dtype)
+            ms = timed(lambda: _lib.check(L.ldconv_gather_gemm_fwd(xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(),
+                                                                   pr.wt.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                                   out.data_ptr(), O, B, C, H, W, N, s, O, _lib.ACT_SILU, dt,
+                                                                   st.cuda_stream), "ldconv_gather_gemm_fwd"))
+            nb = e * B * C * H * W + 4 * B * 2 * N * h * w + e * B * h * w * O
+            row.update({"gg_MB": round(nb / 1e6, 1), "gg_us": round(ms * 1e3, 1), "gg_GBps": round(nb / ms / 1e6, 1),
+                        "gg_TFLOPs": round(2.0 * B * h * w * N * C * O / ms / 1e9, 1)})
+            tot["gg"][0] += nb
+            tot["gg"][1] += ms
+        per_layer.append(row)
     peak = peaks.get("hbm_gbs", 6650.0)
-    return {"bound": "hbm", "kernel": "ldconv gather_fwd (10 launches of one step)", "achieved": round(achieved, 1),
-            "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else
-            "B200_PROFILING.md fallback 6650 (of fallback)", "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "frac_of_8TBs_nominal": round(achieved / 8000.0, 4), "traffic": None,
-            "algorithmic_bytes_per_launch": round(tot_bytes / len(per_layer)), "avg_us_per_launch":
-            round(tot_ms * 1e3 / len(per_layer), 2), "per_layer": per_layer}
+    src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 (of fallback)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+    except Exception:
+        pass
+    big = max((r for r in per_layer if "gg_us" in r), key=lambda r: r["gg_MB"], default=None)
+    roof = None
+    if big is not None:
+        ach = big["gg_MB"] * 1e3 / big["gg_us"]
+        roof = {"bound": "hbm", "kernel": f"ldconv_gg_kernel (LDConv gather + GEMM + BN + SiLU, layer {big['layer']}: the largest "
+                "LDConv launch of the step)", "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "frac_of_8TBs_nominal": round(ach / 8000.0, 4),
+                "traffic": traffic.get("ldconv_gg_kernel_layer1_bytes"), "algorithmic_bytes_per_launch": round(big["gg_MB"] * 1e6),
+                "us_per_launch": big["gg_us"], "timing": "CUDA events on the launching stream, median of %d" % iters,
+                "all_gg_launches": {"GBps": round(tot["gg"][0] / max(tot["gg"][1], 1e-9) / 1e6, 1),
+                                    "us_per_step": round(tot["gg"][1] * 1e3, 1)},
+                "per_layer": per_layer}
+    g_ach = tot["gather"][0] / max(tot["gather"][1], 1e-9) / 1e6
+    roof_gather = {"bound": "hbm", "kernel": "gather_fwd_tiled_kernel (stand-alone LDConv resampling, training path; the 9 launches "
+                   "with C >= 16 of one step)", "achieved": round(g_ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
+                   "frac": round(g_ach / peak, 4), "frac_of_8TBs_nominal": round(g_ach / 8000.0, 4),
+                   "traffic": traffic.get("gather_fwd_tiled_kernel_layer1_bytes"),
+                   "us_per_step": round(tot["gather"][1] * 1e3, 1)}
+    return roof, roof_gather
 
 
 def run_gpu_arm(args):
@@ -309,7 +388,7 @@ def run_gpu_arm(args):
 
     line = None
     if rank == 0:
-        roof = ldconv_gather_roofline(model, xs[0], peaks, iters=5)
+        roof, roof_gather = ldconv_roofline(model, xs[0], peaks, iters=7)
         cpu_best, cpu_mean, cpu_sec, cores = cpu_port_images_per_s(CPU_SAMPLE_BATCH, 3, 1) if world == 1 else (None,) * 4
         line = {"metric": "images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4),
@@ -320,7 +399,7 @@ def run_gpu_arm(args):
                         else "DealYolo.forward", "input": "uint8 NCHW batch in pinned host memory, normalised on device",
                         "result": "decoded detections (B,10,33600) bf16 copied to pinned host memory"},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "clocks": clk.summary(), "roofline": roof}
+                "clocks": clk.summary(), "roofline": roof, "roofline_gather": roof_gather}
         if cpu_mean is not None:
             line["cpu_baseline"] = {"value": round(cpu_mean, 3), "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"batch {CPU_SAMPLE_BATCH} x 3 forwards of the same graph in fp32 (eager CPU port "

@@ -41,7 +41,7 @@ struct TileGeom {
 };
 
 // Two phases per CTA (the kernel was issue-bound when every (sample, channel vector) item redid the coordinate arithmetic
-// and its integer divisions -- profiles/r1_ncu_gather_L1_v1.csv: 432 instructions per item, issue slots 79 % busy):
+// and its integer divisions -- profiles/r1_ncu_gatherL1v1.txt: 432 instructions per item, issue slots 79 % busy):
 //   phase 1  one thread per SAMPLE (pixel, n) of the tile: make_point once, the four corner positions as 16-byte-vector
 //            offsets (into the staged tile, or into the image when a corner lies outside tile + halo) and the four bilinear
 //            weights go to shared memory.  Runs while the TMA load of the tile is in flight.

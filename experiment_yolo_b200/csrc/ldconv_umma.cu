@@ -46,7 +46,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a)
 
 // Epilogue of one 16-column chunk of one accumulator row: raw accumulator -> `pre`, affine + activation (+ residual) -> `out`.
 // aff_s = shared-space address of the (scale, shift) pair of column c0 (explicit LDS: the generic loads this replaces were
-// the top stall of the kernel, profiles/r1_ncu_gemm_L1_v2.txt).
+// the top stall of the kernel, profiles/r1_ncu_gemmL1b.txt).
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
                                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
                                                     const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store)

@@ -74,7 +74,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // Wait of a single control thread (TMA producer / MMA issuer) that shares its SM with issue-bound worker warps: sleep between
-// polls so the spin does not eat issue slots (profiles/r1_ncu_gg_L1_v1.txt: two spinning lanes executed 21 % of all
+// polls so the spin does not eat issue slots (profiles/r1_ncu_ggL1v1.txt: two spinning lanes executed 21 % of all
 // instructions of the kernel).  Still bounded: traps after ~4 s.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 128)
 {
