@@ -124,7 +124,7 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 const float z = fmaf(acc[o0 + e], s_sc[o0 + e], s_sc[O + o0 + e]);
-                y[e] = act == LDCONV_ACT_SILU ? silu(z) : z;
+                y[e] = act == LDCONV_ACT_SILU ? (sizeof(T) == 2 ? silu_fast(z) : silu(z)) : z;   // bf16: one MUFU, error below bf16's ulp
             }
             Vec16<T>::store(dst + o0, y);
         }
