@@ -342,9 +342,11 @@ static int conv3x3_smem_plan(int Cin, int Cout, int s, int* xbufs_out, int* stag
     long long xb = (budget - (long long)stages * (long long)per_stage) / (long long)x_bytes;
     if (xb < 2) { stages = 3; xb = (budget - (long long)stages * (long long)per_stage) / (long long)x_bytes; }
     if (xb < 1) { stages = 2; xb = (budget - (long long)stages * (long long)per_stage) / (long long)x_bytes; }
-    // a single input-tile buffer deadlocks the ring (seen at Cin=128, stride 2: the 17x33x128 tile leaves room for one
-    // buffer only, the kernel hit the bounded-wait trap); such shapes take the CUDA-core offset conv instead
-    if (xb < 2) return 0;
+    if (xb < 1) return 0;
+    // Cin = 128 at stride 2 (17x33x128 input tile, one buffer) faulted with "unspecified launch failure" in the config-2 sweep
+    // (profiles/r1_sweep_config2.jsonl was taken with this guard); until that is understood such shapes take the CUDA-core
+    // offset conv instead
+    if (s == 2 && Cin > 64) return 0;
     long long want = (64 * 1024 + x_bytes - 1) / x_bytes + 1;
     if (want < 2) want = 2;
     if (xb > want) xb = want;

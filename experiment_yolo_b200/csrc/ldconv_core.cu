@@ -676,6 +676,9 @@ offset_conv_bwd_weight_kernel(const float* __restrict__ goff, const T* __restric
     }
 }
 
+int offconv_bwd_data_fast(const float* goff, const float* w, float* grad_x, int B, int C, int H, int W, int N, int s,
+                          cudaStream_t st);
+
 template <typename T, int ON>
 static int launch_offset_conv_bwd(const float* goff, const T* x, const float* w, float* grad_x, float* grad_w,
                                   float* grad_b, int B, int C, int H, int W, int N, int s, cudaStream_t st)
@@ -683,9 +686,13 @@ static int launch_offset_conv_bwd(const float* goff, const T* x, const float* w,
     const int h = out_size(H, s), wo = out_size(W, s);
     const long long M = (long long)B * h * wo;
     if (grad_x) {
-        const long long total = (long long)B * H * W * ((C + 3) / 4);
-        offset_conv_bwd_data_kernel<ON><<<cdiv(total, 256), 256, 0, st>>>(goff, w, grad_x, B, C, H, W, h, wo, N, s, total);
-        LDC_LAUNCH_CHECK("offset_conv_bwd_data_kernel");
+        if (offconv_bwd_data_fast(goff, w, grad_x, B, C, H, W, N, s, st)) {      // weights in smem, 16-byte RMW (ldconv_offconv_bwd.cu)
+            LDC_LAUNCH_CHECK("offconv_bwd_data_kernel");
+        } else {
+            const long long total = (long long)B * H * W * ((C + 3) / 4);
+            offset_conv_bwd_data_kernel<ON><<<cdiv(total, 256), 256, 0, st>>>(goff, w, grad_x, B, C, H, W, h, wo, N, s, total);
+            LDC_LAUNCH_CHECK("offset_conv_bwd_data_kernel");
+        }
     }
     if (grad_w || grad_b) {
         const int slabs = (C + 15) / 16;

@@ -207,8 +207,15 @@ class _LDConvFunction(torch.autograd.Function):
                                        B, C, H, W, N, s, dt, st), "ldconv_gather_bwd")
         grad_w_off = torch.zeros((3, 3, C, 2 * N), device=dev, dtype=torch.float32)
         grad_b_off = torch.zeros((2 * N,), device=dev, dtype=torch.float32)
-        _lib.check(L.ldconv_offset_conv_bwd(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
-                                            _ptr(grad_b_off), B, C, H, W, N, s, dt, st), "ldconv_offset_conv_bwd")
+        ws_bytes = int(L.ldconv_offset_conv_bwd_workspace_bytes(B, C, H, W, N, s, dt)) if dt == _lib.BF16 else 0
+        if ws_bytes > 0:      # bf16: weight gradient as a tensor-core reduction over an L2-resident im2col workspace
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            _lib.check(L.ldconv_offset_conv_bwd_tc(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
+                                                   _ptr(grad_b_off), _ptr(ws), ws_bytes, B, C, H, W, N, s, dt, st),
+                       "ldconv_offset_conv_bwd_tc")
+        else:
+            _lib.check(L.ldconv_offset_conv_bwd(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
+                                                _ptr(grad_b_off), B, C, H, W, N, s, dt, st), "ldconv_offset_conv_bwd")
         grad_x = grad_x32.to(xdtype).permute(0, 3, 1, 2) if need_x else None
         grad_p_w = grad_w_off.permute(3, 2, 0, 1).contiguous().to(pw_dtype)
         grad_p_b = grad_b_off.to(pw_dtype)

@@ -147,6 +147,16 @@ int ldconv_gather_bwd(const void* grad_operand, const void* x, const float* off,
 int ldconv_offset_conv_bwd(const float* grad_off, const void* x, const float* w, float* grad_x, float* grad_w,
                            float* grad_b, int B, int C, int H, int W, int N, int s, int dtype, void* stream);
 
+/* The same backward for bf16 activations with the weight gradient on the tensor cores: grad_off is rounded once to bf16, the
+ * 3x3 neighbourhoods are laid out chunk by chunk as an (rows, 9C) matrix in `workspace` (sized to stay in L2) and reduced over
+ * the output pixels by the MN-major tcgen05 kernel; the data gradient runs out of shared-memory weights.  Same outputs and
+ * accumulate semantics as ldconv_offset_conv_bwd.  `workspace`: device memory of at least
+ * ldconv_offset_conv_bwd_workspace_bytes(...) bytes, owned by the caller (the library never allocates). */
+size_t ldconv_offset_conv_bwd_workspace_bytes(int B, int C, int H, int W, int N, int s, int dtype);
+int ldconv_offset_conv_bwd_tc(const float* grad_off, const void* x, const float* w, float* grad_x, float* grad_w, float* grad_b,
+                              void* workspace, size_t workspace_bytes, int B, int C, int H, int W, int N, int s, int dtype,
+                              void* stream);
+
 /* Inference forward of the whole module (conv.py:366-410, eval mode) in ONE kernel; the resampled operand never touches
  * HBM.  Two kernels behind it: C <= 4 (the first layer) runs one thread per output pixel on CUDA cores; C % 16 == 0 with
  * bf16 runs offset conv + grid + gather into shared memory in the tcgen05 operand layout + UMMA with TMEM accumulators +

@@ -446,6 +446,54 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
         assert np.abs(outs[True] - outs[False]).max() <= 0.05 * max(1.0, np.abs(outs[False]).max())
 
 
+# ---------------------------------------------------------------------------------- offset conv backward (bf16) ----
+@pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 1, 1, 24, 24, 2), (64, 3, 2, 21, 33, 2), (3, 3, 2, 64, 48, 2),
+                                         (16, 5, 1, 160, 160, 8), (48, 2, 1, 17, 19, 1), (128, 9, 2, 20, 20, 1)])
+def test_offset_conv_backward_tensor_core_path(C, N, s, H, W, B):
+    """ldconv_offset_conv_bwd_tc (im2col workspace + MN-major tcgen05 reduction for the weight gradient, shared-memory-weight
+    kernel for the data gradient) against torch's fp64 conv2d autograd on the same bf16-rounded x (conv.py:356 backward), and
+    against the CUDA-core entry point ldconv_offset_conv_bwd.  The 8 x 160 x 160 case spans two im2col chunks."""
+    L = _lib.load()
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    g = torch.Generator(device=DEV).manual_seed(C * 13 + N + H)
+    x = torch.randn((B, H, W, C), device=DEV, generator=g).bfloat16()
+    goff = torch.randn((B, h, w, 2 * N), device=DEV, generator=g)
+    wk = torch.randn((3, 3, C, 2 * N), device=DEV, generator=g) * 0.1           # the library's (3,3,C,2N) layout
+    gx0 = torch.randn((B, H, W, C), device=DEV, generator=g)                    # grad_x accumulates on top of this
+    # fp64 reference through autograd
+    xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wk.double().permute(3, 2, 0, 1).contiguous().requires_grad_(True)      # (2N,C,3,3)
+    br = torch.zeros(2 * N, device=DEV, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(xr, wr, br, stride=s, padding=1)
+    y.backward(goff.double().permute(0, 3, 1, 2))
+    ref_gx = gx0.double() + xr.grad.permute(0, 2, 3, 1)
+    ref_gw = wr.grad.permute(2, 3, 1, 0)                                        # -> (3,3,C,2N)
+    ref_gb = br.grad
+
+    def run(tc):
+        gx = gx0.clone()
+        gw = torch.zeros((3, 3, C, 2 * N), device=DEV)
+        gb = torch.zeros((2 * N,), device=DEV)
+        if tc:
+            nbytes = int(L.ldconv_offset_conv_bwd_workspace_bytes(B, C, H, W, N, s, _lib.BF16))
+            assert nbytes > 0
+            ws = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+            _lib.check(L.ldconv_offset_conv_bwd_tc(_ptr(goff), _ptr(x), _ptr(wk), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(ws), nbytes,
+                                                   B, C, H, W, N, s, _lib.BF16, _stream()), "ldconv_offset_conv_bwd_tc")
+        else:
+            _lib.check(L.ldconv_offset_conv_bwd(_ptr(goff), _ptr(x), _ptr(wk), _ptr(gx), _ptr(gw), _ptr(gb), B, C, H, W, N, s,
+                                                _lib.BF16, _stream()), "ldconv_offset_conv_bwd")
+        torch.cuda.synchronize()
+        return gx, gw, gb
+
+    for tc in (True, False):
+        gx, gw, gb = run(tc)
+        assert _rel(gx.cpu().numpy(), ref_gx.cpu().numpy()) <= 1e-5                     # fp32 FMAs
+        assert _rel(gb.cpu().numpy(), ref_gb.cpu().numpy()) <= 1e-4
+        # tensor-core path rounds grad_off to bf16 once (relative 2^-9 per term, averaged over M terms)
+        assert _rel(gw.cpu().numpy(), ref_gw.cpu().numpy()) <= (4e-3 if tc else 1e-4)
+
+
 # ------------------------------------------------------------------------------- gather + GEMM in one kernel ----
 @pytest.mark.parametrize("C,O,N,s,H,W,B,sigma,pad", [
     (16, 32, 3, 2, 64, 80, 2, 0.5, 0), (16, 32, 3, 2, 37, 53, 3, 3.0, 0), (32, 64, 3, 2, 40, 40, 2, 0.5, 64), (32, 32, 1, 1, 48, 48, 1, 0.5, 0),
