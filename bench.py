@@ -156,7 +156,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": round(mean, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(mean, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -277,7 +277,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+        if "BENCH_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().ldconv_device_check(), "ldconv_device_check")
     peaks = {}
@@ -404,14 +405,27 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": round(cpu_mean, 3), "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"batch {CPU_SAMPLE_BATCH} x 3 forwards of the same graph in fp32 (eager CPU port "
                                               f"of the reference LDConv, best {cpu_best:.2f} images/s)"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else a library prints lands on stderr (see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # keep stdout to the one JSON line: NCCL prints its version banner to fd 1, torch / ctypes libraries may print too
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
