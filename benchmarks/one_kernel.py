@@ -21,6 +21,10 @@ def main():
     ap.add_argument("--direct", action="store_true")
     ap.add_argument("--ffma", action="store_true")
     ap.add_argument("--sigma", type=float, default=0.5)
+    ap.add_argument("--cin", type=int, default=32, help="--kernel conv3x3 / conv1x1: input channels")
+    ap.add_argument("--cout", type=int, default=32)
+    ap.add_argument("--hw", type=int, default=160)
+    ap.add_argument("--stride", type=int, default=1)
     args = ap.parse_args()
     L = _lib.load()
     dev = torch.device("cuda", 0)
@@ -42,8 +46,22 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, int(args.direct))
     L.ldconv_set_flag(_lib.FLAG_FORCE_FFMA, int(args.ffma))
+    if args.kernel in ("conv3x3", "conv1x1"):
+        ci, co, hw, cs = args.cin, args.cout, args.hw, args.stride
+        ho = (hw - 1) // cs + 1
+        xc = torch.randn((B, hw, hw, ci), device=dev, generator=g).to(dtype)
+        kk = 9 if args.kernel == "conv3x3" else 1
+        wc = (torch.randn((co, kk * ci), device=dev, generator=g) * 0.05).to(dtype)
+        sc, sh = torch.ones(co, device=dev), torch.zeros(co, device=dev)
+        oc = torch.empty((B, ho, ho, co), device=dev, dtype=dtype)
     for _ in range(args.reps):
-        if args.kernel == "gemm":
+        if args.kernel == "conv3x3":
+            _lib.check(L.ldconv_conv3x3_bn_act_fwd(xc.data_ptr(), ci, wc.data_ptr(), sc.data_ptr(), sh.data_ptr(), None, 0,
+                                                   oc.data_ptr(), co, B, ci, hw, hw, co, cs, _lib.ACT_SILU, dt, st))
+        elif args.kernel == "conv1x1":
+            _lib.check(L.ldconv_conv1x1_bn_act_fwd(xc.data_ptr(), ci, wc.data_ptr(), sc.data_ptr(), sh.data_ptr(), None, 0,
+                                                   oc.data_ptr(), co, B * hw * hw, ci, co, _lib.ACT_SILU, dt, st))
+        elif args.kernel == "gemm":
             _lib.check(L.ldconv_gemm_fwd(operand.data_ptr(), wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
                                          None, None, None, M, K, O, _lib.ACT_SILU, dt, st))
         elif args.kernel == "gather":

@@ -59,7 +59,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 {
     using T = __nv_bfloat16;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* sI = smem + g.ofs_i;        // [stages][128 rows][128 B]  im2col ring, SWIZZLE_128B
     uint8_t* sB = smem + g.ofs_b;        // resident: [num_kb][ON][128 B]; streamed: [stages][ON][128 B]
     uint8_t* sX = smem + g.ofs_x;        // [2][THin][TWin][Cin]

@@ -45,7 +45,7 @@ fused_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 {
     using T = __nv_bfloat16;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* sA = smem;                                            // [num_kb][128 rows][128 B], SWIZZLE_128B
     uint8_t* sB = smem + g.ofs_b;                                  // [num_kb][ON rows][128 B], SWIZZLE_128B (TMA)
     T* sX = reinterpret_cast<T*>(smem + g.ofs_x);                  // [THin][TWin][C]

@@ -107,7 +107,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int G)
 {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
     const int b_bytes = ON * kBlockK * 2;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)stages * kABytes;

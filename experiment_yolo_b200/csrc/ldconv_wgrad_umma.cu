@@ -41,7 +41,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                   int M, int K, int O, int nb, int chunks_total)
 {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
     const uint32_t g_bytes = 2u * kWgRows * 128u;                 // two 64-column boxes of grad_pre
     const uint32_t a_bytes = (uint32_t)nb * kWgRows * 128u;       // nb 64-column boxes of the operand
     const uint32_t stage_bytes = g_bytes + a_bytes;
