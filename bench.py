@@ -293,6 +293,8 @@ def run_gpu_arm(args):
     model = dealyolo.channels_last_(model.to(dev).bfloat16().eval())
     # the public inference call: the fused executor (every Conv / C2f / SPPF / ScalSeq / Detect block and every LDConv through
     # the library's kernels); --engine eager runs the plain torch graph around the CUDA LDConv instead
+    if args.micro_batch:
+        engine.FusedDealYolo.micro_batch = args.micro_batch
     run = engine.FusedDealYolo(model) if args.engine == "fused" else model
 
     B = PER_GPU_BATCH
@@ -432,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default="fused", choices=["fused", "eager"])
+    ap.add_argument("--micro-batch", type=int, default=0, help="images per pass of the fused executor (0 = its default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -312,6 +312,10 @@ class LDConv(nn.Module):
         _check_input(x)
         conv, bn = self.conv[0], self.conv[1]
         training = self.training
+        if x.shape[0] == 0 and not (training and bn.track_running_stats):
+            # empty batch: the reference returns an empty (0, O, h, w) tensor in eval mode (nothing to launch)
+            s_ = int(self.stride)
+            return x.new_empty((0, conv.out_channels, (x.shape[2] - 1) // s_ + 1, (x.shape[3] - 1) // s_ + 1))
         momentum = bn.momentum
         if training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)

@@ -446,6 +446,67 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
         assert np.abs(outs[True] - outs[False]).max() <= 0.05 * max(1.0, np.abs(outs[False]).max())
 
 
+# ------------------------------------------------------------------------------------------------- edge cases ----
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_empty_batch_and_single_pixel(dtype):
+    """B = 0 (the reference returns an empty (0,O,h,w) tensor), a 1x1 image (every sample clamps onto the only pixel: the
+    reference's border doubling for all N samples) and a 2x3 image at stride 2, eval mode, against the oracle."""
+    torch.manual_seed(5)
+    for (C, O, N, s, H, W) in [(16, 32, 3, 2, 1, 1), (16, 16, 5, 1, 1, 1), (32, 16, 3, 2, 2, 3)]:
+        mod = E.LDConv(C, O, N, s)
+        with torch.no_grad():
+            mod.p_conv.weight.normal_(0, 0.3)
+            mod.conv[1].running_mean.normal_(0, 0.3)
+            mod.conv[1].running_var.uniform_(0.5, 1.5)
+        rnd = (lambda t: t.detach().bfloat16().float().numpy()) if dtype == torch.bfloat16 else (lambda t: t.detach().numpy())
+        bn = mod.conv[1]
+        prm = oracle.LDConvParams(rnd(mod.p_conv.weight), rnd(mod.p_conv.bias), rnd(mod.conv[0].weight), rnd(bn.weight),
+                                  rnd(bn.bias), rnd(bn.running_mean), rnd(bn.running_var), N, s, bn.eps, bn.momentum)
+        x = torch.randn(2, C, H, W)
+        f = oracle.forward(rnd(x), prm, training=False)
+        dmod = mod.to(DEV).to(dtype).eval()
+        with torch.no_grad():
+            y = dmod(x.to(DEV).to(dtype))
+            y0 = dmod(torch.empty(0, C, H, W, device=DEV, dtype=dtype))
+        assert tuple(y0.shape) == (0, O, (H - 1) // s + 1, (W - 1) // s + 1)
+        if dtype == torch.float32:
+            assert np.abs(y.cpu().numpy() - f["out"]).max() <= 1e-4
+        else:
+            assert _rel(y.float().cpu().numpy(), f["out"]) <= 1e-2
+
+
+def test_offsets_far_outside_the_image_bf16_kernels_agree():
+    """Offsets of +-50 px on a 24x40 image: every sample leaves the staged halo and most leave the image (all corners clamp).
+    The TMA-tiled gather, the direct gather and the gather+GEMM kernel must produce the same operand / output."""
+    L = _lib.load()
+    B, C, H, W, N, s, O = 2, 32, 24, 40, 3, 1, 32
+    h, w = H, W
+    M, K = B * h * w, N * C
+    g = torch.Generator(device=DEV).manual_seed(77)
+    x = torch.randn((B, H, W, C), device=DEV, generator=g).bfloat16()
+    off = (torch.rand((B, h, w, 2 * N), device=DEV, generator=g) - 0.5) * 100.0
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    ops = []
+    for direct in (0, 1):
+        L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, direct)
+        op = torch.empty((M, K), device=DEV, dtype=torch.bfloat16)
+        _lib.check(L.ldconv_gather_fwd(_ptr(x), _ptr(off), _ptr(pn), _ptr(op), None, None, B, C, H, W, N, s, _lib.BF16, _stream()),
+                   "ldconv_gather_fwd")
+        ops.append(op)
+    L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, 0)
+    assert torch.equal(ops[0], ops[1])
+    wt = (torch.randn((O, K), device=DEV, generator=g) * 0.1).bfloat16()
+    sc, sh = torch.ones(O, device=DEV), torch.zeros(O, device=DEV)
+    ref = torch.empty((M, O), device=DEV, dtype=torch.bfloat16)
+    out = torch.empty((M, O), device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.ldconv_gemm_fwd(_ptr(ops[0]), _ptr(wt), _ptr(sc), _ptr(sh), _ptr(ref), None, None, None, M, K, O, _lib.ACT_SILU,
+                                 _lib.BF16, _stream()), "ldconv_gemm_fwd")
+    _lib.check(L.ldconv_gather_gemm_fwd(_ptr(x), _ptr(off), _ptr(pn), _ptr(wt), _ptr(sc), _ptr(sh), _ptr(out), O, B, C, H, W, N, s,
+                                        O, _lib.ACT_SILU, _lib.BF16, _stream()), "ldconv_gather_gemm_fwd")
+    torch.cuda.synchronize()
+    assert _rel(out.float().cpu().numpy(), ref.float().cpu().numpy()) <= 2e-3
+
+
 # ---------------------------------------------------------------------------------- offset conv backward (bf16) ----
 @pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 1, 1, 24, 24, 2), (64, 3, 2, 21, 33, 2), (3, 3, 2, 64, 48, 2),
                                          (16, 5, 1, 160, 160, 8), (48, 2, 1, 17, 19, 1), (128, 9, 2, 20, 20, 1)])
