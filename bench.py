@@ -295,6 +295,8 @@ def run_gpu_arm(args):
     # the library's kernels); --engine eager runs the plain torch graph around the CUDA LDConv instead
     if args.micro_batch:
         engine.FusedDealYolo.micro_batch = args.micro_batch
+    if os.environ.get("BENCH_SERIAL_HEAD") == "1":       # A/B: Detect branches back to back on one stream
+        engine._Detect.parallel_branches = False
     run = engine.FusedDealYolo(model) if args.engine == "fused" else model
 
     B = PER_GPU_BATCH

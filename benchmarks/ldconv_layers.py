@@ -86,6 +86,15 @@ def main():
                        args.iters, flush)
             rec("offset_conv_fwd", "tcgen05", ms, bytes_off, 2.0 * M * 9 * C * 2 * N)
 
+        if s == 2 and L.ldconv_offset_conv_s2d_supported(C, N, H, W, dt):
+            from experiment_yolo_b200.ldconv import _prepare, base_grid
+            pw = (w_off.permute(3, 2, 0, 1).contiguous()).to(dtype)          # (2N,C,3,3)
+            pr = _prepare(pw, b_off, torch.zeros(8, C, N, 1, device=dev), base_grid(N), dtype, False)
+            ms = timed(lambda: _lib.check(L.ldconv_offset_conv_s2d_fwd(x.data_ptr(), pr.w_off_s2d.data_ptr(), b_off.data_ptr(),
+                                                                       off_out.data_ptr(), B, C, H, W, N, dt, st)),
+                       args.iters, flush)
+            rec("offset_conv_fwd", "tcgen05_s2d", ms, bytes_off, 2.0 * M * 9 * C * 2 * N)
+
         bytes_g = e * B * C * H * W + 4 * B * 2 * N * h * w + e * M * K
         for variant, direct in (("tma_tile", 0), ("direct", 1)):
             L.ldconv_set_flag(_lib.FLAG_GATHER_DIRECT, direct)

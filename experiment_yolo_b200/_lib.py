@@ -34,6 +34,8 @@ SIGNATURES = {
     "ldconv_offset_conv_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "ldconv_offset_conv_tc_supported": (_i, [_i] * 4),
     "ldconv_offset_conv_tc_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
+    "ldconv_offset_conv_s2d_supported": (_i, [_i] * 5),
+    "ldconv_offset_conv_s2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 6 + [_vp]),
     "ldconv_gather_fwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_gemm_fwd": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
     "ldconv_bn_finalize": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _vp]),

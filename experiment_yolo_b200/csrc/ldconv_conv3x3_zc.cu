@@ -12,6 +12,12 @@
 // stride-byte-offset = one staged row, the tile's swizzle mode, and (for starts that are not aligned to the swizzle
 // pattern) the matrix-base-offset field.  Nine taps x Cin/16 MMAs accumulate the whole convolution in TMEM.
 //
+// Stride 2 (TAPS = 4): the same kernel on the space-to-depth view x'[i, j, (sy, sx, c)] = x[2i + sy, 2j + sx, c] (4C channels,
+// H/2 x W/2): a 3x3 / stride-2 / pad-1 conv over x is a 2x2 / stride-1 conv over x' with taps (row' i-1 | i) x (col' j-1 | j)
+// and zero weights for the (row' i-1, sy = 0) / (col' j-1, sx = 0) combinations.  x' is never materialised: a 5-D tensor map
+// with dimensions (2C, sy, W/2, H/2, B) lets the TMA unit stage the two sy halves of every pixel' (2C channels each, one
+// swizzle row per pixel) as two channel blocks, exactly like the two 64-channel blocks of a 128-channel stride-1 tile.
+//
 //   warp 0     TMA: input tiles (+1 pixel halo, zero fill = padding) into a ring; the weights once (resident)
 //   warp 1     one thread issues the MMAs of a tile back to back; tcgen05.commit frees the tile slot and publishes the accumulator
 //   warps 2-9  epilogue: tcgen05.ld -> folded BatchNorm / bias -> activation (-> + residual) -> 16-byte stores
@@ -62,7 +68,7 @@ __device__ __forceinline__ uint64_t zc_desc(uint32_t addr, uint32_t sbo_bytes, u
     return d;
 }
 
-template <int MODE, int CIN>
+template <int MODE, int CIN, int TAPS = 9>
 __global__ void __launch_bounds__(kZcThreads, 2)
 conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const float* __restrict__ scale, const float* __restrict__ shift,
@@ -115,9 +121,14 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
                 tr(it, 100000 + it * 100);
                 mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
-                for (int hf = 0; hf < g.halves; ++hf)
-                    tma_load_4d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], hf * (g.pb / 2),
-                                tj * kZcTileW - 1, ti * kZcTileH - 1, b);
+                for (int hf = 0; hf < g.halves; ++hf) {
+                    if (TAPS == 4)      // space-to-depth view: dims (2C, sy, W/2, H/2, B); half hf = the sy = hf rows
+                        tma_load_5d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], 0, hf,
+                                    tj * kZcTileW - 1, ti * kZcTileH - 1, b);
+                    else
+                        tma_load_4d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], hf * (g.pb / 2),
+                                    tj * kZcTileW - 1, ti * kZcTileH - 1, b);
+                }
             }
         }
     } else if (warp == 1) {
@@ -126,8 +137,11 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             // per MMA when the descriptors are rebuilt with run-time arithmetic), so everything that depends only on the
             // channel count is a compile-time constant and the 9 * CIN/16 MMAs of a tile are fully unrolled: per MMA one add
             // for the A descriptor (tile base + constant) and one for the B descriptor.
-            constexpr int PB = CIN >= 64 ? 128 : CIN * 2;          // bytes per pixel row
-            constexpr int HALVES = CIN >= 64 ? CIN / 64 : 1;
+            // bytes per pixel row / channel blocks per pixel.  Space-to-depth (TAPS = 4, CIN = 4C): a block is one sy half of
+            // the pixel' (2C channels = CIN bytes), always two blocks: a TMA box row narrower than the swizzle span is padded to
+            // the span in shared memory (measured), so [sy][sx][c] cannot be one 128-byte row when 2C = 32 channels
+            constexpr int PB = TAPS == 4 ? CIN : (CIN >= 64 ? 128 : CIN * 2);
+            constexpr int HALVES = TAPS == 4 ? 2 : (CIN >= 64 ? CIN / 64 : 1);
             constexpr int KS = PB / 32;                            // K steps of 16 per pixel row
             constexpr uint32_t LAYOUT = PB == 128 ? 2u : (PB == 64 ? 4u : 6u);
             const uint32_t idesc = make_idesc_bf16(128, g.ON);
@@ -149,13 +163,14 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
                 const uint64_t descA = descA_hi | (uint64_t)(x0 + (uint32_t)xb * xstep);
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
                     for (int hf = 0; hf < HALVES; ++hf) {
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             constexpr int dummy = 0; (void)dummy;
-                            const uint32_t a_delta = (uint32_t)((((tap / 3) * kZcTWs + (tap % 3)) * PB + ks * 32) >> 4);
+                            constexpr int TW_ = TAPS == 9 ? 3 : 2;      // taps per row of the filter
+                            const uint32_t a_delta = (uint32_t)((((tap / TW_) * kZcTWs + (tap % TW_)) * PB + ks * 32) >> 4);
                             const int k = tap * CIN + hf * (PB / 2) + ks * 16;
                             const uint32_t b_delta = (uint32_t)(k >> 6) * b16 + (uint32_t)(((k & 63) * 2) >> 4);
                             mma_bf16_ss(d_tmem, descA + (uint64_t)(a_delta + (uint32_t)hf * hstep), descB0 + (uint64_t)b_delta, idesc,
@@ -341,7 +356,111 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     return LDCONV_OK;
 }
 
+// ---- stride-2 offset conv on the space-to-depth view (TAPS = 4) ---------------------------------------------------------
+int conv3x3_zc_s2d_supported(int C, int N, int H, int W)
+{
+    if (!zc_enabled()) return 0;
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("LDCONV_CONV_S2D"); en = e ? atoi(e) : 1; }
+    if (!en) return 0;
+    return (C == 16 || C == 32) && N >= 1 && 2 * N <= 16 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2;
+}
+
+// x (B,H,W,C) bf16 dense; wt (2N, 16C) bf16 with k = ((ty*2+tx)*2+sy)*2C + sx*C + c (see the header comment); bias (2N) fp32
+// or NULL; off (B,H/2,W/2,2N) fp32
+int conv3x3_zc_s2d(const void* x, const void* wt, const float* bias, float* off, int B, int C, int H, int W, int N,
+                   cudaStream_t st)
+{
+    if (!aligned16(x) || !aligned16(wt)) return fail(LDCONV_E_ALIGN, "offset conv (space-to-depth): x / wt must be 16-byte aligned");
+    const int Cin = 4 * C, Cout = 2 * N, h = H / 2, w = W / 2;
+    ZcGeom g;
+    g.Cin = Cin; g.Cout = Cout; g.ON = 16; g.H = h; g.W = w; g.B = B;
+    g.tiles_h = (h + kZcTileH - 1) / kZcTileH;
+    g.tiles_w = (w + kZcTileW - 1) / kZcTileW;
+    const long long nt = (long long)B * g.tiles_h * g.tiles_w;
+    if (nt > 0x7fffffffll) return fail(LDCONV_E_ARG, "offset conv (space-to-depth): too many tiles");
+    g.num_tiles = (int)nt;
+    g.pb = Cin;                       // one sy half of a pixel' = 2C channels = Cin bytes (64 or 128)
+    g.halves = 2;
+    g.layout = g.pb == 128 ? 2 : 4;
+    g.num_kb = (4 * Cin + 63) / 64;
+    g.b_bytes = (uint32_t)g.ON * 128;
+    const uint32_t half_tx = (uint32_t)kZcTHs * kZcTWs * g.pb;
+    const uint32_t half_pitch = (half_tx + 1023) & ~1023u;
+    g.x_tx_bytes = half_tx * g.halves;
+    g.x_bytes = half_pitch * g.halves;
+    g.ldo = Cout; g.ldr = 0;
+    g.base_mode = 0;
+    { const char* e = getenv("LDCONV_DBG"); g.dbg = e ? atoi(e) : 0; }
+    const size_t wbytes = (size_t)g.num_kb * g.b_bytes;
+    // two CTAs (two MMA issuers) per SM when the weights + two input tiles fit in half the shared memory (C = 16)
+    const bool two = wbytes + 2 * (size_t)g.x_bytes + 4096 <= 104 * 1024;
+    long long xb = ((long long)(two ? 104 : 220) * 1024 - (long long)wbytes - 4096) / (long long)g.x_bytes;
+    if (xb > kZcMaxX) xb = kZcMaxX;
+    if (xb > 3) xb = 3;
+    if (xb < 2) return fail(LDCONV_E_ARG, "offset conv (space-to-depth): does not fit shared memory");
+    g.xbufs = (int)xb;
+    uint32_t ofs = 0;
+    g.ofs_x = ofs; ofs += (uint32_t)g.xbufs * g.x_bytes;
+    g.ofs_b = ofs; ofs += (uint32_t)wbytes;
+    g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8;
+    ofs = (ofs + 7) & ~7u;
+    g.ofs_bar = ofs; ofs += (uint32_t)(2 * kZcMaxX + 5) * 8 + 16;
+    const size_t smem = ofs + 1024;
+    g.tmem_cols = 32;
+
+    CUtensorMap tmX, tmW;
+    {
+        // x viewed as (2C [sx, c], sy, W/2, H/2, B): innermost two dimensions make pixel' = [sy][sx][c]
+        cuuint64_t gdim[5] = {(cuuint64_t)(2 * C), 2, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t gstr[4] = {(cuuint64_t)W * C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[5] = {(cuuint32_t)(2 * C), 1, (cuuint32_t)kZcTWs, (cuuint32_t)kZcTHs, 1};
+        if (int e = encode_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gdim, gstr, box,
+                               g.pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    }
+    {
+        const int K = 4 * Cin;
+        cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)g.ON};
+        if (int e = encode_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
+    int grid = num_sms() * (two ? 2 : 1);
+    if (grid > g.num_tiles) grid = g.num_tiles;
+    if (Cin == 64) {
+        auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS, 64, 4>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, nullptr, bias, nullptr, off, LDCONV_ACT_NONE, g);
+    } else {
+        auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS, 128, 4>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, nullptr, bias, nullptr, off, LDCONV_ACT_NONE, g);
+    }
+    LDC_LAUNCH_CHECK("conv3x3_zc_kernel (space-to-depth)");
+    set_impl(LDCONV_IMPL_TCGEN05);
+    return LDCONV_OK;
+}
+
 }  // namespace ldc
+
+// LDConv's offset conv at stride 2 (conv.py:356,368) as a zero-copy tcgen05 implicit GEMM on the space-to-depth view of x.
+// w_s2d (2N, 16*C) bf16: the reference's (2N,C,3,3) weight scattered into k = ((ty*2+tx)*2+sy)*2C + sx*C + c with
+// (ty, sy) = (0,1), (1,0), (1,1) for ky = 0, 1, 2 (same for kx -> (tx, sx)) and zeros elsewhere; the Python module builds it.
+LDC_API int ldconv_offset_conv_s2d_supported(int C, int N, int H, int W, int dtype)
+{
+    return dtype == LDCONV_BF16 ? ldc::conv3x3_zc_s2d_supported(C, N, H, W) : 0;
+}
+
+LDC_API int ldconv_offset_conv_s2d_fwd(const void* x, const void* w_s2d, const float* bias, float* off, int B, int C, int H, int W,
+                                       int N, int dtype, void* stream)
+{
+    using namespace ldc;
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_offset_conv_s2d_fwd: bf16 only");
+    LDC_REQUIRE(x && w_s2d && off && B >= 0, "ldconv_offset_conv_s2d_fwd: bad arguments");
+    LDC_REQUIRE(conv3x3_zc_s2d_supported(C, N, H, W), "ldconv_offset_conv_s2d_fwd: shape not covered (C=%d N=%d H=%d W=%d)", C, N, H, W);
+    if (B == 0) return LDCONV_OK;
+    return conv3x3_zc_s2d(x, w_s2d, bias, off, B, C, H, W, N, (cudaStream_t)stream);
+}
 
 LDC_API int ldconv_debug_trace_zc(long long* host_out, int max_pairs)
 {

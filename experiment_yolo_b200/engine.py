@@ -176,26 +176,55 @@ class _ScalSeq:
 
 
 class _Detect:
+    # The six conv chains of the head (3 pyramid levels x {box, class} branch) are independent until the decode: they are forked
+    # onto side streams (captured as parallel branches of the CUDA graph) so that the small P3 / P4 kernels and the two
+    # branches of a level share the GPU instead of running back to back.  Every buffer is allocated on the calling stream
+    # before the fork, the side streams only launch kernels, and the join precedes any reuse.
+    parallel_branches = True
+
     def __init__(self, m: dealyolo.Detect):
         self.nc, self.reg_max, self.no = m.nc, m.reg_max, m.no
         self.stride = [float(s) for s in m.stride]
         self.box = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv2]
         self.cls = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv3]
+        self.streams = None
+
+    @staticmethod
+    def _chain(x, ps, bufs):
+        t = conv3x3(x, ps[0], bufs[0])
+        t = conv3x3(t, ps[1], bufs[1])
+        return conv1x1(t, ps[2], bufs[2], act="none")
 
     def __call__(self, xs):
         L = _lib.load()
         B = xs[0].shape[0]
         total = sum(x.shape[1] * x.shape[2] for x in xs)
         y = torch.empty((B, 4 + self.nc, total), device=xs[0].device, dtype=torch.bfloat16)
+        bufs = []
+        for lvl, x in enumerate(xs):
+            _, H, W, _ = x.shape
+            bb = [_new(x, B, H, W, self.box[lvl][0].cout), _new(x, B, H, W, self.box[lvl][1].cout), _new(x, B, H, W, 4 * self.reg_max)]
+            cb = [_new(x, B, H, W, self.cls[lvl][0].cout), _new(x, B, H, W, self.cls[lvl][1].cout), _new(x, B, H, W, self.nc)]
+            bufs.append((bb, cb))
+        cur = torch.cuda.current_stream(xs[0].device)
+        if self.parallel_branches:
+            if self.streams is None:
+                self.streams = [torch.cuda.Stream(xs[0].device) for _ in range(2 * len(xs))]
+            for k, st in enumerate(self.streams):
+                lvl, br = k // 2, k % 2
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    self._chain(xs[lvl], self.box[lvl] if br == 0 else self.cls[lvl], bufs[lvl][br])
+            for st in self.streams:
+                cur.wait_stream(st)
+        else:
+            for lvl, x in enumerate(xs):
+                self._chain(x, self.box[lvl], bufs[lvl][0])
+                self._chain(x, self.cls[lvl], bufs[lvl][1])
         feats, a0 = [], 0
         for lvl, x in enumerate(xs):
             _, H, W, _ = x.shape
-            b = conv3x3(x, self.box[lvl][0], _new(x, B, H, W, self.box[lvl][0].cout))
-            b = conv3x3(b, self.box[lvl][1], _new(x, B, H, W, self.box[lvl][1].cout))
-            b = conv1x1(b, self.box[lvl][2], _new(x, B, H, W, 4 * self.reg_max), act="none")
-            c = conv3x3(x, self.cls[lvl][0], _new(x, B, H, W, self.cls[lvl][0].cout))
-            c = conv3x3(c, self.cls[lvl][1], _new(x, B, H, W, self.cls[lvl][1].cout))
-            c = conv1x1(c, self.cls[lvl][2], _new(x, B, H, W, self.nc), act="none")
+            b, c = bufs[lvl][0][2], bufs[lvl][1][2]
             _lib.check(L.ldconv_detect_decode(b.data_ptr(), c.data_ptr(), y.data_ptr(), B, H, W, self.nc, self.reg_max,
                                               self.stride[lvl], a0, total, _lib.BF16, _stream()), "ldconv_detect_decode")
             feats.append((b, c))

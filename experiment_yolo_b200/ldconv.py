@@ -64,7 +64,7 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 
 class _Prepared:
     """Per-call operand forms of the parameters (tiny tensors; cached by the module while the parameters are unchanged)."""
-    __slots__ = ("w_off", "b_off", "w_off_tc", "wt", "wt_t", "pn", "key")
+    __slots__ = ("w_off", "b_off", "w_off_tc", "w_off_s2d", "wt", "wt_t", "pn", "key")
 
 
 def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepared:
@@ -78,6 +78,18 @@ def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepar
     # tensor-core offset conv (bf16): (2N,C,3,3) -> (2N, 3,3,C) -> (2N, 9C), k = tap*C + c
     pr.w_off_tc = (p_w.detach().to(dtype).permute(0, 2, 3, 1).reshape(2 * N, 9 * C).contiguous()
                    if dtype == torch.bfloat16 else None)
+    # stride-2 offset conv on the space-to-depth view (ldconv_offset_conv_s2d_fwd): (2N,C,3,3) -> (2N, ty, tx, sy, sx, C),
+    # ky = 0,1,2 -> (ty, sy) = (0,1), (1,0), (1,1); the unused (ty=0, sy=0) / (tx=0, sx=0) combinations stay zero
+    pr.w_off_s2d = None
+    if dtype == torch.bfloat16 and C in (16, 32) and 2 * N <= 16:
+        w6 = torch.zeros((2 * N, 2, 2, 2, 2, C), device=p_w.device, dtype=dtype)
+        tmap = ((0, 1), (1, 0), (1, 1))
+        pw = p_w.detach().to(dtype)
+        for ky in range(3):
+            for kx in range(3):
+                (ty, sy), (tx, sx) = tmap[ky], tmap[kx]
+                w6[:, ty, tx, sy, sx, :] = pw[:, :, ky, kx]
+        pr.w_off_s2d = w6.reshape(2 * N, 16 * C).contiguous()
     # (N,1) conv weight (O,C,N,1) -> (O, N*C), k = n*C + c: the order the NHWC gather produces
     pr.wt = c_w.detach().to(dtype).reshape(O, C, N).permute(0, 2, 1).reshape(O, N * C).contiguous()
     pr.wt_t = pr.wt.t().contiguous() if need_wt_t else None
@@ -108,7 +120,10 @@ class _LDConvFunction(torch.autograd.Function):
 
         xh = _nhwc(x)
         off = torch.empty((B, h, w, 2 * N), device=dev, dtype=torch.float32)
-        if pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
+        if s == 2 and pr.w_off_s2d is not None and L.ldconv_offset_conv_s2d_supported(C, N, H, W, dt):
+            _lib.check(L.ldconv_offset_conv_s2d_fwd(_ptr(xh), _ptr(pr.w_off_s2d), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, dt, st),
+                       "ldconv_offset_conv_s2d_fwd")
+        elif pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
             _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(xh), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt,
                                                    st), "ldconv_offset_conv_tc_fwd")
         else:
@@ -359,7 +374,10 @@ def infer_nhwc(mod: "LDConv", x: torch.Tensor, out: Optional[torch.Tensor] = Non
         return out
     M, K = B * h * w, N * C
     off = torch.empty((B, h, w, 2 * N), device=x.device, dtype=torch.float32)
-    if pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
+    if s == 2 and pr.w_off_s2d is not None and L.ldconv_offset_conv_s2d_supported(C, N, H, W, dt):
+        _lib.check(L.ldconv_offset_conv_s2d_fwd(_ptr(x), _ptr(pr.w_off_s2d), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, dt, st),
+                   "ldconv_offset_conv_s2d_fwd")
+    elif pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
         _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(x), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
                    "ldconv_offset_conv_tc_fwd")
     else:

@@ -86,6 +86,14 @@ int ldconv_offset_conv_tc_supported(int C, int N, int stride, int dtype);
 int ldconv_offset_conv_tc_fwd(const void* x, const void* w_bf16, const float* bias, float* off,
                               int B, int C, int H, int W, int N, int stride, int dtype, void* stream);
 
+/* Stride 2 only: the same conv as a ZERO-COPY tcgen05 implicit GEMM on the space-to-depth view x'[i,j,(sy,sx,c)] =
+ * x[2i+sy, 2j+sx, c] (never materialised: a 5-D TMA tensor map produces it), i.e. a 2x2 / stride-1 conv with 4C channels.
+ * w_s2d (2N, 16*C) bf16: the reference's (2N,C,3,3) weight scattered to k = ((ty*2+tx)*2+sy)*2C + sx*C + c with
+ * (ty,sy) = (0,1),(1,0),(1,1) for ky = 0,1,2 (likewise kx -> (tx,sx)), zeros elsewhere.  C in {16, 32}, H and W even. */
+int ldconv_offset_conv_s2d_supported(int C, int N, int H, int W, int dtype);
+int ldconv_offset_conv_s2d_fwd(const void* x, const void* w_s2d, const float* bias, float* off, int B, int C, int H, int W,
+                               int N, int dtype, void* stream);
+
 /* conv.py:369-407 + 413-503: sampling grid p = p_0 + p_n + offset, floor / independent clamps, four corner indices,
  * four bilinear weights, the four gathers, the bilinear sum and the 'b c h w n -> b c (h n) w' rearrange, fused.
  *   x (B,H,W,C) dtype; off (B,h,w,2N) fp32; p_n (2N) int32 device table

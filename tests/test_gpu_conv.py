@@ -44,6 +44,36 @@ def test_offset_conv_tensor_core_vs_oracle(C, N, s, H, W, B):
     assert np.abs(got - want).max() <= 2e-4 * max(1.0, float(np.abs(want).max()))
 
 
+@pytest.mark.parametrize("C,N,H,W,B", [(16, 3, 40, 56, 2), (32, 3, 38, 42, 2), (16, 1, 16, 24, 1), (32, 5, 160, 160, 2), (16, 8, 2, 2, 3),
+                                       (16, 3, 320, 320, 2)])
+def test_offset_conv_stride2_space_to_depth_vs_oracle(C, N, H, W, B):
+    """ldconv_offset_conv_s2d_fwd: the stride-2 offset conv (conv.py:356,368) as a zero-copy tcgen05 GEMM on the space-to-depth
+    view (5-D TMA map), weights scattered by the module's own _prepare -- against the CPU oracle's offset conv and against the
+    im2col tensor-core kernel on the same inputs."""
+    from experiment_yolo_b200.ldconv import _prepare, base_grid
+    L = _lib.load()
+    assert L.ldconv_offset_conv_s2d_supported(C, N, H, W, _lib.BF16) == 1
+    g = torch.Generator().manual_seed(C + N + H)
+    x = torch.randn(B, C, H, W, generator=g).bfloat16()
+    w = (torch.randn(2 * N, C, 3, 3, generator=g) * 0.1).bfloat16()
+    b = torch.randn(2 * N, generator=g).bfloat16().float()      # _prepare rounds the bias through the activation dtype
+    want = oracle.offset_conv(x.float().numpy(), w.float().numpy(), b.numpy(), N, 2)            # (B,2N,h,w)
+    h, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    pr = _prepare(w.to(DEV), b.to(DEV), torch.zeros(8, C, N, 1, device=DEV), base_grid(N), torch.bfloat16, False)
+    assert pr.w_off_s2d is not None
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    off = torch.full((B, h, wo, 2 * N), float("nan"), device=DEV)
+    _lib.check(L.ldconv_offset_conv_s2d_fwd(_p(xd), _p(pr.w_off_s2d), _p(pr.b_off), _p(off), B, C, H, W, N, _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    got = off.cpu().numpy().transpose(0, 3, 1, 2)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, float(np.abs(want).max()))
+    off2 = torch.empty_like(off)
+    _lib.check(L.ldconv_offset_conv_tc_fwd(_p(xd), _p(pr.w_off_tc), _p(pr.b_off), _p(off2), B, C, H, W, N, 2, _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    assert float((off - off2).abs().max()) <= 2e-4 * max(1.0, float(off2.abs().max()))
+
+
 @pytest.mark.parametrize("Cin,Cout,s,H,W,B,res", [(16, 16, 1, 40, 40, 2, True), (32, 32, 1, 37, 21, 2, True), (64, 64, 1, 20, 20, 2, False),
                                                   (32, 64, 1, 24, 40, 1, False), (128, 64, 1, 17, 17, 2, False), (64, 32, 2, 40, 40, 1, False),
                                                   (16, 48, 1, 8, 8, 3, False), (64, 64, 1, 80, 80, 2, True), (256, 128, 1, 10, 12, 1, False)])
