@@ -43,6 +43,35 @@ inline int out_size(int H, int s) { return (H - 1) / s + 1; }
 inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 int num_sms();
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------------
+// The inference step is ~85 short kernels (20-150 us each); with plain stream order every kernel pays its prologue (barrier
+// init, TMEM allocation, tensor-map fetch, pipeline fill) after the previous one has drained.  Kernels launched through
+// launch_pdl() may start while the previous kernel is still running: they execute pdl_launch_dependents() first (so the next
+// launch can be scheduled as early as possible), run their prologue, and block in pdl_wait() until every prerequisite grid has
+// completed and flushed -- BEFORE the first access to any global memory a predecessor may have written (parameters included:
+// in training the folded BatchNorm scale / shift come from the preceding kernel).  LDCONV_PDL=0 launches without the attribute.
+int pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- element types ---------------------------------------------------------------------------------------------------
 template <typename T> struct Elem;
 template <> struct Elem<float> {

@@ -80,6 +80,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const bool tracing = (g.dbg & 32) && blockIdx.x == 0 && lane == 0 && warp < 3;
     Tracer tr{s_trace + (warp < 3 ? warp : 0) * kTraceN * 2, 0, tracing};
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -99,6 +100,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    pdl_wait();       // everything below may read what the previous kernel wrote
     for (int o = threadIdx.x; o < g.ON; o += blockDim.x)
         sAff[o] = make_float2((scale && o < g.Cout) ? scale[o] : 1.f, (shift && o < g.Cout) ? shift[o] : 0.f);
     for (int t = threadIdx.x; t < g.num_kb * 8; t += blockDim.x) {
@@ -436,11 +438,13 @@ int conv3x3_umma(const void* x, int ldx, const void* wt, const float* scale, con
     if (mode == CONV_MODE_OFFSETS) {
         auto kern = conv3x3_umma_kernel<CONV_MODE_OFFSETS>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kConvThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kConvThreads), smem, st, tmX, tmW, scale, shift, (const __nv_bfloat16*)residual,
+                            out, act, g));
     } else {
         auto kern = conv3x3_umma_kernel<CONV_MODE_BN_ACT>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kConvThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);
+        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kConvThreads), smem, st, tmX, tmW, scale, shift, (const __nv_bfloat16*)residual,
+                            out, act, g));
     }
     LDC_LAUNCH_CHECK("conv3x3_umma_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);

@@ -91,6 +91,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __shared__ long long s_trace[3 * kZcTraceN * 2];
     const bool tracing = (g.dbg & 32) && blockIdx.x == 0 && lane == 0 && warp < 3;
     ZcTracer tr{s_trace + (warp < 3 ? warp : 0) * kZcTraceN * 2, 0, tracing};
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -100,6 +101,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    pdl_wait();       // everything below may read what the previous kernel wrote
     for (int o = threadIdx.x; o < g.ON; o += blockDim.x)
         sAff[o] = make_float2((scale && o < g.Cout) ? scale[o] : 1.f, (shift && o < g.Cout) ? shift[o] : 0.f);
     tc_fence_before_sync();
@@ -339,7 +341,8 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     do {                                                                                                               \
         auto kern = conv3x3_zc_kernel<MODE_, CIN_>;                                                                    \
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, scale, shift, (const __nv_bfloat16*)residual, out, act, g);     \
+        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, scale, shift,                        \
+                            (const __nv_bfloat16*)residual, out, act, g));                                            \
     } while (0)
 #define LDC_ZC_CIN(MODE_)                                                                                              \
     switch (Cin) {                                                                                                     \
@@ -430,11 +433,13 @@ int conv3x3_zc_s2d(const void* x, const void* wt, const float* bias, float* off,
     if (Cin == 64) {
         auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS, 64, 4>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, nullptr, bias, nullptr, off, LDCONV_ACT_NONE, g);
+        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, (const float*)nullptr, bias,
+                            (const __nv_bfloat16*)nullptr, (void*)off, (int)LDCONV_ACT_NONE, g));
     } else {
         auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS, 128, 4>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kZcThreads, smem, st>>>(tmX, tmW, nullptr, bias, nullptr, off, LDCONV_ACT_NONE, g);
+        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, (const float*)nullptr, bias,
+                            (const __nv_bfloat16*)nullptr, (void*)off, (int)LDCONV_ACT_NONE, g));
     }
     LDC_LAUNCH_CHECK("conv3x3_zc_kernel (space-to-depth)");
     set_impl(LDCONV_IMPL_TCGEN05);

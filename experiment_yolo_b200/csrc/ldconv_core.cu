@@ -23,6 +23,13 @@ int fail(int code, const char* fmt, ...)
     va_end(ap);
     return code;
 }
+int pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_PDL"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 int num_sms()
 {
     static thread_local int cached = 0;

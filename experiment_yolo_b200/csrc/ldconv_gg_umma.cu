@@ -97,6 +97,7 @@ ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tma_load_4d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, j0 * g.s - g.halo, i0 * g.s - g.halo, b);
     };
 
+    pdl_launch_dependents();
     if (tid == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
@@ -105,6 +106,7 @@ ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    pdl_wait();       // everything below may read what the previous kernel wrote (x, offsets, scale / shift)
     for (int o = tid; o < g.ON; o += kGGThreads)
         sAff[o] = make_float2((scale && o < g.O) ? scale[o] : 1.f, (shift && o < g.O) ? shift[o] : 0.f);
     tc_fence_before_sync();
@@ -457,7 +459,8 @@ int gather_gemm_fwd(const void* x, const float* off, const int* pn, const void* 
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * g.per_sm;
     if (grid > g.num_tiles) grid = g.num_tiles;
-    kern<<<grid, kGGThreads, smem, st>>>(tmX, tmW, (const __nv_bfloat16*)x, off, pn, scale, shift, (__nv_bfloat16*)out, g);
+    LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kGGThreads), smem, st, tmX, tmW, (const __nv_bfloat16*)x, off, pn, scale, shift,
+                        (__nv_bfloat16*)out, g));
     LDC_LAUNCH_CHECK("ldconv_gg_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     return LDCONV_OK;

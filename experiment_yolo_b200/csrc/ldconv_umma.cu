@@ -122,6 +122,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int num_units = (num_tiles + G - 1) / G;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -130,6 +131,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    pdl_wait();       // everything below may read what the previous kernel wrote (operand, scale / shift)
     for (int o = threadIdx.x; o < ON; o += blockDim.x)
         s_affine[o] = make_float2((scale && o < O) ? scale[o] : 1.f, (shift && o < O) ? shift[o] : 0.f);
     tc_fence_before_sync();
@@ -299,9 +301,9 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     const int num_units = (num_tiles + G - 1) / G;
     if (grid > num_units) grid = num_units;
     const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
-    umma_gemm_kernel<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, scale, shift, (__nv_bfloat16*)out, (__nv_bfloat16*)pre,
-                                                       (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages,
-                                                       act, tmem_cols, vec_store, ldo, ldr, G);
+    LDC_CUDA(launch_pdl(umma_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
+                        (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
+                        vec_store, ldo, ldr, G));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
