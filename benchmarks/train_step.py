@@ -42,7 +42,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     x = torch.rand((B, 3, args.img, args.img), device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     targets = [torch.zeros((B, 70, args.img // s, args.img // s), device=dev) for s in (4, 8, 16)]
-    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.01, momentum=0.937, nesterov=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.937, nesterov=True)
     red = xdist.FlatGradAllReduce(model.parameters())
 
     def step():
@@ -52,6 +53,7 @@ def main():
         loss = xdist.surrogate_detection_loss(outs, targets)
         loss.backward()
         red()
+        torch.nn.utils.clip_grad_norm_(params, max_norm=10.0)      # reference optimizer_step, engine/trainer.py:952
         opt.step()
         return loss
 

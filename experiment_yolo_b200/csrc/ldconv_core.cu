@@ -554,15 +554,64 @@ gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const floa
             acc_r += g[e] * (-q.ak0 * x00[e] + q.ak1 * x11[e] - q.ak1 * x01[e] + q.ak0 * x10[e]);
             acc_k += g[e] * (-q.ar0 * x00[e] + q.ar1 * x11[e] + q.ar0 * x01[e] - q.ar1 * x10[e]);
         }
-        // scatter_add_ of the four GatherBackward nodes; V floats per corner as 128-bit vector reductions
+        // scatter_add_ of the four GatherBackward nodes; V floats per corner as 128-bit vector reductions.
+        // Corners that coincide (a clamped axis: r0 == r1 and / or k0 == k1, the reference's border doubling) are merged in
+        // the thread first; lanes of the warp that still hit the SAME address (many samples clamped onto one border pixel --
+        // the regime a diverging offset conv drives the layer into) are aggregated with match.any + shuffles so that one lane
+        // issues the reduction for all of them.
+        if (grad_x != nullptr) {
+            const bool same_r = q.r0 == q.r1, same_k = q.k0 == q.k1;
+            if (same_r && same_k) {
 #pragma unroll
-        for (int e0 = 0; e0 < V; e0 += 4) {
-            const int cnt = V - e0 < 4 ? V - e0 : 4;
-            if (grad_x == nullptr) break;
-            red_add_vec(grad_x + o00 + e0, v00 + e0, cnt);
-            red_add_vec(grad_x + o11 + e0, v11 + e0, cnt);
-            red_add_vec(grad_x + o01 + e0, v01 + e0, cnt);
-            red_add_vec(grad_x + o10 + e0, v10 + e0, cnt);
+                for (int e = 0; e < V; ++e) v00[e] = (v00[e] + v11[e]) + (v01[e] + v10[e]);
+            } else if (same_r) {           // (r0,k0) == (r1,k0) and (r0,k1) == (r1,k1)
+#pragma unroll
+                for (int e = 0; e < V; ++e) { v00[e] += v10[e]; v01[e] += v11[e]; }
+            } else if (same_k) {           // (r0,k0) == (r0,k1) and (r1,k0) == (r1,k1)
+#pragma unroll
+                for (int e = 0; e < V; ++e) { v00[e] += v01[e]; v10[e] += v11[e]; }
+            }
+            auto emit = [&](size_t o, float (&v)[V], bool clamped) {
+                if (clamped) {                                  // lanes here: the warp's clamped corners only
+                    const unsigned act = __activemask();
+                    const unsigned peers = __match_any_sync(act, (unsigned long long)o);
+                    if (__any_sync(act, (peers & (peers - 1)) != 0)) {          // some address is shared: aggregate
+                        const int lane = threadIdx.x & 31;
+                        const int leader = __ffs(peers) - 1;
+                        float acc[V];
+#pragma unroll
+                        for (int e = 0; e < V; ++e) acc[e] = 0.f;
+                        for (unsigned m = act; m; m &= m - 1) {
+                            const int src = __ffs(m) - 1;
+                            const bool take = (peers >> src) & 1u;
+#pragma unroll
+                            for (int e = 0; e < V; ++e) {
+                                const float t = __shfl_sync(act, v[e], src);
+                                if (take) acc[e] += t;
+                            }
+                        }
+                        if (lane != leader) return;
+#pragma unroll
+                        for (int e = 0; e < V; ++e) v[e] = acc[e];
+                    }
+                }
+#pragma unroll
+                for (int e0 = 0; e0 < V; e0 += 4) red_add_vec(grad_x + o + e0, v + e0, V - e0 < 4 ? V - e0 : 4);
+            };
+            if (same_r && same_k) {
+                emit(o00, v00, true);
+            } else if (same_r) {
+                emit(o00, v00, true);
+                emit(o01, v01, true);
+            } else if (same_k) {
+                emit(o00, v00, true);
+                emit(o10, v10, true);
+            } else {
+                emit(o00, v00, false);
+                emit(o11, v11, false);
+                emit(o01, v01, false);
+                emit(o10, v10, false);
+            }
         }
     }
     // grad_off: reduce over the channel lanes of the sample.  group = CV when CV is a power of two <= 32 (the lanes of

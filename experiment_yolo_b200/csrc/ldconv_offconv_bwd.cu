@@ -238,9 +238,11 @@ int offconv_bwd_tc(const float* goff, const __nv_bfloat16* x, const float* w, fl
     float* dW = reinterpret_cast<float*>(ws + g16_bytes + col_bytes);
 
     if (grad_x) {       // data gradient first: it only needs grad_off
-        if (!offconv_bwd_data_fast(goff, w, grad_x, B, C, H, W, N, s, st))
-            return fail(LDCONV_E_ARG, "offset conv backward: data-gradient kernel does not cover C=%d num_param=%d", C, N);
-        LDC_LAUNCH_CHECK("offconv_bwd_data_kernel");
+        if (offconv_bwd_data_fast(goff, w, grad_x, B, C, H, W, N, s, st)) {
+            LDC_LAUNCH_CHECK("offconv_bwd_data_kernel");
+        } else {        // weights do not fit shared memory (e.g. C=256, N=9): the generic kernel of ldconv_core.cu
+            if (int e = ldconv_offset_conv_bwd(goff, x, w, grad_x, nullptr, nullptr, B, C, H, W, N, s, LDCONV_BF16, (void*)st)) return e;
+        }
     }
     if (!grad_w && !grad_b) return LDCONV_OK;
     {

@@ -324,6 +324,13 @@ class LDConv(nn.Module):
                                                        self.conv[0].out_channels, _DTYPES[x.dtype]))
 
     def forward(self, x):
+        # Under bf16 autocast (the reference trainer runs the forward under torch.cuda.amp.autocast, engine/trainer.py:693)
+        # the reference's own convs inside LDConv run in the low-precision dtype; an fp32 input (the image, layer 0) is cast
+        # here so that the layer takes the bf16 tensor-core kernels instead of the fp32 CUDA-core ones.  fp16 autocast is not
+        # covered by the kernels and keeps fp32.
+        if x.is_cuda and x.dtype == torch.float32 and torch.is_autocast_enabled() \
+                and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+            x = x.to(torch.bfloat16)
         _check_input(x)
         conv, bn = self.conv[0], self.conv[1]
         training = self.training

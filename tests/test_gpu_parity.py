@@ -507,6 +507,37 @@ def test_offsets_far_outside_the_image_bf16_kernels_agree():
     assert _rel(out.float().cpu().numpy(), ref.float().cpu().numpy()) <= 2e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("scale", [3.0, 60.0, 4000.0])
+def test_scatter_backward_with_clamped_and_colliding_samples(dtype, scale):
+    """gather_bwd with offsets of `scale` pixels on a 12x20 image: at 60 px most samples clamp onto a border row / column, at
+    4000 px every sample lands on one of the four corner pixels (what a diverging offset conv does to the layer).  The merged
+    coincident corners + warp-aggregated reductions must still equal the oracle's scatter (autograd of conv.py:386-405)."""
+    L = _lib.load()
+    B, C, H, W, N, s = 2, 16, 12, 20, 3, 1
+    rng = np.random.default_rng(int(scale))
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    off = (rng.standard_normal((B, 2 * N, H, W)) * scale).astype(np.float32)
+    g = rng.standard_normal((B, C, N, H, W)).astype(np.float32)              # dL/dsamp
+    if dtype == torch.bfloat16:
+        x, g = _bf16_round(x), _bf16_round(g)
+    gx_ref, goff_ref = oracle.sample_bwd(np.ascontiguousarray(g.transpose(0, 1, 3, 2, 4)).reshape(B, C, H * N, W), x, off, N, s)
+    M = B * H * W
+    xd = _t(_nhwc(x), dtype)
+    offd = _t(_nhwc(off))
+    gop = _t(np.ascontiguousarray(g.transpose(0, 3, 4, 2, 1)).reshape(M, N * C), dtype)
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    gx = torch.zeros((B, H, W, C), device=DEV)
+    goff = torch.empty((B, H, W, 2 * N), device=DEV)
+    dt = _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+    _lib.check(L.ldconv_gather_bwd(_ptr(gop), _ptr(xd), _ptr(offd), _ptr(pn), _ptr(gx), _ptr(goff), B, C, H, W, N, s, dt, _stream()),
+               "ldconv_gather_bwd")
+    torch.cuda.synchronize()
+    assert _rel(gx.cpu().numpy().transpose(0, 3, 1, 2), gx_ref) <= 2e-5
+    got_off = goff.cpu().numpy().transpose(0, 3, 1, 2)
+    assert np.abs(got_off - goff_ref).max() <= 2e-4 * max(1.0, float(np.abs(goff_ref).max()))
+
+
 # ---------------------------------------------------------------------------------- offset conv backward (bf16) ----
 @pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 1, 1, 24, 24, 2), (64, 3, 2, 21, 33, 2), (3, 3, 2, 64, 48, 2),
                                          (16, 5, 1, 160, 160, 8), (48, 2, 1, 17, 19, 1), (128, 9, 2, 20, 20, 1)])
