@@ -68,8 +68,11 @@ __device__ __forceinline__ uint64_t zc_desc(uint32_t addr, uint32_t sbo_bytes, u
     return d;
 }
 
-template <int MODE, int CIN, int TAPS = 9>
-__global__ void __launch_bounds__(kZcThreads, 2)
+// ISSUERS = 2 (one CTA per SM, i.e. the 64 / 128-channel shapes): a second MMA-issuing warp (warp 10) takes the odd tiles.  The
+// issuing thread pays ~1000 cycles of barrier round trips per tile on top of its MMAs (benchmarks/trace_zc.py: 2600 cycles of
+// MMA issue, 3650 per tile); with two issuers the waits of one overlap the MMAs of the other and the tensor pipe stays fed.
+template <int MODE, int CIN, int TAPS = 9, int ISSUERS = 1>
+__global__ void __launch_bounds__(kZcThreads + 32 * (ISSUERS - 1), ISSUERS == 1 ? 2 : 1)
 conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const float* __restrict__ scale, const float* __restrict__ shift,
                   const __nv_bfloat16* __restrict__ residual, void* __restrict__ out_v, int act, ZcGeom g)
@@ -133,8 +136,9 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || (ISSUERS == 2 && warp == 10)) {
         if (lane == 0) {
+            const int q = warp == 1 ? 0 : 1;          // this issuer's tiles: it = q, q + ISSUERS, ...
             // The single issuing thread is the serial resource of this kernel (profiles/r1_conv3x3_timeline.txt: ~230 cycles
             // per MMA when the descriptors are rebuilt with run-time arithmetic), so everything that depends only on the
             // channel count is a compile-time constant and the 9 * CIN/16 MMAs of a tile are fully unrolled: per MMA one add
@@ -153,8 +157,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t b16 = g.b_bytes >> 4;
             const uint32_t x0 = smem_u32(sX) >> 4;
             const uint32_t xstep = g.x_bytes >> 4, hstep = half_bytes >> 4;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+            for (int it = q; (long long)blockIdx.x + (long long)it * gridDim.x < g.num_tiles; it += ISSUERS) {
                 const int buf = it & 1, xb = it % g.xbufs;
                 tr(it, 600000 + it * 100);
                 mbar_wait(&t_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -185,7 +188,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 tr(it, 300000 + it * 100);
             }
         }
-    } else {
+    } else if (warp < 10) {
         const int ww = warp - 2;
         const int lg = warp & 3, half = ww >> 2;
         const int chunks16 = g.ON / 16;
@@ -254,6 +257,13 @@ static int zc_enabled()
 {
     static int v = -1;
     if (v < 0) { const char* e = getenv("LDCONV_CONV_ZC"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
+static int zc_two_issuers()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_ZC_ISSUERS"); v = e ? (atoi(e) >= 2) : 1; }
     return v;
 }
 
@@ -339,10 +349,17 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     if (grid > g.num_tiles) grid = g.num_tiles;
 #define LDC_ZC_LAUNCH(MODE_, CIN_)                                                                                     \
     do {                                                                                                               \
-        auto kern = conv3x3_zc_kernel<MODE_, CIN_>;                                                                    \
-        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, scale, shift,                        \
-                            (const __nv_bfloat16*)residual, out, act, g));                                            \
+        if (two || !zc_two_issuers()) {                                                                                \
+            auto kern = conv3x3_zc_kernel<MODE_, CIN_, 9, 1>;                                                          \
+            LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+            LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, scale, shift,                    \
+                                (const __nv_bfloat16*)residual, out, act, g));                                        \
+        } else {                                                                                                       \
+            auto kern = conv3x3_zc_kernel<MODE_, CIN_, 9, 2>;                                                          \
+            LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+            LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads + 32), smem, st, tmX, tmW, scale, shift,               \
+                                (const __nv_bfloat16*)residual, out, act, g));                                        \
+        }                                                                                                              \
     } while (0)
 #define LDC_ZC_CIN(MODE_)                                                                                              \
     switch (Cin) {                                                                                                     \

@@ -95,16 +95,16 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
     }
 }
 
-// A pipeline UNIT is G consecutive 128-row tiles accumulated side by side in one TMEM buffer (G * ON columns, two buffers):
-// for the narrow outputs of the model (O = 16..64) one tile is only 1-4 column chunks, and with one tile per buffer the
-// per-tile latency chain (tfull wait -> tcgen05.ld -> wait::ld -> math -> store -> tempty arrive) bounded the kernel at
-// ~1.9 us per tile per CTA (3.2 TB/s at K=48, O=32).  With G tiles per buffer every epilogue warp has 2 tcgen05.ld in
-// flight per wait and pays the barrier round trip once per unit.
+// Pipeline depth.  The accumulator lives in one of NB TMEM buffers (NB * ON <= 256 columns, so two CTAs share an SM's 512):
+// with two buffers the dependency cycle MMA(t) -> commit -> epilogue(t) -> tempty -> MMA(t+2) costs ~2700 cycles per buffer
+// and bounded the kernel at ~1350 cycles per tile whatever the tile did (scripts/gemm_dbg.sh: 31 us of pure hand-offs at
+// K=48, O=32, M=1.6M, and operand traffic / epilogue added on top instead of overlapping).  With up to eight buffers the MMA
+// warp runs ahead, and the eight epilogue warps work as two groups of four on alternate tiles, so two epilogues are in flight.
 __global__ void __launch_bounds__(kGemmThreads, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
-                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int G)
+                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
@@ -113,21 +113,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* sB = sA + (size_t)stages * kABytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)stages * b_bytes);
     uint64_t* empty = full + stages;
-    uint64_t* tfull = empty + stages;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tfull = empty + stages;         // [8]
+    uint64_t* tempty = tfull + 8;             // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
     float2* s_affine = reinterpret_cast<float2*>(tmem_slot + 4);     // [ON] (scale, shift)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_units = (num_tiles + G - 1) / G;
+    const int nb_shift = NB == 8 ? 3 : (NB == 4 ? 2 : (NB == 2 ? 1 : 0));
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -143,86 +143,77 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int t_end = min(num_tiles, (unit + 1) * G);
-                for (int tile = unit * G; tile < t_end; ++tile) {
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&empty[s], ph ^ 1);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (dbg & 1) {          // experiment: no operand traffic (results are garbage)
+                        mbar_arrive(&full[s]);
+                    } else {
                         mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
                         tma_load_2d(sA + (size_t)s * kABytes, &tmA, &full[s], kb * kBlockK, tile * kTileM);
                         tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], kb * kBlockK, 0);
-                        if (++s == stages) { s = 0; ph ^= 1; }
                     }
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
+        // (three issuing warps on alternate tiles were tried: the pure hand-off time fell from 31 to 20 us at layer 1, the full
+        // kernel did not move -- it is bound by the TMA box-row rate of the operand loads, ~1 row per 10 cycles per SM whatever
+        // the row width, scripts/gemm_dbg.sh -- and sharing the stage ring between issuers needs per-issuer sub-rings)
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(kTileM, ON);
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t tph = (it >> 1) & 1;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & (NB - 1);
+                const uint32_t tph = (uint32_t)(it >> nb_shift) & 1u;
                 mbar_wait(&tempty[buf], tph ^ 1);
                 tc_fence_after_sync();
-                const int t_end = min(num_tiles, (unit + 1) * G);
-                uint32_t d_tmem = tmem_base + (uint32_t)(buf * G * ON);
-                for (int tile = unit * G; tile < t_end; ++tile, d_tmem += (uint32_t)ON) {
-                    for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(&full[s], ph);
-                        tc_fence_after_sync();
-                        const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
-                        const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ON);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
-                                        (uint32_t)((kb | k) != 0));
-                        }
-                        mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
-                        if (++s == stages) { s = 0; ph ^= 1; }
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                                    (uint32_t)((kb | k) != 0));
                     }
+                    mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+                    if (++s == stages) { s = 0; ph ^= 1; }
                 }
                 mma_commit(&tfull[buf]);
             }
         }
     } else {
-        const int lg = warp & 3;              // TMEM lane group this warp may access
-        const int half = (warp - 2) >> 2;     // warps 2..5 take the first half of the unit's column chunks, 6..9 the second
-        const int chunks = ON / 16;           // per tile
-        const int uc = G * chunks;            // per unit
-        const int ch_begin = half == 0 ? 0 : (uc + 1) / 2, ch_end = half == 0 ? (uc + 1) / 2 : uc;
-        const int g_begin = ch_begin / chunks, c_begin = ch_begin - g_begin * chunks;
+        const int lg = warp & 3;              // TMEM lane group this warp may access (warps 2..9)
+        const int grp = (warp - 2) >> 2;      // warps 2..5 take the even tiles of this CTA, warps 6..9 the odd ones
+        const int chunks = ON / 16;
         const uint32_t aff_s = smem_u32(s_affine);
-        int it = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t tph = (it >> 1) & 1;
+        for (int it = grp; (long long)blockIdx.x + (long long)it * gridDim.x < num_tiles; it += 2) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int buf = it & (NB - 1);
+            const uint32_t tph = (uint32_t)(it >> nb_shift) & 1u;
             mbar_wait(&tfull[buf], tph);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * G * ON);
-            const long long m_unit = (long long)unit * G * kTileM + lg * 32 + lane;
-            int g = g_begin, c = c_begin;                 // tile within the unit, chunk within the tile
-            for (int ch = ch_begin; ch < ch_end; ch += 2) {
-                const bool two = ch + 1 < ch_end;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ON);
+            const long long m = (long long)tile * kTileM + lg * 32 + lane;
+            for (int ch = 0; ch < chunks; ch += 2) {
+                const bool two = ch + 1 < chunks;
                 uint32_t v0[16], v1[16];
                 tmem_ld_32x32b_x16(taddr + (uint32_t)ch * 16u, v0);
                 if (two) tmem_ld_32x32b_x16(taddr + (uint32_t)(ch + 1) * 16u, v1);
                 tmem_ld_wait();
-                {
-                    const long long m = m_unit + (long long)g * kTileM;
-                    if (m < M && c * 16 < O)
-                        gemm_epilogue_chunk(v0, m, c * 16, O, aff_s + (uint32_t)c * 128u, act, out, pre, residual, ldo, ldr,
+                if (m < M && !(dbg & 2)) {
+                    if (ch * 16 < O)
+                        gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 128u, act, out, pre, residual, ldo, ldr,
                                             vec_store != 0);
-                    if (++c == chunks) { c = 0; ++g; }
-                }
-                if (two) {
-                    const long long m = m_unit + (long long)g * kTileM;
-                    if (m < M && c * 16 < O)
-                        gemm_epilogue_chunk(v1, m, c * 16, O, aff_s + (uint32_t)c * 128u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0);
-                    if (++c == chunks) { c = 0; ++g; }
+                    if (two && (ch + 1) * 16 < O)
+                        gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 128u, act, out, pre, residual,
+                                            ldo, ldr, vec_store != 0);
                 }
             }
             tc_fence_before_sync();
@@ -233,6 +224,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static int gemm_dbg()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_GEMM_DBG"); v = e ? atoi(e) : 0; }
+    return v;
 }
 
 int umma_gemm_supported(int M, int K, int O, int dtype, const void* a, const void* wt, const void* out, const void* pre)
@@ -277,19 +275,18 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     // two CTAs per SM when both accumulator pairs fit TMEM (2 x 2 x ON <= 512 columns): ~100 KB of smem ring each;
     // one CTA with the whole ~200 KB otherwise
     const bool two_per_sm = 4 * ON <= 512;
-    // tiles per accumulator buffer.  Measured (profiles/r1_layers_gemm_group.txt): grouping does not move the needle -- the
-    // kernel is bound by the TMA request rate of narrow operand rows (K*2 < 128 B), not by the epilogue chain -- so the
-    // default stays 1; LDCONV_GEMM_GROUP=n selects n tiles per buffer (n * ON <= 128) for experiments.
-    int G = 1;
-    static int g_env_group = -2;
-    if (g_env_group == -2) { const char* e = getenv("LDCONV_GEMM_GROUP"); g_env_group = e ? atoi(e) : -1; }
-    if (g_env_group >= 1 && g_env_group * ON <= 128) G = g_env_group;
+    // accumulator buffers: as many as fit 256 TMEM columns (two CTAs per SM), at most 8, a power of two
+    int NB = 8;
+    while (NB > 2 && NB * ON > 256) NB >>= 1;
+    static int g_env_nb = -2;
+    if (g_env_nb == -2) { const char* e = getenv("LDCONV_GEMM_NB"); g_env_nb = e ? atoi(e) : -1; }
+    if ((g_env_nb == 2 || g_env_nb == 4 || g_env_nb == 8) && g_env_nb <= NB) NB = g_env_nb;
     int stages = ((two_per_sm ? 100 : 200) * 1024) / (kABytes + b_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(LDCONV_E_ARG, "tcgen05 GEMM: tile does not fit shared memory (O=%d)", O);
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(2 * G * ON)) tmem_cols <<= 1;
-    const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 4) * sizeof(uint64_t) + 16 +
+    while (tmem_cols < (uint32_t)(NB * ON)) tmem_cols <<= 1;
+    const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 16) * sizeof(uint64_t) + 16 +
                         (size_t)ON * sizeof(float2);
 
     CUtensorMap tmA, tmB;
@@ -298,12 +295,11 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
 
     LDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * (two_per_sm ? 2 : 1);
-    const int num_units = (num_tiles + G - 1) / G;
-    if (grid > num_units) grid = num_units;
+    if (grid > num_tiles) grid = num_tiles;
     const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
     LDC_CUDA(launch_pdl(umma_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
                         (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
-                        vec_store, ldo, ldr, G));
+                        vec_store, ldo, ldr, NB, gemm_dbg()));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
