@@ -1,8 +1,9 @@
 """BASELINE.json config 4: DEAL-YOLO-LD training step on synthetic 640x640 batches, random-init weights, bf16 autocast,
 per-GPU BatchNorm statistics, ONE flat gradient all-reduce over NCCL per step (experiment_yolo_b200/dist.py), SGD with
 nesterov momentum (lr 0.01, momentum 0.937: reference engine/trainer.py:1164, cfg/default.yaml:90-92).
-The loss is a dense surrogate on the raw head maps (dist.surrogate_detection_loss): the reference's TAL + WIoU + NWD loss
-is a "next" row and cannot travel to the GPU box.
+The loss is the reference's criterion for this config -- task-aligned assignment + BCE + Wise-IoU v3 + NWD + DFL
+(experiment_yolo_b200/loss.py, pinned against the reference's v8DetectionLoss by tests/test_loss_cpu.py) -- on synthetic UAV
+targets (16 boxes of 6-32 px per image); --loss surrogate keeps the earlier dense stand-in for A/B.
     python benchmarks/train_step.py [--batch 128] [--steps 10]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 benchmarks/train_step.py --batch 128
 (--batch is the GLOBAL batch, split evenly over ranks.)
@@ -18,6 +19,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from experiment_yolo_b200 import _lib, dealyolo  # noqa: E402
 from experiment_yolo_b200 import dist as xdist  # noqa: E402
+from experiment_yolo_b200.loss import DealYoloLoss, synthetic_uav_targets  # noqa: E402
 
 
 def main():
@@ -26,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--img", type=int, default=640)
+    ap.add_argument("--loss", default="wiou_nwd", choices=["wiou_nwd", "surrogate"])
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -42,6 +45,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     x = torch.rand((B, 3, args.img, args.img), device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     targets = [torch.zeros((B, 70, args.img // s, args.img // s), device=dev) for s in (4, 8, 16)]
+    crit = DealYoloLoss(nc=6, strides=[float(v) for v in model.stride], max_boxes=16).to(dev)
+    batch = synthetic_uav_targets(B, boxes_per_image=16, nc=6, seed=200 + rank, device=dev)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.SGD(params, lr=0.01, momentum=0.937, nesterov=True)
     red = xdist.FlatGradAllReduce(model.parameters())
@@ -50,7 +55,10 @@ def main():
         with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
             opt.zero_grad(set_to_none=True)
             outs = model(x)
-        loss = xdist.surrogate_detection_loss(outs, targets)
+        if args.loss == "surrogate":
+            loss = xdist.surrogate_detection_loss(outs, targets)
+        else:       # loss.sum() * local batch like the reference (utils/loss.py:361); the all-reduce below sums over ranks
+            loss, _ = crit(outs, batch)
         loss.backward()
         red()
         torch.nn.utils.clip_grad_norm_(params, max_norm=10.0)      # reference optimizer_step, engine/trainer.py:952
@@ -76,7 +84,8 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "train_images_per_sec", "value": round(args.batch / ms * 1e3, 1), "ms_per_step": round(ms, 3),
                           "n_gpus": world, "global_batch": args.batch, "per_gpu_batch": B, "dtype": "bf16 autocast (fp32 master weights)",
-                          "loss": "dense surrogate (not the reference WIoU+NWD loss)", "final_loss": float(loss.detach()),
+                          "loss": ("dense surrogate (not the reference WIoU+NWD loss)" if args.loss == "surrogate" else
+                                   "TAL(topk 10) + BCE + Wise-IoU v3 + NWD (ratio 0.5) + DFL, box 7.5 / cls 0.5 / dfl 1.5, 16 synthetic UAV boxes per image"), "final_loss": float(loss.detach()),
                           "grad_allreduce": f"one flat fp32 buffer, {red.numel} values" + (" over NCCL" if world > 1 else " (single rank: none)"),
                           "ldconv_calls_per_step": {k: v // args.steps for k, v in sorted(_lib.call_counts.items())}}), flush=True)
     if world > 1:

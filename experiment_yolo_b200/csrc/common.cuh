@@ -156,13 +156,12 @@ struct SamplePoint {
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
-__device__ __forceinline__ SamplePoint make_point(int i, int j, int s, int pn_r, int pn_k, float off_r, float off_k,
-                                                  int H, int W)
+// (ri, ki) = (i*s + pn_r, j*s + pn_k): the integer grid point p_0 + p_n; (hm, wm) = (float)(H-1), (float)(W-1)
+__device__ __forceinline__ SamplePoint make_point_grid(int ri, int ki, float off_r, float off_k, float hm, float wm)
 {
     SamplePoint q;
-    const float pr = __fadd_rn((float)(i * s + pn_r), off_r);
-    const float pk = __fadd_rn((float)(j * s + pn_k), off_k);
-    const float hm = (float)(H - 1), wm = (float)(W - 1);
+    const float pr = __fadd_rn((float)ri, off_r);
+    const float pk = __fadd_rn((float)ki, off_k);
     const float fr = floorf(pr), fk = floorf(pk);
     q.r0 = (int)clampf(fr, 0.f, hm);
     q.r1 = (int)clampf(__fadd_rn(fr, 1.f), 0.f, hm);
@@ -177,6 +176,12 @@ __device__ __forceinline__ SamplePoint make_point(int i, int j, int s, int pn_r,
     q.in_r = (pr >= 0.f) && (pr <= hm);
     q.in_k = (pk >= 0.f) && (pk <= wm);
     return q;
+}
+
+__device__ __forceinline__ SamplePoint make_point(int i, int j, int s, int pn_r, int pn_k, float off_r, float off_k,
+                                                  int H, int W)
+{
+    return make_point_grid(i * s + pn_r, j * s + pn_k, off_r, off_k, (float)(H - 1), (float)(W - 1));
 }
 
 // reference summation order lt, rb, lb, rt (conv.py:402-405), products and sums rounded separately like the
@@ -196,6 +201,45 @@ __device__ __forceinline__ float bilinear_fma(float g_lt, float g_rb, float g_lb
                                               float x01, float x10)
 {
     return fmaf(g_rt, x10, fmaf(g_lb, x01, fmaf(g_rb, x11, g_lt * x00)));
+}
+
+// ---- packed fp32 pairs (FFMA2 / FMUL2 on sm_100a): two independent IEEE fp32 operations per issued instruction, each
+// lane rounds exactly like the scalar fmaf / multiply it replaces
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// two bf16 lanes of four corner words -> the bilinear sum of bilinear_fma() per lane, rounded once to bf16x2
+__device__ __forceinline__ uint32_t bilinear_bf16x2(uint32_t w00, uint32_t w11, uint32_t w01, uint32_t w10, const float4& g)
+{
+    auto widen = [](uint32_t w) { return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
+    uint64_t acc = f2_mul(widen(w00), f2_pack(g.x, g.x));
+    acc = f2_fma(widen(w11), f2_pack(g.y, g.y), acc);
+    acc = f2_fma(widen(w01), f2_pack(g.z, g.z), acc);
+    acc = f2_fma(widen(w10), f2_pack(g.w, g.w), acc);
+    float lo, hi;
+    f2_unpack(acc, lo, hi);
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 __device__ __forceinline__ float silu(float z) { return z / (1.f + __expf(-z)); }

@@ -35,6 +35,9 @@ struct GGGeom {
     int C, CV, cv_shift, N, s, H, W, h, w, O, ON, K, num_kb, ksteps;
     int TH, TW, tw_shift, THin, TWin, halo, tiles_h, tiles_w, num_tiles;
     int XB, AB, ldo, act, per_sm, dbg;
+    int xb_mask, xb_shift, ab_mask;      // XB, AB in {1, 2}: buffer = it & mask, mbarrier parity = (it >> shift) & 1
+    float hm, wm;                        // (float)(H - 1), (float)(W - 1)
+    unsigned long long img_bytes;        // H * W * C * 2
     unsigned inv_n, inv_img, inv_tw;
     uint32_t ofs_a, ofs_b, ofs_x, ofs_rec, ofs_aff, ofs_bar, x_bytes, x_tx_bytes, a_bytes, b_bytes, rec_bytes, tmem_cols;
 };
@@ -204,8 +207,8 @@ ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tile_coords(tile, b, i0, j0);
         const int r_org = i0 * g.s - g.halo, k_org = j0 * g.s - g.halo;
         const int r_end = r_org + g.THin, k_end = k_org + g.TWin;
-        // records are double-buffered: buffer it&1 was last read in phase 2 of tile it-2, two block barriers ago
-        uint4* rec_o = reinterpret_cast<uint4*>(smem + g.ofs_rec + (size_t)(it & 1) * g.rec_bytes);
+        // one record buffer: it was last read in phase 2 of the previous tile, and block barrier (B) lies in between
+        uint4* rec_o = reinterpret_cast<uint4*>(smem + g.ofs_rec);
         float4* rec_g = reinterpret_cast<float4*>(rec_o + samples);
 
         // ---- phase 1: one record per sample --------------------------------------------------------------------------------
@@ -325,6 +328,305 @@ ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
+// ---- v2 of the kernel: same pipeline, specialised index arithmetic ------------------------------------------------------------
+// profiles/r1_ncu_ggL1v3.txt: the kernel above is issue-bound (114.6 M warp instructions at layer 1, 72 % of the issue slots),
+// and ~40 % of those instructions are index arithmetic on run-time geometry.  This version removes them:
+//   * samples are ordered n-major inside a tile (sample = n * 128 + pixel), so a thread keeps ONE pixel for all of its
+//     phase-1 samples and for the epilogue, and every phase-2 round of 256 items keeps its channel vector: the pixel / n /
+//     swizzled-slot decomposition is shifts and masks, and immediates once (N, C / 8, s) are template constants;
+//   * tile coordinates are computed once per tile (for the offset prefetch) and carried over, buffer indices are masks,
+//     records hold byte offsets, invalid edge pixels get an all-zero record instead of a branch per item;
+//   * the bilinear sum and the folded BatchNorm + SiLU run on packed fp32 pairs (FFMA2): half the FMA-pipe instructions with
+//     bit-identical results; the SiLU's 0.5 is folded into the affine.
+// Requires C / 8 to be a power of two; other channel counts keep the kernel above.
+template <int TN, int TCVS, int TS, int MINB>
+__global__ void __launch_bounds__(kGGThreads, MINB)
+ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __nv_bfloat16* __restrict__ x, const float* __restrict__ off, const int* __restrict__ pn,
+                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                  const GGGeom g)
+{
+    using T = __nv_bfloat16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t smem_s = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
+    uint64_t* x_full = bars;
+    uint64_t* mma_done = bars + 2;
+    uint64_t* w_full = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    float* sAff = reinterpret_cast<float*>(smem + g.ofs_aff);      // [0, ON) scale, [ON, 2 ON) shift (halved for SiLU)
+    const uint32_t aff_s = smem_s + g.ofs_aff;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int N = TN > 0 ? TN : g.N;
+    const int cvs = TCVS >= 0 ? TCVS : g.cv_shift;
+    const int s = TS > 0 ? TS : g.s;
+    const int tiles_per_img = g.tiles_h * g.tiles_w;
+    const uint32_t rec_g_ofs = (uint32_t)(128 * N) * 16u;          // weights follow the 128 N offset records
+
+    struct TC { int b, i0, j0; };
+    auto tile_coords = [&](int tile) {
+        TC t;
+        t.b = g.inv_img ? (int)__umulhi((unsigned)tile, g.inv_img) : tile;
+        const int rem = tile - t.b * tiles_per_img;
+        const int ti = g.inv_tw ? (int)__umulhi((unsigned)rem, g.inv_tw) : rem;
+        t.i0 = ti * g.TH;
+        t.j0 = (rem - ti * g.tiles_w) * g.TW;
+        return t;
+    };
+    auto issue_x_tile = [&](int tile, int xb) {                         // thread 0 only
+        const TC t = tile_coords(tile);
+        mbar_arrive_expect_tx(&x_full[xb], g.x_tx_bytes);
+        tma_load_4d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, t.j0 * s - g.halo, t.i0 * s - g.halo, t.b);
+    };
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&mma_done[i], 1); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
+    pdl_wait();       // everything below may read what the previous kernel wrote (x, offsets, scale / shift)
+    const bool act_silu = g.act == LDCONV_ACT_SILU;
+    {
+        const float pre = act_silu ? 0.5f : 1.f;      // silu(z) = hz + hz tanh(hz), hz = z / 2: the halving is exact
+        for (int o = tid; o < g.ON; o += kGGThreads) {
+            sAff[o] = pre * ((scale && o < g.O) ? scale[o] : 1.f);
+            sAff[g.ON + o] = pre * ((shift && o < g.O) ? shift[o] : 0.f);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes);
+        for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(smem + g.ofs_b + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+        for (int k = 0; k < g.XB; ++k)
+            if ((int)blockIdx.x + k * (int)gridDim.x < g.num_tiles) issue_x_tile(blockIdx.x + k * gridDim.x, k);
+    }
+
+    // ---- per-thread constants: one pixel of the tile for phase 1 and the epilogue, one channel vector for phase 2 ------------
+    const int p = tid & 127, n0 = tid >> 7;
+    const int di = p >> g.tw_shift, dj = p & (g.TW - 1);
+    const int pix_f = (di * g.w + dj) * 2 * N;                 // this pixel's offsets, in floats from the tile's origin pixel
+    bool has[2];
+    int br[2], bk[2];                                          // di * s + pn_r[n], dj * s + pn_k[n] of sample rounds 0, 1
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int n = n0 + 2 * r;
+        has[r] = n < N;
+        br[r] = di * s + (has[r] ? pn[n] : 0);
+        bk[r] = dj * s + (has[r] ? pn[N + n] : 0);
+    }
+    float2 ofs[2];                                             // offsets of those samples, prefetched one tile ahead
+    auto fetch_offsets = [&](const TC& t) {
+        const bool valid = t.i0 + di < g.h && t.j0 + dj < g.w;
+        const float* op = off + (((size_t)t.b * g.h + t.i0) * g.w + t.j0) * (size_t)(2 * N) + pix_f + n0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (valid && has[r]) ofs[r] = make_float2(__ldg(op + 2 * r), __ldg(op + N + 2 * r));
+    };
+    ofs[0] = ofs[1] = make_float2(0.f, 0.f);
+
+    const int cv = tid & ((1 << cvs) - 1), sx0 = tid >> cvs;   // phase 2: item round k handles sample sx0 + k * (256 >> cvs)
+    const int spr = 256 >> cvs;
+    const int rounds = (N << cvs) >> 1;                        // 128 N CV items / 256 threads (K % 16 == 0 makes it exact)
+    const int half = warp >> 2;
+    const int chunks = g.ON / 16;
+    const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2, ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
+
+    // epilogue of one finished tile: TMEM lane = this thread's pixel, this warp's half of the 16-column chunks
+    auto epilogue = [&](T* orow, int eit) {
+        const int tb = eit & 1;
+        mbar_wait(&mma_done[tb], (eit >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * g.ON);
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+            const int c0 = ch * 16;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (orow == nullptr || c0 >= g.O) continue;
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                const float4 sc = gg_lds_f4(aff_s + (uint32_t)(c0 + e) * 4u);
+                const float4 sh = gg_lds_f4(aff_s + (uint32_t)(g.ON + c0 + e) * 4u);
+                uint64_t z0 = f2_fma(f2_pack(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), f2_pack(sc.x, sc.y),
+                                     f2_pack(sh.x, sh.y));
+                uint64_t z1 = f2_fma(f2_pack(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])), f2_pack(sc.z, sc.w),
+                                     f2_pack(sh.z, sh.w));
+                float a0, a1, a2, a3;
+                f2_unpack(z0, a0, a1);
+                f2_unpack(z1, a2, a3);
+                if (act_silu) {
+                    float t0, t1, t2, t3;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t2) : "f"(a2));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t3) : "f"(a3));
+                    z0 = f2_fma(z0, f2_pack(t0, t1), z0);
+                    z1 = f2_fma(z1, f2_pack(t2, t3), z1);
+                    f2_unpack(z0, a0, a1);
+                    f2_unpack(z1, a2, a3);
+                } else if (g.act == LDCONV_ACT_LEAKY01) {
+                    a0 = a0 > 0.f ? a0 : 0.1f * a0; a1 = a1 > 0.f ? a1 : 0.1f * a1;
+                    a2 = a2 > 0.f ? a2 : 0.1f * a2; a3 = a3 > 0.f ? a3 : 0.1f * a3;
+                }
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[e >> 1]) : "f"(a1), "f"(a0));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[(e >> 1) + 1]) : "f"(a3), "f"(a2));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        tc_fence_before_sync();       // ordered before the block barrier that precedes the next MMA into this buffer
+    };
+
+    const uint32_t idesc = make_idesc_bf16(128, g.ON);
+    const int rowB = g.TWin << (cvs + 4), pixB = 16 << cvs;    // bytes per staged tile row / per pixel
+    const int imgRowB = g.W << (cvs + 4);
+    TC cur = tile_coords(blockIdx.x);
+    if ((int)blockIdx.x < g.num_tiles) fetch_offsets(cur);
+    T* prev_out = nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int xb = it & g.xb_mask, ab = it & g.ab_mask, tb = it & 1;
+        const uint32_t rec_s = smem_s + g.ofs_rec;      // last read in phase 2 of the previous tile: barrier (B) lies in between
+        const int r_org = cur.i0 * s - g.halo, k_org = cur.j0 * s - g.halo;
+        const bool valid = cur.i0 + di < g.h && cur.j0 + dj < g.w;
+        T* cur_out = valid ? out + (((size_t)cur.b * g.h + cur.i0 + di) * g.w + cur.j0 + dj) * (size_t)g.ldo : nullptr;
+
+        // ---- phase 1: one record per sample (n-major: sample = n * 128 + pixel) ------------------------------------------------
+        auto make_record = [&](int n, int ri, int ki, float o_r, float o_k) {
+            const uint32_t ra = rec_s + (uint32_t)(n * 128 + p) * 16u;
+            if (!valid) {
+                gg_sts128(ra, 0u, 0u, 0u, 0u);
+                gg_sts128(ra + rec_g_ofs, 0u, 0u, 0u, 0u);
+                return;
+            }
+            const SamplePoint q = make_point_grid(ri, ki, o_r, o_k, g.hm, g.wm);
+            gg_sts128(ra + rec_g_ofs, __float_as_uint(__fmul_rn(q.ar0, q.ak0)), __float_as_uint(__fmul_rn(q.ar1, q.ak1)),
+                      __float_as_uint(__fmul_rn(q.ar0, q.ak1)), __float_as_uint(__fmul_rn(q.ar1, q.ak0)));
+            const int t0 = q.r0 - r_org, t1 = q.r1 - r_org, u0 = q.k0 - k_org, u1 = q.k1 - k_org;
+            const bool inside = (unsigned)t0 < (unsigned)g.THin && (unsigned)t1 < (unsigned)g.THin &&
+                                (unsigned)u0 < (unsigned)g.TWin && (unsigned)u1 < (unsigned)g.TWin;
+            if (inside) {
+                const int a0 = t0 * rowB, a1 = t1 * rowB, b0 = u0 * pixB, b1 = u1 * pixB;
+                gg_sts128(ra, (uint32_t)(a0 + b0), (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
+            } else {      // served from global memory (L2): image-relative byte offsets, bit 31 of .x marks it
+                const int a0 = q.r0 * imgRowB, a1 = q.r1 * imgRowB, b0 = q.k0 * pixB, b1 = q.k1 * pixB;
+                gg_sts128(ra, (uint32_t)(a0 + b0) | 0x80000000u, (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
+            }
+        };
+        const int gr = cur.i0 * s, gk = cur.j0 * s;
+        if (has[0]) make_record(n0, gr + br[0], gk + bk[0], ofs[0].x, ofs[0].y);
+        if (has[1]) make_record(n0 + 2, gr + br[1], gk + bk[1], ofs[1].x, ofs[1].y);
+        if (TN == 0 || TN > 4) {
+            for (int n = n0 + 4; n < N; n += 2) {
+                float o_r = 0.f, o_k = 0.f;
+                if (valid) {
+                    const float* op = off + (((size_t)cur.b * g.h + cur.i0) * g.w + cur.j0) * (size_t)(2 * N) + pix_f;
+                    o_r = __ldg(op + n); o_k = __ldg(op + N + n);
+                }
+                make_record(n, gr + di * s + pn[n], gk + dj * s + pn[N + n], o_r, o_k);
+            }
+        }
+        // next tile: coordinates once, offsets prefetched behind phase 2
+        TC nxt = cur;
+        if (tile + (int)gridDim.x < g.num_tiles) {
+            nxt = tile_coords(tile + gridDim.x);
+            fetch_offsets(nxt);
+        }
+        __syncthreads();                                              // (A) records of this tile are visible
+        mbar_wait(&x_full[xb], (uint32_t)(it >> g.xb_shift) & 1u);   // the staged input tile has landed
+        if (g.ab_mask == 0 && it > 0) mbar_wait(&mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1);   // operand buffer free again
+
+        // ---- phase 2: bilinear resampling into the swizzled operand tile; two items per step, loads first --------------------
+        {
+            const uint32_t x_s = smem_s + g.ofs_x + (uint32_t)xb * g.x_bytes + ((uint32_t)cv << 4);
+            const uint32_t a_s = smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes;
+            const uint8_t* xg = reinterpret_cast<const uint8_t*>(x) + (size_t)cur.b * g.img_bytes + ((uint32_t)cv << 4);
+            auto load_item = [&](int sx, float4& gw, uint4 (&q)[4]) {
+                const uint4 o = gg_lds128(rec_s + (uint32_t)sx * 16u);
+                gw = gg_lds_f4(rec_s + rec_g_ofs + (uint32_t)sx * 16u);
+                if ((int)o.x >= 0) {
+                    q[0] = gg_lds128(x_s + o.x); q[1] = gg_lds128(x_s + o.y); q[2] = gg_lds128(x_s + o.z); q[3] = gg_lds128(x_s + o.w);
+                } else {
+                    // cold path: the sample left the staged halo, its corners come from global memory (L2).  Written as a
+                    // non-unrolled rotate loop so the compiler keeps it a branch instead of if-converting ~14 predicated
+                    // instructions into the hot path of every item.
+                    uint4 oo = make_uint4(o.x & 0x7fffffffu, o.y, o.z, o.w);
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        q[0] = q[1]; q[1] = q[2]; q[2] = q[3];
+                        q[3] = __ldg(reinterpret_cast<const uint4*>(xg + oo.x));
+                        oo = make_uint4(oo.y, oo.z, oo.w, oo.x);
+                    }
+                }
+            };
+            auto store_item = [&](int sx, const float4& gw, const uint4 (&q)[4]) {
+                const uint32_t px = (uint32_t)sx & 127u, n = (uint32_t)sx >> 7;
+                const uint32_t k8 = (n << cvs) + (uint32_t)cv;            // 16-byte chunk index along K
+                gg_sts128(a_s + (k8 >> 3) * 16384u + px * 128u + (((k8 ^ px) & 7u) << 4),
+                          bilinear_bf16x2(q[0].x, q[1].x, q[2].x, q[3].x, gw), bilinear_bf16x2(q[0].y, q[1].y, q[2].y, q[3].y, gw),
+                          bilinear_bf16x2(q[0].z, q[1].z, q[2].z, q[3].z, gw), bilinear_bf16x2(q[0].w, q[1].w, q[2].w, q[3].w, gw));
+            };
+            // IF items in flight per thread (loads first, then the arithmetic): two under the 80-register cap of three CTAs
+            // per SM, four when the shared-memory footprint allows fewer CTAs anyway (latency-bound there)
+            constexpr int IF = (MINB >= 3 || TN == 0) ? 2 : 4;
+            auto step = [&](int k, int nrounds) {
+                float4 gw[IF];
+                uint4 q[IF][4];
+#pragma unroll
+                for (int u = 0; u < IF; ++u)
+                    if (k + u < nrounds) load_item(sx0 + (k + u) * spr, gw[u], q[u]);
+#pragma unroll
+                for (int u = 0; u < IF; ++u)
+                    if (k + u < nrounds) store_item(sx0 + (k + u) * spr, gw[u], q[u]);
+            };
+            if constexpr (TN > 0 && TCVS >= 0) {
+                constexpr int R = (TN << TCVS) >> 1;
+#pragma unroll
+                for (int k = 0; k < R; k += IF) step(k, R);
+            } else {
+                for (int k = 0; k < rounds; k += IF) step(k, rounds);
+            }
+        }
+        fence_proxy_async_smem();      // generic-proxy stores of the operand tile -> visible to tcgen05 (async proxy)
+        __syncthreads();               // (B) operand tile complete, input tile consumed, epilogue(it-2) done by every warp
+
+        if (tid == 0) {
+            if (tile + g.XB * (int)gridDim.x < g.num_tiles) issue_x_tile(tile + g.XB * gridDim.x, xb);
+            if (it == 0) mbar_wait(w_full, 0);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(tb * g.ON);
+            const uint32_t a_addr = smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes;
+            const uint32_t b_addr = smem_s + g.ofs_b;
+            for (int st = 0; st < g.ksteps; ++st) {
+                const uint32_t kb = (uint32_t)st >> 2, kk = (uint32_t)st & 3;
+                mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + kb * 16384u + kk * 32u),
+                            make_desc_k_sw128(b_addr + kb * g.b_bytes + kk * 32u), idesc, (uint32_t)(st != 0));
+            }
+            mma_commit(&mma_done[tb]);
+        }
+        __syncwarp();
+        if (it > 0) epilogue(prev_out, it - 1);      // the previous tile's MMA ran during this tile's phases
+        prev_out = cur_out;
+        cur = nxt;
+    }
+    if (it > 0) epilogue(prev_out, it - 1);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
 static void gg_pn_extent(int N, int* max_r, int* max_k)
 {
     int32_t table[64];
@@ -352,7 +654,9 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     for (int sh = 0; sh < 8; ++sh)
         if ((1 << sh) == g.CV) g.cv_shift = sh;
     g.inv_n = (65536u + (unsigned)N - 1) / (unsigned)N;
-    if ((long long)H * W * g.CV >= 0x7fffffffll) return 0;
+    if ((long long)H * W * C * 2 >= 0x7fffffffll) return 0;
+    g.hm = (float)(H - 1); g.wm = (float)(W - 1);
+    g.img_bytes = (unsigned long long)H * W * C * 2;
     int mr, mk;
     gg_pn_extent(N, &mr, &mk);
     auto waste = [&](int th, int tw) {
@@ -387,7 +691,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
         g.ofs_a = ofs; ofs += (uint32_t)g.AB * g.a_bytes;
         g.ofs_b = ofs; ofs += (uint32_t)g.num_kb * g.b_bytes;
         g.ofs_x = ofs; ofs += (uint32_t)g.XB * g.x_bytes;
-        g.ofs_rec = ofs; ofs += 2u * g.rec_bytes;
+        g.ofs_rec = ofs; ofs += g.rec_bytes;
         g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8u;
         ofs = (ofs + 7u) & ~7u;
         g.ofs_bar = ofs; ofs += 6u * 8u + 16u;
@@ -402,6 +706,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     if (best_ctas == 0) return 0;
     g = best;
     g.per_sm = best_ctas;
+    g.xb_mask = g.XB - 1; g.xb_shift = g.XB - 1; g.ab_mask = g.AB - 1;
     g.tiles_h = (g.h + g.TH - 1) / g.TH;
     g.tiles_w = (g.w + g.TW - 1) / g.TW;
     const long long nt = (long long)B * g.tiles_h * g.tiles_w;
@@ -455,7 +760,27 @@ int gather_gemm_fwd(const void* x, const float* off, const int* pn, const void* 
         cuuint32_t box[2] = {64, (cuuint32_t)g.ON};
         if (int e = encode_map(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wt, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
     }
-    auto kern = ldconv_gg_kernel<3>;      // <= 84 registers, no spills; a 64-register build for four CTAs per SM measured equal
+    using Kern = void (*)(CUtensorMap, CUtensorMap, const __nv_bfloat16*, const float*, const int*, const float*, const float*,
+                          __nv_bfloat16*, GGGeom);
+    Kern kern = ldconv_gg_kernel<3>;      // <= 84 registers, no spills; a 64-register build for four CTAs per SM measured equal
+    static int env_v = -1;                // LDCONV_GG_V=1: the generic kernel everywhere (A/B partner)
+    if (env_v < 0) { const char* e = getenv("LDCONV_GG_V"); env_v = e ? atoi(e) : 2; }
+    if (env_v >= 2 && g.cv_shift >= 0) {
+        // the register cap follows the CTAs per SM the shared-memory plan allows (80 / 128 / 255 registers)
+        kern = g.per_sm >= 3 ? ldconv_gg2_kernel<0, -1, 0, 3> : g.per_sm == 2 ? ldconv_gg2_kernel<0, -1, 0, 2> : ldconv_gg2_kernel<0, -1, 0, 1>;
+        const int key = N * 1000 + g.cv_shift * 100 + s * 10 + g.per_sm;      // yolov8-LD-P2 shapes: compile-time index arithmetic
+        if (env_v == 2) switch (key) {
+            case 3123: kern = ldconv_gg2_kernel<3, 1, 2, 3>; break;      // C = 16 (layer 1)
+            case 3222: kern = ldconv_gg2_kernel<3, 2, 2, 2>; break;      // C = 32 (layers 3, 18)
+            case 3221: kern = ldconv_gg2_kernel<3, 2, 2, 1>; break;
+            case 3321: kern = ldconv_gg2_kernel<3, 3, 2, 1>; break;      // C = 64 (layers 5, 21)
+            case 1213: kern = ldconv_gg2_kernel<1, 2, 1, 3>; break;      // C = 32 (layer 15)
+            case 1313: kern = ldconv_gg2_kernel<1, 3, 1, 3>; break;      // C = 64 (layers 10, 13)
+            case 1412: kern = ldconv_gg2_kernel<1, 4, 1, 2>; break;      // C = 128 (layer 8)
+            case 1411: kern = ldconv_gg2_kernel<1, 4, 1, 1>; break;
+            default: break;
+        }
+    }
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * g.per_sm;
     if (grid > g.num_tiles) grid = g.num_tiles;

@@ -1,0 +1,80 @@
+"""experiment_yolo_b200.loss.DealYoloLoss (TAL + BCE + Wise-IoU v3 + NWD + DFL) against fixtures minted from the reference's
+own v8DetectionLoss (oracle/gen_loss_golden.py imports the unmodified /root/reference criterion, utils/loss.py:293-433, and
+stores totals, loss items, head-map gradients and Wise-IoU's running mean).  CPU only; the head maps are regenerated from
+the recorded seeds (a stored checksum guards the RNG stream)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from experiment_yolo_b200.loss import DealYoloLoss, TaskAlignedAssigner, synthetic_uav_targets
+from oracle.gen_loss_golden import make_feats
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "loss_*.npz")))
+
+
+def _rel(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
+def test_fixtures_present():
+    assert len(GOLDEN) == 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[5:-4])
+@pytest.mark.parametrize("max_boxes_hint", [False, True])
+def test_loss_matches_reference_fixture(path, max_boxes_hint):
+    z = np.load(path)
+    img, calls, ci = int(z["img"]), int(z["calls"]), int(z["case_index"])
+    batch = {k: torch.from_numpy(z[k]) for k in ("batch_idx", "cls", "bboxes")}
+    n_max = None
+    if max_boxes_hint:      # the sync-free path: the caller states the padding width
+        n_max = int(np.bincount(z["batch_idx"].astype(np.int64)).max()) if z["batch_idx"].size else 0
+    crit = DealYoloLoss(nc=6, max_boxes=n_max)
+    for c in range(calls):
+        b = z[f"grad{c}_0"].shape[0]
+        feats = [f.requires_grad_(True) for f in make_feats(b, img, 2000 + 10 * ci + c)]
+        for i, f in enumerate(feats):      # same RNG stream as when the fixture was minted
+            assert abs(float(f.detach().double().sum()) - float(z[f"featsum{c}_{i}"])) < 1e-6 * f.numel()
+        total, items = crit(feats, batch)
+        total.backward()
+        assert abs(float(total) - float(z[f"total{c}"])) <= 2e-5 * abs(float(z[f"total{c}"]))
+        np.testing.assert_allclose(items.numpy(), z[f"items{c}"], rtol=2e-5, atol=1e-6)
+        assert abs(float(crit.wiou_loss.iou_mean) - float(z[f"iou_mean{c}"])) <= 1e-6
+        for i, f in enumerate(feats):
+            ref = z[f"grad{c}_{i}"]
+            got = f.grad.numpy() if f.grad is not None else np.zeros_like(ref)
+            assert _rel(got, ref) <= 1e-4, (c, i, _rel(got, ref))
+
+
+def test_assigner_invariants_on_uav_targets():
+    """Size-independent properties on a larger synthetic batch: every positive anchor lies inside its assigned box, no gt gets
+    more than topk positives, target scores are one-hot times a factor in [0, 1], padded gts never receive anchors."""
+    torch.manual_seed(0)
+    b, img = 4, 256
+    crit = DealYoloLoss(nc=6)
+    batch = synthetic_uav_targets(b, boxes_per_image=16, seed=3)
+    feats = make_feats(b, img, 77)
+    shapes = [tuple(f.shape[2:]) for f in feats]
+    from experiment_yolo_b200.loss import make_anchors
+    anc, st = make_anchors(shapes, crit.strides)
+    x = torch.cat([f.reshape(b, crit.no, -1) for f in feats], 2)
+    dist, scores = x.split((64, 6), 1)
+    dist = dist.permute(0, 2, 1).reshape(b, -1, 4, 16).softmax(3).matmul(torch.arange(16.0))
+    boxes = torch.cat((anc - dist[..., :2], anc + dist[..., 2:]), -1) * st
+    tg = crit.preprocess(batch, b, (img, img), "cpu")
+    labels, gtb = tg.split((1, 4), 2)
+    mask = (gtb.sum(2, keepdim=True) > 0).float()
+    tl, tb, ts, fg, gi = TaskAlignedAssigner(10, 6)(scores.permute(0, 2, 1).sigmoid(), boxes, anc * st, labels, gtb, mask)
+    assert fg.any()
+    pts = (anc * st).unsqueeze(0).expand(b, -1, -1)[fg]
+    box = tb[fg]
+    assert bool(((pts[:, 0] > box[:, 0]) & (pts[:, 0] < box[:, 2]) & (pts[:, 1] > box[:, 1]) & (pts[:, 1] < box[:, 3])).all())
+    for i in range(b):
+        cnt = torch.bincount(gi[i][fg[i]], minlength=16)
+        assert int(cnt.max()) <= 10
+    assert float(ts.max()) <= 1.0 + 1e-6 and float(ts.min()) >= 0.0
+    assert bool(((ts > 0).sum(-1) <= 1).all()) and float(ts[~fg].abs().max()) == 0.0
+    assert bool((ts[fg].argmax(-1) == tl[fg]).logical_or(ts[fg].sum(-1) == 0).all())
