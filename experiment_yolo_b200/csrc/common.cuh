@@ -227,6 +227,57 @@ __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// bilinear() on two fp32 lanes at once: products and sums rounded separately, term order lt, rb, lb, rt -- bit-identical to
+// two scalar bilinear() calls (the reference's element-wise kernels, conv.py:402-405).  The products stay scalar FMULs on
+// purpose: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even under -fmad=false), which would drop a rounding;
+// scalar mul.rn.f32 feeding add.rn.f32x2 is left alone (8 FMUL + 3 FADD2 instead of 8 FMUL + 6 FADD).
+__device__ __forceinline__ uint64_t bilinear_pair(uint64_t x00, uint64_t x11, uint64_t x01, uint64_t x10, const float4& g)
+{
+    auto scaled = [](uint64_t x, float w) {
+        float lo, hi;
+        f2_unpack(x, lo, hi);
+        return f2_pack(__fmul_rn(w, lo), __fmul_rn(w, hi));
+    };
+    uint64_t v = f2_add(scaled(x00, g.x), scaled(x11, g.y));
+    v = f2_add(v, scaled(x01, g.z));
+    v = f2_add(v, scaled(x10, g.w));
+    return v;
+}
+// one 16-byte vector of T from its four corner vectors (exact reference rounding; bf16: rounded once at the end)
+template <typename T> __device__ __forceinline__ uint4 bilinear_vec16(const uint4& q00, const uint4& q11, const uint4& q01,
+                                                                      const uint4& q10, const float4& g);
+template <> __device__ __forceinline__ uint4 bilinear_vec16<float>(const uint4& q00, const uint4& q11, const uint4& q01,
+                                                                   const uint4& q10, const float4& g)
+{
+    auto pr = [](uint32_t lo, uint32_t hi) { return f2_pack(__uint_as_float(lo), __uint_as_float(hi)); };
+    const uint64_t a = bilinear_pair(pr(q00.x, q00.y), pr(q11.x, q11.y), pr(q01.x, q01.y), pr(q10.x, q10.y), g);
+    const uint64_t b = bilinear_pair(pr(q00.z, q00.w), pr(q11.z, q11.w), pr(q01.z, q01.w), pr(q10.z, q10.w), g);
+    float a0, a1, b0, b1;
+    f2_unpack(a, a0, a1);
+    f2_unpack(b, b0, b1);
+    return make_uint4(__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(b0), __float_as_uint(b1));
+}
+template <> __device__ __forceinline__ uint4 bilinear_vec16<__nv_bfloat16>(const uint4& q00, const uint4& q11, const uint4& q01,
+                                                                           const uint4& q10, const float4& g)
+{
+    auto widen = [](uint32_t w) { return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
+    auto one = [&](uint32_t w00, uint32_t w11, uint32_t w01, uint32_t w10) {
+        float lo, hi;
+        f2_unpack(bilinear_pair(widen(w00), widen(w11), widen(w01), widen(w10), g), lo, hi);
+        uint32_t r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+    };
+    return make_uint4(one(q00.x, q11.x, q01.x, q10.x), one(q00.y, q11.y, q01.y, q10.y), one(q00.z, q11.z, q01.z, q10.z),
+                      one(q00.w, q11.w, q01.w, q10.w));
+}
+
 // two bf16 lanes of four corner words -> the bilinear sum of bilinear_fma() per lane, rounded once to bf16x2
 __device__ __forceinline__ uint32_t bilinear_bf16x2(uint32_t w00, uint32_t w11, uint32_t w01, uint32_t w10, const float4& g)
 {

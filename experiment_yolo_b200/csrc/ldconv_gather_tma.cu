@@ -140,15 +140,8 @@ gather_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmX, const T* __rest
             const uint4* g0 = xb4 + cv;
             q00 = __ldg(g0 + (o.x & 0x7fffffffu)); q11 = __ldg(g0 + o.y); q01 = __ldg(g0 + o.z); q10 = __ldg(g0 + o.w);
         }
-        float x00[V], x11[V], x01[V], x10[V], r[V];
-        Vec16<T>::unpack(q00, x00);
-        Vec16<T>::unpack(q11, x11);
-        Vec16<T>::unpack(q01, x01);
-        Vec16<T>::unpack(q10, x10);
-#pragma unroll
-        for (int v = 0; v < V; ++v) r[v] = bilinear(gw.x, gw.y, gw.z, gw.w, x00[v], x11[v], x01[v], x10[v]);
         const int pi = (int)__umulhi((unsigned)it, g.inv_row);
-        out4[(long long)pi * row_stride + (it - pi * row_items)] = Vec16<T>::pack(r);
+        out4[(long long)pi * row_stride + (it - pi * row_items)] = bilinear_vec16<T>(q00, q11, q01, q10, gw);
     }
     if (miss_counter) {
         misses = (unsigned)__reduce_add_sync(0xffffffffu, misses);

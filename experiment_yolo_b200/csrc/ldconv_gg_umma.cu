@@ -36,6 +36,7 @@ struct GGGeom {
     int TH, TW, tw_shift, THin, TWin, halo, tiles_h, tiles_w, num_tiles;
     int XB, AB, ldo, act, per_sm, dbg;
     int xb_mask, xb_shift, ab_mask;      // XB, AB in {1, 2}: buffer = it & mask, mbarrier parity = (it >> shift) & 1
+    int TG;                              // v2 kernel: thread groups of 128 per CTA (3 when N % 3 == 0: one sample per thread)
     float hm, wm;                        // (float)(H - 1), (float)(W - 1)
     unsigned long long img_bytes;        // H * W * C * 2
     unsigned inv_n, inv_img, inv_tw;
@@ -339,8 +340,8 @@ ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 //   * the bilinear sum and the folded BatchNorm + SiLU run on packed fp32 pairs (FFMA2): half the FMA-pipe instructions with
 //     bit-identical results; the SiLU's 0.5 is folded into the affine.
 // Requires C / 8 to be a power of two; other channel counts keep the kernel above.
-template <int TN, int TCVS, int TS, int MINB>
-__global__ void __launch_bounds__(kGGThreads, MINB)
+template <int TN, int TCVS, int TS, int TG, int MINB>
+__global__ void __launch_bounds__(128 * TG, MINB)
 ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __nv_bfloat16* __restrict__ x, const float* __restrict__ off, const int* __restrict__ pn,
                   const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
@@ -358,6 +359,8 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float* sAff = reinterpret_cast<float*>(smem + g.ofs_aff);      // [0, ON) scale, [ON, 2 ON) shift (halved for SiLU)
     const uint32_t aff_s = smem_s + g.ofs_aff;
 
+    constexpr int NTHR = 128 * TG;       // TG thread groups of 128: group = n phase of the samples, slice of the epilogue chunks
+    constexpr int kIssuer = TG == 2 ? 128 : 0;      // the group with the least other work issues TMA / tcgen05.mma
     const int tid = threadIdx.x, warp = tid >> 5;
     const int N = TN > 0 ? TN : g.N;
     const int cvs = TCVS >= 0 ? TCVS : g.cv_shift;
@@ -375,7 +378,7 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         t.j0 = (rem - ti * g.tiles_w) * g.TW;
         return t;
     };
-    auto issue_x_tile = [&](int tile, int xb) {                         // thread 0 only
+    auto issue_x_tile = [&](int tile, int xb) {                         // one thread
         const TC t = tile_coords(tile);
         mbar_arrive_expect_tx(&x_full[xb], g.x_tx_bytes);
         tma_load_4d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, t.j0 * s - g.halo, t.i0 * s - g.halo, t.b);
@@ -394,7 +397,7 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const bool act_silu = g.act == LDCONV_ACT_SILU;
     {
         const float pre = act_silu ? 0.5f : 1.f;      // silu(z) = hz + hz tanh(hz), hz = z / 2: the halving is exact
-        for (int o = tid; o < g.ON; o += kGGThreads) {
+        for (int o = tid; o < g.ON; o += NTHR) {
             sAff[o] = pre * ((scale && o < g.O) ? scale[o] : 1.f);
             sAff[g.ON + o] = pre * ((shift && o < g.O) ? shift[o] : 0.f);
         }
@@ -419,30 +422,30 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     int br[2], bk[2];                                          // di * s + pn_r[n], dj * s + pn_k[n] of sample rounds 0, 1
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        const int n = n0 + 2 * r;
-        has[r] = n < N;
+        const int n = n0 + TG * r;
+        has[r] = (TN > 0 && TN <= TG * r) ? false : n < N;
         br[r] = di * s + (has[r] ? pn[n] : 0);
         bk[r] = dj * s + (has[r] ? pn[N + n] : 0);
     }
-    float2 ofs[2];                                             // offsets of those samples, prefetched one tile ahead
-    auto fetch_offsets = [&](const TC& t) {
+    float2 ofs[2], ofs_n[2];                                   // offsets of those samples: this tile / prefetched for the next
+    auto fetch_offsets = [&](const TC& t, float2 (&dst)[2]) {
         const bool valid = t.i0 + di < g.h && t.j0 + dj < g.w;
         const float* op = off + (((size_t)t.b * g.h + t.i0) * g.w + t.j0) * (size_t)(2 * N) + pix_f + n0;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
-            if (valid && has[r]) ofs[r] = make_float2(__ldg(op + 2 * r), __ldg(op + N + 2 * r));
+            if (valid && has[r]) dst[r] = make_float2(__ldg(op + TG * r), __ldg(op + N + TG * r));
     };
-    ofs[0] = ofs[1] = make_float2(0.f, 0.f);
+    ofs[0] = ofs[1] = ofs_n[0] = ofs_n[1] = make_float2(0.f, 0.f);
 
-    const int cv = tid & ((1 << cvs) - 1), sx0 = tid >> cvs;   // phase 2: item round k handles sample sx0 + k * (256 >> cvs)
-    const int spr = 256 >> cvs;
-    const int rounds = (N << cvs) >> 1;                        // 128 N CV items / 256 threads (K % 16 == 0 makes it exact)
-    const int half = warp >> 2;
+    const int cv = tid & ((1 << cvs) - 1), sx0 = tid >> cvs;   // phase 2: item round k handles sample sx0 + k * (NTHR >> cvs)
+    const int spr = NTHR >> cvs;
+    const int rounds = (N << cvs) / TG;                        // 128 N CV items / NTHR threads (the host checks divisibility)
+    const int grp = warp >> 2;
     const int chunks = g.ON / 16;
-    const int ch_begin = half == 0 ? 0 : (chunks + 1) / 2, ch_end = half == 0 ? (chunks + 1) / 2 : chunks;
+    const int ch_begin = chunks * grp / TG, ch_end = chunks * (grp + 1) / TG;
 
     // epilogue of one finished tile: TMEM lane = this thread's pixel, this warp's half of the 16-column chunks
-    auto epilogue = [&](T* orow, int eit) {
+    auto epilogue = [&](int m_out, int eit) {      // m_out: output pixel index ((b h + i) w + j) of this thread, -1 outside the map
         const int tb = eit & 1;
         mbar_wait(&mma_done[tb], (eit >> 1) & 1);
         tc_fence_after_sync();
@@ -452,7 +455,7 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             uint32_t v[16];
             tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
             tmem_ld_wait();
-            if (orow == nullptr || c0 >= g.O) continue;
+            if (m_out < 0 || c0 >= g.O) continue;
             uint32_t w[8];
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
@@ -482,7 +485,7 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[e >> 1]) : "f"(a1), "f"(a0));
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[(e >> 1) + 1]) : "f"(a3), "f"(a2));
             }
-            uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m_out * (size_t)g.ldo + c0);
             dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
             dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
@@ -493,15 +496,17 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int rowB = g.TWin << (cvs + 4), pixB = 16 << cvs;    // bytes per staged tile row / per pixel
     const int imgRowB = g.W << (cvs + 4);
     TC cur = tile_coords(blockIdx.x);
-    if ((int)blockIdx.x < g.num_tiles) fetch_offsets(cur);
-    T* prev_out = nullptr;
+    if ((int)blockIdx.x < g.num_tiles) fetch_offsets(cur, ofs);
+    int prev_m = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
         const int xb = it & g.xb_mask, ab = it & g.ab_mask, tb = it & 1;
         const uint32_t rec_s = smem_s + g.ofs_rec;      // last read in phase 2 of the previous tile: barrier (B) lies in between
         const int r_org = cur.i0 * s - g.halo, k_org = cur.j0 * s - g.halo;
         const bool valid = cur.i0 + di < g.h && cur.j0 + dj < g.w;
-        T* cur_out = valid ? out + (((size_t)cur.b * g.h + cur.i0 + di) * g.w + cur.j0 + dj) * (size_t)g.ldo : nullptr;
+        const int cur_m = valid ? ((cur.b * g.h + cur.i0 + di) * g.w + cur.j0 + dj) : -1;
+        // next tile: its offsets are requested now and have both phases to arrive
+        if (tile + (int)gridDim.x < g.num_tiles) fetch_offsets(tile_coords(tile + gridDim.x), ofs_n);
 
         // ---- phase 1: one record per sample (n-major: sample = n * 128 + pixel) ------------------------------------------------
         auto make_record = [&](int n, int ri, int ki, float o_r, float o_k) {
@@ -527,9 +532,9 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         };
         const int gr = cur.i0 * s, gk = cur.j0 * s;
         if (has[0]) make_record(n0, gr + br[0], gk + bk[0], ofs[0].x, ofs[0].y);
-        if (has[1]) make_record(n0 + 2, gr + br[1], gk + bk[1], ofs[1].x, ofs[1].y);
-        if (TN == 0 || TN > 4) {
-            for (int n = n0 + 4; n < N; n += 2) {
+        if (has[1]) make_record(n0 + TG, gr + br[1], gk + bk[1], ofs[1].x, ofs[1].y);
+        if (TN == 0 || TN > 2 * TG) {
+            for (int n = n0 + 2 * TG; n < N; n += TG) {
                 float o_r = 0.f, o_k = 0.f;
                 if (valid) {
                     const float* op = off + (((size_t)cur.b * g.h + cur.i0) * g.w + cur.j0) * (size_t)(2 * N) + pix_f;
@@ -537,12 +542,6 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
                 make_record(n, gr + di * s + pn[n], gk + dj * s + pn[N + n], o_r, o_k);
             }
-        }
-        // next tile: coordinates once, offsets prefetched behind phase 2
-        TC nxt = cur;
-        if (tile + (int)gridDim.x < g.num_tiles) {
-            nxt = tile_coords(tile + gridDim.x);
-            fetch_offsets(nxt);
         }
         __syncthreads();                                              // (A) records of this tile are visible
         mbar_wait(&x_full[xb], (uint32_t)(it >> g.xb_shift) & 1u);   // the staged input tile has landed
@@ -578,9 +577,9 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                           bilinear_bf16x2(q[0].x, q[1].x, q[2].x, q[3].x, gw), bilinear_bf16x2(q[0].y, q[1].y, q[2].y, q[3].y, gw),
                           bilinear_bf16x2(q[0].z, q[1].z, q[2].z, q[3].z, gw), bilinear_bf16x2(q[0].w, q[1].w, q[2].w, q[3].w, gw));
             };
-            // IF items in flight per thread (loads first, then the arithmetic): two under the 80-register cap of three CTAs
-            // per SM, four when the shared-memory footprint allows fewer CTAs anyway (latency-bound there)
-            constexpr int IF = (MINB >= 3 || TN == 0) ? 2 : 4;
+            // IF items in flight per thread (loads first, then the arithmetic): two under an 80-register cap, four when the
+            // shared-memory footprint allows so few CTAs that 120+ registers are free anyway (latency-bound there)
+            constexpr int IF = (65536 / (NTHR * MINB) >= 120 && TN != 0) ? 4 : 2;
             auto step = [&](int k, int nrounds) {
                 float4 gw[IF];
                 uint4 q[IF][4];
@@ -592,7 +591,8 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     if (k + u < nrounds) store_item(sx0 + (k + u) * spr, gw[u], q[u]);
             };
             if constexpr (TN > 0 && TCVS >= 0) {
-                constexpr int R = (TN << TCVS) >> 1;
+                constexpr int R = (TN << TCVS) / TG;
+                static_assert((TN << TCVS) % TG == 0, "items per tile must divide evenly over the threads");
 #pragma unroll
                 for (int k = 0; k < R; k += IF) step(k, R);
             } else {
@@ -602,29 +602,37 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         fence_proxy_async_smem();      // generic-proxy stores of the operand tile -> visible to tcgen05 (async proxy)
         __syncthreads();               // (B) operand tile complete, input tile consumed, epilogue(it-2) done by every warp
 
-        if (tid == 0) {
+        if (tid == kIssuer) {
             if (tile + g.XB * (int)gridDim.x < g.num_tiles) issue_x_tile(tile + g.XB * gridDim.x, xb);
             if (it == 0) mbar_wait(w_full, 0);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)(tb * g.ON);
-            const uint32_t a_addr = smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes;
-            const uint32_t b_addr = smem_s + g.ofs_b;
+            const uint64_t da = make_desc_k_sw128(smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes);
+            const uint64_t desc_b0 = make_desc_k_sw128(smem_s + g.ofs_b);      // + (bytes >> 4): address field, bits [0, 14), no carry
             for (int st = 0; st < g.ksteps; ++st) {
                 const uint32_t kb = (uint32_t)st >> 2, kk = (uint32_t)st & 3;
-                mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + kb * 16384u + kk * 32u),
-                            make_desc_k_sw128(b_addr + kb * g.b_bytes + kk * 32u), idesc, (uint32_t)(st != 0));
+                mma_bf16_ss(d_tmem, da + (uint64_t)(kb * 1024u + kk * 2u), desc_b0 + (uint64_t)(kb * (g.b_bytes >> 4) + kk * 2u), idesc,
+                            (uint32_t)(st != 0));
             }
             mma_commit(&mma_done[tb]);
         }
         __syncwarp();
-        if (it > 0) epilogue(prev_out, it - 1);      // the previous tile's MMA ran during this tile's phases
-        prev_out = cur_out;
-        cur = nxt;
+        if (it > 0) epilogue(prev_m, it - 1);      // the previous tile's MMA ran during this tile's phases
+        prev_m = cur_m;
+        if (tile + (int)gridDim.x < g.num_tiles) cur = tile_coords(tile + gridDim.x);      // recomputed: cheaper than 3 live registers
+        ofs[0] = ofs_n[0]; ofs[1] = ofs_n[1];
     }
-    if (it > 0) epilogue(prev_out, it - 1);
+    if (it > 0) epilogue(prev_m, it - 1);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+static int gg_v2_enabled()      // LDCONV_GG_V=1: the generic kernel everywhere (A/B partner); 3: v2 without shape specialisation
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_GG_V"); v = e ? atoi(e) : 2; }
+    return v >= 2 ? v : 0;
 }
 
 static void gg_pn_extent(int N, int* max_r, int* max_k)
@@ -676,7 +684,15 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     int best_ctas = 0;
     GGGeom best = g;
     size_t best_smem = 0;
-    static int env_plan = -2, env_ctas = -2;      // experiments: LDCONV_GG_PLAN=<plan index>, LDCONV_GG_CTAS=<CTAs per SM>
+    static int env_plan = -2, env_ctas = -2, env_tg = -2;      // experiments: LDCONV_GG_PLAN=<plan index>, LDCONV_GG_CTAS=<CTAs per SM>
+    if (env_tg == -2) { const char* e = getenv("LDCONV_GG_TG"); env_tg = e ? atoi(e) : -1; }
+    // N = 3 (every strided LDConv of yolov8-LD-P2): 384 samples per tile -> 384 threads make phase 1 one balanced round
+    // (profiles/r1_ncu_ggL1v4.txt: 17 % of the stall samples were warps 4-7 waiting at barrier A for the second round of warps 0-3)
+    // measured (B = 64, bf16): C = 32 / 64 gain 3-7 % with 384 threads (shared memory limits them to 1-2 CTAs per SM, so the extra
+    // warps are free); C = 16 (layer 1) loses 9 % (two CTAs of 12 warps instead of three of 8) and keeps 256 threads
+    g.TG = (gg_v2_enabled() && g.cv_shift >= 2 && N % 3 == 0) ? 3 : 2;
+    if (env_tg == 2 || env_tg == 3) g.TG = (env_tg == 3 && (N * g.CV) % 3 != 0) ? 2 : env_tg;
+    const int reg_cap = g.TG == 3 ? 2 : 3;      // CTAs per SM the register file allows at 80 registers per thread
     if (env_plan == -2) { const char* e = getenv("LDCONV_GG_PLAN"); env_plan = e ? atoi(e) : -1; }
     if (env_ctas == -2) { const char* e = getenv("LDCONV_GG_CTAS"); env_ctas = e ? atoi(e) : -1; }
     for (int ci = 0; ci < 5; ++ci) {
@@ -698,7 +714,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
         const size_t need = (size_t)ofs + 1024;
         if (need > 225 * 1024) continue;
         int ctas = (int)((227 * 1024) / (need + 1024));          // + the per-CTA reservation of the driver
-        if (ctas > 3) ctas = 3;
+        if (ctas > reg_cap) ctas = reg_cap;
         if (ctas > (int)(512u / g.tmem_cols)) ctas = (int)(512u / g.tmem_cols);
         if (env_ctas >= 1 && ctas > env_ctas) ctas = env_ctas;
         if (ctas > best_ctas) { best_ctas = ctas; best = g; best_smem = need; }
@@ -710,7 +726,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     g.tiles_h = (g.h + g.TH - 1) / g.TH;
     g.tiles_w = (g.w + g.TW - 1) / g.TW;
     const long long nt = (long long)B * g.tiles_h * g.tiles_w;
-    if (nt > 0x7fffffffll) return 0;
+    if (nt > 0x7fffffffll || (long long)B * g.h * g.w > 0x7fffffffll) return 0;
     g.num_tiles = (int)nt;
     { static int d = -1; if (d < 0) { const char* e = getenv("LDCONV_GG_DBG"); d = e ? atoi(e) : 0; } g.dbg = d; }
     // tile / tiles_per_img and rem / tiles_w as __umulhi(x, ceil(2^32 / d)): exact while x * d < 2^32
@@ -763,28 +779,33 @@ int gather_gemm_fwd(const void* x, const float* off, const int* pn, const void* 
     using Kern = void (*)(CUtensorMap, CUtensorMap, const __nv_bfloat16*, const float*, const int*, const float*, const float*,
                           __nv_bfloat16*, GGGeom);
     Kern kern = ldconv_gg_kernel<3>;      // <= 84 registers, no spills; a 64-register build for four CTAs per SM measured equal
-    static int env_v = -1;                // LDCONV_GG_V=1: the generic kernel everywhere (A/B partner)
-    if (env_v < 0) { const char* e = getenv("LDCONV_GG_V"); env_v = e ? atoi(e) : 2; }
-    if (env_v >= 2 && g.cv_shift >= 0) {
-        // the register cap follows the CTAs per SM the shared-memory plan allows (80 / 128 / 255 registers)
-        kern = g.per_sm >= 3 ? ldconv_gg2_kernel<0, -1, 0, 3> : g.per_sm == 2 ? ldconv_gg2_kernel<0, -1, 0, 2> : ldconv_gg2_kernel<0, -1, 0, 1>;
-        const int key = N * 1000 + g.cv_shift * 100 + s * 10 + g.per_sm;      // yolov8-LD-P2 shapes: compile-time index arithmetic
+    int threads = kGGThreads;
+    const int env_v = gg_v2_enabled();
+    if (env_v && g.cv_shift >= 0) {
+        threads = 128 * g.TG;
+        // the register cap follows the CTAs per SM the shared-memory plan allows (80 / 128 / 255 registers at 256 threads)
+        if (g.TG == 3) kern = g.per_sm >= 2 ? ldconv_gg2_kernel<0, -1, 0, 3, 2> : ldconv_gg2_kernel<0, -1, 0, 3, 1>;
+        else kern = g.per_sm >= 3 ? ldconv_gg2_kernel<0, -1, 0, 2, 3> : g.per_sm == 2 ? ldconv_gg2_kernel<0, -1, 0, 2, 2> : ldconv_gg2_kernel<0, -1, 0, 2, 1>;
+        const int key = (((N * 10 + g.cv_shift) * 10 + s) * 10 + g.TG) * 10 + g.per_sm;      // yolov8-LD-P2 shapes: compile-time indices
         if (env_v == 2) switch (key) {
-            case 3123: kern = ldconv_gg2_kernel<3, 1, 2, 3>; break;      // C = 16 (layer 1)
-            case 3222: kern = ldconv_gg2_kernel<3, 2, 2, 2>; break;      // C = 32 (layers 3, 18)
-            case 3221: kern = ldconv_gg2_kernel<3, 2, 2, 1>; break;
-            case 3321: kern = ldconv_gg2_kernel<3, 3, 2, 1>; break;      // C = 64 (layers 5, 21)
-            case 1213: kern = ldconv_gg2_kernel<1, 2, 1, 3>; break;      // C = 32 (layer 15)
-            case 1313: kern = ldconv_gg2_kernel<1, 3, 1, 3>; break;      // C = 64 (layers 10, 13)
-            case 1412: kern = ldconv_gg2_kernel<1, 4, 1, 2>; break;      // C = 128 (layer 8)
-            case 1411: kern = ldconv_gg2_kernel<1, 4, 1, 1>; break;
+            case 31232: kern = ldconv_gg2_kernel<3, 1, 2, 3, 2>; break;      // C = 16 (layer 1)
+            case 32232: kern = ldconv_gg2_kernel<3, 2, 2, 3, 2>; break;      // C = 32 (layers 3, 18)
+            case 32231: kern = ldconv_gg2_kernel<3, 2, 2, 3, 1>; break;
+            case 33231: kern = ldconv_gg2_kernel<3, 3, 2, 3, 1>; break;      // C = 64 (layers 5, 21)
+            case 31223: kern = ldconv_gg2_kernel<3, 1, 2, 2, 3>; break;      // the 256-thread variants (LDCONV_GG_TG=2)
+            case 32222: kern = ldconv_gg2_kernel<3, 2, 2, 2, 2>; break;
+            case 33221: kern = ldconv_gg2_kernel<3, 3, 2, 2, 1>; break;
+            case 12123: kern = ldconv_gg2_kernel<1, 2, 1, 2, 3>; break;      // C = 32 (layer 15)
+            case 13123: kern = ldconv_gg2_kernel<1, 3, 1, 2, 3>; break;      // C = 64 (layers 10, 13)
+            case 14122: kern = ldconv_gg2_kernel<1, 4, 1, 2, 2>; break;      // C = 128 (layer 8)
+            case 14121: kern = ldconv_gg2_kernel<1, 4, 1, 2, 1>; break;
             default: break;
         }
     }
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * g.per_sm;
     if (grid > g.num_tiles) grid = g.num_tiles;
-    LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kGGThreads), smem, st, tmX, tmW, (const __nv_bfloat16*)x, off, pn, scale, shift,
+    LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, tmX, tmW, (const __nv_bfloat16*)x, off, pn, scale, shift,
                         (__nv_bfloat16*)out, g));
     LDC_LAUNCH_CHECK("ldconv_gg_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
