@@ -57,9 +57,12 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
     const T* xb = x + (size_t)b * H * W * C;
 
     // ---- offset conv (conv.py:368): 3x3 / pad 1 / stride s, fp32 accumulation ------------------------------------------
-    float offv[2 * NLOOP];
+    // accumulators as packed fp32 pairs (FFMA2: two FMAs per issued instruction, each lane rounds like the scalar fmaf; the
+    // kernel is issue-bound, profiles/r1_ncu_smallcL0b.txt); pair o2 = outputs (2 o2, 2 o2 + 1), rows of s_woff are 8-byte aligned
+    uint64_t offp[NLOOP];
 #pragma unroll
-    for (int o = 0; o < 2 * NLOOP; ++o) offv[o] = (o < O2 && b_off) ? b_off[o] : 0.f;
+    for (int o2 = 0; o2 < NLOOP; ++o2)
+        offp[o2] = f2_pack((2 * o2 < O2 && b_off) ? b_off[2 * o2] : 0.f, (2 * o2 + 1 < O2 && b_off) ? b_off[2 * o2 + 1] : 0.f);
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         const int r = i * s + tap / 3 - 1, k = j * s + tap % 3 - 1;
@@ -68,12 +71,16 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const float xv = Elem<T>::to_f(xp[c]);
-            const float* wp = s_woff + (tap * C + c) * O2;
+            const uint64_t xx = f2_pack(xv, xv);
+            const float2* wp = reinterpret_cast<const float2*>(s_woff + (tap * C + c) * O2);
 #pragma unroll
-            for (int o = 0; o < 2 * NLOOP; ++o)
-                if (o < O2) offv[o] = fmaf(xv, wp[o], offv[o]);
+            for (int o2 = 0; o2 < NLOOP; ++o2)
+                if (2 * o2 < O2) { const float2 wv = wp[o2]; offp[o2] = f2_fma(xx, f2_pack(wv.x, wv.y), offp[o2]); }
         }
     }
+    float offv[2 * NLOOP];
+#pragma unroll
+    for (int o2 = 0; o2 < NLOOP; ++o2) f2_unpack(offp[o2], offv[2 * o2], offv[2 * o2 + 1]);
     if (off_out) {
         float* op = off_out + (size_t)m * O2;
 #pragma unroll
@@ -83,9 +90,9 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
 
     // ---- sampling + (N,1) conv, one sample at a time (conv.py:369-408) ----------------------------------------------------
     constexpr int OMAX = OFIX ? OFIX : 32;
-    float acc[OMAX];
+    uint64_t accp[OMAX / 2];
 #pragma unroll
-    for (int o = 0; o < OMAX; ++o) acc[o] = 0.f;
+    for (int o = 0; o < OMAX / 2; ++o) accp[o] = 0ull;
 #pragma unroll
     for (int n = 0; n < NLOOP; ++n) {
         if (n >= N) break;
@@ -101,20 +108,22 @@ smallc_fused_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
             float v = bilinear(g_lt, g_rb, g_lb, g_rt, Elem<T>::to_f(p00[c]), Elem<T>::to_f(p11[c]), Elem<T>::to_f(p01[c]),
                                Elem<T>::to_f(p10[c]));
             v = Elem<T>::to_f(Elem<T>::from_f(v));       // the operand is rounded to the activation dtype, as in the 3-kernel path
+            const uint64_t vv = f2_pack(v, v);
             const float4* wrow = reinterpret_cast<const float4*>(s_wt + (n * C + c) * O);
 #pragma unroll
             for (int o4 = 0; o4 < OMAX / 4; ++o4) {
                 if (o4 * 4 < O) {
                     const float4 wv = wrow[o4];
-                    acc[o4 * 4 + 0] = fmaf(v, wv.x, acc[o4 * 4 + 0]);
-                    acc[o4 * 4 + 1] = fmaf(v, wv.y, acc[o4 * 4 + 1]);
-                    acc[o4 * 4 + 2] = fmaf(v, wv.z, acc[o4 * 4 + 2]);
-                    acc[o4 * 4 + 3] = fmaf(v, wv.w, acc[o4 * 4 + 3]);
+                    accp[o4 * 2 + 0] = f2_fma(vv, f2_pack(wv.x, wv.y), accp[o4 * 2 + 0]);
+                    accp[o4 * 2 + 1] = f2_fma(vv, f2_pack(wv.z, wv.w), accp[o4 * 2 + 1]);
                 }
             }
         }
     }
     // ---- folded BatchNorm + SiLU, 16-byte stores ----------------------------------------------------------------------
+    float acc[OMAX];
+#pragma unroll
+    for (int o = 0; o < OMAX / 2; ++o) f2_unpack(accp[o], acc[2 * o], acc[2 * o + 1]);
     T* dst = out + (size_t)m * O;
     constexpr int V = Vec16<T>::N;
 #pragma unroll

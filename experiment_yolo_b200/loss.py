@@ -64,8 +64,44 @@ def ciou(b1, b2, eps=1e-7):
 class TaskAlignedAssigner:
     """tal.py:13-290 on dense, statically shaped tensors (no boolean-mask indexing, no data-dependent branches)."""
 
-    def __init__(self, topk=10, num_classes=80, alpha=0.5, beta=6.0, eps=1e-9):
+    def __init__(self, topk=10, num_classes=80, alpha=0.5, beta=6.0, eps=1e-9, fused=True):
         self.topk, self.nc, self.alpha, self.beta, self.eps = topk, num_classes, alpha, beta, eps
+        self.fused = fused      # CUDA tensors: the three kernels of csrc/ldconv_tal.cu instead of ~60 dense PyTorch passes
+
+    def _fused(self, pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, valid_gt):
+        """Same assignment through libldconv_b200 (ldconv_tal_metric / ldconv_tal_assign); torch.topk stays a library call."""
+        from . import _lib
+        L = _lib.load()
+        b, na, nc = pd_scores.shape
+        n = gt_bboxes.shape[1]
+        dev = pd_scores.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        f32 = dict(device=dev, dtype=torch.float32)
+        scores, boxes = pd_scores.float().contiguous(), pd_bboxes.float().contiguous()
+        anc, gtb = anc_points.float().contiguous(), gt_bboxes.float().contiguous()
+        labels = gt_labels.reshape(b, n).to(torch.int32).contiguous()
+        valid = valid_gt.reshape(b, n).to(torch.uint8).contiguous()
+        align, overlaps = torch.empty((b, n, na), **f32), torch.empty((b, n, na), **f32)
+        _lib.check(L.ldconv_tal_metric(scores.data_ptr(), boxes.data_ptr(), anc.data_ptr(), labels.data_ptr(), gtb.data_ptr(),
+                                       valid.data_ptr(), align.data_ptr(), overlaps.data_ptr(), b, na, n, nc, self.alpha, self.beta,
+                                       self.eps, st), "ldconv_tal_metric")
+        k = min(self.topk, na)
+        idx = torch.topk(align, k, dim=-1).indices.contiguous()
+        mask_ws = torch.empty((b, n, na), device=dev, dtype=torch.uint8)
+        fg = torch.empty((b, na), device=dev, dtype=torch.uint8)
+        gt_idx = torch.empty((b, na), device=dev, dtype=torch.int64)
+        align_sel = torch.empty((b, na), **f32)
+        pos_align, pos_over = torch.empty((b, n), **f32), torch.empty((b, n), **f32)
+        _lib.check(L.ldconv_tal_assign(idx.data_ptr(), anc.data_ptr(), gtb.data_ptr(), valid.data_ptr(), align.data_ptr(),
+                                       overlaps.data_ptr(), mask_ws.data_ptr(), fg.data_ptr(), gt_idx.data_ptr(), align_sel.data_ptr(),
+                                       pos_align.data_ptr(), pos_over.data_ptr(), b, na, n, k, self.eps, st), "ldconv_tal_assign")
+        fgb = fg.bool()
+        flat = gt_idx + torch.arange(b, device=dev).view(-1, 1) * n
+        target_labels = gt_labels.long().flatten()[flat].clamp(min=0)
+        target_bboxes = gt_bboxes.reshape(-1, 4)[flat]
+        norm = align_sel * pos_over.flatten()[flat] / (pos_align.flatten()[flat] + self.eps)      # 0 on the background
+        target_scores = F.one_hot(target_labels, self.nc).to(align.dtype) * norm.unsqueeze(-1)
+        return target_labels, target_bboxes, target_scores, fgb, gt_idx
 
     @torch.no_grad()
     def __call__(self, pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, mask_gt):
@@ -79,6 +115,8 @@ class TaskAlignedAssigner:
                     torch.zeros_like(pd_scores), torch.zeros((b, na), device=pd_scores.device, dtype=torch.bool),
                     torch.zeros((b, na), device=pd_scores.device, dtype=torch.long))
         valid_gt = mask_gt.bool()                                                         # (b,n,1)
+        if pd_scores.is_cuda and self.fused and n <= 256:
+            return self._fused(pd_scores, pd_bboxes, anc_points, gt_labels, gt_bboxes, valid_gt)
         # anchors strictly inside each gt box (tal.py:226-243)
         lt, rb = gt_bboxes.view(b, n, 1, 4).chunk(2, -1)
         ap = anc_points.view(1, 1, na, 2)
@@ -164,12 +202,12 @@ class DealYoloLoss(nn.Module):
     """
 
     def __init__(self, nc=6, reg_max=16, strides=(4.0, 8.0, 16.0), box=7.5, cls=0.5, dfl=1.5, topk=10, use_wiseiou=True,
-                 nwd_loss=True, iou_ratio=0.5, max_boxes=None):
+                 nwd_loss=True, iou_ratio=0.5, max_boxes=None, fused_assigner=True):
         super().__init__()
         self.nc, self.reg_max, self.no = nc, reg_max, nc + 4 * reg_max
         self.strides = [float(s) for s in strides]
         self.hyp = SimpleNamespace(box=box, cls=cls, dfl=dfl)
-        self.assigner = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=0.5, beta=6.0)
+        self.assigner = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=0.5, beta=6.0, fused=fused_assigner)
         self.topk = topk
         self.use_wiseiou, self.nwd_loss, self.iou_ratio = use_wiseiou, nwd_loss, iou_ratio
         self.wiou_loss = WiseIoU()
@@ -197,13 +235,14 @@ class DealYoloLoss(nn.Module):
         return out
 
     def forward(self, feats, batch):
-        feats = [f.float() for f in feats[:len(self.strides)]]
+        feats = list(feats[:len(self.strides)])
         b = feats[0].shape[0]
         dev = feats[0].device
+        # one concatenation in the maps' own dtype (bf16 under autocast), one fp32 conversion fused with the transposition
         x = torch.cat([f.reshape(b, self.no, -1) for f in feats], 2)
         pred_distri, pred_scores = x.split((self.reg_max * 4, self.nc), 1)
-        pred_scores = pred_scores.permute(0, 2, 1).contiguous()                            # (b,na,nc)
-        pred_distri = pred_distri.permute(0, 2, 1).contiguous()                            # (b,na,4*reg_max)
+        pred_scores = pred_scores.permute(0, 2, 1).float().contiguous()                    # (b,na,nc)
+        pred_distri = pred_distri.permute(0, 2, 1).float().contiguous()                    # (b,na,4*reg_max)
         na = pred_scores.shape[1]
         shapes = [tuple(f.shape[2:]) for f in feats]
         imgsz = (shapes[0][0] * self.strides[0], shapes[0][1] * self.strides[0])

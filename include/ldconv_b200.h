@@ -209,6 +209,20 @@ int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const floa
 int ldconv_detect_decode(const void* box, const void* cls, void* y, int B, int H, int W, int nc, int reg_max, float stride,
                          int anchor_offset, int total_anchors, int dtype, void* stream);
 
+/* Task-aligned assigner of the training criterion (utils/tal.py:13-290), dense part, fp32:
+ * ldconv_tal_metric: scores (B,na,nc) in [0,1], boxes (B,na,4) xyxy px, anchors (na,2) px, gt_labels (B,n) int32, gt_boxes (B,n,4)
+ *   xyxy px, gt_valid (B,n) bytes -> align = score[label]^alpha * max(CIoU, 0)^beta and overlaps = max(CIoU, 0) on anchors
+ *   strictly inside the gt box (tal.py:98-122, :226-243, utils/metrics.py:103-128), 0 elsewhere; both (B,n,na).
+ * ldconv_tal_assign: topk_idx (B,n,k) int64 = torch.topk(align, k).indices -> foreground flags fg (B,na) bytes, assigned gt
+ *   gt_idx (B,na) int64, align_sel (B,na) = metric of the assigned pair, pos_align / pos_over (B,n) = per-gt maxima over its
+ *   positives (tal.py:124-157, :245-272, :83-88).  mask_ws: B*n*na bytes of workspace (zeroed by the call). */
+int ldconv_tal_metric(const float* scores, const float* boxes, const float* anchors, const int32_t* gt_labels,
+                      const float* gt_boxes, const unsigned char* gt_valid, float* align, float* overlaps, int B, int na, int n,
+                      int nc, float alpha, float beta, float eps, void* stream);
+int ldconv_tal_assign(const long long* topk_idx, const float* anchors, const float* gt_boxes, const unsigned char* gt_valid,
+                      const float* align, const float* overlaps, unsigned char* mask_ws, unsigned char* fg, long long* gt_idx,
+                      float* align_sel, float* pos_align, float* pos_over, int B, int na, int n, int k, float eps, void* stream);
+
 /* Glue ops of the graph (bf16 NHWC, channel-slice aware through the pixel strides ld*):
  * nearest up-sampling by an integer factor (yolov8-LD-P2.yaml:26,33); the SSFF tail = max over the three pyramid levels,
  * coarser levels indexed like torch's nearest interpolation, + optional residual (nn/extra_modules/block.py:3432-3443,
