@@ -245,7 +245,7 @@ def ldconv_roofline(model, x, peaks, iters: int):
     roof = None
     if big is not None:
         ach = big["gg_MB"] * 1e3 / big["gg_us"]
-        roof = {"bound": "hbm", "kernel": f"ldconv_gg_kernel (LDConv gather + GEMM + BN + SiLU, layer {big['layer']}: the largest "
+        roof = {"bound": "hbm", "kernel": f"ldconv_gg2_kernel (LDConv gather + GEMM + BN + SiLU, layer {big['layer']}: the largest "
                 "LDConv launch of the step)", "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "frac_of_8TBs_nominal": round(ach / 8000.0, 4),
                 "traffic": traffic.get("ldconv_gg_kernel_layer1_bytes"), "algorithmic_bytes_per_launch": round(big["gg_MB"] * 1e6),

@@ -276,7 +276,8 @@ int conv3x3_zc_supported(int Cin, int Cout, int s, int mode)
     const int ON = (Cout + 15) / 16 * 16;
     const size_t wbytes = (size_t)((9 * Cin + 63) / 64) * ON * 128;
     const size_t xbytes = (size_t)kZcTHs * kZcTWs * Cin * 2 + 2048;
-    return wbytes + 2 * xbytes + 4096 <= 220 * 1024;
+    // one input buffer is enough to run (TMA and MMA of consecutive tiles then alternate): Cin = 128 -> Cout = 64 (Detect, P4)
+    return wbytes + xbytes + 4096 <= 220 * 1024;
 }
 
 int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const float* shift, const void* residual,
@@ -316,7 +317,7 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     if (want < 2) want = 2;
     if (xb > want) xb = want;
     if (xb > kZcMaxX) xb = kZcMaxX;
-    if (xb < 2) return fail(LDCONV_E_ARG, "conv3x3 zero-copy: does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
+    if (xb < 1) return fail(LDCONV_E_ARG, "conv3x3 zero-copy: does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
     g.xbufs = (int)xb;
     uint32_t ofs = 0;
     g.ofs_x = ofs; ofs += (uint32_t)g.xbufs * g.x_bytes;

@@ -502,27 +502,30 @@ __device__ __forceinline__ void red_add_vec(float* dst, const float* v, int n)
     for (int e = 0; e < n; ++e) atomicAdd(dst + e, v[e]);
 }
 
-template <typename T, bool VECX>
+// IDX: the integer type of the item decomposition -- unsigned 32-bit whenever the item count fits (always at the benchmark
+// sizes); the 64-bit divisions of the general case cost several hundred instructions per item
+template <typename T, bool VECX, typename IDX>
 __global__ void __launch_bounds__(256)
 gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const float* __restrict__ off,
                   const int* __restrict__ pn, float* __restrict__ grad_x, float* __restrict__ grad_off, int C, int H,
                   int W, int h, int w, int N, int s, int CV, int group, long long total)
 {
     constexpr int V = VECX ? Vec16<T>::N : 1;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = t < total;
+    const IDX t = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;
+    const bool valid = (long long)t < total;
     float acc_r = 0.f, acc_k = 0.f;
-    long long sn = 0, m = 0;
+    IDX sn = 0, m = 0;
     int n = 0;
     bool in_r = false, in_k = false;
     if (valid) {
-        const int cv = (int)(t % CV);
-        sn = t / CV;
-        n = (int)(sn % N);
-        m = sn / N;
-        const int j = (int)(m % w);
-        const int i = (int)((m / w) % h);
-        const int b = (int)(m / ((long long)w * h));
+        const int cv = (int)(t % (IDX)CV);
+        sn = t / (IDX)CV;
+        n = (int)(sn % (IDX)N);
+        m = sn / (IDX)N;
+        const int j = (int)(m % (IDX)w);
+        const IDX mi = m / (IDX)w;
+        const int i = (int)(mi % (IDX)h);
+        const int b = (int)(mi / (IDX)h);
         const float* op = off + (size_t)m * 2 * N;
         const SamplePoint q = make_point(i, j, s, pn[n], pn[N + n], op[n], op[N + n], H, W);
         in_r = q.in_r;
@@ -620,7 +623,7 @@ gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const floa
         acc_r += __shfl_xor_sync(0xffffffffu, acc_r, o);
         acc_k += __shfl_xor_sync(0xffffffffu, acc_k, o);
     }
-    if (valid && (group == 1 || (t % group) == 0)) {
+    if (valid && (t & (IDX)(group - 1)) == 0) {      // group is 1 or a power of two
         float* gp = grad_off + (size_t)m * 2 * N;
         if (in_r) atomicAdd(gp + n, acc_r);
         if (in_k) atomicAdd(gp + N + n, acc_k);
@@ -1072,12 +1075,19 @@ static int gather_bwd_t(const T* gop, const T* x, const float* off, const int* p
     if (total == 0) return LDCONV_OK;
     const int group = (CV <= 32 && (CV & (CV - 1)) == 0) ? CV : 1;
     const unsigned blocks = cdiv(total, 256);
-    if (vec)
-        gather_bwd_kernel<T, true><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV, group,
-                                                           total);
+    const bool small = total + 256 < 0xffffffffll;      // the last block's thread ids must not wrap
+    if (vec && small)
+        gather_bwd_kernel<T, true, unsigned><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV, group,
+                                                                     total);
+    else if (vec)
+        gather_bwd_kernel<T, true, long long><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV, group,
+                                                                      total);
+    else if (small)
+        gather_bwd_kernel<T, false, unsigned><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
+                                                                      group, total);
     else
-        gather_bwd_kernel<T, false><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
-                                                            group, total);
+        gather_bwd_kernel<T, false, long long><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
+                                                                       group, total);
     LDC_LAUNCH_CHECK("gather_bwd_kernel");
     return LDCONV_OK;
 }

@@ -149,6 +149,102 @@ gather_fwd_tiled_kernel(const __grid_constant__ CUtensorMap tmX, const T* __rest
     }
 }
 
+// ---- shape-specialised variant (bf16) ------------------------------------------------------------------------------------------
+// profiles/r1_ncu_gatherL1v3.txt: the kernel above is purely issue-bound at layer 1 (82.3 M warp instructions, issue slots 86 %
+// busy, DRAM 58 %): its index arithmetic runs on run-time geometry (divisions by N, C/8, the tile row length; 64-bit pixel
+// indices).  For the shapes of yolov8-LD-P2 -- (N, C/8, s) compile-time constants, an 8 x 16 tile, 32-bit indexing checked by
+// the host -- every division becomes a shift or a constant multiply and the item rounds unroll with immediate offsets.
+// Same records, same arithmetic (make_point_grid / bilinear_vec16): the operand bits are identical to the generic kernel.
+template <int TN, int TCVS, int TS>
+__global__ void __launch_bounds__(256)
+gather_fwd_tiled2_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ x, const float* __restrict__ off,
+                         const int* __restrict__ pn, __nv_bfloat16* __restrict__ operand, int H, int W, int h, int w, float hm,
+                         float wm, TileGeom g)
+{
+    using T = __nv_bfloat16;
+    constexpr int CV = 1 << TCVS, C = CV * 8, TW = 16, TH = 8;
+    constexpr int SAMPLES = TH * TW * TN, ROW_ITEMS = TW * TN * CV, ITEMS = TH * ROW_ITEMS;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const uint32_t tile_bytes = ((uint32_t)(g.THin * g.TWin * C * 2) + 15u) & ~15u;
+    const uint32_t tile_s = smem_u32(sm);
+    const uint32_t rec_o = tile_s + tile_bytes, rec_g = rec_o + SAMPLES * 16u;
+
+    const unsigned bid = blockIdx.x;
+    const unsigned tpi = (unsigned)(g.tiles_w * g.tiles_h);
+    const int b = (int)(bid / tpi);
+    const unsigned rem = bid - (unsigned)b * tpi;
+    const int ti = (int)(rem / (unsigned)g.tiles_w), tj = (int)(rem - (unsigned)ti * (unsigned)g.tiles_w);
+    const int i0 = ti * TH, j0 = tj * TW;
+    const int r_org = i0 * TS - g.halo, k_org = j0 * TS - g.halo;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&bar, (uint32_t)(g.THin * g.TWin * C * 2));
+        tma_load_4d(sm, &tmX, &bar, 0, k_org, r_org, b);
+    }
+
+    // ---- phase 1: one record per sample; sample = pixel * N + n like the operand's row layout ---------------------------------
+    const int rowB = g.TWin * (C * 2), imgRowB = W * (C * 2);
+    const int m0 = (b * h + i0) * w + j0;                       // pixel index of the tile origin (host: B h w N C < 2^31)
+#pragma unroll
+    for (int r = 0; r < (SAMPLES + 255) / 256; ++r) {
+        const int sidx = tid + r * 256;
+        if (SAMPLES % 256 != 0 && sidx >= SAMPLES) break;
+        const int p = sidx / TN, n = sidx - p * TN;
+        const int di = p >> 4, dj = p & 15;
+        if (i0 + di >= h || j0 + dj >= w) {
+            sts128(rec_o + sidx * 16, 0xffffffffu, 0, 0, 0);
+            continue;
+        }
+        const float* op = off + (size_t)(unsigned)((m0 + di * w + dj) * (2 * TN));
+        const SamplePoint q = make_point_grid((i0 + di) * TS + pn[n], (j0 + dj) * TS + pn[TN + n], op[n], op[TN + n], hm, wm);
+        sts128(rec_g + sidx * 16, __float_as_uint(__fmul_rn(q.ar0, q.ak0)), __float_as_uint(__fmul_rn(q.ar1, q.ak1)),
+               __float_as_uint(__fmul_rn(q.ar0, q.ak1)), __float_as_uint(__fmul_rn(q.ar1, q.ak0)));
+        const int t0 = q.r0 - r_org, t1 = q.r1 - r_org, u0 = q.k0 - k_org, u1 = q.k1 - k_org;
+        const bool inside = (unsigned)t0 < (unsigned)g.THin && (unsigned)t1 < (unsigned)g.THin &&
+                            (unsigned)u0 < (unsigned)g.TWin && (unsigned)u1 < (unsigned)g.TWin;
+        if (inside) {      // byte offsets into the staged tile
+            const int a0 = t0 * rowB, a1 = t1 * rowB, b0 = u0 * (C * 2), b1 = u1 * (C * 2);
+            sts128(rec_o + sidx * 16, (uint32_t)(a0 + b0), (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
+        } else {           // served from global memory (L2): image-relative byte offsets, bit 31 of .x marks it
+            const int a0 = q.r0 * imgRowB, a1 = q.r1 * imgRowB, b0 = q.k0 * (C * 2), b1 = q.k1 * (C * 2);
+            sts128(rec_o + sidx * 16, (uint32_t)(a0 + b0) | 0x80000000u, (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
+        }
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    // ---- phase 2: one 16-byte channel vector per item; a tile row of the operand is one contiguous run of ROW_ITEMS vectors ----
+    const uint8_t* xg = reinterpret_cast<const uint8_t*>(x) + (size_t)b * H * W * (C * 2);
+    uint4* out4 = reinterpret_cast<uint4*>(operand) + (size_t)(unsigned)(m0 * (TN * CV));
+    const int row_stride = w * (TN * CV);
+#pragma unroll
+    for (int r = 0; r < (ITEMS + 255) / 256; ++r) {
+        const int it = tid + r * 256;
+        if (ITEMS % 256 != 0 && it >= ITEMS) break;
+        const int sidx = it >> TCVS, cv = it & (CV - 1);
+        const uint4 o = lds128(rec_o + sidx * 16);
+        if (o.x == 0xffffffffu) continue;
+        const uint4 gq = lds128(rec_g + sidx * 16);
+        const float4 gw = make_float4(__uint_as_float(gq.x), __uint_as_float(gq.y), __uint_as_float(gq.z), __uint_as_float(gq.w));
+        uint4 q00, q11, q01, q10;
+        if ((int)o.x >= 0) {
+            const uint32_t t0 = tile_s + (uint32_t)cv * 16u;
+            q00 = lds128(t0 + o.x); q11 = lds128(t0 + o.y); q01 = lds128(t0 + o.z); q10 = lds128(t0 + o.w);
+        } else {
+            const uint8_t* g0 = xg + cv * 16;
+            q00 = __ldg(reinterpret_cast<const uint4*>(g0 + (o.x & 0x7fffffffu))); q11 = __ldg(reinterpret_cast<const uint4*>(g0 + o.y));
+            q01 = __ldg(reinterpret_cast<const uint4*>(g0 + o.z)); q10 = __ldg(reinterpret_cast<const uint4*>(g0 + o.w));
+        }
+        const int pi = it / ROW_ITEMS;
+        out4[pi * row_stride + (it - pi * ROW_ITEMS)] = bilinear_vec16<T>(q00, q11, q01, q10, gw);
+    }
+}
+
 static thread_local int g_gather_direct = 0;
 static thread_local unsigned long long* g_miss_counter = nullptr;
 
@@ -200,6 +296,30 @@ static int gather_tiled_t(const T* x, const float* off, const int* pn, T* operan
     if (int e = encode_map(&tm, dt, 4, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
 
     const size_t smem = smem_of(g) + 16 + rec_bytes(g) + 128;
+    if constexpr (sizeof(T) == 2) {      // shape-specialised instances (yolov8-LD-P2, 8 x 16 tile, no debug outputs, 32-bit indices)
+        static int env_v = -1;           // LDCONV_GATHER_V=1: the generic kernel everywhere (A/B partner)
+        if (env_v < 0) { const char* e = getenv("LDCONV_GATHER_V"); env_v = e ? atoi(e) : 2; }
+        if (env_v >= 2 && g.TH == 8 && g.TW == 16 && g.cv_shift >= 0 && !dbg_idx && !dbg_coord && !g_miss_counter &&
+            (long long)B * h * w * N * C < 0x7fffffffll && (long long)H * W * C * 2 < 0x7fffffffll) {
+            using K2 = void (*)(CUtensorMap, const __nv_bfloat16*, const float*, const int*, __nv_bfloat16*, int, int, int, int, float,
+                                float, TileGeom);
+            K2 k2 = nullptr;
+            switch (N * 100 + g.cv_shift * 10 + s) {
+                case 312: k2 = gather_fwd_tiled2_kernel<3, 1, 2>; break;      // C = 16 (layer 1)
+                case 322: k2 = gather_fwd_tiled2_kernel<3, 2, 2>; break;      // C = 32 (layers 3, 18)
+                case 121: k2 = gather_fwd_tiled2_kernel<1, 2, 1>; break;      // C = 32 (layer 15)
+                case 131: k2 = gather_fwd_tiled2_kernel<1, 3, 1>; break;      // C = 64 (layers 10, 13)
+                case 141: k2 = gather_fwd_tiled2_kernel<1, 4, 1>; break;      // C = 128 (layer 8)
+                default: break;
+            }
+            if (k2) {
+                LDC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k2<<<(unsigned)ctas, 256, smem, st>>>(tm, x, off, pn, operand, H, W, h, w, (float)(H - 1), (float)(W - 1), g);
+                LDC_LAUNCH_CHECK("gather_fwd_tiled2_kernel");
+                return LDCONV_OK;
+            }
+        }
+    }
     auto kern = gather_fwd_tiled_kernel<T>;
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)ctas, 256, smem, st>>>(tm, x, off, pn, operand, dbg_idx, dbg_coord, g_miss_counter, C, H, W, h, w, N, s,
