@@ -350,7 +350,7 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     if (grid > g.num_tiles) grid = g.num_tiles;
 #define LDC_ZC_LAUNCH(MODE_, CIN_)                                                                                     \
     do {                                                                                                               \
-        if (two || !zc_two_issuers()) {                                                                                \
+        if (two || !zc_two_issuers() || g.xbufs < 2) {      /* two issuers alternate tiles: each needs its own input buffer */ \
             auto kern = conv3x3_zc_kernel<MODE_, CIN_, 9, 1>;                                                          \
             LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
             LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, scale, shift,                    \
