@@ -127,9 +127,12 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 tr(it, 100000 + it * 100);
                 mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
                 for (int hf = 0; hf < g.halves; ++hf) {
-                    if (TAPS == 4)      // space-to-depth view: dims (2C, sy, W/2, H/2, B); half hf = the sy = hf rows
-                        tma_load_5d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], 0, hf,
-                                    tj * kZcTileW - 1, ti * kZcTileH - 1, b);
+                    if (TAPS == 4) {    // space-to-depth view: dims (2C [sx, c], sy, W/2, H/2, B); halves = 2 (block = one sy row of
+                        // 2C channels) or, for C = 64, 4 (block = one (sy, sx) cell of 64 channels = one 128-byte swizzle row)
+                        const int per_sy = g.halves >> 1;
+                        tma_load_5d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf],
+                                    (hf % per_sy) * (g.pb / 2), hf / per_sy, tj * kZcTileW - 1, ti * kZcTileH - 1, b);
+                    }
                     else
                         tma_load_4d(sX + (size_t)buf * g.x_bytes + (size_t)hf * half_bytes, &tmX, &x_full[buf], hf * (g.pb / 2),
                                     tj * kZcTileW - 1, ti * kZcTileH - 1, b);
@@ -146,8 +149,8 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             // bytes per pixel row / channel blocks per pixel.  Space-to-depth (TAPS = 4, CIN = 4C): a block is one sy half of
             // the pixel' (2C channels = CIN bytes), always two blocks: a TMA box row narrower than the swizzle span is padded to
             // the span in shared memory (measured), so [sy][sx][c] cannot be one 128-byte row when 2C = 32 channels
-            constexpr int PB = TAPS == 4 ? CIN : (CIN >= 64 ? 128 : CIN * 2);
-            constexpr int HALVES = TAPS == 4 ? 2 : (CIN >= 64 ? CIN / 64 : 1);
+            constexpr int PB = TAPS == 4 ? (CIN > 128 ? 128 : CIN) : (CIN >= 64 ? 128 : CIN * 2);
+            constexpr int HALVES = TAPS == 4 ? (CIN > 128 ? 4 : 2) : (CIN >= 64 ? CIN / 64 : 1);
             constexpr int KS = PB / 32;                            // K steps of 16 per pixel row
             constexpr uint32_t LAYOUT = PB == 128 ? 2u : (PB == 64 ? 4u : 6u);
             const uint32_t idesc = make_idesc_bf16(128, g.ON);
@@ -384,7 +387,7 @@ int conv3x3_zc_s2d_supported(int C, int N, int H, int W)
     static int en = -1;
     if (en < 0) { const char* e = getenv("LDCONV_CONV_S2D"); en = e ? atoi(e) : 1; }
     if (!en) return 0;
-    return (C == 16 || C == 32) && N >= 1 && 2 * N <= 16 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2;
+    return (C == 16 || C == 32 || C == 64) && N >= 1 && 2 * N <= 16 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2;
 }
 
 // x (B,H,W,C) bf16 dense; wt (2N, 16C) bf16 with k = ((ty*2+tx)*2+sy)*2C + sx*C + c (see the header comment); bias (2N) fp32
@@ -401,8 +404,8 @@ int conv3x3_zc_s2d(const void* x, const void* wt, const float* bias, float* off,
     const long long nt = (long long)B * g.tiles_h * g.tiles_w;
     if (nt > 0x7fffffffll) return fail(LDCONV_E_ARG, "offset conv (space-to-depth): too many tiles");
     g.num_tiles = (int)nt;
-    g.pb = Cin;                       // one sy half of a pixel' = 2C channels = Cin bytes (64 or 128)
-    g.halves = 2;
+    g.pb = Cin > 128 ? 128 : Cin;     // one sy half of a pixel' = 2C channels = Cin bytes (64 or 128); C = 64: one (sy, sx) cell
+    g.halves = Cin > 128 ? 4 : 2;
     g.layout = g.pb == 128 ? 2 : 4;
     g.num_kb = (4 * Cin + 63) / 64;
     g.b_bytes = (uint32_t)g.ON * 128;
@@ -435,7 +438,7 @@ int conv3x3_zc_s2d(const void* x, const void* wt, const float* bias, float* off,
         // x viewed as (2C [sx, c], sy, W/2, H/2, B): innermost two dimensions make pixel' = [sy][sx][c]
         cuuint64_t gdim[5] = {(cuuint64_t)(2 * C), 2, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
         cuuint64_t gstr[4] = {(cuuint64_t)W * C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * W * C * 2};
-        cuuint32_t box[5] = {(cuuint32_t)(2 * C), 1, (cuuint32_t)kZcTWs, (cuuint32_t)kZcTHs, 1};
+        cuuint32_t box[5] = {(cuuint32_t)(g.pb / 2), 1, (cuuint32_t)kZcTWs, (cuuint32_t)kZcTHs, 1};
         if (int e = encode_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gdim, gstr, box,
                                g.pb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     }
@@ -448,7 +451,12 @@ int conv3x3_zc_s2d(const void* x, const void* wt, const float* bias, float* off,
     }
     int grid = num_sms() * (two ? 2 : 1);
     if (grid > g.num_tiles) grid = g.num_tiles;
-    if (Cin == 64) {
+    if (Cin == 256) {
+        auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS, 256, 4>;
+        LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, (const float*)nullptr, bias,
+                            (const __nv_bfloat16*)nullptr, (void*)off, (int)LDCONV_ACT_NONE, g));
+    } else if (Cin == 64) {
         auto kern = conv3x3_zc_kernel<ZC_MODE_OFFSETS, 64, 4>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kZcThreads), smem, st, tmX, tmW, (const float*)nullptr, bias,

@@ -81,7 +81,7 @@ def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepar
     # stride-2 offset conv on the space-to-depth view (ldconv_offset_conv_s2d_fwd): (2N,C,3,3) -> (2N, ty, tx, sy, sx, C),
     # ky = 0,1,2 -> (ty, sy) = (0,1), (1,0), (1,1); the unused (ty=0, sy=0) / (tx=0, sx=0) combinations stay zero
     pr.w_off_s2d = None
-    if dtype == torch.bfloat16 and C in (16, 32) and 2 * N <= 16:
+    if dtype == torch.bfloat16 and C in (16, 32, 64) and 2 * N <= 16:
         w6 = torch.zeros((2 * N, 2, 2, 2, 2, C), device=p_w.device, dtype=dtype)
         tmap = ((0, 1), (1, 0), (1, 1))
         pw = p_w.detach().to(dtype)

@@ -45,7 +45,7 @@ def test_offset_conv_tensor_core_vs_oracle(C, N, s, H, W, B):
 
 
 @pytest.mark.parametrize("C,N,H,W,B", [(16, 3, 40, 56, 2), (32, 3, 38, 42, 2), (16, 1, 16, 24, 1), (32, 5, 160, 160, 2), (16, 8, 2, 2, 3),
-                                       (16, 3, 320, 320, 2)])
+                                       (16, 3, 320, 320, 2), (64, 3, 40, 40, 2), (64, 3, 80, 80, 5), (64, 1, 18, 34, 1)])
 def test_offset_conv_stride2_space_to_depth_vs_oracle(C, N, H, W, B):
     """ldconv_offset_conv_s2d_fwd: the stride-2 offset conv (conv.py:356,368) as a zero-copy tcgen05 GEMM on the space-to-depth
     view (5-D TMA map), weights scattered by the module's own _prepare -- against the CPU oracle's offset conv and against the
