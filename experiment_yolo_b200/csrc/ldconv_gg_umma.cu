@@ -37,6 +37,7 @@ struct GGGeom {
     int XB, AB, ldo, act, per_sm, dbg;
     int xb_mask, xb_shift, ab_mask;      // XB, AB in {1, 2}: buffer = it & mask, mbarrier parity = (it >> shift) & 1
     int TG;                              // v2 kernel: thread groups of 128 per CTA (3 when N % 3 == 0: one sample per thread)
+    int merge;                           // v2 kernel: phase 1 of the next tile shares the barrier interval of phase 2 (two record buffers)
     float hm, wm;                        // (float)(H - 1), (float)(W - 1)
     unsigned long long img_bytes;        // H * W * C * 2
     unsigned inv_n, inv_img, inv_tw;
@@ -340,7 +341,7 @@ ldconv_gg_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 //   * the bilinear sum and the folded BatchNorm + SiLU run on packed fp32 pairs (FFMA2): half the FMA-pipe instructions with
 //     bit-identical results; the SiLU's 0.5 is folded into the affine.
 // Requires C / 8 to be a power of two; other channel counts keep the kernel above.
-template <int TN, int TCVS, int TS, int TG, int MINB>
+template <int TN, int TCVS, int TS, int TG, int MINB, bool MERGE>
 __global__ void __launch_bounds__(128 * TG, MINB)
 ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __nv_bfloat16* __restrict__ x, const float* __restrict__ off, const int* __restrict__ pn,
@@ -495,20 +496,11 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t idesc = make_idesc_bf16(128, g.ON);
     const int rowB = g.TWin << (cvs + 4), pixB = 16 << cvs;    // bytes per staged tile row / per pixel
     const int imgRowB = g.W << (cvs + 4);
-    TC cur = tile_coords(blockIdx.x);
-    if ((int)blockIdx.x < g.num_tiles) fetch_offsets(cur, ofs);
-    int prev_m = -1;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const int xb = it & g.xb_mask, ab = it & g.ab_mask, tb = it & 1;
-        const uint32_t rec_s = smem_s + g.ofs_rec;      // last read in phase 2 of the previous tile: barrier (B) lies in between
-        const int r_org = cur.i0 * s - g.halo, k_org = cur.j0 * s - g.halo;
-        const bool valid = cur.i0 + di < g.h && cur.j0 + dj < g.w;
-        const int cur_m = valid ? ((cur.b * g.h + cur.i0 + di) * g.w + cur.j0 + dj) : -1;
-        // next tile: its offsets are requested now and have both phases to arrive
-        if (tile + (int)gridDim.x < g.num_tiles) fetch_offsets(tile_coords(tile + gridDim.x), ofs_n);
-
-        // ---- phase 1: one record per sample (n-major: sample = n * 128 + pixel) ------------------------------------------------
+    // ---- phase 1 of one tile: one record per sample (n-major: sample = n * 128 + pixel) into the record buffer at rec_s; uses the
+    // prefetched offsets in `ofs`; returns this thread's output pixel index ((b h + i) w + j), -1 outside the map
+    auto phase1 = [&](const TC& t, uint32_t rec_s) -> int {
+        const int r_org = t.i0 * s - g.halo, k_org = t.j0 * s - g.halo;
+        const bool valid = t.i0 + di < g.h && t.j0 + dj < g.w;
         auto make_record = [&](int n, int ri, int ki, float o_r, float o_k) {
             const uint32_t ra = rec_s + (uint32_t)(n * 128 + p) * 16u;
             if (!valid) {
@@ -530,20 +522,43 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 gg_sts128(ra, (uint32_t)(a0 + b0) | 0x80000000u, (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
             }
         };
-        const int gr = cur.i0 * s, gk = cur.j0 * s;
+        const int gr = t.i0 * s, gk = t.j0 * s;
         if (has[0]) make_record(n0, gr + br[0], gk + bk[0], ofs[0].x, ofs[0].y);
         if (has[1]) make_record(n0 + TG, gr + br[1], gk + bk[1], ofs[1].x, ofs[1].y);
         if (TN == 0 || TN > 2 * TG) {
             for (int n = n0 + 2 * TG; n < N; n += TG) {
                 float o_r = 0.f, o_k = 0.f;
                 if (valid) {
-                    const float* op = off + (((size_t)cur.b * g.h + cur.i0) * g.w + cur.j0) * (size_t)(2 * N) + pix_f;
+                    const float* op = off + (((size_t)t.b * g.h + t.i0) * g.w + t.j0) * (size_t)(2 * N) + pix_f;
                     o_r = __ldg(op + n); o_k = __ldg(op + N + n);
                 }
                 make_record(n, gr + di * s + pn[n], gk + dj * s + pn[N + n], o_r, o_k);
             }
         }
-        __syncthreads();                                              // (A) records of this tile are visible
+        return valid ? ((t.b * g.h + t.i0 + di) * g.w + t.j0 + dj) : -1;
+    };
+
+    TC cur = tile_coords(blockIdx.x);
+    if ((int)blockIdx.x < g.num_tiles) fetch_offsets(cur, ofs);
+    int prev_m = -1, cur_m = -1;
+    int it = 0;
+    if (MERGE && (int)blockIdx.x < g.num_tiles) {      // one-barrier flow: the records of the first tile are made ahead of the loop
+        cur_m = phase1(cur, smem_s + g.ofs_rec);
+        if ((int)(blockIdx.x + gridDim.x) < g.num_tiles) fetch_offsets(tile_coords(blockIdx.x + gridDim.x), ofs);
+        __syncthreads();
+    }
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const int xb = it & g.xb_mask, ab = it & g.ab_mask, tb = it & 1;
+        // MERGE: two record buffers, this tile's were written during the previous tile's interval.  Otherwise one buffer, last
+        // read in phase 2 of the previous tile with barrier (B) in between.
+        const uint32_t rec_s = smem_s + g.ofs_rec + (MERGE ? (uint32_t)(it & 1) * g.rec_bytes : 0u);
+        const bool more = tile + (int)gridDim.x < g.num_tiles;
+        if (!MERGE) {
+            // next tile: its offsets are requested now and have both phases to arrive
+            if (more) fetch_offsets(tile_coords(tile + gridDim.x), ofs_n);
+            cur_m = phase1(cur, rec_s);
+            __syncthreads();                                          // (A) records of this tile are visible
+        }
         mbar_wait(&x_full[xb], (uint32_t)(it >> g.xb_shift) & 1u);   // the staged input tile has landed
         if (g.ab_mask == 0 && it > 0) mbar_wait(&mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1);   // operand buffer free again
 
@@ -599,6 +614,15 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 for (int k = 0; k < rounds; k += IF) step(k, rounds);
             }
         }
+        int next_m = -1;
+        TC nxt = cur;
+        if (MERGE && more) {
+            // phase 1 of the NEXT tile in the same barrier interval (its ALU work fills the load latencies of phase 2, and the
+            // tile needs one block barrier instead of two); then request the offsets of the tile after it
+            nxt = tile_coords(tile + gridDim.x);
+            next_m = phase1(nxt, smem_s + g.ofs_rec + (uint32_t)((it + 1) & 1) * g.rec_bytes);
+            if (tile + 2 * (int)gridDim.x < g.num_tiles) fetch_offsets(tile_coords(tile + 2 * gridDim.x), ofs);
+        }
         fence_proxy_async_smem();      // generic-proxy stores of the operand tile -> visible to tcgen05 (async proxy)
         __syncthreads();               // (B) operand tile complete, input tile consumed, epilogue(it-2) done by every warp
 
@@ -619,8 +643,13 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         __syncwarp();
         if (it > 0) epilogue(prev_m, it - 1);      // the previous tile's MMA ran during this tile's phases
         prev_m = cur_m;
-        if (tile + (int)gridDim.x < g.num_tiles) cur = tile_coords(tile + gridDim.x);      // recomputed: cheaper than 3 live registers
-        ofs[0] = ofs_n[0]; ofs[1] = ofs_n[1];
+        if (MERGE) {
+            cur_m = next_m;
+            cur = nxt;
+        } else {
+            if (more) cur = tile_coords(tile + gridDim.x);      // recomputed: cheaper than 3 live registers
+            ofs[0] = ofs_n[0]; ofs[1] = ofs_n[1];
+        }
     }
     if (it > 0) epilogue(prev_m, it - 1);
     tc_fence_before_sync();
@@ -682,6 +711,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     // ties go to the deeper buffering / wider halo (listed first)
     static const int cfg[5][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 2, 1}, {1, 1, 1}};
     int best_ctas = 0;
+    g.merge = 0;
     GGGeom best = g;
     size_t best_smem = 0;
     static int env_plan = -2, env_ctas = -2, env_tg = -2;      // experiments: LDCONV_GG_PLAN=<plan index>, LDCONV_GG_CTAS=<CTAs per SM>
@@ -695,29 +725,47 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     const int reg_cap = g.TG == 3 ? 2 : 3;      // CTAs per SM the register file allows at 80 registers per thread
     if (env_plan == -2) { const char* e = getenv("LDCONV_GG_PLAN"); env_plan = e ? atoi(e) : -1; }
     if (env_ctas == -2) { const char* e = getenv("LDCONV_GG_CTAS"); env_ctas = e ? atoi(e) : -1; }
-    for (int ci = 0; ci < 5; ++ci) {
-        if (env_plan >= 0 && ci != env_plan) continue;
-        g.halo = cfg[ci][0]; g.XB = cfg[ci][1]; g.AB = cfg[ci][2];
-        g.THin = (g.TH - 1) * s + 2 + mr + 2 * g.halo;
-        g.TWin = (g.TW - 1) * s + 2 + mk + 2 * g.halo;
-        if (g.THin > 256 || g.TWin > 256) continue;
-        g.x_tx_bytes = (uint32_t)((size_t)g.THin * g.TWin * C * 2);
-        g.x_bytes = (g.x_tx_bytes + 127u) & ~127u;
+    static int env_merge = -2;
+    if (env_merge == -2) { const char* e = getenv("LDCONV_GG_MERGE"); env_merge = e ? atoi(e) : -1; }
+    // shared-memory layout of plan ci with (mg + 1) record buffers -> CTAs per SM (0: does not fit)
+    auto layout = [&](int ci, int mg, GGGeom& q, size_t& need) {
+        q.halo = cfg[ci][0]; q.XB = cfg[ci][1]; q.AB = cfg[ci][2];
+        q.THin = (q.TH - 1) * s + 2 + mr + 2 * q.halo;
+        q.TWin = (q.TW - 1) * s + 2 + mk + 2 * q.halo;
+        if (q.THin > 256 || q.TWin > 256) return 0;
+        q.x_tx_bytes = (uint32_t)((size_t)q.THin * q.TWin * C * 2);
+        q.x_bytes = (q.x_tx_bytes + 127u) & ~127u;
         uint32_t ofs = 0;
-        g.ofs_a = ofs; ofs += (uint32_t)g.AB * g.a_bytes;
-        g.ofs_b = ofs; ofs += (uint32_t)g.num_kb * g.b_bytes;
-        g.ofs_x = ofs; ofs += (uint32_t)g.XB * g.x_bytes;
-        g.ofs_rec = ofs; ofs += g.rec_bytes;
-        g.ofs_aff = ofs; ofs += (uint32_t)g.ON * 8u;
+        q.ofs_a = ofs; ofs += (uint32_t)q.AB * q.a_bytes;
+        q.ofs_b = ofs; ofs += (uint32_t)q.num_kb * q.b_bytes;
+        q.ofs_x = ofs; ofs += (uint32_t)q.XB * q.x_bytes;
+        q.ofs_rec = ofs; ofs += (uint32_t)(mg + 1) * q.rec_bytes;
+        q.ofs_aff = ofs; ofs += (uint32_t)q.ON * 8u;
         ofs = (ofs + 7u) & ~7u;
-        g.ofs_bar = ofs; ofs += 6u * 8u + 16u;
-        const size_t need = (size_t)ofs + 1024;
-        if (need > 225 * 1024) continue;
+        q.ofs_bar = ofs; ofs += 6u * 8u + 16u;
+        need = (size_t)ofs + 1024;
+        if (need > 225 * 1024) return 0;
         int ctas = (int)((227 * 1024) / (need + 1024));          // + the per-CTA reservation of the driver
         if (ctas > reg_cap) ctas = reg_cap;
-        if (ctas > (int)(512u / g.tmem_cols)) ctas = (int)(512u / g.tmem_cols);
+        if (ctas > (int)(512u / q.tmem_cols)) ctas = (int)(512u / q.tmem_cols);
         if (env_ctas >= 1 && ctas > env_ctas) ctas = env_ctas;
-        if (ctas > best_ctas) { best_ctas = ctas; best = g; best_smem = need; }
+        q.merge = mg;
+        return ctas;
+    };
+    int best_ci = -1;
+    for (int ci = 0; ci < 5; ++ci) {
+        if (env_plan >= 0 && ci != env_plan) continue;
+        size_t need = 0;
+        const int ctas = layout(ci, 0, g, need);
+        if (ctas > best_ctas) { best_ctas = ctas; best = g; best_smem = need; best_ci = ci; }
+    }
+    // One-barrier flow (phase 1 of the next tile shares the barrier interval of phase 2; two record buffers): measured to pay
+    // for N = 1 (layer 15: 95 -> 86 us; phase 1 occupies half the warps there) and not for N = 3 (layer 1: 127 -> 134 us), and
+    // only taken when the SAME buffering plan keeps its CTAs per SM with the second record buffer.
+    if (best_ci >= 0 && gg_v2_enabled() && g.cv_shift >= 0 && (env_merge == 1 || (env_merge != 0 && N == 1))) {
+        size_t need = 0;
+        GGGeom q = g;
+        if (layout(best_ci, 1, q, need) == best_ctas) { best = q; best_smem = need; }
     }
     if (best_ctas == 0) return 0;
     g = best;
@@ -784,21 +832,33 @@ int gather_gemm_fwd(const void* x, const float* off, const int* pn, const void* 
     if (env_v && g.cv_shift >= 0) {
         threads = 128 * g.TG;
         // the register cap follows the CTAs per SM the shared-memory plan allows (80 / 128 / 255 registers at 256 threads)
-        if (g.TG == 3) kern = g.per_sm >= 2 ? ldconv_gg2_kernel<0, -1, 0, 3, 2> : ldconv_gg2_kernel<0, -1, 0, 3, 1>;
-        else kern = g.per_sm >= 3 ? ldconv_gg2_kernel<0, -1, 0, 2, 3> : g.per_sm == 2 ? ldconv_gg2_kernel<0, -1, 0, 2, 2> : ldconv_gg2_kernel<0, -1, 0, 2, 1>;
-        const int key = (((N * 10 + g.cv_shift) * 10 + s) * 10 + g.TG) * 10 + g.per_sm;      // yolov8-LD-P2 shapes: compile-time indices
+        const int key0 = (g.TG * 10 + g.per_sm) * 10 + g.merge;
+        switch (key0) {      // run-time geometry: the register cap follows the CTAs per SM (80 / 128 / 255 registers at 256 threads)
+            case 320: kern = ldconv_gg2_kernel<0, -1, 0, 3, 2, false>; break;
+            case 321: kern = ldconv_gg2_kernel<0, -1, 0, 3, 2, true>; break;
+            case 310: kern = ldconv_gg2_kernel<0, -1, 0, 3, 1, false>; break;
+            case 311: kern = ldconv_gg2_kernel<0, -1, 0, 3, 1, true>; break;
+            case 230: kern = ldconv_gg2_kernel<0, -1, 0, 2, 3, false>; break;
+            case 231: kern = ldconv_gg2_kernel<0, -1, 0, 2, 3, true>; break;
+            case 220: kern = ldconv_gg2_kernel<0, -1, 0, 2, 2, false>; break;
+            case 221: kern = ldconv_gg2_kernel<0, -1, 0, 2, 2, true>; break;
+            case 210: kern = ldconv_gg2_kernel<0, -1, 0, 2, 1, false>; break;
+            default: kern = ldconv_gg2_kernel<0, -1, 0, 2, 1, true>; break;
+        }
+        const int key = ((((N * 10 + g.cv_shift) * 10 + s) * 10 + g.TG) * 10 + g.per_sm) * 10 + g.merge;      // yolov8-LD-P2 shapes
         if (env_v == 2) switch (key) {
-            case 31232: kern = ldconv_gg2_kernel<3, 1, 2, 3, 2>; break;      // C = 16 (layer 1)
-            case 32232: kern = ldconv_gg2_kernel<3, 2, 2, 3, 2>; break;      // C = 32 (layers 3, 18)
-            case 32231: kern = ldconv_gg2_kernel<3, 2, 2, 3, 1>; break;
-            case 33231: kern = ldconv_gg2_kernel<3, 3, 2, 3, 1>; break;      // C = 64 (layers 5, 21)
-            case 31223: kern = ldconv_gg2_kernel<3, 1, 2, 2, 3>; break;      // the 256-thread variants (LDCONV_GG_TG=2)
-            case 32222: kern = ldconv_gg2_kernel<3, 2, 2, 2, 2>; break;
-            case 33221: kern = ldconv_gg2_kernel<3, 3, 2, 2, 1>; break;
-            case 12123: kern = ldconv_gg2_kernel<1, 2, 1, 2, 3>; break;      // C = 32 (layer 15)
-            case 13123: kern = ldconv_gg2_kernel<1, 3, 1, 2, 3>; break;      // C = 64 (layers 10, 13)
-            case 14122: kern = ldconv_gg2_kernel<1, 4, 1, 2, 2>; break;      // C = 128 (layer 8)
-            case 14121: kern = ldconv_gg2_kernel<1, 4, 1, 2, 1>; break;
+            case 312231: kern = ldconv_gg2_kernel<3, 1, 2, 2, 3, true>; break;       // C = 16 (layer 1)
+            case 312230: kern = ldconv_gg2_kernel<3, 1, 2, 2, 3, false>; break;
+            case 322320: kern = ldconv_gg2_kernel<3, 2, 2, 3, 2, false>; break;      // C = 32 (layers 3, 18)
+            case 322310: kern = ldconv_gg2_kernel<3, 2, 2, 3, 1, false>; break;
+            case 332311: kern = ldconv_gg2_kernel<3, 3, 2, 3, 1, true>; break;       // C = 64 (layers 5, 21)
+            case 332310: kern = ldconv_gg2_kernel<3, 3, 2, 3, 1, false>; break;
+            case 121231: kern = ldconv_gg2_kernel<1, 2, 1, 2, 3, true>; break;       // C = 32 (layer 15)
+            case 121230: kern = ldconv_gg2_kernel<1, 2, 1, 2, 3, false>; break;
+            case 131231: kern = ldconv_gg2_kernel<1, 3, 1, 2, 3, true>; break;       // C = 64 (layers 10, 13)
+            case 131230: kern = ldconv_gg2_kernel<1, 3, 1, 2, 3, false>; break;
+            case 141221: kern = ldconv_gg2_kernel<1, 4, 1, 2, 2, true>; break;       // C = 128 (layer 8)
+            case 141220: kern = ldconv_gg2_kernel<1, 4, 1, 2, 2, false>; break;
             default: break;
         }
     }
