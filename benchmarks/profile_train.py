@@ -11,6 +11,7 @@ from torch.profiler import ProfilerActivity, profile
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from experiment_yolo_b200 import dealyolo  # noqa: E402
 from experiment_yolo_b200 import dist as xdist  # noqa: E402
+from experiment_yolo_b200.loss import DealYoloLoss, synthetic_uav_targets  # noqa: E402
 
 
 def main():
@@ -24,7 +25,8 @@ def main():
     model = dealyolo.channels_last_(model.to(dev)).train()
     B = args.batch
     x = torch.rand((B, 3, 640, 640), device=dev).contiguous(memory_format=torch.channels_last)
-    targets = [torch.zeros((B, 70, 640 // s, 640 // s), device=dev) for s in (4, 8, 16)]
+    crit = DealYoloLoss(nc=6, strides=[float(v) for v in model.stride], max_boxes=16).to(dev)
+    batch = synthetic_uav_targets(B, boxes_per_image=16, nc=6, seed=200, device=dev)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.SGD(params, lr=0.01, momentum=0.937, nesterov=True)
     red = xdist.FlatGradAllReduce(model.parameters())
@@ -33,7 +35,7 @@ def main():
         with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
             opt.zero_grad(set_to_none=True)
             outs = model(x)
-        loss = xdist.surrogate_detection_loss(outs, targets)
+        loss, _ = crit(outs, batch)
         loss.backward()
         red()
         torch.nn.utils.clip_grad_norm_(params, max_norm=10.0)      # reference optimizer_step, engine/trainer.py:952

@@ -219,10 +219,151 @@ gemm_tn_kernel(const T* __restrict__ G, const T* __restrict__ A, float* __restri
     }
 }
 
+
+// ---- thin shapes (the model's first layer: K = N*C = 9, O = 16, M = B*320*320) ---------------------------------------------------
+// The tiled kernels above waste > 90 % of their 128 x 64 / 64 x 64 tiles on such shapes (benchmarks/profile_train.py: 1.7 ms
+// forward, 3.1 ms weight gradient at batch 128 for ~0.1 ms of HBM traffic).  Thin kernels: one thread per row of A, the O x K
+// weight in shared memory as fp32, accumulators in registers; rows are walked grid-stride so that the BatchNorm sums / the weight
+// gradient are reduced per thread first, then per warp (shuffles), per CTA (shared memory) and once per CTA in global memory.
+constexpr int kThinO = 16, kThinK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+thin_nt_kernel(const T* __restrict__ A, const T* __restrict__ Wt, const float* __restrict__ scale, const float* __restrict__ shift,
+               T* __restrict__ out, T* __restrict__ pre, double* __restrict__ stat_sum, double* __restrict__ stat_sqsum, int M, int K,
+               int O, int act)
+{
+    __shared__ __align__(16) float sW[kThinK][kThinO];       // [k][o], zero padded
+    __shared__ float sAff[2][kThinO];
+    __shared__ double sStat[2][kThinO];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < kThinK * kThinO; t += blockDim.x) {
+        const int k = t / kThinO, o = t % kThinO;
+        sW[k][o] = (k < K && o < O) ? Elem<T>::to_f(Wt[(size_t)o * K + k]) : 0.f;
+    }
+    if (tid < kThinO) {
+        sAff[0][tid] = (scale && tid < O) ? scale[tid] : 1.f;
+        sAff[1][tid] = (shift && tid < O) ? shift[tid] : 0.f;
+        sStat[0][tid] = 0.0; sStat[1][tid] = 0.0;
+    }
+    __syncthreads();
+    float csum[kThinO], csq[kThinO];
+#pragma unroll
+    for (int o = 0; o < kThinO; ++o) csum[o] = csq[o] = 0.f;
+    for (long long m = (long long)blockIdx.x * blockDim.x + tid; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const T* a = A + m * K;
+        float acc[kThinO];
+#pragma unroll
+        for (int o = 0; o < kThinO; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kThinK; ++k) {
+            if (k < K) {
+                const float av = Elem<T>::to_f(a[k]);
+                // volatile shared loads: the compiler otherwise hoists all 256 weights out of the row loop and spills them
+                const uint32_t wrow = (uint32_t)__cvta_generic_to_shared(&sW[k][0]);
+#pragma unroll
+                for (int o4 = 0; o4 < kThinO / 4; ++o4) {
+                    float4 wv;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wv.x), "=f"(wv.y), "=f"(wv.z), "=f"(wv.w)
+                                 : "r"(wrow + o4 * 16));
+                    acc[o4 * 4 + 0] = fmaf(av, wv.x, acc[o4 * 4 + 0]);
+                    acc[o4 * 4 + 1] = fmaf(av, wv.y, acc[o4 * 4 + 1]);
+                    acc[o4 * 4 + 2] = fmaf(av, wv.z, acc[o4 * 4 + 2]);
+                    acc[o4 * 4 + 3] = fmaf(av, wv.w, acc[o4 * 4 + 3]);
+                }
+            }
+        }
+        if (stat_sum) {
+#pragma unroll
+            for (int o = 0; o < kThinO; ++o) { csum[o] += acc[o]; csq[o] = fmaf(acc[o], acc[o], csq[o]); }
+        }
+        if (pre) {
+            T* d = pre + m * O;
+#pragma unroll
+            for (int o = 0; o < kThinO; ++o)
+                if (o < O) d[o] = Elem<T>::from_f(acc[o]);
+        }
+        if (out) {
+            T* d = out + m * O;
+#pragma unroll
+            for (int o = 0; o < kThinO; ++o) {
+                if (o < O) {
+                    const float z = fmaf(acc[o], sAff[0][o], sAff[1][o]);
+                    d[o] = Elem<T>::from_f(act == LDCONV_ACT_SILU ? silu(z) : z);
+                }
+            }
+        }
+    }
+    if (stat_sum) {
+#pragma unroll
+        for (int o = 0; o < kThinO; ++o) {
+            const float a = warp_sum(csum[o]), b = warp_sum(csq[o]);
+            if ((tid & 31) == 0 && o < O) { atomicAdd(&sStat[0][o], (double)a); atomicAdd(&sStat[1][o], (double)b); }
+        }
+        __syncthreads();
+        if (tid < O) { atomicAdd(stat_sum + tid, sStat[0][tid]); atomicAdd(stat_sqsum + tid, sStat[1][tid]); }
+    }
+}
+
+// dWt(O,K) += G(M,O)^T . A(M,K) for O <= 16, K <= 12: two threads per row (each owns 8 of the output channels).
+constexpr int kThinWK = 12;
+template <typename T>
+__global__ void __launch_bounds__(256)
+thin_tn_kernel(const T* __restrict__ G, const T* __restrict__ A, float* __restrict__ dW, int M, int K, int O)
+{
+    __shared__ float sAcc[kThinO][kThinWK];
+    const int tid = threadIdx.x, half = tid & 1;
+    for (int t = tid; t < kThinO * kThinWK; t += blockDim.x) (&sAcc[0][0])[t] = 0.f;
+    __syncthreads();
+    float acc[8][kThinWK];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int k = 0; k < kThinWK; ++k) acc[o][k] = 0.f;
+    const long long pairs = ((long long)gridDim.x * blockDim.x) >> 1;
+    for (long long m = ((long long)blockIdx.x * blockDim.x + tid) >> 1; m < M; m += pairs) {
+        float g[8], a[kThinWK];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) g[o] = half * 8 + o < O ? Elem<T>::to_f(G[m * O + half * 8 + o]) : 0.f;
+#pragma unroll
+        for (int k = 0; k < kThinWK; ++k) a[k] = k < K ? Elem<T>::to_f(A[m * K + k]) : 0.f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int k = 0; k < kThinWK; ++k) acc[o][k] = fmaf(g[o], a[k], acc[o][k]);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int k = 0; k < kThinWK; ++k) {
+            float v = acc[o][k];                      // lanes of equal parity own the same output channels
+#pragma unroll
+            for (int d = 16; d >= 2; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if ((tid & 31) < 2 && k < K && half * 8 + o < O) atomicAdd(&sAcc[half * 8 + o][k], v);
+        }
+    __syncthreads();
+    for (int t = tid; t < O * K; t += blockDim.x) atomicAdd(dW + t, sAcc[t / K][t % K]);
+}
+
+static int thin_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LDCONV_THIN_GEMM"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 template <typename T>
 static int gemm_nt_t(const T* a, const T* wt, const float* scale, const float* shift, T* out, T* pre, double* stat_sum,
                      double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
 {
+    if (thin_enabled() && K <= kThinK && O <= kThinO && M >= 4096) {
+        unsigned blocks = cdiv(M, 256 * 8);
+        if (blocks > (unsigned)num_sms() * 8) blocks = (unsigned)num_sms() * 8;
+        thin_nt_kernel<T><<<blocks, 256, 0, st>>>(a, wt, scale, shift, out, pre, stat_sum, stat_sqsum, M, K, O, act);
+        LDC_LAUNCH_CHECK("thin_nt_kernel");
+        set_impl(LDCONV_IMPL_FFMA);
+        return LDCONV_OK;
+    }
     const int vec_in = (K % 8 == 0) && aligned16(a);
     const int vec_out = (O % 4 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
     dim3 grid(cdiv(M, BM), cdiv(O, BN));
@@ -236,6 +377,13 @@ static int gemm_nt_t(const T* a, const T* wt, const float* scale, const float* s
 template <typename T>
 static int gemm_tn_t(const T* g, const T* a, float* dw, int M, int K, int O, cudaStream_t st)
 {
+    if (thin_enabled() && K <= kThinWK && O <= kThinO && M >= 4096) {
+        unsigned blocks = cdiv(M, 128 * 16);
+        if (blocks > (unsigned)num_sms() * 4) blocks = (unsigned)num_sms() * 4;
+        thin_tn_kernel<T><<<blocks, 256, 0, st>>>(g, a, dw, M, K, O);
+        LDC_LAUNCH_CHECK("thin_tn_kernel");
+        return LDCONV_OK;
+    }
     const int tiles = (int)(cdiv(K, 64) * cdiv(O, 64));
     long long splits = (long long)num_sms() * 4 / tiles;
     if (splits < 1) splits = 1;

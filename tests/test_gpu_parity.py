@@ -291,6 +291,30 @@ def test_weight_gradient_tensor_core_reduction(M, K, O):
     assert _rel(dw32.cpu().numpy(), ref.cpu().numpy()) <= 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,K,O", [(50001, 9, 16), (50001, 16, 9), (4096, 12, 8), (70000, 4, 16)])
+def test_thin_gemm_shapes_first_layer(M, K, O, dtype):
+    """The thread-per-row kernels for the model's first layer (K = N*C = 9, O = 16; the data gradient is the same call with K and
+    O swapped): forward with BatchNorm sums, and the weight gradient, against fp64."""
+    impl, out, pre, st, ref_pre, ref_out = _gemm_case(M, K, O, dtype, True, True)
+    assert impl == _lib.IMPL_FFMA
+    tol = 1e-5 if dtype == torch.float32 else 4e-3
+    assert _rel(pre.float().cpu().numpy(), ref_pre.cpu().numpy()) <= tol
+    assert _rel(out.float().cpu().numpy(), ref_out.cpu().numpy()) <= tol
+    assert _rel(st[0].cpu().numpy(), ref_pre.sum(0).cpu().numpy()) <= 1e-4
+    assert _rel(st[1].cpu().numpy(), (ref_pre ** 2).sum(0).cpu().numpy()) <= 1e-5
+    if K <= 12:
+        L = _lib.load()
+        g = torch.Generator(device=DEV).manual_seed(M + K)
+        gp = torch.randn((M, O), device=DEV, generator=g).to(dtype)
+        a = torch.randn((M, K), device=DEV, generator=g).to(dtype)
+        dw = torch.zeros((O, K), device=DEV)
+        _lib.check(L.ldconv_gemm_bwd_weight(_ptr(gp), _ptr(a), _ptr(dw), M, K, O, _lib.F32 if dtype == torch.float32 else _lib.BF16,
+                                            _stream()), "wgrad")
+        torch.cuda.synchronize()
+        assert _rel(dw.cpu().numpy(), (gp.double().t() @ a.double()).cpu().numpy()) <= 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ whole module, fp32 ----
 def _module_from_golden(z, prm, m, dtype=torch.float32):
     mod = E.LDConv(m["inc"], m["outc"], m["N"], m["s"])
