@@ -1062,6 +1062,7 @@ LDC_API int ldconv_bn_act_bwd_apply(const void* pre, const void* grad_out, const
                                              mean, invstd, red, (__nv_bfloat16*)grad_pre, M, O, act, training, st);
 }
 
+
 template <typename T>
 static int gather_bwd_t(const T* gop, const T* x, const float* off, const int* pn, float* grad_x, float* grad_off, int B,
                         int C, int H, int W, int N, int s, cudaStream_t st)

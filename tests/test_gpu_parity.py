@@ -562,6 +562,34 @@ def test_scatter_backward_with_clamped_and_colliding_samples(dtype, scale):
     assert np.abs(got_off - goff_ref).max() <= 2e-4 * max(1.0, float(np.abs(goff_ref).max()))
 
 
+@pytest.mark.parametrize("scale", [0.5, 3.0, 60.0])
+@pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 37, 53, 2), (32, 3, 2, 40, 24, 2), (64, 3, 2, 18, 34, 1), (32, 1, 1, 21, 40, 2),
+                                         (64, 1, 1, 19, 17, 2), (128, 1, 1, 12, 20, 1)])
+def test_scatter_backward_model_shapes_vs_oracle(C, N, s, H, W, B, scale):
+    """ldconv_gather_bwd on the model's (N, C, s) shapes in bf16 with odd image sizes: offsets of 0.5 px (the benchmark regime),
+    3 px, and 60 px (most samples clamp onto the borders).  Against the oracle's scatter (autograd of conv.py:386-405)."""
+    L = _lib.load()
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    rng = np.random.default_rng(int(scale * 10) + C + N)
+    x = _bf16_round(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    off = (rng.standard_normal((B, 2 * N, h, w)) * scale).astype(np.float32)
+    g = _bf16_round(rng.standard_normal((B, C, N, h, w)).astype(np.float32))              # dL/dsamp
+    gx_ref, goff_ref = oracle.sample_bwd(np.ascontiguousarray(g.transpose(0, 1, 3, 2, 4)).reshape(B, C, h * N, w), x, off, N, s)
+    M = B * h * w
+    xd = _t(_nhwc(x), torch.bfloat16)
+    offd = _t(_nhwc(off))
+    gop = _t(np.ascontiguousarray(g.transpose(0, 3, 4, 2, 1)).reshape(M, N * C), torch.bfloat16)
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    gx = torch.zeros((B, H, W, C), device=DEV)
+    goff = torch.full((B, h, w, 2 * N), 123.0, device=DEV)      # the kernel must overwrite every element
+    _lib.check(L.ldconv_gather_bwd(_ptr(gop), _ptr(xd), _ptr(offd), _ptr(pn), _ptr(gx), _ptr(goff), B, C, H, W, N, s, _lib.BF16,
+                                   _stream()), "ldconv_gather_bwd")
+    torch.cuda.synchronize()
+    assert _rel(gx.cpu().numpy().transpose(0, 3, 1, 2), gx_ref) <= 2e-5
+    got_off = goff.cpu().numpy().transpose(0, 3, 1, 2)
+    assert np.abs(got_off - goff_ref).max() <= 2e-4 * max(1.0, float(np.abs(goff_ref).max()))
+
+
 # ---------------------------------------------------------------------------------- offset conv backward (bf16) ----
 @pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 1, 1, 24, 24, 2), (64, 3, 2, 21, 33, 2), (3, 3, 2, 64, 48, 2),
                                          (16, 5, 1, 160, 160, 8), (48, 2, 1, 17, 19, 1), (128, 9, 2, 20, 20, 1)])
