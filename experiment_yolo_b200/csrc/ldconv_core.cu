@@ -505,7 +505,7 @@ __device__ __forceinline__ void red_add_vec(float* dst, const float* v, int n)
 // IDX: the integer type of the item decomposition -- unsigned 32-bit whenever the item count fits (always at the benchmark
 // sizes); the 64-bit divisions of the general case cost several hundred instructions per item
 template <typename T, bool VECX, typename IDX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)      // <= 51 registers: 40 warps per SM instead of 24
 gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const float* __restrict__ off,
                   const int* __restrict__ pn, float* __restrict__ grad_x, float* __restrict__ grad_off, int C, int H,
                   int W, int h, int w, int N, int s, int CV, int group, long long total)
@@ -537,25 +537,29 @@ gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const floa
         const size_t o11 = base + ((size_t)q.r1 * W + q.k1) * C + cofs;
         const size_t o01 = base + ((size_t)q.r0 * W + q.k1) * C + cofs;
         const size_t o10 = base + ((size_t)q.r1 * W + q.k0) * C + cofs;
-        float g[V], x00[V], x11[V], x01[V], x10[V];
+        // Registers decide this kernel: it is load-latency-bound (profiles/r1_ncu_scatterL1.txt: 7.7 cycles of long scoreboard per
+        // issued instruction at 24 warps per SM), so the four corner vectors of x live only while the offset gradient is formed,
+        // and coincident corners are merged by adding their WEIGHTS -- one 8-value vector per emitted corner instead of four.
+        float g[V];
         const T* gp = gop + (size_t)m * N * C + (size_t)n * C + cofs;
-        if constexpr (VECX) {
-            Vec16<T>::load(gp, g);
-            Vec16<T>::load(x + o00, x00);
-            Vec16<T>::load(x + o11, x11);
-            Vec16<T>::load(x + o01, x01);
-            Vec16<T>::load(x + o10, x10);
-        } else {
-            g[0] = Elem<T>::to_f(*gp);
-            x00[0] = Elem<T>::to_f(x[o00]); x11[0] = Elem<T>::to_f(x[o11]);
-            x01[0] = Elem<T>::to_f(x[o01]); x10[0] = Elem<T>::to_f(x[o10]);
-        }
-        float v00[V], v11[V], v01[V], v10[V];
+        {
+            float x00[V], x11[V], x01[V], x10[V];
+            if constexpr (VECX) {
+                Vec16<T>::load(gp, g);
+                Vec16<T>::load(x + o00, x00);
+                Vec16<T>::load(x + o11, x11);
+                Vec16<T>::load(x + o01, x01);
+                Vec16<T>::load(x + o10, x10);
+            } else {
+                g[0] = Elem<T>::to_f(*gp);
+                x00[0] = Elem<T>::to_f(x[o00]); x11[0] = Elem<T>::to_f(x[o11]);
+                x01[0] = Elem<T>::to_f(x[o01]); x10[0] = Elem<T>::to_f(x[o10]);
+            }
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            v00[e] = g[e] * g_lt; v11[e] = g[e] * g_rb; v01[e] = g[e] * g_lb; v10[e] = g[e] * g_rt;
-            acc_r += g[e] * (-q.ak0 * x00[e] + q.ak1 * x11[e] - q.ak1 * x01[e] + q.ak0 * x10[e]);
-            acc_k += g[e] * (-q.ar0 * x00[e] + q.ar1 * x11[e] + q.ar0 * x01[e] - q.ar1 * x10[e]);
+            for (int e = 0; e < V; ++e) {
+                acc_r += g[e] * (-q.ak0 * x00[e] + q.ak1 * x11[e] - q.ak1 * x01[e] + q.ak0 * x10[e]);
+                acc_k += g[e] * (-q.ar0 * x00[e] + q.ar1 * x11[e] + q.ar0 * x01[e] - q.ar1 * x10[e]);
+            }
         }
         // scatter_add_ of the four GatherBackward nodes; V floats per corner as 128-bit vector reductions.
         // Corners that coincide (a clamped axis: r0 == r1 and / or k0 == k1, the reference's border doubling) are merged in
@@ -564,16 +568,6 @@ gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const floa
         // issues the reduction for all of them.
         if (grad_x != nullptr) {
             const bool same_r = q.r0 == q.r1, same_k = q.k0 == q.k1;
-            if (same_r && same_k) {
-#pragma unroll
-                for (int e = 0; e < V; ++e) v00[e] = (v00[e] + v11[e]) + (v01[e] + v10[e]);
-            } else if (same_r) {           // (r0,k0) == (r1,k0) and (r0,k1) == (r1,k1)
-#pragma unroll
-                for (int e = 0; e < V; ++e) { v00[e] += v10[e]; v01[e] += v11[e]; }
-            } else if (same_k) {           // (r0,k0) == (r0,k1) and (r1,k0) == (r1,k1)
-#pragma unroll
-                for (int e = 0; e < V; ++e) { v00[e] += v01[e]; v10[e] += v11[e]; }
-            }
             auto emit = [&](size_t o, float (&v)[V], bool clamped) {
                 if (clamped) {                                  // lanes here: the warp's clamped corners only
                     const unsigned act = __activemask();
@@ -601,19 +595,25 @@ gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const floa
 #pragma unroll
                 for (int e0 = 0; e0 < V; e0 += 4) red_add_vec(grad_x + o + e0, v + e0, V - e0 < 4 ? V - e0 : 4);
             };
+            auto corner = [&](size_t o, float wgt, bool clamped) {
+                float v[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) v[e] = g[e] * wgt;
+                emit(o, v, clamped);
+            };
             if (same_r && same_k) {
-                emit(o00, v00, true);
-            } else if (same_r) {
-                emit(o00, v00, true);
-                emit(o01, v01, true);
-            } else if (same_k) {
-                emit(o00, v00, true);
-                emit(o10, v10, true);
+                corner(o00, (g_lt + g_rb) + (g_lb + g_rt), true);
+            } else if (same_r) {           // (r0,k0) == (r1,k0) and (r0,k1) == (r1,k1)
+                corner(o00, g_lt + g_rt, true);
+                corner(o01, g_lb + g_rb, true);
+            } else if (same_k) {           // (r0,k0) == (r0,k1) and (r1,k0) == (r1,k1)
+                corner(o00, g_lt + g_lb, true);
+                corner(o10, g_rt + g_rb, true);
             } else {
-                emit(o00, v00, false);
-                emit(o11, v11, false);
-                emit(o01, v01, false);
-                emit(o10, v10, false);
+                corner(o00, g_lt, false);
+                corner(o11, g_rb, false);
+                corner(o01, g_lb, false);
+                corner(o10, g_rt, false);
             }
         }
     }
