@@ -567,8 +567,10 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t x_s = smem_s + g.ofs_x + (uint32_t)xb * g.x_bytes + ((uint32_t)cv << 4);
             const uint32_t a_s = smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes;
             const uint8_t* xg = reinterpret_cast<const uint8_t*>(x) + (size_t)cur.b * g.img_bytes + ((uint32_t)cv << 4);
-            auto load_item = [&](int sx, float4& gw, uint4 (&q)[4]) {
-                const uint4 o = gg_lds128(rec_s + (uint32_t)sx * 16u);
+            // the offset record of an item is fetched one step ahead of its corner loads (load_rec), so that a step's dependent
+            // chain is corner loads -> arithmetic instead of record -> corner loads -> arithmetic
+            auto load_rec = [&](int sx) { return gg_lds128(rec_s + (uint32_t)sx * 16u); };
+            auto load_item = [&](int sx, const uint4& o, float4& gw, uint4 (&q)[4]) {
                 gw = gg_lds_f4(rec_s + rec_g_ofs + (uint32_t)sx * 16u);
                 if ((int)o.x >= 0) {
                     q[0] = gg_lds128(x_s + o.x); q[1] = gg_lds128(x_s + o.y); q[2] = gg_lds128(x_s + o.z); q[3] = gg_lds128(x_s + o.w);
@@ -595,12 +597,19 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             // IF items in flight per thread (loads first, then the arithmetic): two under an 80-register cap, four when the
             // shared-memory footprint allows so few CTAs that 120+ registers are free anyway (latency-bound there)
             constexpr int IF = (65536 / (NTHR * MINB) >= 120 && TN != 0) ? 4 : 2;
+            uint4 orec[IF];      // offset records of the step about to run
+            auto fetch_recs = [&](int k, int nrounds) {
+#pragma unroll
+                for (int u = 0; u < IF; ++u)
+                    if (k + u < nrounds) orec[u] = load_rec(sx0 + (k + u) * spr);
+            };
             auto step = [&](int k, int nrounds) {
                 float4 gw[IF];
                 uint4 q[IF][4];
 #pragma unroll
                 for (int u = 0; u < IF; ++u)
-                    if (k + u < nrounds) load_item(sx0 + (k + u) * spr, gw[u], q[u]);
+                    if (k + u < nrounds) load_item(sx0 + (k + u) * spr, orec[u], gw[u], q[u]);
+                fetch_recs(k + IF, nrounds);      // next step's records, in flight during this step's arithmetic
 #pragma unroll
                 for (int u = 0; u < IF; ++u)
                     if (k + u < nrounds) store_item(sx0 + (k + u) * spr, gw[u], q[u]);
@@ -608,9 +617,11 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if constexpr (TN > 0 && TCVS >= 0) {
                 constexpr int R = (TN << TCVS) / TG;
                 static_assert((TN << TCVS) % TG == 0, "items per tile must divide evenly over the threads");
+                fetch_recs(0, R);
 #pragma unroll
                 for (int k = 0; k < R; k += IF) step(k, R);
             } else {
+                fetch_recs(0, rounds);
                 for (int k = 0; k < rounds; k += IF) step(k, rounds);
             }
         }
