@@ -23,11 +23,12 @@ echo "=== per-layer kernels ==="
 timeout 600 python benchmarks/ldconv_layers.py --bwd > $OUT/layers_$TAG.jsonl 2> $OUT/layers_$TAG.err
 echo "exit $?"
 if [ $BRC -eq 0 ]; then
-  echo "=== ncu launch list (same command run plain first) ==="
-  timeout 600 python bench.py --steps 2 --warmup 3 > $OUT/plain_$TAG.log 2>&1 &&
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_$TAG.csv \
-      python bench.py --steps 2 --warmup 3 > $OUT/ncu_launch_$TAG.log 2>&1
-  echo "exit $?"; tail -2 $OUT/ncu_launch_$TAG.log
+  echo "=== ncu launch list of exactly one step (cudaProfilerStart/Stop around it; the same script run plain first) ==="
+  # `ncu -c N python bench.py` only catches the model-initialisation kernels (several hundred element-wise launches)
+  timeout 300 python benchmarks/profile_step.py > $OUT/profstep_plain_$TAG.log 2>&1 &&
+  timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+      --clock-control none --csv --log-file $OUT/step_launches_$TAG.csv python benchmarks/profile_step.py > $OUT/profstep_ncu_$TAG.log 2>&1
+  echo "exit $?"; tail -2 $OUT/profstep_ncu_$TAG.log
 fi
 echo "=== ncu --set full: gather+GEMM kernel at layer 1, stand-alone gather at layer 1 ==="
 bash scripts/gpu_ncu_kernel.sh ggL1_$TAG ldconv_gg2 --kernel gg --layer 1
