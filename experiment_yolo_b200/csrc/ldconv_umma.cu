@@ -45,11 +45,20 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a)
 }
 
 // Epilogue of one 16-column chunk of one accumulator row: raw accumulator -> `pre`, affine + activation (+ residual) -> `out`.
+// Optional second destination of the activated output: the channel window [c_lo, c_lo + c_n) (multiples of 16) is ALSO stored
+// densely at out2 + m * ld2.  Lets a C2f's first 1x1 conv write its concat buffer and, in the same pass, a dense copy of the half
+// the first Bottleneck reads: a 16-channel slice of a 48-channel NHWC buffer costs the whole buffer in DRAM traffic.
+struct GemmOut2 {
+    __nv_bfloat16* ptr;
+    int ld, c_lo, c_n;
+};
+
 // aff_s = shared-space address of the (scale, shift) pair of column c0 (explicit LDS: the generic loads this replaces were
 // the top stall of the kernel, profiles/r1_ncu_gemmL1b.txt).
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
                                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
-                                                    const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store)
+                                                    const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store,
+                                                    const GemmOut2& o2)
 {
     const bool full16 = vec_store && (c0 + 16 <= O);
     if (pre) {
@@ -87,6 +96,11 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
             for (int e = 0; e < 8; ++e) { lo[e] = z[e]; hi[e] = z[8 + e]; }
             Vec16<__nv_bfloat16>::store(dst, lo);
             Vec16<__nv_bfloat16>::store(dst + 8, hi);
+            if (o2.ptr && (unsigned)(c0 - o2.c_lo) < (unsigned)o2.c_n) {      // host: window 16-aligned, out2 16-byte aligned
+                __nv_bfloat16* d2 = o2.ptr + m * o2.ld + (c0 - o2.c_lo);
+                Vec16<__nv_bfloat16>::store(d2, lo);
+                Vec16<__nv_bfloat16>::store(d2 + 8, hi);
+            }
         } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e)
@@ -104,7 +118,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
-                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg)
+                 int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg,
+                 GemmOut2 o2)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
@@ -210,10 +225,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < M && !(dbg & 2)) {
                     if (ch * 16 < O)
                         gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 128u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0);
+                                            vec_store != 0, o2);
                     if (two && (ch + 1) * 16 < O)
                         gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 128u, act, out, pre, residual,
-                                            ldo, ldr, vec_store != 0);
+                                            ldo, ldr, vec_store != 0, o2);
                 }
             }
             tc_fence_before_sync();
@@ -256,6 +271,7 @@ int umma_set_force_ffma(int v)
 int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                      const void* residual, int ldr, int ldo, double* stat_sum, double* stat_sqsum, int M, int K, int O, int act,
                      cudaStream_t st);
+static thread_local GemmOut2 g_out2 = {nullptr, 0, 0, 0};      // consumed (and cleared) by the next umma_gemm_fwd_ld of this thread
 
 int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                   double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
@@ -297,9 +313,13 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > num_tiles) grid = num_tiles;
     const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
+    const GemmOut2 o2 = g_out2;
+    g_out2 = GemmOut2{nullptr, 0, 0, 0};
+    if (o2.ptr && (!vec_store || !out || O % 16 != 0))
+        return fail(LDCONV_E_ARG, "tcgen05 GEMM: the second output needs 16-byte stores and Cout %% 16 == 0");
     LDC_CUDA(launch_pdl(umma_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
                         (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
-                        vec_store, ldo, ldr, NB, gemm_dbg()));
+                        vec_store, ldo, ldr, NB, gemm_dbg(), o2));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
@@ -312,6 +332,26 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
 }  // namespace ldc
 
 using namespace ldc;
+
+// The same 1x1 `Conv` block with a second, dense destination for the output channels [c2_lo, c2_lo + c2_n) (multiples of 16):
+// out2 (rows, c2_n | ld2).  Used by the C2f executor (nn/modules/block.py:209-232: y = cv1(x).chunk(2); the second chunk feeds the
+// first Bottleneck) so that the Bottleneck reads a dense tensor instead of a channel slice of the concat buffer.
+LDC_API int ldconv_conv1x1_bn_act_fwd2(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                                       const void* residual, int ldr, void* out, int ldo, void* out2, int ld2, int c2_lo, int c2_n,
+                                       long long rows, int Cin, int Cout, int act, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_conv1x1_bn_act_fwd2: bf16 only");
+    LDC_REQUIRE(x && wt && out && out2 && rows >= 0 && rows < (1ll << 31), "ldconv_conv1x1_bn_act_fwd2: bad arguments");
+    LDC_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo >= Cout && Cout <= 256 && Cout % 16 == 0,
+                "ldconv_conv1x1_bn_act_fwd2: needs Cin %% 8 == 0, ldx %% 8 == 0, Cout %% 16 == 0, Cout <= 256");
+    LDC_REQUIRE(c2_lo >= 0 && c2_n >= 16 && c2_lo % 16 == 0 && c2_n % 16 == 0 && c2_lo + c2_n <= Cout && ld2 >= c2_n && ld2 % 8 == 0,
+                "ldconv_conv1x1_bn_act_fwd2: the second output's channel window must be 16-aligned and inside [0, Cout)");
+    LDC_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(out) && aligned16(out2), "ldconv_conv1x1_bn_act_fwd2: 16-byte alignment");
+    if (rows == 0) return LDCONV_OK;
+    g_out2 = GemmOut2{(__nv_bfloat16*)out2, ld2, c2_lo, c2_n};
+    return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, out, nullptr, residual, ldr, ldo, nullptr, nullptr, (int)rows, Cin, Cout,
+                            act, (cudaStream_t)stream);
+}
 
 // 1x1 `Conv` block (Conv2d(1x1, no bias) + folded BatchNorm + activation, nn/modules/conv.py:41-59) = the same GEMM with
 // pixel strides: x and out may be channel slices of wider NHWC buffers.

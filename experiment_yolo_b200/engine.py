@@ -23,6 +23,8 @@ the golden output of the reference DetectionModel.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -75,11 +77,19 @@ class _Folded:
             self.shift = bias.contiguous()
 
 
-def conv1x1(x: torch.Tensor, p: _Folded, out: torch.Tensor, act: str = "silu", residual=None):
+def conv1x1(x: torch.Tensor, p: _Folded, out: torch.Tensor, act: str = "silu", residual=None, out2=None, c2_lo=0):
+    """out2: optional dense (B,H,W,c) tensor that also receives the output channels [c2_lo, c2_lo + c) (same pass)."""
     B, H, W, C, ldx = _nhwc_geometry(x)
     _, _, _, O, ldo = _nhwc_geometry(out)
     assert C == p.cin and O == p.cout
     ldr = _nhwc_geometry(residual)[4] if residual is not None else 0
+    if out2 is not None:
+        _, _, _, c2, ld2 = _nhwc_geometry(out2)
+        _lib.check(_lib.load().ldconv_conv1x1_bn_act_fwd2(
+            x.data_ptr(), ldx, p.w.data_ptr(), p.scale.data_ptr(), p.shift.data_ptr(),
+            None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, out2.data_ptr(), ld2, c2_lo, c2, B * H * W,
+            C, O, _ACT[act], _lib.BF16, _stream()), "ldconv_conv1x1_bn_act_fwd2")
+        return out
     _lib.check(_lib.load().ldconv_conv1x1_bn_act_fwd(
         x.data_ptr(), ldx, p.w.data_ptr(), p.scale.data_ptr(), p.shift.data_ptr(),
         None if residual is None else residual.data_ptr(), ldr, out.data_ptr(), ldo, B * H * W, C, O, _ACT[act], _lib.BF16,
@@ -103,6 +113,12 @@ def _new(like: torch.Tensor, B, H, W, C):
     return torch.empty((B, H, W, C), device=like.device, dtype=torch.bfloat16)
 
 
+# Dense second output of C2f.cv1 (ldconv_conv1x1_bn_act_fwd2).  OFF: measured 0.7 % slower in the step (3.658 vs 3.634 ms) -- the
+# slice the first Bottleneck reads is still L2-resident right after cv1 wrote it; the 3x DRAM over-fetch the one-step ncu launch list
+# shows for those convs (157 MB for a 52 MB slice) is a cold-cache artefact of the serialised capture.  LDCONV_C2F_DUAL_STORE=1 enables.
+_DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
+
+
 class _C2f:
     def __init__(self, m: dealyolo.C2f):
         self.c = m.c
@@ -115,10 +131,12 @@ class _C2f:
         B, H, W, _ = x.shape
         c, n = self.c, self.n
         cat = _new(x, B, H, W, (2 + n) * c)
-        conv1x1(x, self.cv1, cat[..., : 2 * c])
+        # optional: the chunk the first Bottleneck reads is also written densely by cv1 (see _DUAL_STORE)
+        y1 = _new(x, B, H, W, c) if (c % 16 == 0 and (2 * c) % 16 == 0 and _DUAL_STORE) else None
+        conv1x1(x, self.cv1, cat[..., : 2 * c], out2=y1, c2_lo=c)
         tmp = _new(x, B, H, W, c)
         for i, (p1, p2, add) in enumerate(self.blocks):
-            src = cat[..., (1 + i) * c: (2 + i) * c]
+            src = y1 if (i == 0 and y1 is not None) else cat[..., (1 + i) * c: (2 + i) * c]
             conv3x3(src, p1, tmp)
             conv3x3(tmp, p2, cat[..., (2 + i) * c: (3 + i) * c], residual=src if add else None)
         return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout))

@@ -198,6 +198,12 @@ int ldconv_gather_gemm_fwd(const void* x, const float* off, const int32_t* p_n, 
 int ldconv_conv1x1_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                               const void* residual, int ldr, void* out, int ldo, long long rows, int Cin, int Cout, int act,
                               int dtype, void* stream);
+/* Same block with a second, dense destination out2 (rows, c2_n | ld2) for the output channels [c2_lo, c2_lo + c2_n) (multiples of
+ * 16; Cout % 16 == 0): C2f's y = cv1(x).chunk(2) (nn/modules/block.py:222-226) -- the chunk the first Bottleneck reads is written
+ * densely in the same pass, because reading a channel slice of the NHWC concat buffer costs the whole buffer in DRAM traffic. */
+int ldconv_conv1x1_bn_act_fwd2(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                               const void* residual, int ldr, void* out, int ldo, void* out2, int ld2, int c2_lo, int c2_n,
+                               long long rows, int Cin, int Cout, int act, int dtype, void* stream);
 int ldconv_conv3x3_supported(int Cin, int Cout, int stride, int dtype);
 int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                               const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout,

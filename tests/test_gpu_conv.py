@@ -124,3 +124,31 @@ def test_conv3x3_channel_slices_in_and_out():
     got = obuf[..., 64:96].permute(0, 3, 1, 2).float()
     assert float((got - ref).norm() / ref.norm()) <= 6e-3
     assert float(obuf[..., :64].abs().max()) == 0.0 and float(obuf[..., 96:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("Cin,Cout,lo,n,rows,ldo", [(32, 32, 16, 16, 5000, 48), (64, 64, 32, 32, 777, 96), (128, 128, 64, 64, 300, 192),
+                                                    (32, 64, 0, 16, 129, 64), (64, 32, 16, 16, 40000, 48)])
+def test_conv1x1_second_dense_output(Cin, Cout, lo, n, rows, ldo):
+    """ldconv_conv1x1_bn_act_fwd2: the 1x1 Conv block (conv.py:41-59) writing a channel slice of a wider buffer AND, in the same
+    pass, a dense copy of the output channels [lo, lo + n) (C2f's second chunk, block.py:222-226): both must equal the plain call."""
+    L = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(Cin + Cout + rows)
+    x = torch.randn((rows, Cin), device=DEV, generator=g).bfloat16()
+    wt = (torch.randn((Cout, Cin), device=DEV, generator=g) * 0.2).bfloat16()
+    scale = torch.rand(Cout, device=DEV, generator=g) + 0.5
+    shift = torch.randn(Cout, device=DEV, generator=g) * 0.1
+    ref = torch.empty((rows, Cout), device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.ldconv_conv1x1_bn_act_fwd(_p(x), Cin, _p(wt), _p(scale), _p(shift), None, 0, _p(ref), Cout, rows, Cin, Cout,
+                                           _lib.ACT_SILU, _lib.BF16, _st()), "conv1x1")
+    buf = torch.full((rows, ldo), 3.0, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.full((rows, n), 5.0, device=DEV, dtype=torch.bfloat16)
+    _lib.check(L.ldconv_conv1x1_bn_act_fwd2(_p(x), Cin, _p(wt), _p(scale), _p(shift), None, 0, _p(buf), ldo, _p(out2), n, lo, n, rows,
+                                            Cin, Cout, _lib.ACT_SILU, _lib.BF16, _st()), "conv1x1 (two outputs)")
+    torch.cuda.synchronize()
+    assert torch.equal(buf[:, :Cout], ref)
+    assert torch.equal(out2, ref[:, lo:lo + n])
+    if ldo > Cout:
+        assert float((buf[:, Cout:].float() - 3.0).abs().max()) == 0.0      # the neighbouring channels are untouched
+    z = (x.double() @ wt.double().t()) * scale.double() + shift.double()
+    want = (z * torch.sigmoid(z)).float()
+    assert float((ref.float() - want).norm() / want.norm()) <= 6e-3
