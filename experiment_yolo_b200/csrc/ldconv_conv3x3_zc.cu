@@ -82,7 +82,8 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* sX = smem + g.ofs_x;        // [xbufs][halves][18][10][pb]  (each half 1024-aligned)
     uint8_t* sB = smem + g.ofs_b;        // [num_kb][ON][128 B] SWIZZLE_128B
-    float2* sAff = reinterpret_cast<float2*>(smem + g.ofs_aff);
+    float* sAff = reinterpret_cast<float*>(smem + g.ofs_aff);
+    const uint32_t aff_s = smem_u32(sAff);
     uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + g.ofs_bar);
     uint64_t* x_empty = x_full + kZcMaxX;
     uint64_t* t_full = x_empty + kZcMaxX;
@@ -105,8 +106,12 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     if (warp == 1) tmem_alloc(tmem_slot, g.tmem_cols);
     pdl_wait();       // everything below may read what the previous kernel wrote
-    for (int o = threadIdx.x; o < g.ON; o += blockDim.x)
-        sAff[o] = make_float2((scale && o < g.Cout) ? scale[o] : 1.f, (shift && o < g.Cout) ? shift[o] : 0.f);
+    // [0, ON) scale, [ON, 2 ON) shift; halved for SiLU (affine_act16)
+    const float aff_pre = MODE == ZC_MODE_OFFSETS ? 1.f : affine_half_for(act);
+    for (int o = threadIdx.x; o < g.ON; o += blockDim.x) {
+        sAff[o] = aff_pre * ((scale && o < g.Cout) ? scale[o] : 1.f);
+        sAff[g.ON + o] = aff_pre * ((shift && o < g.Cout) ? shift[o] : 0.f);
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -220,25 +225,19 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     float* dst = reinterpret_cast<float*>(out_v) + m * g.ldo + c0;
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
-                        if (c0 + e < g.Cout) dst[e] = __uint_as_float(v[e]) + sAff[c0 + e].y;
+                        if (c0 + e < g.Cout) dst[e] = __uint_as_float(v[e]) + sAff[g.ON + c0 + e];
                 } else {
-                    float lo[8], hi[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float2 a0 = sAff[c0 + e], a1 = sAff[c0 + 8 + e];
-                        lo[e] = apply_act_fast(fmaf(__uint_as_float(v[e]), a0.x, a0.y), act);
-                        hi[e] = apply_act_fast(fmaf(__uint_as_float(v[8 + e]), a1.x, a1.y), act);
-                    }
+                    float z[16];
+                    affine_act16(v, aff_s + (uint32_t)c0 * 4u, aff_s + (uint32_t)(g.ON + c0) * 4u, act, z);
                     if (residual) {
                         float r0[8], r1[8];
                         Vec16<T>::load(residual + m * g.ldr + c0, r0);
                         Vec16<T>::load(residual + m * g.ldr + c0 + 8, r1);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) { lo[e] += r0[e]; hi[e] += r1[e]; }
+                        for (int e = 0; e < 8; ++e) { z[e] += r0[e]; z[8 + e] += r1[e]; }
                     }
-                    T* dst = reinterpret_cast<T*>(out_v) + m * g.ldo + c0;
-                    Vec16<T>::store(dst, lo);
-                    Vec16<T>::store(dst + 8, hi);
+                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(out_v) + m * g.ldo + c0);
+                    pack16_bf16(z, dst[0], dst[1]);
                 }
             }
             tc_fence_before_sync();

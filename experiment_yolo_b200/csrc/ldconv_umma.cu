@@ -53,12 +53,12 @@ struct GemmOut2 {
     int ld, c_lo, c_n;
 };
 
-// aff_s = shared-space address of the (scale, shift) pair of column c0 (explicit LDS: the generic loads this replaces were
+// aff_s = shared-space address of the scale of column c0, aff_s + sh_ofs = of its shift (explicit LDS: the generic loads this replaces were
 // the top stall of the kernel, profiles/r1_ncu_gemmL1b.txt).
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
                                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
                                                     const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store,
-                                                    const GemmOut2& o2)
+                                                    const GemmOut2& o2, uint32_t sh_ofs)
 {
     const bool full16 = vec_store && (c0 + 16 <= O);
     if (pre) {
@@ -77,12 +77,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
     }
     if (out) {
         float z[16];
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-            const float4 a = lds_f4(aff_s + (uint32_t)e * 8u);      // (scale, shift) of columns c0+e, c0+e+1
-            z[e] = apply_act_fast(fmaf(__uint_as_float(v[e]), a.x, a.y), act);
-            z[e + 1] = apply_act_fast(fmaf(__uint_as_float(v[e + 1]), a.z, a.w), act);
-        }
+        affine_act16(v, aff_s, aff_s + sh_ofs, act, z);
         if (residual) {
             const __nv_bfloat16* rp = residual + m * ldr + c0;
 #pragma unroll
@@ -91,15 +86,14 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
         }
         __nv_bfloat16* dst = out + m * ldo + c0;
         if (full16) {
-            float lo[8], hi[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { lo[e] = z[e]; hi[e] = z[8 + e]; }
-            Vec16<__nv_bfloat16>::store(dst, lo);
-            Vec16<__nv_bfloat16>::store(dst + 8, hi);
+            uint4 lo, hi;
+            pack16_bf16(z, lo, hi);
+            reinterpret_cast<uint4*>(dst)[0] = lo;
+            reinterpret_cast<uint4*>(dst)[1] = hi;
             if (o2.ptr && (unsigned)(c0 - o2.c_lo) < (unsigned)o2.c_n) {      // host: window 16-aligned, out2 16-byte aligned
-                __nv_bfloat16* d2 = o2.ptr + m * o2.ld + (c0 - o2.c_lo);
-                Vec16<__nv_bfloat16>::store(d2, lo);
-                Vec16<__nv_bfloat16>::store(d2 + 8, hi);
+                uint4* d2 = reinterpret_cast<uint4*>(o2.ptr + m * o2.ld + (c0 - o2.c_lo));
+                d2[0] = lo;
+                d2[1] = hi;
             }
         } else {
 #pragma unroll
@@ -131,7 +125,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = empty + stages;         // [8]
     uint64_t* tempty = tfull + 8;             // [8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
-    float2* s_affine = reinterpret_cast<float2*>(tmem_slot + 4);     // [ON] (scale, shift)
+    float* s_affine = reinterpret_cast<float*>(tmem_slot + 4);      // [0, ON) scale, [ON, 2 ON) shift; halved for SiLU (affine_act16)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -147,8 +141,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
     pdl_wait();       // everything below may read what the previous kernel wrote (operand, scale / shift)
-    for (int o = threadIdx.x; o < ON; o += blockDim.x)
-        s_affine[o] = make_float2((scale && o < O) ? scale[o] : 1.f, (shift && o < O) ? shift[o] : 0.f);
+    {
+        const float aff_pre = affine_half_for(act);
+        for (int o = threadIdx.x; o < ON; o += blockDim.x) {
+            s_affine[o] = aff_pre * ((scale && o < O) ? scale[o] : 1.f);
+            s_affine[ON + o] = aff_pre * ((shift && o < O) ? shift[o] : 0.f);
+        }
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -224,11 +223,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld_wait();
                 if (m < M && !(dbg & 2)) {
                     if (ch * 16 < O)
-                        gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 128u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0, o2);
+                        gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 64u, act, out, pre, residual, ldo, ldr,
+                                            vec_store != 0, o2, (uint32_t)ON * 4u);
                     if (two && (ch + 1) * 16 < O)
-                        gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 128u, act, out, pre, residual,
-                                            ldo, ldr, vec_store != 0, o2);
+                        gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 64u, act, out, pre, residual,
+                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u);
                 }
             }
             tc_fence_before_sync();
