@@ -119,6 +119,9 @@ def _new(like: torch.Tensor, B, H, W, C):
 _DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
 
 
+_DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
+
+
 class _C2f:
     def __init__(self, m: dealyolo.C2f):
         self.c = m.c
@@ -206,10 +209,25 @@ class _Detect:
         self.box = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv2]
         self.cls = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv3]
         self.streams = None
+        # The first convs of the two branches of a level read the same input (nn/modules/head.py:43-52: cv2[i][0] ch -> 64, cv3[i][0]
+        # ch -> 32).  As ONE conv with the weights stacked (Cout = 96) the input is read once and the MMAs run at N = 96: the wide
+        # convs are tensor-pipe-bound and a 128 x N x 16 MMA costs the same pipe time for any N <= 128.  The second
+        # convs then read channel slices of the 96-channel buffer.  Levels with more than 64 input channels keep two convs (the
+        # stacked weights no longer fit the zero-copy kernel's shared memory).
+        self.first = []
+        for b, c in zip(self.box, self.cls):
+            f = None
+            if _DETECT_FUSE and b[0].cin <= 64 and (b[0].cout + c[0].cout) % 16 == 0 and b[0].cout % 16 == 0:
+                f = object.__new__(_Folded)
+                f.w = torch.cat([b[0].w, c[0].w], 0).contiguous()
+                f.scale = torch.cat([b[0].scale, c[0].scale]).contiguous()
+                f.shift = torch.cat([b[0].shift, c[0].shift]).contiguous()
+                f.k, f.stride, f.cin, f.cout = b[0].k, b[0].stride, b[0].cin, b[0].cout + c[0].cout
+            self.first.append(f)
 
     @staticmethod
-    def _chain(x, ps, bufs):
-        t = conv3x3(x, ps[0], bufs[0])
+    def _chain(x, ps, bufs, skip_first=False):
+        t = x if skip_first else conv3x3(x, ps[0], bufs[0])
         t = conv3x3(t, ps[1], bufs[1])
         return conv1x1(t, ps[2], bufs[2], act="none")
 
@@ -221,24 +239,46 @@ class _Detect:
         bufs = []
         for lvl, x in enumerate(xs):
             _, H, W, _ = x.shape
-            bb = [_new(x, B, H, W, self.box[lvl][0].cout), _new(x, B, H, W, self.box[lvl][1].cout), _new(x, B, H, W, 4 * self.reg_max)]
-            cb = [_new(x, B, H, W, self.cls[lvl][0].cout), _new(x, B, H, W, self.cls[lvl][1].cout), _new(x, B, H, W, self.nc)]
-            bufs.append((bb, cb))
+            if self.first[lvl] is not None:      # one buffer for the stacked first conv; the branches read its channel slices
+                both = _new(x, B, H, W, self.first[lvl].cout)
+                b0, c0 = both[..., : self.box[lvl][0].cout], both[..., self.box[lvl][0].cout:]
+            else:
+                both, b0, c0 = None, _new(x, B, H, W, self.box[lvl][0].cout), _new(x, B, H, W, self.cls[lvl][0].cout)
+            bb = [b0, _new(x, B, H, W, self.box[lvl][1].cout), _new(x, B, H, W, 4 * self.reg_max)]
+            cb = [c0, _new(x, B, H, W, self.cls[lvl][1].cout), _new(x, B, H, W, self.nc)]
+            bufs.append((bb, cb, both))
         cur = torch.cuda.current_stream(xs[0].device)
         if self.parallel_branches:
             if self.streams is None:
                 self.streams = [torch.cuda.Stream(xs[0].device) for _ in range(2 * len(xs))]
+            stacked_done = {}
             for k, st in enumerate(self.streams):
                 lvl, br = k // 2, k % 2
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    self._chain(xs[lvl], self.box[lvl] if br == 0 else self.cls[lvl], bufs[lvl][br])
+                fused = self.first[lvl] is not None
+                if br == 0:
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        if fused:
+                            conv3x3(xs[lvl], self.first[lvl], bufs[lvl][2])
+                            stacked_done[lvl] = torch.cuda.Event()
+                            stacked_done[lvl].record(st)      # the class branch starts here, not after the whole box chain
+                        self._chain(bufs[lvl][0][0] if fused else xs[lvl], self.box[lvl], bufs[lvl][0], skip_first=fused)
+                else:
+                    if fused:
+                        st.wait_event(stacked_done[lvl])
+                    else:
+                        st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        self._chain(bufs[lvl][1][0] if fused else xs[lvl], self.cls[lvl], bufs[lvl][1], skip_first=fused)
             for st in self.streams:
                 cur.wait_stream(st)
         else:
             for lvl, x in enumerate(xs):
-                self._chain(x, self.box[lvl], bufs[lvl][0])
-                self._chain(x, self.cls[lvl], bufs[lvl][1])
+                fused = self.first[lvl] is not None
+                if fused:
+                    conv3x3(x, self.first[lvl], bufs[lvl][2])
+                self._chain(bufs[lvl][0][0] if fused else x, self.box[lvl], bufs[lvl][0], skip_first=fused)
+                self._chain(bufs[lvl][1][0] if fused else x, self.cls[lvl], bufs[lvl][1], skip_first=fused)
         feats, a0 = [], 0
         for lvl, x in enumerate(xs):
             _, H, W, _ = x.shape
