@@ -7,6 +7,8 @@
 //   * small-C kernel (C <= 4; the first layer, 3 -> 16 channels: 23 % of the model's gather bytes and far too narrow for
 //     128-bit NHWC vectors or for an MMA): one thread per output pixel on CUDA cores, x read through L1.
 //   * tcgen05 kernel (C % 16 == 0, K = N*C <= 512, O % 16 == 0, O <= 256), see below.
+#include <mutex>
+
 #include "common.cuh"
 #include "tmap.cuh"
 #include "umma.cuh"
@@ -288,6 +290,287 @@ smallc_tiled_kernel(const T* __restrict__ x, const float* __restrict__ w_off, co
     }
 }
 
+// =====================================================================================================================
+// first-layer kernel (bf16, C = 3 -> O = 16, num_param = 3, stride 2, even H and W): rows of output pixels per CTA.
+// The thread-per-pixel kernel above executed ~1570 instructions per pixel of which ~150 are the packed FMAs: a quarter went
+// into the per-CTA weight staging and the 64-bit index decomposition, another quarter into the addressing of 63 two-byte
+// loads (profiles/r1_ncu_smallcL0b.txt: 79 % of the issue slots, DRAM at 10 %).  Here
+//   * a CTA stages the weights ONCE and then walks over whole output rows (grid = resident CTAs, row = blockIdx.x + k * grid),
+//   * the 3 x 3 x 3 window of the offset conv (conv.py:368) is read as five aligned 4-byte words per input row (the 18
+//     bytes of three NHWC pixels starting at byte 12 j - 6 sit inside the 20 bytes from 12 j - 8), the left / top padding
+//     is a predicate on the words,
+//   * the offset conv contracts PAIRS of window elements per packed FMA (the two halves of a word are the two lanes of the
+//     FFMA2, weights pre-paired in shared memory, the two partial sums added once at the end): no broadcast moves,
+//   * corner addresses are 32-bit element indices relative to the image.
+// Sampling arithmetic is make_point / bilinear as everywhere else, the operand is rounded to bf16 like the 3-kernel path.
+// =====================================================================================================================
+constexpr int L0_KP = 14;      // pairs of the 27 window elements: 12 word pairs + (e1 row 0, e1 row 1) + (e1 row 2, 1 * bias)
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// the layer's weights in the order the kernel consumes them (1408 bytes)
+struct L0Weights {
+    float wo[L0_KP * 3 * 4];     // [pair][q] -> (wA[2q], wB[2q], wA[2q+1], wB[2q+1]) of the offset conv
+    float wt[9 * 16];            // [k = n*C + c][o] of the (N,1) conv
+    float sc[2 * 16];            // scale | shift (halved for SiLU: 0.5 z (1 + tanh(0.5 z)))
+    int pn[6];
+    int pad[2];
+};
+// Uniform weights read from shared memory cost one L1 wavefront per 8 bytes per warp: 174 of the rows kernel's 336 wavefronts
+// per 32 pixels, and the L1 data pipe is what bounds it (profiles/r1_ncu_l0rows_v1.txt: 83.5 % of peak, issue slots 57 %).
+// From the constant bank they are operands of the FFMA2s and cost nothing.  The library keeps no per-module state, so the
+// bank has L0_SLOTS slots per device, a slot belongs to the first (w_off, wt, scale) pointer triple that asks for it for
+// the life of the process, and its content is rewritten in stream order by l0_prep_kernel before EVERY launch (the same
+// bytes unless the caller changed the weights); a fifth distinct layer on a device uses the shared-memory variant (SLOT -1).
+constexpr int L0_SLOTS = 4;
+__constant__ L0Weights c_l0[L0_SLOTS];
+
+__device__ __forceinline__ void l0_fill(L0Weights* dst, const float* __restrict__ w_off, const float* __restrict__ b_off,
+                                        const int* __restrict__ pn, const __nv_bfloat16* __restrict__ wt,
+                                        const float* __restrict__ scale, const float* __restrict__ shift, int act)
+{
+    constexpr int O = 16, O2 = 6, K = 9;
+    for (int t = threadIdx.x; t < L0_KP * 12; t += blockDim.x) {
+        const int p = t / 12, q = (t % 12) / 4, e = t % 4;
+        const int o = 2 * q + (e >> 1), second = e & 1;
+        int k;                                               // window element tr*9 + tc*3 + c (w_off is [3][3][C][2N])
+        if (p < 12) k = (p / 4) * 9 + 2 * (p % 4) + 1 + second;
+        else if (p == 12) k = second ? 9 : 0;
+        else k = second ? -1 : 18;                           // the pad element is the constant 1: its weight is the bias
+        dst->wo[t] = k >= 0 ? w_off[k * O2 + o] : (b_off ? b_off[o] : 0.f);
+    }
+    for (int t = threadIdx.x; t < K * O; t += blockDim.x) dst->wt[t] = __bfloat162float(wt[(t % O) * K + t / O]);
+    const float half = act == LDCONV_ACT_SILU ? 0.5f : 1.f;
+    for (int t = threadIdx.x; t < O; t += blockDim.x) {
+        dst->sc[t] = half * (scale ? scale[t] : 1.f);
+        dst->sc[O + t] = half * (shift ? shift[t] : 0.f);
+    }
+    if (threadIdx.x < 6) dst->pn[threadIdx.x] = pn[threadIdx.x];
+}
+
+__global__ void l0_prep_kernel(L0Weights* dst, const float* __restrict__ w_off, const float* __restrict__ b_off,
+                               const int* __restrict__ pn, const __nv_bfloat16* __restrict__ wt,
+                               const float* __restrict__ scale, const float* __restrict__ shift, int act)
+{
+    l0_fill(dst, w_off, b_off, pn, wt, scale, shift, act);
+}
+
+template <int MINB, int SLOT>
+__global__ void __launch_bounds__(160, MINB)
+l0_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w_off, const float* __restrict__ b_off,
+               const int* __restrict__ pn, const __nv_bfloat16* __restrict__ wt, const float* __restrict__ scale,
+               const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, float* __restrict__ off_out, int rows, int H,
+               int W, int h, int w, int act)
+{
+    constexpr int C = 3, N = 3, O = 16, O2 = 6;
+    __shared__ __align__(16) L0Weights s_w;
+    if (SLOT < 0) {
+        l0_fill(&s_w, w_off, b_off, pn, wt, scale, shift, act);
+        __syncthreads();
+    }
+    const float* s_wo = SLOT < 0 ? s_w.wo : c_l0[SLOT < 0 ? 0 : SLOT].wo;
+    const float* s_wt = SLOT < 0 ? s_w.wt : c_l0[SLOT < 0 ? 0 : SLOT].wt;
+    const float* s_sc = SLOT < 0 ? s_w.sc : c_l0[SLOT < 0 ? 0 : SLOT].sc;
+    const int* s_pn = SLOT < 0 ? s_w.pn : c_l0[SLOT < 0 ? 0 : SLOT].pn;
+
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;     // a thread keeps its column and walks down the rows
+    if (j >= w) return;
+    const float hm = (float)(H - 1), wm = (float)(W - 1);
+    const uint32_t row_words = (uint32_t)W * C / 2;          // W even: rows are whole 4-byte words
+    const uint32_t* xcol = reinterpret_cast<const uint32_t*>(x) + 3 * j;          // word of byte 12 j of a row
+    const unsigned short* xs0 = reinterpret_cast<const unsigned short*>(x);
+    int b = blockIdx.y / h, i = blockIdx.y - b * h;
+    for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+        {
+            // ---- offset conv ------------------------------------------------------------------------------------------
+            uint64_t accp[O2];
+#pragma unroll
+            for (int o = 0; o < O2; ++o) accp[o] = 0ull;
+            float e1[3];
+#pragma unroll
+            for (int tr = 0; tr < 3; ++tr) {
+                uint32_t wd[5] = {0u, 0u, 0u, 0u, 0u};
+                if (tr > 0 || i > 0) {                                            // input row 2 i - 1 + tr of image b (H = 2 h)
+                    const uint32_t* rp = xcol + (size_t)(uint32_t)(2 * row - 1 + tr) * row_words;
+                    if (j > 0) { wd[0] = rp[-2]; wd[1] = rp[-1]; }
+                    wd[2] = rp[0]; wd[3] = rp[1]; wd[4] = rp[2];
+                }
+                e1[tr] = bf16_hi(wd[0]);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint64_t xx = f2_pack(bf16_lo(wd[q4 + 1]), bf16_hi(wd[q4 + 1]));
+                    const float4* wp = reinterpret_cast<const float4*>(s_wo + (tr * 4 + q4) * 12);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const float4 wv = wp[q];
+                        accp[2 * q] = f2_fma(xx, f2_pack(wv.x, wv.y), accp[2 * q]);
+                        accp[2 * q + 1] = f2_fma(xx, f2_pack(wv.z, wv.w), accp[2 * q + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 12; p < 14; ++p) {
+                const uint64_t xx = p == 12 ? f2_pack(e1[0], e1[1]) : f2_pack(e1[2], 1.f);
+                const float4* wp = reinterpret_cast<const float4*>(s_wo + p * 12);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float4 wv = wp[q];
+                    accp[2 * q] = f2_fma(xx, f2_pack(wv.x, wv.y), accp[2 * q]);
+                    accp[2 * q + 1] = f2_fma(xx, f2_pack(wv.z, wv.w), accp[2 * q + 1]);
+                }
+            }
+            float offv[O2];
+#pragma unroll
+            for (int o = 0; o < O2; ++o) {
+                float lo, hi;
+                f2_unpack(accp[o], lo, hi);
+                offv[o] = lo + hi;
+            }
+            const size_t m = (size_t)row * w + j;
+            const unsigned short* xs = xs0 + (size_t)b * ((size_t)H * W * C);
+            if (off_out) {
+                float2* op = reinterpret_cast<float2*>(off_out + m * O2);
+                op[0] = make_float2(offv[0], offv[1]);
+                op[1] = make_float2(offv[2], offv[3]);
+                op[2] = make_float2(offv[4], offv[5]);
+            }
+
+            // ---- sampling + (N,1) conv -----------------------------------------------------------------------------------
+            uint64_t acc[O / 2];
+#pragma unroll
+            for (int o = 0; o < O / 2; ++o) acc[o] = 0ull;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const SamplePoint q = make_point_grid(2 * i + s_pn[n], 2 * j + s_pn[N + n], offv[n], offv[N + n], hm, wm);
+                const float g_lt = __fmul_rn(q.ar0, q.ak0), g_rb = __fmul_rn(q.ar1, q.ak1);
+                const float g_lb = __fmul_rn(q.ar0, q.ak1), g_rt = __fmul_rn(q.ar1, q.ak0);
+                const uint32_t ra = (uint32_t)q.r0 * (uint32_t)(W * C), rb = (uint32_t)q.r1 * (uint32_t)(W * C);
+                const uint32_t ka = (uint32_t)q.k0 * C, kb = (uint32_t)q.k1 * C;
+                const unsigned short* p00 = xs + (ra + ka);
+                const unsigned short* p11 = xs + (rb + kb);
+                const unsigned short* p01 = xs + (ra + kb);
+                const unsigned short* p10 = xs + (rb + ka);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float v = bilinear(g_lt, g_rb, g_lb, g_rt, bf16_lo(p00[c]), bf16_lo(p11[c]), bf16_lo(p01[c]), bf16_lo(p10[c]));
+                    v = __bfloat162float(__float2bfloat16_rn(v));     // the operand is rounded to bf16, as in the 3-kernel path
+                    const uint64_t vv = f2_pack(v, v);
+                    const float4* wrow = reinterpret_cast<const float4*>(s_wt + (n * C + c) * O);
+#pragma unroll
+                    for (int o4 = 0; o4 < O / 4; ++o4) {
+                        const float4 wv = wrow[o4];
+                        acc[o4 * 2 + 0] = f2_fma(vv, f2_pack(wv.x, wv.y), acc[o4 * 2 + 0]);
+                        acc[o4 * 2 + 1] = f2_fma(vv, f2_pack(wv.z, wv.w), acc[o4 * 2 + 1]);
+                    }
+                }
+            }
+            // ---- folded BatchNorm + SiLU, two 16-byte stores ----------------------------------------------------------------
+            uint32_t pk[O / 2];
+#pragma unroll
+            for (int o4 = 0; o4 < O / 4; ++o4) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_sc + o4 * 4);
+                const float4 sh = *reinterpret_cast<const float4*>(s_sc + O + o4 * 4);
+                float z[4];
+                f2_unpack(f2_fma(acc[o4 * 2 + 0], f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y)), z[0], z[1]);
+                f2_unpack(f2_fma(acc[o4 * 2 + 1], f2_pack(sc.z, sc.w), f2_pack(sh.z, sh.w)), z[2], z[3]);
+                if (act == LDCONV_ACT_SILU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {                  // z holds 0.5 (scale acc + shift): y = z tanh(z) + z
+                        float t;
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z[e]));
+                        z[e] = fmaf(z[e], t, z[e]);
+                    }
+                }
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[o4 * 2 + 0]) : "f"(z[1]), "f"(z[0]));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[o4 * 2 + 1]) : "f"(z[3]), "f"(z[2]));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out + m * O);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        i += gridDim.y;
+        while (i >= h) { i -= h; ++b; }
+    }
+}
+
+static bool l0_rows_applicable(const void* x, int B, int C, int H, int W, int N, int s, int O)
+{
+    static const int enabled = getenv("LDCONV_L0_ROWS") ? atoi(getenv("LDCONV_L0_ROWS")) : 1;
+    return enabled && C == 3 && N == 3 && O == 16 && s == 2 && H % 2 == 0 && W % 2 == 0 && ((uintptr_t)x & 3) == 0 &&
+           (long long)H * W * C < (1ll << 31) && (long long)B * (H / 2) < (1ll << 31);
+}
+
+struct L0Slot { int dev; const void *w_off, *wt, *scale; L0Weights* addr; };
+
+// slot of this (device, weights) pair in the constant bank, or -1 (bank full: shared-memory variant)
+static int l0_slot(int dev, const void* w_off, const void* wt, const void* scale, L0Weights** addr)
+{
+    static std::mutex mu;
+    static L0Slot table[64];
+    static int used = 0;
+    static const int enabled = getenv("LDCONV_L0_CONST") ? atoi(getenv("LDCONV_L0_CONST")) : 1;
+    if (!enabled) return -1;
+    std::lock_guard<std::mutex> lock(mu);
+    int on_dev = 0;
+    for (int t = 0; t < used; ++t) {
+        if (table[t].dev != dev) continue;
+        if (table[t].w_off == w_off && table[t].wt == wt && table[t].scale == scale) { *addr = table[t].addr; return on_dev; }
+        ++on_dev;
+    }
+    if (on_dev >= L0_SLOTS || used >= 64) return -1;
+    L0Weights* base = nullptr;
+    if (cudaGetSymbolAddress((void**)&base, c_l0) != cudaSuccess) { cudaGetLastError(); return -1; }
+    table[used] = L0Slot{dev, w_off, wt, scale, base + on_dev};
+    *addr = table[used].addr;
+    ++used;
+    return on_dev;
+}
+
+typedef void (*l0_kernel_t)(const __nv_bfloat16*, const float*, const float*, const int*, const __nv_bfloat16*, const float*,
+                            const float*, __nv_bfloat16*, float*, int, int, int, int, int, int);
+
+static int launch_l0_rows(const __nv_bfloat16* x, const float* w_off, const float* b_off, const int* pn, const __nv_bfloat16* wt,
+                          const float* scale, const float* shift, __nv_bfloat16* out, float* off_out, int B, int H, int W,
+                          int act, cudaStream_t st)
+{
+    const int h = H / 2, w = W / 2, rows = B * h;
+    const int threads = w % 160 == 0 ? 160 : (w >= 128 ? 128 : ((w + 31) / 32) * 32);
+    // CTAs per SM the register budget is compiled for: 6 (64 registers) or 5 (80 registers)
+    static const int minb = getenv("LDCONV_L0_MINB") ? atoi(getenv("LDCONV_L0_MINB")) : 6;
+    int dev = 0;
+    LDC_CUDA(cudaGetDevice(&dev));
+    L0Weights* slot_addr = nullptr;
+    const int slot = l0_slot(dev, w_off, wt, scale, &slot_addr);
+    static const l0_kernel_t kerns[2][L0_SLOTS + 1] = {
+        {l0_rows_kernel<6, -1>, l0_rows_kernel<6, 0>, l0_rows_kernel<6, 1>, l0_rows_kernel<6, 2>, l0_rows_kernel<6, 3>},
+        {l0_rows_kernel<5, -1>, l0_rows_kernel<5, 0>, l0_rows_kernel<5, 1>, l0_rows_kernel<5, 2>, l0_rows_kernel<5, 3>}};
+    const int v = minb == 5 ? 1 : 0;
+    l0_kernel_t kern = kerns[v][slot + 1];
+    static int sms = 0, per_sm[2][2][3] = {};
+    const int tslot = threads == 160 ? 0 : (threads == 128 ? 1 : 2), cslot = slot >= 0 ? 1 : 0;
+    if (!sms) LDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!per_sm[v][cslot][tslot]) {
+        int n = 0;
+        LDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, tslot == 2 ? 128 : threads, 0));
+        per_sm[v][cslot][tslot] = n < 1 ? 1 : n;
+    }
+    const int segs = (w + threads - 1) / threads;            // column segments: grid.x; grid.y CTAs share the rows of a segment
+    long long gy = (long long)sms * per_sm[v][cslot][tslot] / segs;
+    if (gy < 1) gy = 1;
+    if (gy > rows) gy = rows;
+    if (gy > 65535) gy = 65535;
+    if (slot >= 0) {
+        l0_prep_kernel<<<1, 192, 0, st>>>(slot_addr, w_off, b_off, pn, wt, scale, shift, act);
+        LDC_LAUNCH_CHECK("l0_prep_kernel");
+    }
+    kern<<<dim3((unsigned)segs, (unsigned)gy), threads, 0, st>>>(x, w_off, b_off, pn, wt, scale, shift, out, off_out, rows, H, W, h,
+                                                                  w, act);
+    LDC_LAUNCH_CHECK("l0_rows_kernel");
+    set_impl(LDCONV_IMPL_FFMA);
+    return LDCONV_OK;
+}
+
 template <typename T, int C>
 static int launch_smallc(const T* x, const float* w_off, const float* b_off, const int* pn, const T* wt, const float* scale,
                          const float* shift, T* out, float* off_out, int B, int H, int W, int N, int s, int O, int act,
@@ -377,6 +660,9 @@ LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_o
     LDC_REQUIRE(aligned16(out), "ldconv_fused_fwd: out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     if (C <= 4) {
+        if (dtype == LDCONV_BF16 && l0_rows_applicable(x, B, C, H, W, N, s, O))
+            return launch_l0_rows((const __nv_bfloat16*)x, w_off, b_off, p_n, (const __nv_bfloat16*)wt, scale, shift,
+                                  (__nv_bfloat16*)out, off_out, B, H, W, act, st);
         if (dtype == LDCONV_BF16)
             return dispatch_smallc<__nv_bfloat16>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O,
                                                   act, st);

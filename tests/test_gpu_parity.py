@@ -5,6 +5,7 @@ Bars (BASELINE.json north_star): sampling indices and grid coordinates bit-exact
 bf16 outputs rel-L2 <= 1e-2 against the fp32 reference evaluated on bf16-rounded inputs / parameters; gradients
 rel-L2 (atomics reorder the sums).
 """
+import ctypes
 import numpy as np
 import pytest
 import torch
@@ -429,7 +430,11 @@ def test_module_train_bf16(name):
     (16, 32, 3, 2, 64, 80, 2, 0.05), (16, 32, 3, 2, 37, 53, 2, 0.3), (32, 64, 3, 2, 40, 40, 2, 0.05), (64, 128, 3, 2, 24, 40, 2, 0.05),
     (128, 64, 1, 1, 20, 20, 2, 0.05), (64, 64, 1, 1, 40, 24, 1, 0.1), (64, 32, 1, 1, 17, 19, 2, 0.05), (32, 32, 1, 1, 48, 48, 1, 0.05),
     (64, 64, 3, 2, 40, 40, 2, 0.5), (32, 48, 5, 1, 20, 28, 1, 0.05), (16, 16, 9, 2, 33, 47, 2, 0.05), (48, 32, 2, 1, 16, 16, 2, 0.05),
-    (3, 16, 3, 2, 64, 96, 2, 0.05), (4, 8, 5, 1, 21, 17, 2, 0.2), (1, 16, 9, 2, 30, 30, 1, 0.3)])
+    (3, 16, 3, 2, 64, 96, 2, 0.05), (4, 8, 5, 1, 21, 17, 2, 0.2), (1, 16, 9, 2, 30, 30, 1, 0.3),
+    # the first-layer rows kernel (bf16, 3 -> 16, num_param 3, stride 2, even H / W): 160- and 128-thread CTAs, a partial
+    # column segment, far offsets, a 2 x 2 image; odd sizes fall back to the thread-per-pixel kernel
+    (3, 16, 3, 2, 16, 320, 2, 0.05), (3, 16, 3, 2, 24, 400, 1, 0.1), (3, 16, 3, 2, 30, 50, 3, 0.3), (3, 16, 3, 2, 2, 2, 1, 0.05),
+    (3, 16, 3, 2, 31, 50, 2, 0.05), (3, 16, 3, 2, 30, 51, 2, 0.05)])
 def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s, H, W, B, sigma):
     """ldconv_fused_fwd (small-C CUDA-core kernel / tcgen05 kernel) against (a) the offset_conv -> gather -> gemm path on
     the same inputs and (b) the fp32 oracle on bf16-rounded tensors (rel-L2 <= 1e-2).  sigma scales p_conv.weight: large
@@ -468,6 +473,39 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
     assert _rel(outs[True], outs[False]) <= 6e-3
     if sigma <= 0.1:
         assert np.abs(outs[True] - outs[False]).max() <= 0.05 * max(1.0, np.abs(outs[False]).max())
+
+
+@pytest.mark.parametrize("H,W,B,sigma", [(16, 320, 2, 0.05), (30, 50, 3, 0.3), (24, 400, 1, 0.1), (2, 2, 2, 0.1)])
+def test_first_layer_rows_kernel_offsets(H, W, B, sigma):
+    """The offsets ldconv_fused_fwd can write out (off_out) from the first-layer rows kernel against ldconv_offset_conv_fwd
+    on the same bf16 input: same fp32 accumulation, another summation order (pairs of window elements), so max-abs 1e-4 x
+    the offsets' scale instead of bit equality."""
+    L = _lib.load()
+    C, O, N, s = 3, 16, 3, 2
+    torch.manual_seed(H * 31 + W)
+    mod = E.LDConv(C, O, N, s)
+    with torch.no_grad():
+        mod.p_conv.weight.normal_(0, sigma)
+        mod.p_conv.bias.normal_(0, 1.0)
+    mod = mod.to(DEV).bfloat16().eval()
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    xh = x.permute(0, 2, 3, 1)
+    assert xh.is_contiguous()
+    pr = mod._prepared(torch.bfloat16, False)
+    h, w = H // 2, W // 2
+    out = torch.empty((B, h, w, O), device=DEV, dtype=torch.bfloat16)
+    off_a = torch.full((B, h, w, 2 * N), float("nan"), device=DEV)
+    off_b = torch.full((B, h, w, 2 * N), float("nan"), device=DEV)
+    one, zero = torch.ones(O, device=DEV), torch.zeros(O, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(L.ldconv_fused_fwd(ptr(xh), ptr(pr.w_off), ptr(pr.b_off), ptr(pr.pn), ptr(pr.wt), ptr(one), ptr(zero), ptr(out),
+                                  ptr(off_a), B, C, H, W, N, s, O, _lib.ACT_SILU, _lib.BF16, ctypes.c_void_p(st)), "ldconv_fused_fwd")
+    _lib.check(L.ldconv_offset_conv_fwd(ptr(xh), ptr(pr.w_off), ptr(pr.b_off), ptr(off_b), B, C, H, W, N, s, _lib.BF16,
+                                        ctypes.c_void_p(st)), "ldconv_offset_conv_fwd")
+    torch.cuda.synchronize()
+    assert torch.isfinite(off_a).all() and torch.isfinite(out.float()).all()
+    assert (off_a - off_b).abs().max().item() <= 1e-4 * max(1.0, off_b.abs().max().item())
 
 
 # ------------------------------------------------------------------------------------------------- edge cases ----
