@@ -119,6 +119,8 @@ def _new(like: torch.Tensor, B, H, W, C):
 _DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
 
 
+# A/B switch: C2f outputs that also feed a later Concat are written into its buffer by the C2f's last conv (second output)
+_C2F_DUAL_OUT = os.environ.get("LDCONV_C2F_DUAL_OUT", "1") != "0"
 _DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
 
 
@@ -130,7 +132,8 @@ class _C2f:
         self.cv2 = _Folded(m.cv2.conv, m.cv2.bn)
         self.blocks = [(_Folded(b.cv1.conv, b.cv1.bn), _Folded(b.cv2.conv, b.cv2.bn), b.add) for b in m.m]
 
-    def __call__(self, x):
+    def __call__(self, x, out2=None):
+        """out2: optional NHWC slice (of a later Concat's buffer) that receives a second copy of the output in the same pass"""
         B, H, W, _ = x.shape
         c, n = self.c, self.n
         cat = _new(x, B, H, W, (2 + n) * c)
@@ -142,7 +145,7 @@ class _C2f:
             src = y1 if (i == 0 and y1 is not None) else cat[..., (1 + i) * c: (2 + i) * c]
             conv3x3(src, p1, tmp)
             conv3x3(tmp, p2, cat[..., (2 + i) * c: (3 + i) * c], residual=src if add else None)
-        return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout))
+        return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout), out2=out2, c2_lo=0)
 
 
 class _SPPF:
@@ -334,6 +337,7 @@ class FusedDealYolo:
         self.save = set(model.save)
         # LDConv whose ONLY consumer is a Concat writes its output straight into that Concat's buffer
         self.cat_plan = {}
+        self.dual_plan = {}
         consumers = {}
         for (kind, arg), f, i in self.layers:
             for j in ([f] if isinstance(f, int) else f):
@@ -361,8 +365,14 @@ class FusedDealYolo:
                 continue
             c0 = 0
             for sidx, wd in zip(srcs, widths):
-                if self.layers[sidx][0][0] == "ldconv" and consumers.get(sidx) == [i] and c0 % 8 == 0:
+                k2, a2 = self.layers[sidx][0]
+                if k2 == "ldconv" and consumers.get(sidx) == [i] and c0 % 8 == 0:
                     self.cat_plan[sidx] = (i, c0, sum(widths))
+                elif (_C2F_DUAL_OUT and k2 == "fn" and isinstance(a2, _C2f) and c0 % 8 == 0 and wd % 16 == 0
+                      and sidx not in self.dual_plan):
+                    # a C2f with further consumers (yaml row 12 -> 13 and 19): its last 1x1 conv writes the dense output AND the
+                    # Concat's slice in one pass instead of a strided copy_ later (62 us for 52 MB at P3)
+                    self.dual_plan[sidx] = (i, c0, sum(widths))
                 c0 += wd
         # ScalSeq -> Add (yolov8-LD-P2.yaml rows 24, 25): the Add's other operand is folded into the ScalSeq tail kernel
         for n, ((kind, arg), f, i) in enumerate(self.layers[:-1]):
@@ -452,9 +462,23 @@ class FusedDealYolo:
             elif kind == "scalseq_add":     # ScalSeq whose only consumer is the next Add layer: one tail kernel does both
                 x = arg[0](x, addend=saved[arg[1]])
             elif kind == "fn":
-                x = arg(x)
+                plan = self.dual_plan.get(i)
+                if plan is None:
+                    x = arg(x)
+                else:
+                    cat_i, c0, ctot = plan
+                    B, H, W, _ = x.shape
+                    buf = cat_bufs.get(cat_i)
+                    if buf is None:
+                        buf = cat_bufs[cat_i] = _new(x, B, H, W, ctot)
+                    x = arg(x, out2=buf[..., c0:c0 + arg.cv2.cout])
             elif kind == "cat":
-                x = self._concat(x, cat_bufs.pop(i, None))
+                buf = cat_bufs.pop(i, None)
+                for pos, j in enumerate(f):          # inputs a C2f already wrote into the buffer: hand _concat the slice itself
+                    plan = self.dual_plan.get((i + j) if j < 0 else j)
+                    if plan is not None and plan[0] == i and buf is not None:
+                        x[pos] = buf[..., plan[1]:plan[1] + x[pos].shape[3]]
+                x = self._concat(x, buf)
             elif kind == "add":
                 x = x[0] + x[1]
             elif kind == "up":
