@@ -121,6 +121,7 @@ _DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
 
 # A/B switch: C2f outputs that also feed a later Concat are written into its buffer by the C2f's last conv (second output)
 _C2F_DUAL_OUT = os.environ.get("LDCONV_C2F_DUAL_OUT", "1") != "0"
+_CAT_VIA_UP = os.environ.get("LDCONV_CAT_VIA_UP", "1") != "0"
 _DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
 
 
@@ -366,7 +367,10 @@ class FusedDealYolo:
             c0 = 0
             for sidx, wd in zip(srcs, widths):
                 k2, a2 = self.layers[sidx][0]
-                if k2 == "ldconv" and consumers.get(sidx) == [i] and c0 % 8 == 0:
+                # other consumers may be up-samplings: they read the slice through its pixel stride (yaml row 8 -> 9 and 22)
+                others_up = all(self.layers[cj][0][0] == "up" for cj in consumers.get(sidx, []) if cj != i)
+                if k2 == "ldconv" and c0 % 8 == 0 and sidx not in self.cat_plan and (
+                        consumers.get(sidx) == [i] or (_CAT_VIA_UP and others_up)):
                     self.cat_plan[sidx] = (i, c0, sum(widths))
                 elif (_C2F_DUAL_OUT and k2 == "fn" and isinstance(a2, _C2f) and c0 % 8 == 0 and wd % 16 == 0
                       and sidx not in self.dual_plan):

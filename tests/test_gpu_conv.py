@@ -152,3 +152,22 @@ def test_conv1x1_second_dense_output(Cin, Cout, lo, n, rows, ldo):
     z = (x.double() @ wt.double().t()) * scale.double() + shift.double()
     want = (z * torch.sigmoid(z)).float()
     assert float((ref.float() - want).norm() / want.norm()) <= 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,f,ldx,ldo,c0", [(2, 5, 7, 32, 2, 32, 64, 32), (1, 40, 40, 64, 2, 128, 128, 64), (3, 3, 4, 16, 3, 16, 16, 0),
+                                                 (2, 1, 1, 8, 2, 24, 8, 0)])
+def test_upsample_nearest_slices_bit_exact(B, H, W, C, f, ldx, ldo, c0):
+    """nn.Upsample(scale_factor=f, mode='nearest') (yaml rows 9, 14) from an NHWC channel slice into an NHWC channel slice:
+    a pure copy, so bit-exact; the bytes around the destination slice stay untouched."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(B * 100 + C)
+    src = torch.randn(B, H, W, ldx, generator=g).bfloat16().to(DEV)
+    dst = torch.full((B, H * f, W * f, ldo), 7.0, dtype=torch.bfloat16, device=DEV)
+    x = src[..., ldx - C:]
+    out = dst[..., c0:c0 + C]
+    _lib.check(L.ldconv_upsample_nearest(x.data_ptr(), ldx, out.data_ptr(), ldo, B, H, W, C, f, _lib.BF16, _st()))
+    want = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=f, mode="nearest").permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(out, want)
+    rest = torch.ones(ldo, dtype=torch.bool)
+    rest[c0:c0 + C] = False
+    assert bool((dst[..., rest.to(DEV)] == 7.0).all())
