@@ -320,7 +320,7 @@ struct L0Weights {
 // Uniform weights read from shared memory cost one L1 wavefront per 8 bytes per warp: 174 of the rows kernel's 336 wavefronts
 // per 32 pixels, and the L1 data pipe is what bounds it (profiles/r1_ncu_l0rows_v1.txt: 83.5 % of peak, issue slots 57 %).
 // From the constant bank they are operands of the FFMA2s and cost nothing.  The library keeps no per-module state, so the
-// bank has L0_SLOTS slots per device, a slot belongs to the first (w_off, wt, scale) pointer triple that asks for it for
+// bank has L0_SLOTS slots per device, a slot belongs to the first set of argument pointers (one layer's parameters) that asks for it for
 // the life of the process, and its content is rewritten in stream order by l0_prep_kernel before EVERY launch (the same
 // bytes unless the caller changed the weights); a fifth distinct layer on a device uses the shared-memory variant (SLOT -1).
 constexpr int L0_SLOTS = 4;
@@ -501,10 +501,11 @@ static bool l0_rows_applicable(const void* x, int B, int C, int H, int W, int N,
            (long long)H * W * C < (1ll << 31) && (long long)B * (H / 2) < (1ll << 31);
 }
 
-struct L0Slot { int dev; const void *w_off, *wt, *scale; L0Weights* addr; };
+struct L0Slot { int dev, act; const void *w_off, *b_off, *pn, *wt, *scale, *shift; L0Weights* addr; };
 
 // slot of this (device, weights) pair in the constant bank, or -1 (bank full: shared-memory variant)
-static int l0_slot(int dev, const void* w_off, const void* wt, const void* scale, L0Weights** addr)
+static int l0_slot(int dev, int act, const void* w_off, const void* b_off, const void* pn, const void* wt, const void* scale,
+                   const void* shift, L0Weights** addr)
 {
     static std::mutex mu;
     static L0Slot table[64];
@@ -515,13 +516,17 @@ static int l0_slot(int dev, const void* w_off, const void* wt, const void* scale
     int on_dev = 0;
     for (int t = 0; t < used; ++t) {
         if (table[t].dev != dev) continue;
-        if (table[t].w_off == w_off && table[t].wt == wt && table[t].scale == scale) { *addr = table[t].addr; return on_dev; }
+        const L0Slot& e = table[t];
+        if (e.act == act && e.w_off == w_off && e.b_off == b_off && e.pn == pn && e.wt == wt && e.scale == scale && e.shift == shift) {
+            *addr = e.addr;
+            return on_dev;
+        }
         ++on_dev;
     }
     if (on_dev >= L0_SLOTS || used >= 64) return -1;
     L0Weights* base = nullptr;
     if (cudaGetSymbolAddress((void**)&base, c_l0) != cudaSuccess) { cudaGetLastError(); return -1; }
-    table[used] = L0Slot{dev, w_off, wt, scale, base + on_dev};
+    table[used] = L0Slot{dev, act, w_off, b_off, pn, wt, scale, shift, base + on_dev};
     *addr = table[used].addr;
     ++used;
     return on_dev;
@@ -541,7 +546,7 @@ static int launch_l0_rows(const __nv_bfloat16* x, const float* w_off, const floa
     int dev = 0;
     LDC_CUDA(cudaGetDevice(&dev));
     L0Weights* slot_addr = nullptr;
-    const int slot = l0_slot(dev, w_off, wt, scale, &slot_addr);
+    const int slot = l0_slot(dev, act, w_off, b_off, pn, wt, scale, shift, &slot_addr);
     static const l0_kernel_t kerns[2][L0_SLOTS + 1] = {
         {l0_rows_kernel<6, -1>, l0_rows_kernel<6, 0>, l0_rows_kernel<6, 1>, l0_rows_kernel<6, 2>, l0_rows_kernel<6, 3>},
         {l0_rows_kernel<5, -1>, l0_rows_kernel<5, 0>, l0_rows_kernel<5, 1>, l0_rows_kernel<5, 2>, l0_rows_kernel<5, 3>}};
