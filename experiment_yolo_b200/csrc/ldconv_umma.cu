@@ -53,12 +53,23 @@ struct GemmOut2 {
     int ld, c_lo, c_n;
 };
 
+// Optional "maximum with two coarser maps" stage of the epilogue (SSFF ScalSeq, nn/extra_modules/block.py:3414-3443: the three
+// pyramid levels go through the same point-wise Conv3d + BatchNorm3d + LeakyReLU, the coarser two are up-sampled with `nearest` and
+// MaxPool3d((3,1,1)) takes the maximum over the levels): the finest level's GEMM takes the other two levels' outputs z1 (B,H1,W1,O)
+// and z2 (B,H2,W2,O), dense bf16, and writes max(bf16(act(.)), z1[up], z2[up]) (+ residual = the following Add layer) -- the finest
+// level's own (B,H,W,O) map never makes the round trip through HBM.
+struct GemmMaxUp {
+    const __nv_bfloat16 *z1, *z2;
+    int H, W, H1, W1, H2, W2;
+};
+
 // aff_s = shared-space address of the scale of column c0, aff_s + sh_ofs = of its shift (explicit LDS: the generic loads this replaces were
 // the top stall of the kernel, profiles/r1_ncu_gemmL1b.txt).
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
                                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
                                                     const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store,
-                                                    const GemmOut2& o2, uint32_t sh_ofs)
+                                                    const GemmOut2& o2, uint32_t sh_ofs, const __nv_bfloat16* mx1 = nullptr,
+                                                    const __nv_bfloat16* mx2 = nullptr)
 {
     const bool full16 = vec_store && (c0 + 16 <= O);
     if (pre) {
@@ -78,11 +89,31 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
     if (out) {
         float z[16];
         affine_act16(v, aff_s, aff_s + sh_ofs, act, z);
+        if (mx1) {      // host: O % 16 == 0, z1 / z2 dense and 16-byte aligned.  The level's own output is a bf16 tensor in the reference
+            float a1[8], a2[8], b1[8], b2[8];
+            Vec16<__nv_bfloat16>::load(mx1 + c0, a1);
+            Vec16<__nv_bfloat16>::load(mx1 + c0 + 8, a2);
+            Vec16<__nv_bfloat16>::load(mx2 + c0, b1);
+            Vec16<__nv_bfloat16>::load(mx2 + c0 + 8, b2);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                z[e] = fmaxf(fmaxf(__bfloat162float(__float2bfloat16_rn(z[e])), a1[e]), b1[e]);
+                z[8 + e] = fmaxf(fmaxf(__bfloat162float(__float2bfloat16_rn(z[8 + e])), a2[e]), b2[e]);
+            }
+        }
         if (residual) {
             const __nv_bfloat16* rp = residual + m * ldr + c0;
+            if (full16 && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+                float r1[8], r2[8];
+                Vec16<__nv_bfloat16>::load(rp, r1);
+                Vec16<__nv_bfloat16>::load(rp + 8, r2);
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-                if (c0 + e < O) z[e] += __bfloat162float(rp[e]);
+                for (int e = 0; e < 8; ++e) { z[e] += r1[e]; z[8 + e] += r2[e]; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (c0 + e < O) z[e] += __bfloat162float(rp[e]);
+            }
         }
         __nv_bfloat16* dst = out + m * ldo + c0;
         if (full16) {
@@ -108,12 +139,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
 // and bounded the kernel at ~1350 cycles per tile whatever the tile did (scripts/gemm_dbg.sh: 31 us of pure hand-offs at
 // K=48, O=32, M=1.6M, and operand traffic / epilogue added on top instead of overlapping).  With up to eight buffers the MMA
 // warp runs ahead, and the eight epilogue warps work as two groups of four on alternate tiles, so two epilogues are in flight.
+template <bool MAXUP>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
                  int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg,
-                 GemmOut2 o2)
+                 GemmOut2 o2, GemmMaxUp mu)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
@@ -215,6 +247,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ON);
             const long long m = (long long)tile * kTileM + lg * 32 + lane;
+            const __nv_bfloat16 *mx1 = nullptr, *mx2 = nullptr;
+            if (MAXUP && m < M) {        // torch `nearest`: src = floor(dst * in / out)
+                const int mi = (int)m, j = mi % mu.W, bi = mi / mu.W, i = bi % mu.H, b = bi / mu.H;
+                const int i1 = (int)(((long long)i * mu.H1) / mu.H), j1 = (int)(((long long)j * mu.W1) / mu.W);
+                const int i2 = (int)(((long long)i * mu.H2) / mu.H), j2 = (int)(((long long)j * mu.W2) / mu.W);
+                mx1 = mu.z1 + (((long long)b * mu.H1 + i1) * mu.W1 + j1) * O;
+                mx2 = mu.z2 + (((long long)b * mu.H2 + i2) * mu.W2 + j2) * O;
+            }
             for (int ch = 0; ch < chunks; ch += 2) {
                 const bool two = ch + 1 < chunks;
                 uint32_t v0[16], v1[16];
@@ -224,10 +264,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < M && !(dbg & 2)) {
                     if (ch * 16 < O)
                         gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 64u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0, o2, (uint32_t)ON * 4u);
+                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2);
                     if (two && (ch + 1) * 16 < O)
                         gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 64u, act, out, pre, residual,
-                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u);
+                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2);
                 }
             }
             tc_fence_before_sync();
@@ -271,6 +311,7 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
                      const void* residual, int ldr, int ldo, double* stat_sum, double* stat_sqsum, int M, int K, int O, int act,
                      cudaStream_t st);
 static thread_local GemmOut2 g_out2 = {nullptr, 0, 0, 0};      // consumed (and cleared) by the next umma_gemm_fwd_ld of this thread
+static thread_local GemmMaxUp g_maxup = {nullptr, nullptr, 0, 0, 0, 0, 0, 0};      // likewise
 
 int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                   double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
@@ -308,7 +349,10 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     if (int e = make_map_2d(&tmA, a, M, K, kTileM, lda)) return e;
     if (int e = make_map_2d(&tmB, wt, O, K, ON, K)) return e;
 
-    LDC_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const GemmMaxUp mu = g_maxup;
+    g_maxup = GemmMaxUp{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+    auto kern = mu.z1 ? umma_gemm_kernel<true> : umma_gemm_kernel<false>;
+    LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > num_tiles) grid = num_tiles;
     const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
@@ -316,9 +360,11 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     g_out2 = GemmOut2{nullptr, 0, 0, 0};
     if (o2.ptr && (!vec_store || !out || O % 16 != 0))
         return fail(LDCONV_E_ARG, "tcgen05 GEMM: the second output needs 16-byte stores and Cout %% 16 == 0");
-    LDC_CUDA(launch_pdl(umma_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
+    if (mu.z1 && (!vec_store || !out || pre || O % 16 != 0))
+        return fail(LDCONV_E_ARG, "tcgen05 GEMM: the max-with-coarser-levels epilogue needs 16-byte stores and Cout %% 16 == 0");
+    LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
                         (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
-                        vec_store, ldo, ldr, NB, gemm_dbg(), o2));
+                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
@@ -350,6 +396,26 @@ LDC_API int ldconv_conv1x1_bn_act_fwd2(const void* x, int ldx, const void* wt, c
     g_out2 = GemmOut2{(__nv_bfloat16*)out2, ld2, c2_lo, c2_n};
     return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, out, nullptr, residual, ldr, ldo, nullptr, nullptr, (int)rows, Cin, Cout,
                             act, (cudaStream_t)stream);
+}
+
+// The point-wise block of the finest SSFF level fused with the maximum over the three levels and the following Add
+// (see GemmMaxUp): out(B,H,W,Cout|ldo) = max(bf16(act(x . wt^T * scale + shift)), up(z1), up(z2)) (+ residual).
+LDC_API int ldconv_conv1x1_bn_act_maxup_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                                            const void* z1, int H1, int W1, const void* z2, int H2, int W2, const void* residual,
+                                            int ldr, void* out, int ldo, int B, int H, int W, int Cin, int Cout, int act, int dtype,
+                                            void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_conv1x1_bn_act_maxup_fwd: bf16 only");
+    LDC_REQUIRE(x && wt && out && z1 && z2 && B >= 0 && H >= 1 && W >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1 &&
+                (long long)B * H * W < (1ll << 31), "ldconv_conv1x1_bn_act_maxup_fwd: bad arguments");
+    LDC_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && ldo >= Cout && ldo % 8 == 0 && Cout <= 256 && Cout % 16 == 0,
+                "ldconv_conv1x1_bn_act_maxup_fwd: needs Cin %% 8 == 0, ldx %% 8 == 0, ldo %% 8 == 0, Cout %% 16 == 0, Cout <= 256");
+    LDC_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(out) && aligned16(z1) && aligned16(z2) && (!residual || aligned16(residual)),
+                "ldconv_conv1x1_bn_act_maxup_fwd: 16-byte alignment");
+    if (B == 0) return LDCONV_OK;
+    g_maxup = GemmMaxUp{(const __nv_bfloat16*)z1, (const __nv_bfloat16*)z2, H, W, H1, W1, H2, W2};
+    return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, out, nullptr, residual, ldr, ldo, nullptr, nullptr, B * H * W, Cin, Cout, act,
+                            (cudaStream_t)stream);
 }
 
 // 1x1 `Conv` block (Conv2d(1x1, no bias) + folded BatchNorm + activation, nn/modules/conv.py:41-59) = the same GEMM with

@@ -121,6 +121,7 @@ _DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
 
 # A/B switch: C2f outputs that also feed a later Concat are written into its buffer by the C2f's last conv (second output)
 _C2F_DUAL_OUT = os.environ.get("LDCONV_C2F_DUAL_OUT", "1") != "0"
+_SCALSEQ_FUSE = os.environ.get("LDCONV_SCALSEQ_FUSE", "1") != "0"     # A/B switch: SSFF maximum + Add in the finest level's GEMM
 _CAT_VIA_UP = os.environ.get("LDCONV_CAT_VIA_UP", "1") != "0"
 _DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
 
@@ -189,9 +190,22 @@ class _ScalSeq:
             fine = conv1x1(fine, self.conv0, _new(fine, *fine.shape[:3], ch))
         mid = conv1x1(mid, self.conv1, _new(mid, *mid.shape[:3], ch))
         coarse = conv1x1(coarse, self.conv2, _new(coarse, *coarse.shape[:3], ch))
-        z = [conv1x1(t, self.mix, _new(t, *t.shape[:3], ch), act="leaky") for t in (fine, mid, coarse)]
         B, H, W, _ = fine.shape
         out = _new(fine, B, H, W, ch)
+        if _SCALSEQ_FUSE and ch % 16 == 0:
+            # the finest level's point-wise GEMM takes the maximum over the levels (and the Add) in its epilogue: its own
+            # (B,H,W,ch) map (105 MB at P2, batch 64) never reaches HBM and the tail kernel disappears
+            z1 = conv1x1(mid, self.mix, _new(mid, *mid.shape[:3], ch), act="leaky")
+            z2 = conv1x1(coarse, self.mix, _new(coarse, *coarse.shape[:3], ch), act="leaky")
+            _, _, _, C, ldx = _nhwc_geometry(fine)
+            p = self.mix
+            _lib.check(_lib.load().ldconv_conv1x1_bn_act_maxup_fwd(
+                fine.data_ptr(), ldx, p.w.data_ptr(), p.scale.data_ptr(), p.shift.data_ptr(), z1.data_ptr(), z1.shape[1], z1.shape[2],
+                z2.data_ptr(), z2.shape[1], z2.shape[2], None if addend is None else addend.data_ptr(),
+                0 if addend is None else _nhwc_geometry(addend)[4], out.data_ptr(), ch, B, H, W, C, ch, _ACT["leaky"], _lib.BF16,
+                _stream()), "ldconv_conv1x1_bn_act_maxup_fwd")
+            return out
+        z = [conv1x1(t, self.mix, _new(t, *t.shape[:3], ch), act="leaky") for t in (fine, mid, coarse)]
         # MaxPool3d((3,1,1)) over the stacked depth axis (+ the following Add layer when it consumes this output)
         _lib.check(_lib.load().ldconv_scalseq_tail(
             z[0].data_ptr(), z[1].data_ptr(), z[2].data_ptr(), None if addend is None else addend.data_ptr(),

@@ -204,6 +204,13 @@ int ldconv_conv1x1_bn_act_fwd(const void* x, int ldx, const void* wt, const floa
 int ldconv_conv1x1_bn_act_fwd2(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                                const void* residual, int ldr, void* out, int ldo, void* out2, int ld2, int c2_lo, int c2_n,
                                long long rows, int Cin, int Cout, int act, int dtype, void* stream);
+/* The point-wise block of the finest SSFF level (ScalSeq, nn/extra_modules/block.py:3414-3443: Conv3d(1x1x1) + BatchNorm3d +
+ * LeakyReLU(0.1) per level, nearest up-sampling of the two coarser levels, MaxPool3d((3,1,1)) over the levels) fused with that
+ * maximum and with the following Add layer (block.py:3479-3484): out = max(bf16(act(x . wt^T * scale + shift)), up(z1), up(z2))
+ * (+ residual); z1 (B,H1,W1,Cout), z2 (B,H2,W2,Cout) dense bf16 = the coarser levels after the same block.  Cout % 16 == 0. */
+int ldconv_conv1x1_bn_act_maxup_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
+                                    const void* z1, int H1, int W1, const void* z2, int H2, int W2, const void* residual, int ldr,
+                                    void* out, int ldo, int B, int H, int W, int Cin, int Cout, int act, int dtype, void* stream);
 int ldconv_conv3x3_supported(int Cin, int Cout, int stride, int dtype);
 int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                               const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout,

@@ -171,3 +171,41 @@ def test_upsample_nearest_slices_bit_exact(B, H, W, C, f, ldx, ldo, c0):
     rest = torch.ones(ldo, dtype=torch.bool)
     rest[c0:c0 + C] = False
     assert bool((dst[..., rest.to(DEV)] == 7.0).all())
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,with_add", [(2, 16, 24, 32, 32, True), (1, 40, 40, 32, 32, False), (3, 8, 12, 64, 48, True),
+                                                   (2, 20, 20, 16, 16, True)])
+def test_conv1x1_maxup_epilogue_bit_exact_vs_unfused(B, H, W, Cin, Cout, with_add):
+    """SSFF tail (ScalSeq + Add, nn/extra_modules/block.py:3414-3443,3479-3484) fused into the finest level's point-wise GEMM
+    (ldconv_conv1x1_bn_act_maxup_fwd) against the unfused sequence conv1x1 -> ldconv_scalseq_tail on the same inputs: the
+    fused epilogue rounds the level's own output to bf16 before the maximum like the stored tensor, so the results are equal
+    bit for bit; and against torch (nearest up-sampling, maximum, add) within bf16 rounding."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(B * 7 + Cout)
+    x = torch.randn(B, H, W, Cin, generator=g).bfloat16().to(DEV)
+    wt = (torch.randn(Cout, Cin, generator=g) * 0.2).bfloat16().to(DEV)
+    scale = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    H1, W1, H2, W2 = H // 2, W // 2, H // 4, W // 4
+    z1 = torch.randn(B, H1, W1, Cout, generator=g).bfloat16().to(DEV)
+    z2 = torch.randn(B, H2, W2, Cout, generator=g).bfloat16().to(DEV)
+    add = torch.randn(B, H, W, Cout, generator=g).bfloat16().to(DEV) if with_add else None
+    z0 = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    want = torch.empty_like(z0)
+    got = torch.full_like(z0, float("nan"))
+    _lib.check(L.ldconv_conv1x1_bn_act_fwd(_p(x), Cin, _p(wt), _p(scale), _p(shift), None, 0, _p(z0), Cout, B * H * W, Cin, Cout,
+                                           _lib.ACT_LEAKY01, _lib.BF16, _st()))
+    _lib.check(L.ldconv_scalseq_tail(_p(z0), _p(z1), _p(z2), _p(add), Cout if with_add else 0, _p(want), Cout, B, H, W, H1, W1, H2, W2,
+                                     Cout, _lib.BF16, _st()))
+    _lib.check(L.ldconv_conv1x1_bn_act_maxup_fwd(_p(x), Cin, _p(wt), _p(scale), _p(shift), _p(z1), H1, W1, _p(z2), H2, W2, _p(add),
+                                                 Cout if with_add else 0, _p(got), Cout, B, H, W, Cin, Cout, _lib.ACT_LEAKY01,
+                                                 _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    pre = (x.float().reshape(-1, Cin) @ wt.float().t()) * scale + shift
+    lvl = F.leaky_relu(pre, 0.1).bfloat16().float().reshape(B, H, W, Cout)
+    up = lambda t: F.interpolate(t.permute(0, 3, 1, 2).float(), size=(H, W), mode="nearest").permute(0, 2, 3, 1)
+    ref = torch.maximum(torch.maximum(lvl, up(z1)), up(z2))
+    if with_add:
+        ref = ref + add.float()
+    assert (got.float() - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
