@@ -209,3 +209,28 @@ def test_conv1x1_maxup_epilogue_bit_exact_vs_unfused(B, H, W, Cin, Cout, with_ad
     if with_add:
         ref = ref + add.float()
     assert (got.float() - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,H,W,nc,stride", [(2, 5, 7, 6, 4.0), (1, 40, 40, 6, 8.0), (3, 3, 3, 1, 16.0), (2, 9, 4, 11, 32.0)])
+def test_detect_decode_vs_torch(B, H, W, nc, stride):
+    """Detect head decode of one level (nn/modules/head.py:55-77: DFL softmax expectation over 16 bins per side,
+    nn/modules/block.py:37-56; dist2bbox xywh around the cell-centre anchors, utils/tal.py:309-319; times the stride; sigmoid of the
+    class logits) against the same arithmetic in torch fp32 on the bf16 logits; columns outside the level's range stay untouched."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(H * 13 + W)
+    box = (torch.randn(B, H, W, 64, generator=g) * 2).bfloat16().to(DEV)
+    cls = (torch.randn(B, H, W, nc, generator=g) * 3).bfloat16().to(DEV)
+    a0, total = 5, H * W + 9
+    y = torch.full((B, 4 + nc, total), 3.0, dtype=torch.bfloat16, device=DEV)
+    _lib.check(L.ldconv_detect_decode(_p(box), _p(cls), _p(y), B, H, W, nc, 16, stride, a0, total, _lib.BF16, _st()))
+    p = box.float().reshape(B, H * W, 4, 16).softmax(-1)
+    d = (p * torch.arange(16, device=DEV, dtype=torch.float32)).sum(-1)                       # (B, A, 4) l, t, r, b
+    jj, ii = torch.meshgrid(torch.arange(W, device=DEV), torch.arange(H, device=DEV), indexing="xy")
+    ax, ay = jj.reshape(-1).float() + 0.5, ii.reshape(-1).float() + 0.5
+    x1, y1, x2, y2 = ax - d[..., 0], ay - d[..., 1], ax + d[..., 2], ay + d[..., 3]
+    want = torch.stack([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], 1) * stride              # (B, 4, A)
+    got = y[:, :, a0:a0 + H * W].float()
+    assert (got[:, :4] - want).abs().max().item() <= 2 ** -7 * max(1.0, want.abs().max().item())
+    assert (got[:, 4:] - cls.float().reshape(B, H * W, nc).permute(0, 2, 1).sigmoid()).abs().max().item() <= 2 ** -8
+    outside = torch.cat([y[:, :, :a0], y[:, :, a0 + H * W:]], 2)
+    assert bool((outside == 3.0).all())
