@@ -38,6 +38,7 @@ struct GGGeom {
     int xb_mask, xb_shift, ab_mask;      // XB, AB in {1, 2}: buffer = it & mask, mbarrier parity = (it >> shift) & 1
     int TG;                              // v2 kernel: thread groups of 128 per CTA (3 when N % 3 == 0: one sample per thread)
     int merge;                           // v2 kernel: phase 1 of the next tile shares the barrier interval of phase 2 (two record buffers)
+    int split;                           // v2 kernel, stride 2: staged tile rows are [column parity][column / 2][C] (see gg_geometry)
     float hm, wm;                        // (float)(H - 1), (float)(W - 1)
     unsigned long long img_bytes;        // H * W * C * 2
     unsigned inv_n, inv_img, inv_tw;
@@ -382,7 +383,11 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     auto issue_x_tile = [&](int tile, int xb) {                         // one thread
         const TC t = tile_coords(tile);
         mbar_arrive_expect_tx(&x_full[xb], g.x_tx_bytes);
-        tma_load_4d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, t.j0 * s - g.halo, t.i0 * s - g.halo, t.b);
+        if (g.split)      // W viewed as (W/2, 2): coordinates (channel, column / 2, parity, row, image); the origin column is even
+            tma_load_5d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, (t.j0 * s - g.halo) >> 1, 0,
+                        t.i0 * s - g.halo, t.b);
+        else
+            tma_load_4d(smem + g.ofs_x + (size_t)xb * g.x_bytes, &tmX, &x_full[xb], 0, t.j0 * s - g.halo, t.i0 * s - g.halo, t.b);
     };
 
     pdl_launch_dependents();
@@ -496,6 +501,7 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t idesc = make_idesc_bf16(128, g.ON);
     const int rowB = g.TWin << (cvs + 4), pixB = 16 << cvs;    // bytes per staged tile row / per pixel
     const int imgRowB = g.W << (cvs + 4);
+    const int halfRowB = rowB >> 1;
     // ---- phase 1 of one tile: one record per sample (n-major: sample = n * 128 + pixel) into the record buffer at rec_s; uses the
     // prefetched offsets in `ofs`; returns this thread's output pixel index ((b h + i) w + j), -1 outside the map
     auto phase1 = [&](const TC& t, uint32_t rec_s) -> int {
@@ -515,7 +521,12 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const bool inside = (unsigned)t0 < (unsigned)g.THin && (unsigned)t1 < (unsigned)g.THin &&
                                 (unsigned)u0 < (unsigned)g.TWin && (unsigned)u1 < (unsigned)g.TWin;
             if (inside) {
-                const int a0 = t0 * rowB, a1 = t1 * rowB, b0 = u0 * pixB, b1 = u1 * pixB;
+                const int a0 = t0 * rowB, a1 = t1 * rowB;
+                int b0 = u0 * pixB, b1 = u1 * pixB;
+                if (g.split) {      // [parity][column / 2][C] rows
+                    b0 = (u0 & 1) * halfRowB + (u0 >> 1) * pixB;
+                    b1 = (u1 & 1) * halfRowB + (u1 >> 1) * pixB;
+                }
                 gg_sts128(ra, (uint32_t)(a0 + b0), (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
             } else {      // served from global memory (L2): image-relative byte offsets, bit 31 of .x marks it
                 const int a0 = q.r0 * imgRowB, a1 = q.r1 * imgRowB, b0 = q.k0 * pixB, b1 = q.k1 * pixB;
@@ -723,6 +734,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     static const int cfg[5][3] = {{2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 2, 1}, {1, 1, 1}};
     int best_ctas = 0;
     g.merge = 0;
+    g.split = 0;
     GGGeom best = g;
     size_t best_smem = 0;
     static int env_plan = -2, env_ctas = -2, env_tg = -2;      // experiments: LDCONV_GG_PLAN=<plan index>, LDCONV_GG_CTAS=<CTAs per SM>
@@ -738,11 +750,20 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     if (env_ctas == -2) { const char* e = getenv("LDCONV_GG_CTAS"); env_ctas = e ? atoi(e) : -1; }
     static int env_merge = -2;
     if (env_merge == -2) { const char* e = getenv("LDCONV_GG_MERGE"); env_merge = e ? atoi(e) : -1; }
+    static int env_split = -2;
+    if (env_split == -2) { const char* e = getenv("LDCONV_GG_SPLIT"); env_split = e ? atoi(e) : 1; }
+    const bool split_ok = env_split != 0 && gg_v2_enabled() && g.cv_shift >= 0 && s == 2 && W % 2 == 0 && C <= 32;
     // shared-memory layout of plan ci with (mg + 1) record buffers -> CTAs per SM (0: does not fit)
     auto layout = [&](int ci, int mg, GGGeom& q, size_t& need) {
         q.halo = cfg[ci][0]; q.XB = cfg[ci][1]; q.AB = cfg[ci][2];
         q.THin = (q.TH - 1) * s + 2 + mr + 2 * q.halo;
         q.TWin = (q.TW - 1) * s + 2 + mk + 2 * q.halo;
+        // Stride 2, pixels of 32 / 64 bytes: the corners of neighbouring output pixels are two input pixels apart, so the four (two)
+        // samples of a quarter-warp's 16-byte LDS sat on two (one) of the four 32-byte bank groups: 41 % of the kernel's shared-memory
+        // wavefronts were bank conflicts (profiles/r1_ncu_ggL1_s4.txt).  With the columns of a staged row split by parity
+        // ([parity][column / 2][C], a 5-D TMA map whose W axis is viewed as (W/2, 2)) those corners are neighbours in shared memory.
+        q.split = (split_ok && q.halo % 2 == 0) ? 1 : 0;
+        if (q.split) q.TWin = (q.TWin + 1) & ~1;
         if (q.THin > 256 || q.TWin > 256) return 0;
         q.x_tx_bytes = (uint32_t)((size_t)q.THin * q.TWin * C * 2);
         q.x_bytes = (q.x_tx_bytes + 127u) & ~127u;
@@ -823,7 +844,12 @@ int gather_gemm_fwd(const void* x, const float* off, const int* pn, const void* 
     if (!aligned16(x) || !aligned16(wt) || !aligned16(out))
         return fail(LDCONV_E_ALIGN, "gather+GEMM kernel: x / wt / out must be 16-byte aligned");
     CUtensorMap tmX, tmW;
-    {
+    if (g.split) {      // (C, W/2, 2, H, B): the box lands in shared memory as [row][column parity][column / 2][C]
+        cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)(W / 2), 2, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstr[4] = {(cuuint64_t)2 * C * 2, (cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[5] = {(cuuint32_t)C, (cuuint32_t)(g.TWin / 2), 2, (cuuint32_t)g.THin, 1};
+        if (int e = encode_map(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    } else {
         cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
         cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)g.TWin, (cuuint32_t)g.THin, 1};

@@ -681,7 +681,9 @@ def test_offset_conv_backward_tensor_core_path(C, N, s, H, W, B):
     (16, 32, 3, 2, 64, 80, 2, 0.5, 0), (16, 32, 3, 2, 37, 53, 3, 3.0, 0), (32, 64, 3, 2, 40, 40, 2, 0.5, 64), (32, 32, 1, 1, 48, 48, 1, 0.5, 0),
     (64, 64, 1, 1, 40, 24, 2, 1.0, 0), (64, 32, 1, 1, 17, 19, 2, 8.0, 32), (128, 64, 1, 1, 20, 20, 2, 0.5, 0), (32, 32, 3, 2, 160, 160, 9, 0.5, 0),
     (16, 16, 1, 1, 160, 160, 4, 0.5, 0), (8, 16, 2, 1, 30, 30, 2, 0.5, 0), (32, 48, 5, 1, 20, 28, 1, 0.5, 0), (16, 32, 4, 2, 33, 47, 2, 1.0, 0),
-    (16, 32, 9, 1, 26, 22, 2, 1.0, 0), (64, 128, 3, 2, 80, 80, 3, 0.5, 0), (24, 32, 2, 1, 20, 20, 2, 0.5, 0)])
+    (16, 32, 9, 1, 26, 22, 2, 1.0, 0), (64, 128, 3, 2, 80, 80, 3, 0.5, 0), (24, 32, 2, 1, 20, 20, 2, 0.5, 0),
+    # stride 2, even W, C <= 32: staged rows split by column parity (5-D TMA map); far offsets, 2-pixel-wide maps, num_param 5
+    (16, 32, 3, 2, 34, 46, 2, 2.5, 0), (32, 32, 5, 2, 36, 44, 1, 1.0, 0), (16, 16, 3, 2, 6, 2, 2, 0.5, 0), (32, 64, 3, 2, 18, 130, 1, 6.0, 0)])
 def test_gather_gemm_kernel_matches_gather_then_gemm(C, O, N, s, H, W, B, sigma, pad):
     """ldconv_gather_gemm_fwd (persistent tcgen05 kernel, operand tile written by the gather warps into shared memory) against
     ldconv_gather_fwd + ldconv_gemm_fwd on the SAME offsets: the operand bits are identical (same make_point / bilinear code),
