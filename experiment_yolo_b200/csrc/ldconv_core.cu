@@ -840,6 +840,65 @@ detect_decode_kernel(const __nv_bfloat16* __restrict__ box, const __nv_bfloat16*
     }
 }
 
+// Same decode with the box logits staged through shared memory: a warp copies the 32 x 128 bytes of its anchors with coalesced
+// 16-byte loads (8 anchors = 8 lines per instruction; a thread reading its own 128-byte row touches 32 lines per instruction) into
+// rows of 144 bytes (conflict-free for both the warp's stores and the per-thread reads), then every thread decodes its anchor.
+template <int REG>
+__global__ void __launch_bounds__(128)
+detect_decode_staged_kernel(const __nv_bfloat16* __restrict__ box, const __nv_bfloat16* __restrict__ cls,
+                            __nv_bfloat16* __restrict__ y, int B, int H, int W, int nc, float stride, int a0, int total)
+{
+    static_assert(REG == 16, "rows of 4 x 16 bins = 128 bytes");
+    __shared__ uint4 s_row[128][9];
+    const long long per_img = (long long)H * W;
+    const long long n = (long long)B * per_img;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const long long w0 = (long long)blockIdx.x * blockDim.x + wrp * 32;      // first anchor of this warp
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = k * 32 + lane, al = idx >> 3, ch = idx & 7;
+        if (w0 + al < n) s_row[wrp * 32 + al][ch] = __ldg(reinterpret_cast<const uint4*>(box + (w0 + al) * (4 * REG)) + ch);
+    }
+    __syncwarp();
+    const long long t = w0 + lane;
+    if (t >= n) return;
+    const int b = (int)(t / per_img);
+    const int a = (int)(t - (long long)b * per_img);
+    const int ai = a / W, aj = a - ai * W;
+    const float ax = (float)aj + 0.5f, ay = (float)ai + 0.5f;
+    float d[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        const uint4 q0 = s_row[threadIdx.x][2 * side], q1 = s_row[threadIdx.x][2 * side + 1];
+        const uint32_t wv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float v[REG];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[2 * e] = __uint_as_float(wv[e] << 16); v[2 * e + 1] = __uint_as_float(wv[e] & 0xffff0000u); }
+        float mx = v[0];
+#pragma unroll
+        for (int k = 1; k < REG; ++k) mx = fmaxf(mx, v[k]);
+        float den = 0.f, num = 0.f;
+#pragma unroll
+        for (int k = 0; k < REG; ++k) {
+            const float e = __expf(v[k] - mx);
+            den += e;
+            num = fmaf(e, (float)k, num);
+        }
+        d[side] = num / den;
+    }
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    __nv_bfloat16* yp = y + (size_t)b * (4 + nc) * total + a0 + a;
+    yp[0] = __float2bfloat16_rn(0.5f * (x1 + x2) * stride);
+    yp[(size_t)total] = __float2bfloat16_rn(0.5f * (y1 + y2) * stride);
+    yp[2 * (size_t)total] = __float2bfloat16_rn((x2 - x1) * stride);
+    yp[3 * (size_t)total] = __float2bfloat16_rn((y2 - y1) * stride);
+    const __nv_bfloat16* cp = cls + t * nc;
+    for (int c = 0; c < nc; ++c) {
+        const float z = __bfloat162float(cp[c]);
+        yp[(size_t)(4 + c) * total] = __float2bfloat16_rn(1.f / (1.f + __expf(-z)));
+    }
+}
+
 static int check_dims(const char* fn, int B, int C, int H, int W, int N, int s)
 {
     if (B < 0 || C < 1 || H < 1 || W < 1 || N < 1 || N > 16 || s < 1)
@@ -1133,8 +1192,13 @@ LDC_API int ldconv_detect_decode(const void* box, const void* cls, void* y, int 
     LDC_REQUIRE(anchor_offset >= 0 && anchor_offset + H * W <= total_anchors, "ldconv_detect_decode: anchor range");
     if (B == 0) return LDCONV_OK;
     const long long n = (long long)B * H * W;
-    detect_decode_kernel<16><<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)box, (const __nv_bfloat16*)cls, (__nv_bfloat16*)y, B, H, W, nc, stride, anchor_offset, total_anchors);
+    static const int staged = getenv("LDCONV_DECODE_STAGED") ? atoi(getenv("LDCONV_DECODE_STAGED")) : 1;
+    if (staged)
+        detect_decode_staged_kernel<16><<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)box, (const __nv_bfloat16*)cls, (__nv_bfloat16*)y, B, H, W, nc, stride, anchor_offset, total_anchors);
+    else
+        detect_decode_kernel<16><<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)box, (const __nv_bfloat16*)cls, (__nv_bfloat16*)y, B, H, W, nc, stride, anchor_offset, total_anchors);
     LDC_LAUNCH_CHECK("detect_decode_kernel");
     return LDCONV_OK;
 }

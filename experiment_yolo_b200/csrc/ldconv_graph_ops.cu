@@ -160,6 +160,58 @@ sppf_pools_smem_kernel(const T* __restrict__ x, T* __restrict__ o1, T* __restric
     }
 }
 
+// SPPF pools as the reference computes them (nn/modules/block.py:166-171: y1 = m(x), y2 = m(y1), y3 = m(y2), m = MaxPool2d(k, 1, k/2)):
+// three cascaded separable passes over TWO shared-memory planes (cur, horizontal maxima) instead of four, so that four CTAs fit an
+// SM and the 512 (image, channel-vector) planes of the model's SPPF are resident in one wave (the four-plane kernel ran 1.7 waves
+// of two CTAs per SM).  Padding is "ignore" (-inf) like MaxPool2d, so the cascade equals the 5 / 9 / 13 windows exactly.
+__global__ void __launch_bounds__(256)
+sppf_pools_cascade_kernel(const T* __restrict__ x, T* __restrict__ o1, T* __restrict__ o2, T* __restrict__ o3, int ld, int H, int W,
+                          int CV, int r)
+{
+    extern __shared__ uint4 s_pl[];            // [2][H*W]: current map, its horizontal maxima
+    const int cv = blockIdx.x % CV;
+    const long long b = blockIdx.x / CV;
+    const int HW = H * W;
+    const T* xb = x + b * HW * ld + cv * 8;
+    for (int t = threadIdx.x; t < HW; t += blockDim.x) s_pl[t] = *reinterpret_cast<const uint4*>(xb + (long long)t * ld);
+    __syncthreads();
+    auto vmax = [](uint4 a, uint4 b2) {
+        uint4 o;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b2);
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) po[e] = __hmax2(pa[e], pb[e]);
+        return o;
+    };
+    T* outs[3] = {o1, o2, o3};
+#pragma unroll 1
+    for (int stage = 0; stage < 3; ++stage) {
+        for (int t = threadIdx.x; t < HW; t += blockDim.x) {
+            const int j = t % W;
+            uint4 m = s_pl[t];
+            for (int d = 1; d <= r; ++d) {
+                if (j - d >= 0) m = vmax(m, s_pl[t - d]);
+                if (j + d < W) m = vmax(m, s_pl[t + d]);
+            }
+            s_pl[HW + t] = m;
+        }
+        __syncthreads();
+        T* op = outs[stage];
+        for (int t = threadIdx.x; t < HW; t += blockDim.x) {
+            const int i = t / W;
+            uint4 m = s_pl[HW + t];
+            for (int d = 1; d <= r; ++d) {
+                if (i - d >= 0) m = vmax(m, s_pl[HW + t - d * W]);
+                if (i + d < H) m = vmax(m, s_pl[HW + t + d * W]);
+            }
+            s_pl[t] = m;
+            *reinterpret_cast<uint4*>(op + (b * HW + t) * ld + cv * 8) = m;
+        }
+        __syncthreads();
+    }
+}
+
 // uint8 NCHW image batch (what the reference's predictor uploads, engine/predictor.py:120-131) -> bf16 NHWC in [0,1]:
 // the `im.half(); im /= 255` of the reference plus the layout change, one pass.
 __global__ void __launch_bounds__(256)
@@ -229,6 +281,15 @@ LDC_API int ldconv_sppf_pools(const void* x, void* o1, void* o2, void* o3, int l
     LDC_REQUIRE(aligned16(x) && aligned16(o1) && aligned16(o2) && aligned16(o3), "ldconv_sppf_pools: alignment");
     const long long total = (long long)B * H * W * (C / 8);
     if (total == 0) return LDCONV_OK;
+    static const int cascade = getenv("LDCONV_SPPF_CASCADE") ? atoi(getenv("LDCONV_SPPF_CASCADE")) : 1;
+    const size_t plane2 = (size_t)2 * H * W * 16;
+    if (cascade && plane2 <= 200 * 1024 && (long long)B * (C / 8) <= 0x7fffffffll) {
+        LDC_CUDA(cudaFuncSetAttribute(sppf_pools_cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane2));
+        sppf_pools_cascade_kernel<<<(unsigned)(B * (C / 8)), 256, plane2, (cudaStream_t)stream>>>((const T*)x, (T*)o1, (T*)o2, (T*)o3,
+                                                                                                 ld, H, W, C / 8, k / 2);
+        LDC_LAUNCH_CHECK("sppf_pools_cascade_kernel");
+        return LDCONV_OK;
+    }
     const size_t plane = (size_t)4 * H * W * 16;
     if (plane <= 200 * 1024 && (long long)B * (C / 8) <= 0x7fffffffll) {
         LDC_CUDA(cudaFuncSetAttribute(sppf_pools_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane));

@@ -234,3 +234,21 @@ def test_detect_decode_vs_torch(B, H, W, nc, stride):
     assert (got[:, 4:] - cls.float().reshape(B, H * W, nc).permute(0, 2, 1).sigmoid()).abs().max().item() <= 2 ** -8
     outside = torch.cat([y[:, :, :a0], y[:, :, a0 + H * W:]], 2)
     assert bool((outside == 3.0).all())
+
+
+@pytest.mark.parametrize("B,H,W,C,k", [(2, 40, 40, 64, 5), (1, 7, 9, 16, 5), (3, 20, 12, 8, 3), (2, 4, 4, 32, 5)])
+def test_sppf_pools_bit_exact_vs_max_pool2d(B, H, W, C, k):
+    """SPPF's three cascaded MaxPool2d(k, 1, k//2) (nn/modules/block.py:166-171) written into the channel slices 1..3 of the 4C-wide
+    concat buffer whose slice 0 holds the input: pure maxima, so bit-exact against torch."""
+    L = _lib.load()
+    g = torch.Generator().manual_seed(H * 17 + C)
+    cat = torch.full((B, H, W, 4 * C), 9.0, dtype=torch.bfloat16, device=DEV)
+    x = torch.randn(B, H, W, C, generator=g).bfloat16().to(DEV)
+    cat[..., :C] = x
+    _lib.check(L.ldconv_sppf_pools(cat.data_ptr(), cat[..., C:].data_ptr(), cat[..., 2 * C:].data_ptr(), cat[..., 3 * C:].data_ptr(),
+                                   4 * C, B, H, W, C, k, _lib.BF16, _st()))
+    y = x.permute(0, 3, 1, 2).float()
+    for lvl in range(1, 4):
+        y = F.max_pool2d(y, k, 1, k // 2)
+        assert torch.equal(cat[..., lvl * C:(lvl + 1) * C], y.permute(0, 2, 3, 1).bfloat16())
+    assert torch.equal(cat[..., :C], x)
