@@ -63,13 +63,22 @@ struct GemmMaxUp {
     int H, W, H1, W1, H2, W2;
 };
 
+// Pixel packing for narrow 1x1 convs: P consecutive pixels form ONE operand row (P * Cin wide, contiguous because x is dense) and
+// the weights are block-diagonal (P * Cout, P * Cin), so a row of the product holds the Cout outputs of P consecutive pixels.  The
+// kernel sees an ordinary (rows / P) x (P Cin) x (P Cout) GEMM; only the epilogue's addressing knows: 16-column chunk c0 of row m is
+// channel c0 mod Cout of pixel m P + c0 / Cout (Cout = 1 << o_shift).  The fixed cost per 128-row tile (~1.8 us per CTA) bounds the
+// P2-resolution GEMMs of the model (12.8 K tiles of 16 KB), not their bytes; packing divides the tiles by P.
+struct GemmPack {
+    int P, o_shift;
+};
+
 // aff_s = shared-space address of the scale of column c0, aff_s + sh_ofs = of its shift (explicit LDS: the generic loads this replaces were
 // the top stall of the kernel, profiles/r1_ncu_gemmL1b.txt).
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
                                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
                                                     const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store,
                                                     const GemmOut2& o2, uint32_t sh_ofs, const __nv_bfloat16* mx1 = nullptr,
-                                                    const __nv_bfloat16* mx2 = nullptr)
+                                                    const __nv_bfloat16* mx2 = nullptr, GemmPack pk = GemmPack{1, 0})
 {
     const bool full16 = vec_store && (c0 + 16 <= O);
     if (pre) {
@@ -116,6 +125,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
             }
         }
         __nv_bfloat16* dst = out + m * ldo + c0;
+        if (pk.P > 1) dst = out + (m * pk.P + (c0 >> pk.o_shift)) * ldo + (c0 & ((1 << pk.o_shift) - 1));
         if (full16) {
             uint4 lo, hi;
             pack16_bf16(z, lo, hi);
@@ -145,7 +155,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
                  int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg,
-                 GemmOut2 o2, GemmMaxUp mu)
+                 GemmOut2 o2, GemmMaxUp mu, GemmPack pk)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
@@ -264,10 +274,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < M && !(dbg & 2)) {
                     if (ch * 16 < O)
                         gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 64u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2);
+                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk);
                     if (two && (ch + 1) * 16 < O)
                         gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 64u, act, out, pre, residual,
-                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2);
+                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk);
                 }
             }
             tc_fence_before_sync();
@@ -312,6 +322,7 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
                      cudaStream_t st);
 static thread_local GemmOut2 g_out2 = {nullptr, 0, 0, 0};      // consumed (and cleared) by the next umma_gemm_fwd_ld of this thread
 static thread_local GemmMaxUp g_maxup = {nullptr, nullptr, 0, 0, 0, 0, 0, 0};      // likewise
+static thread_local GemmPack g_pack = {1, 0};                                       // likewise
 
 int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                   double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
@@ -351,6 +362,10 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
 
     const GemmMaxUp mu = g_maxup;
     g_maxup = GemmMaxUp{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+    const GemmPack pk = g_pack;
+    g_pack = GemmPack{1, 0};
+    if (pk.P > 1 && (mu.z1 || g_out2.ptr || residual || pre || stat_sum))
+        return fail(LDCONV_E_ARG, "tcgen05 GEMM: pixel packing takes no residual / second output / statistics");
     auto kern = mu.z1 ? umma_gemm_kernel<true> : umma_gemm_kernel<false>;
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * (two_per_sm ? 2 : 1);
@@ -364,7 +379,7 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
         return fail(LDCONV_E_ARG, "tcgen05 GEMM: the max-with-coarser-levels epilogue needs 16-byte stores and Cout %% 16 == 0");
     LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
                         (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
-                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu));
+                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu, pk));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
@@ -416,6 +431,27 @@ LDC_API int ldconv_conv1x1_bn_act_maxup_fwd(const void* x, int ldx, const void* 
     g_maxup = GemmMaxUp{(const __nv_bfloat16*)z1, (const __nv_bfloat16*)z2, H, W, H1, W1, H2, W2};
     return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, out, nullptr, residual, ldr, ldo, nullptr, nullptr, B * H * W, Cin, Cout, act,
                             (cudaStream_t)stream);
+}
+
+// The 1x1 `Conv` block on P consecutive pixels per operand row (see GemmPack): x (rows, Cin) dense, wt_packed (P Cout, P Cin) =
+// block_diag(wt, ..., wt), scale_rep / shift_rep = the folded BatchNorm repeated P times, out (rows, Cout | ldo).
+LDC_API int ldconv_conv1x1_bn_act_packed_fwd(const void* x, const void* wt_packed, const float* scale_rep, const float* shift_rep,
+                                             void* out, int ldo, long long rows, int Cin, int Cout, int P, int act, int dtype,
+                                             void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_conv1x1_bn_act_packed_fwd: bf16 only");
+    LDC_REQUIRE(x && wt_packed && out && rows >= 0 && rows < (1ll << 31), "ldconv_conv1x1_bn_act_packed_fwd: bad arguments");
+    int o_shift = 0;
+    while ((1 << o_shift) < Cout) ++o_shift;
+    LDC_REQUIRE((P == 2 || P == 4) && Cout >= 16 && (1 << o_shift) == Cout && P * Cout <= 256 && Cin % 8 == 0 && rows % P == 0 &&
+                ldo >= Cout && ldo % 8 == 0,
+                "ldconv_conv1x1_bn_act_packed_fwd: needs P in {2, 4}, Cout a power of two >= 16, P Cout <= 256, Cin %% 8 == 0, "
+                "rows %% P == 0, ldo %% 8 == 0 (got P=%d Cin=%d Cout=%d rows=%lld ldo=%d)", P, Cin, Cout, rows, ldo);
+    LDC_REQUIRE(aligned16(x) && aligned16(wt_packed) && aligned16(out), "ldconv_conv1x1_bn_act_packed_fwd: 16-byte alignment");
+    if (rows == 0) return LDCONV_OK;
+    g_pack = GemmPack{P, o_shift};
+    return umma_gemm_fwd_ld(x, P * Cin, wt_packed, scale_rep, shift_rep, out, nullptr, nullptr, 0, ldo, nullptr, nullptr,
+                            (int)(rows / P), P * Cin, P * Cout, act, (cudaStream_t)stream);
 }
 
 // 1x1 `Conv` block (Conv2d(1x1, no bias) + folded BatchNorm + activation, nn/modules/conv.py:41-59) = the same GEMM with

@@ -50,7 +50,7 @@ def _nhwc_geometry(t: torch.Tensor):
 
 class _Folded:
     """Conv weight in the kernels' (Cout, K) bf16 layout + folded per-channel affine (fp32)."""
-    __slots__ = ("w", "scale", "shift", "k", "stride", "cin", "cout")
+    __slots__ = ("w", "scale", "shift", "k", "stride", "cin", "cout", "_packed_cache")
 
     def __init__(self, conv: nn.Conv2d, bn=None, extra_bias=None):
         w = conv.weight.detach()
@@ -77,11 +77,40 @@ class _Folded:
             self.shift = bias.contiguous()
 
 
+def _pack_factor(C, O, rows, ldx, ldo):
+    """pixels per GEMM row for a narrow dense 1x1 conv (ldconv_conv1x1_bn_act_packed_fwd), 1 = the plain kernel"""
+    if not _GEMM_PACK or ldx != C or O < 16 or (O & (O - 1)) or C % 8 or ldo % 8:
+        return 1
+    for P in (4, 2):
+        if P * C <= _GEMM_PACK_MAX_K and P * O <= 128 and rows % P == 0:
+            return P
+    return 1
+
+
+def _packed(p: _Folded, P: int):
+    """block-diagonal weights and repeated affine of a folded 1x1 conv, cached on the _Folded"""
+    cache = getattr(p, "_packed_cache", None)
+    if cache is None:
+        cache = p._packed_cache = {}
+    if P not in cache:
+        cache[P] = (torch.block_diag(*([p.w.float()] * P)).to(torch.bfloat16).contiguous(), p.scale.repeat(P).contiguous(),
+                    p.shift.repeat(P).contiguous())
+    return cache[P]
+
+
 def conv1x1(x: torch.Tensor, p: _Folded, out: torch.Tensor, act: str = "silu", residual=None, out2=None, c2_lo=0):
     """out2: optional dense (B,H,W,c) tensor that also receives the output channels [c2_lo, c2_lo + c) (same pass)."""
     B, H, W, C, ldx = _nhwc_geometry(x)
     _, _, _, O, ldo = _nhwc_geometry(out)
     assert C == p.cin and O == p.cout
+    if residual is None and out2 is None:
+        P = _pack_factor(C, O, B * H * W, ldx, ldo)
+        if P > 1:
+            wp, sc, sh = _packed(p, P)
+            _lib.check(_lib.load().ldconv_conv1x1_bn_act_packed_fwd(
+                x.data_ptr(), wp.data_ptr(), sc.data_ptr(), sh.data_ptr(), out.data_ptr(), ldo, B * H * W, C, O, P, _ACT[act],
+                _lib.BF16, _stream()), "ldconv_conv1x1_bn_act_packed_fwd")
+            return out
     ldr = _nhwc_geometry(residual)[4] if residual is not None else 0
     if out2 is not None:
         _, _, _, c2, ld2 = _nhwc_geometry(out2)
@@ -122,6 +151,10 @@ _DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
 # A/B switch: C2f outputs that also feed a later Concat are written into its buffer by the C2f's last conv (second output)
 _C2F_DUAL_OUT = os.environ.get("LDCONV_C2F_DUAL_OUT", "1") != "0"
 _SCALSEQ_FUSE = os.environ.get("LDCONV_SCALSEQ_FUSE", "1") != "0"     # A/B switch: SSFF maximum + Add in the finest level's GEMM
+# narrow dense 1x1 convs run with P pixels per GEMM row (block-diagonal weights): LDCONV_GEMM_PACK=0 switches it off,
+# LDCONV_GEMM_PACK_MAX_K bounds P * Cin
+_GEMM_PACK = os.environ.get("LDCONV_GEMM_PACK", "1") != "0"
+_GEMM_PACK_MAX_K = int(os.environ.get("LDCONV_GEMM_PACK_MAX_K", "256"))
 _CAT_VIA_UP = os.environ.get("LDCONV_CAT_VIA_UP", "1") != "0"
 _DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
 

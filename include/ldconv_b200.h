@@ -211,6 +211,12 @@ int ldconv_conv1x1_bn_act_fwd2(const void* x, int ldx, const void* wt, const flo
 int ldconv_conv1x1_bn_act_maxup_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                                     const void* z1, int H1, int W1, const void* z2, int H2, int W2, const void* residual, int ldr,
                                     void* out, int ldo, int B, int H, int W, int Cin, int Cout, int act, int dtype, void* stream);
+/* The 1x1 `Conv` block (nn/modules/conv.py:41-59) with P in {2, 4} consecutive pixels packed into one GEMM row: x (rows, Cin) dense
+ * bf16, wt_packed (P*Cout, P*Cin) = block_diag(wt, ..., wt), scale_rep / shift_rep = the folded BatchNorm repeated P times,
+ * out (rows, Cout | ldo).  Same arithmetic per output as ldconv_conv1x1_bn_act_fwd (the extra products are exact zeros); for the
+ * narrow layers whose cost is the number of 128-row tiles, not bytes.  Cout a power of two >= 16, P*Cout <= 256, rows % P == 0. */
+int ldconv_conv1x1_bn_act_packed_fwd(const void* x, const void* wt_packed, const float* scale_rep, const float* shift_rep, void* out,
+                                     int ldo, long long rows, int Cin, int Cout, int P, int act, int dtype, void* stream);
 int ldconv_conv3x3_supported(int Cin, int Cout, int stride, int dtype);
 int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift,
                               const void* residual, int ldr, void* out, int ldo, int B, int Cin, int H, int W, int Cout,

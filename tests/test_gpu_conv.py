@@ -21,6 +21,10 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _rel(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-30))
+
+
 @pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 3, 2, 37, 41, 2), (64, 1, 1, 20, 20, 2), (128, 1, 1, 17, 33, 1),
                                          (64, 3, 2, 24, 24, 2), (32, 5, 1, 16, 48, 1), (16, 9, 2, 33, 19, 2), (256, 9, 1, 12, 12, 1),
                                          (48, 2, 1, 9, 9, 3), (32, 1, 1, 160, 160, 2)])
@@ -252,3 +256,33 @@ def test_sppf_pools_bit_exact_vs_max_pool2d(B, H, W, C, k):
         y = F.max_pool2d(y, k, 1, k // 2)
         assert torch.equal(cat[..., lvl * C:(lvl + 1) * C], y.permute(0, 2, 3, 1).bfloat16())
     assert torch.equal(cat[..., :C], x)
+
+
+@pytest.mark.parametrize("Cin,Cout,P,rows,ldo,act", [(32, 32, 4, 4096, 48, "silu"), (48, 32, 2, 1000, 32, "silu"), (64, 64, 2, 2050, 64, "none"),
+                                                     (16, 16, 4, 260, 16, "leaky"), (64, 32, 4, 131072 + 4, 32, "silu")])
+def test_conv1x1_pixel_packed_matches_plain_kernel(Cin, Cout, P, rows, ldo, act):
+    """ldconv_conv1x1_bn_act_packed_fwd (P pixels per GEMM row, block-diagonal weights) against ldconv_conv1x1_bn_act_fwd on the same
+    inputs: the extra products are exact zeros and a row's K-order is unchanged, so the outputs are equal bit for bit; the channels
+    next to an output slice stay untouched; and against fp64 on the bf16 operands."""
+    L = _lib.load()
+    A = {"none": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "leaky": _lib.ACT_LEAKY01}[act]
+    g = torch.Generator().manual_seed(Cin * 3 + Cout + P)
+    x = torch.randn(rows, Cin, generator=g).bfloat16().to(DEV)
+    wt = (torch.randn(Cout, Cin, generator=g) / Cin ** 0.5).bfloat16().to(DEV)
+    scale = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(Cout, generator=g) * 0.2).to(DEV)
+    wp = torch.block_diag(*([wt.float()] * P)).bfloat16().contiguous()
+    want = torch.full((rows, ldo), 5.0, dtype=torch.bfloat16, device=DEV)
+    got = torch.full((rows, ldo), 5.0, dtype=torch.bfloat16, device=DEV)
+    _lib.check(L.ldconv_conv1x1_bn_act_fwd(_p(x), Cin, _p(wt), _p(scale), _p(shift), None, 0, _p(want), ldo, rows, Cin, Cout, A,
+                                           _lib.BF16, _st()))
+    scale_rep, shift_rep = scale.repeat(P).contiguous(), shift.repeat(P).contiguous()      # kept alive across the asynchronous call
+    _lib.check(L.ldconv_conv1x1_bn_act_packed_fwd(_p(x), _p(wp), _p(scale_rep), _p(shift_rep), _p(got), ldo, rows, Cin, Cout, P, A,
+                                                  _lib.BF16, _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    z = (x.double() @ wt.double().t()) * scale.double() + shift.double()
+    ref = {"none": z, "silu": z * torch.sigmoid(z), "leaky": torch.where(z > 0, z, 0.1 * z)}[act]
+    assert _rel(got[:, :Cout].float().cpu().numpy(), ref.cpu().numpy()) <= 6e-3
+    if ldo > Cout:
+        assert bool((got[:, Cout:] == 5.0).all())
