@@ -78,7 +78,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
                                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ pre,
                                                     const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store,
                                                     const GemmOut2& o2, uint32_t sh_ofs, const __nv_bfloat16* mx1 = nullptr,
-                                                    const __nv_bfloat16* mx2 = nullptr, GemmPack pk = GemmPack{1, 0})
+                                                    const __nv_bfloat16* mx2 = nullptr, GemmPack pk = GemmPack{1, 0},
+                                                    uint32_t stage_row_s = 0, uint32_t stage_swz = 0)
 {
     const bool full16 = vec_store && (c0 + 16 <= O);
     if (pre) {
@@ -126,7 +127,15 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
         }
         __nv_bfloat16* dst = out + m * ldo + c0;
         if (pk.P > 1) dst = out + (m * pk.P + (c0 >> pk.o_shift)) * ldo + (c0 & ((1 << pk.o_shift) - 1));
-        if (full16) {
+        if (stage_row_s) {      // warp-staged store (see the kernel): this row's two 16-byte pieces go to the warp's scratch, swizzled
+            uint4 lo, hi;
+            pack16_bf16(z, lo, hi);
+            const uint32_t ch = (uint32_t)c0 >> 3;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row_s + ((ch ^ stage_swz) << 4)), "r"(lo.x), "r"(lo.y),
+                         "r"(lo.z), "r"(lo.w) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row_s + (((ch + 1) ^ stage_swz) << 4)), "r"(hi.x),
+                         "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+        } else if (full16) {
             uint4 lo, hi;
             pack16_bf16(z, lo, hi);
             reinterpret_cast<uint4*>(dst)[0] = lo;
@@ -155,7 +164,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
                  int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg,
-                 GemmOut2 o2, GemmMaxUp mu, GemmPack pk)
+                 GemmOut2 o2, GemmMaxUp mu, GemmPack pk, int stage_rb)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
@@ -168,6 +177,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tempty = tfull + 8;             // [8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
     float* s_affine = reinterpret_cast<float*>(tmem_slot + 4);      // [0, ON) scale, [ON, 2 ON) shift; halved for SiLU (affine_act16)
+    // Warp-staged output (stage_rb = bytes of an output row, 64 or 128; 0 = off): a thread owns a row of the accumulator, so its
+    // 16-byte global stores touched 32 cache lines per warp instruction -- one L1 wavefront per 16 bytes, 1024 per tile at O = 64,
+    // the busiest unit of the kernel (profiles/r1_ncu_gemm_64_64_p2_s4.txt: l1tex 65 %).  Each epilogue warp instead parks its
+    // 32 rows in 32 x stage_rb bytes of shared memory (16-byte pieces XOR-swizzled: conflict-free both ways) and writes them out
+    // with row-contiguous 16-byte stores: 4 (8) lines per instruction.
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_affine + 2 * ON);
+    s_stage += (16u - (smem_u32(s_stage) & 15u)) & 15u;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -257,6 +273,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ON);
             const long long m = (long long)tile * kTileM + lg * 32 + lane;
+            const uint32_t stage_s = stage_rb ? smem_u32(s_stage) + (uint32_t)((warp - 2) * 32 * stage_rb) : 0u;
+            const uint32_t stage_row_s = stage_rb ? stage_s + (uint32_t)(lane * stage_rb) : 0u;
+            const uint32_t stage_swz = stage_rb == 128 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
             const __nv_bfloat16 *mx1 = nullptr, *mx2 = nullptr;
             if (MAXUP && m < M) {        // torch `nearest`: src = floor(dst * in / out)
                 const int mi = (int)m, j = mi % mu.W, bi = mi / mu.W, i = bi % mu.H, b = bi / mu.H;
@@ -274,15 +293,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < M && !(dbg & 2)) {
                     if (ch * 16 < O)
                         gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 64u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk);
+                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk, stage_row_s, stage_swz);
                     if (two && (ch + 1) * 16 < O)
                         gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 64u, act, out, pre, residual,
-                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk);
+                                            ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk, stage_row_s, stage_swz);
                 }
             }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (stage_rb) {      // write the warp's 32 rows out: piece q = (row, 16-byte chunk), a warp instruction covers whole rows
+                const int cpr = stage_rb >> 4;                      // 16-byte pieces per row: 4 or 8
+                const long long m0 = (long long)tile * kTileM + lg * 32;
+#pragma unroll 4
+                for (int q = lane; q < 32 * cpr; q += 32) {
+                    const int row = q / cpr, ch = q - row * cpr;
+                    const uint32_t swz = stage_rb == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                 : "r"(stage_s + (uint32_t)(row * stage_rb) + (((uint32_t)ch ^ swz) << 4)));
+                    if (m0 + row < M) *reinterpret_cast<uint4*>(out + (m0 + row) * ldo + ch * 8) = v;
+                }
+                __syncwarp();      // the scratch is rewritten by this warp's next tile
+            }
         }
     }
     tc_fence_before_sync();
@@ -348,13 +381,21 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     static int g_env_nb = -2;
     if (g_env_nb == -2) { const char* e = getenv("LDCONV_GEMM_NB"); g_env_nb = e ? atoi(e) : -1; }
     if ((g_env_nb == 2 || g_env_nb == 4 || g_env_nb == 8) && g_env_nb <= NB) NB = g_env_nb;
-    int stages = ((two_per_sm ? 100 : 200) * 1024) / (kABytes + b_bytes);
+    // warp-staged stores: plain outputs (no pre / residual / second output / max-up / packing) with rows of 64 or 128 bytes
+    static int env_stage = -2;
+    if (env_stage == -2) { const char* e = getenv("LDCONV_GEMM_STAGE"); env_stage = e ? atoi(e) : 1; }
+    int stage_rb = 0;
+    if (env_stage && out && !pre && !residual && !g_out2.ptr && !g_maxup.z1 && g_pack.P == 1 && (O == 32 || O == 64) && ldo % 8 == 0 &&
+        aligned16(out))
+        stage_rb = O * 2;
+    const int stage_bytes = stage_rb ? 8 * 32 * stage_rb + 16 : 0;
+    int stages = ((two_per_sm ? 100 : 200) * 1024 - stage_bytes) / (kABytes + b_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return fail(LDCONV_E_ARG, "tcgen05 GEMM: tile does not fit shared memory (O=%d)", O);
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(NB * ON)) tmem_cols <<= 1;
     const size_t smem = 1024 + (size_t)stages * (kABytes + b_bytes) + (2 * stages + 16) * sizeof(uint64_t) + 16 +
-                        (size_t)ON * sizeof(float2);
+                        (size_t)ON * sizeof(float2) + (size_t)stage_bytes;
 
     CUtensorMap tmA, tmB;
     if (int e = make_map_2d(&tmA, a, M, K, kTileM, lda)) return e;
@@ -379,7 +420,7 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
         return fail(LDCONV_E_ARG, "tcgen05 GEMM: the max-with-coarser-levels epilogue needs 16-byte stores and Cout %% 16 == 0");
     LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
                         (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
-                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu, pk));
+                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu, pk, stage_rb));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
