@@ -79,7 +79,7 @@ class _Folded:
 
 def _pack_factor(C, O, rows, ldx, ldo):
     """pixels per GEMM row for a narrow dense 1x1 conv (ldconv_conv1x1_bn_act_packed_fwd), 1 = the plain kernel"""
-    if not _GEMM_PACK or ldx != C or O < 16 or (O & (O - 1)) or C % 8 or ldo % 8:
+    if not _GEMM_PACK or ldx != C or C > _GEMM_PACK_MAX_C or O < 16 or (O & (O - 1)) or C % 8 or ldo % 8:
         return 1
     for P in (4, 2):
         if P * C <= _GEMM_PACK_MAX_K and P * O <= 128 and rows % P == 0:
@@ -155,6 +155,9 @@ _SCALSEQ_FUSE = os.environ.get("LDCONV_SCALSEQ_FUSE", "1") != "0"     # A/B swit
 # LDCONV_GEMM_PACK_MAX_K bounds P * Cin
 _GEMM_PACK = os.environ.get("LDCONV_GEMM_PACK", "1") != "0"
 _GEMM_PACK_MAX_K = int(os.environ.get("LDCONV_GEMM_PACK_MAX_K", "256"))
+# widest input that is packed: stand-alone the packing gains 19-25 % at Cin = 32 / 48 and nothing at 64, where the plain kernel's
+# warp-staged stores gain 10 % instead (profiles/r1_gemm_pack_ab_s4.jsonl)
+_GEMM_PACK_MAX_C = int(os.environ.get("LDCONV_GEMM_PACK_MAX_C", "48"))
 _CAT_VIA_UP = os.environ.get("LDCONV_CAT_VIA_UP", "1") != "0"
 _DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
 
