@@ -139,3 +139,33 @@ def test_convert_swaps_class_in_place():
     keys = list(holder.state_dict())
     ldconv.convert(holder)
     assert isinstance(holder[0], E.LDConv) and list(holder.state_dict()) == keys
+
+
+def test_engine_pixel_packing_rule_and_block_diagonal_weights():
+    """Host logic of the pixel-packed 1x1 conv (engine._pack_factor / _packed, ldconv_conv1x1_bn_act_packed_fwd): which layers are
+    packed, and that P pixels times block_diag(W, ..., W) is the same product as the plain conv (the arithmetic the GPU test
+    checks bit for bit)."""
+    from experiment_yolo_b200 import engine
+    pf = engine._pack_factor
+    assert pf(32, 32, 1638400, 32, 48) == 4            # C2f.cv1 at P2: dense input, output slice of the 48-wide concat buffer
+    assert pf(48, 32, 1000, 48, 32) == 4
+    assert pf(64, 64, 1000, 64, 64) == 1               # 64-wide inputs stay on the plain kernel (staged stores)
+    assert pf(32, 32, 1001, 32, 32) == 1               # rows not divisible by P
+    assert pf(32, 32, 1002, 32, 32) == 2
+    assert pf(32, 32, 1000, 64, 32) == 1               # input is a channel slice: P pixels are not one contiguous row
+    assert pf(32, 48, 1000, 32, 48) == 1               # Cout not a power of two
+    assert pf(32, 64, 1000, 32, 64) == 2               # P * Cout <= 128
+    conv = torch.nn.Conv2d(16, 32, 1, bias=False)
+    bn = torch.nn.BatchNorm2d(32).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.2)
+        bn.running_var.uniform_(0.5, 1.5)
+    f = engine._Folded(conv, bn)
+    wp, sc, sh = engine._packed(f, 4)
+    assert engine._packed(f, 4)[0] is wp                # cached on the _Folded
+    assert tuple(wp.shape) == (128, 64) and tuple(sc.shape) == (128,) and torch.equal(sc[:32], sc[96:]) and torch.equal(sh[:32], sh[32:64])
+    x = torch.randn(8, 16).bfloat16().float()
+    plain = (x @ f.w.float().t()) * f.scale + f.shift                                              # (8 pixels, 32)
+    packed = (x.reshape(2, 64) @ wp.float().t()) * sc + sh                                          # (2 rows, 4 x 32)
+    # (the CPU matmul blocks K = 64 and K = 16 differently, so this host-side statement is equal up to fp32 rounding)
+    assert torch.allclose(packed.reshape(8, 32), plain, rtol=0, atol=1e-5)
