@@ -31,6 +31,26 @@ upsample_nearest_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, i
         for (int dj = 0; dj < f; ++dj) *reinterpret_cast<uint4*>(o + (di * Wo + dj) * ldo) = v;
 }
 
+// `Add` rows of the YAML (nn/extra_modules/block.py:3479-3484: torch.sum(torch.stack(x), 0)) for up to four NHWC inputs /
+// channel slices: fp32 accumulation, one rounding -- what torch's reduction does for bf16 tensors
+struct AddArgs { const T* src[4]; int ld[4]; int n; };
+__global__ void __launch_bounds__(256)
+add_nhwc_kernel(AddArgs a, T* __restrict__ out, int ldo, int CV, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    const long long pix = t / CV;
+    float acc[8], v[8];
+    Vec16<T>::load(a.src[0] + pix * a.ld[0] + cv * 8, acc);
+    for (int k = 1; k < a.n; ++k) {
+        Vec16<T>::load(a.src[k] + pix * a.ld[k] + cv * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+    Vec16<T>::store(out + pix * ldo + cv * 8, acc);
+}
+
 __global__ void __launch_bounds__(256)
 scalseq_tail_kernel(const T* __restrict__ z0, const T* __restrict__ z1, const T* __restrict__ z2, const T* __restrict__ add,
                     int ld_add, T* __restrict__ out, int ldo, int H, int W, int H1, int W1, int H2, int W2, int CV,
@@ -253,6 +273,25 @@ LDC_API int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, 
     upsample_nearest_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, ldo, H, W, C / 8,
                                                                                factor, total);
     LDC_LAUNCH_CHECK("upsample_nearest_kernel");
+    return LDCONV_OK;
+}
+
+LDC_API int ldconv_add_nhwc(const void* const* srcs, const int* lds, int n, void* out, int ldo, long long pixels, int C, int dtype,
+                            void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_add_nhwc: bf16 only");
+    LDC_REQUIRE(srcs && lds && out && n >= 1 && n <= 4 && C % 8 == 0 && ldo % 8 == 0 && aligned16(out), "ldconv_add_nhwc: bad arguments");
+    AddArgs a;
+    a.n = n;
+    for (int k = 0; k < 4; ++k) {
+        a.src[k] = (const T*)srcs[k < n ? k : 0];
+        a.ld[k] = lds[k < n ? k : 0];
+        LDC_REQUIRE(a.src[k] && aligned16(a.src[k]) && a.ld[k] % 8 == 0, "ldconv_add_nhwc: input %d must be 16-byte aligned, stride % 8 == 0", k);
+    }
+    const long long total = pixels * (C / 8);
+    if (total == 0) return LDCONV_OK;
+    add_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(a, (T*)out, ldo, C / 8, total);
+    LDC_LAUNCH_CHECK("add_nhwc_kernel");
     return LDCONV_OK;
 }
 

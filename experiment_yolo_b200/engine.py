@@ -1,6 +1,7 @@
 """Fused bf16 inference executor for the DEAL-YOLO-LD graph (SURVEY.md 8f "next" rows, widened after the LDConv path).
 
-`FusedDealYolo(model)` takes an eval-mode `dealyolo.DealYolo` on a B200 and runs the same graph with the library's kernels
+`FusedDealYolo(model)` takes an eval-mode `dealyolo.DealYolo` -- or the reference's own `DetectionModel` built from
+yolov8-LD-P2.yaml (rows are recognised by class name and structure) -- on a B200 and runs the same graph with the library's kernels
 instead of the eager torch modules around LDConv:
 
   * every `Conv` block (Conv2d no-bias + BatchNorm2d + SiLU, reference nn/modules/conv.py:41-59) is ONE kernel: the
@@ -23,14 +24,11 @@ the golden output of the reference DetectionModel.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
-from . import _lib, dealyolo
-from .ldconv import LDConv, infer_nhwc
+from . import _lib
+from .ldconv import LDConv, convert, infer_nhwc
 
 _ACT = {"none": _lib.ACT_NONE, "silu": _lib.ACT_SILU, "leaky": _lib.ACT_LEAKY01}
 
@@ -46,6 +44,13 @@ def _nhwc_geometry(t: torch.Tensor):
     ld = t.stride(2)
     assert t.stride(3) == 1 and t.stride(1) == W * ld and t.stride(0) == H * W * ld, "not an NHWC (slice) tensor"
     return B, H, W, C, ld
+
+
+def _is_conv_block(m) -> bool:
+    """the reference's `Conv` block (nn/modules/conv.py:41-59): Conv2d + BatchNorm2d + SiLU, or Conv2d(bias) + SiLU once
+    `model.fuse()` (nn/tasks.py:168-195) has folded the BatchNorm away"""
+    return (isinstance(getattr(m, "conv", None), nn.Conv2d) and isinstance(getattr(m, "act", None), nn.SiLU)
+            and (not hasattr(m, "bn") or isinstance(m.bn, nn.BatchNorm2d)))
 
 
 class _Folded:
@@ -77,9 +82,13 @@ class _Folded:
             self.shift = bias.contiguous()
 
 
+def _fold(block) -> _Folded:
+    return _Folded(block.conv, getattr(block, "bn", None))
+
+
 def _pack_factor(C, O, rows, ldx, ldo):
     """pixels per GEMM row for a narrow dense 1x1 conv (ldconv_conv1x1_bn_act_packed_fwd), 1 = the plain kernel"""
-    if not _GEMM_PACK or ldx != C or C > _GEMM_PACK_MAX_C or O < 16 or (O & (O - 1)) or C % 8 or ldo % 8:
+    if ldx != C or C > _GEMM_PACK_MAX_C or O < 16 or (O & (O - 1)) or C % 8 or ldo % 8:
         return 1
     for P in (4, 2):
         if P * C <= _GEMM_PACK_MAX_K and P * O <= 128 and rows % P == 0:
@@ -142,54 +151,44 @@ def _new(like: torch.Tensor, B, H, W, C):
     return torch.empty((B, H, W, C), device=like.device, dtype=torch.bfloat16)
 
 
-# Dense second output of C2f.cv1 (ldconv_conv1x1_bn_act_fwd2).  OFF: measured 0.7 % slower in the step (3.658 vs 3.634 ms) -- the
-# slice the first Bottleneck reads is still L2-resident right after cv1 wrote it; the 3x DRAM over-fetch the one-step ncu launch list
-# shows for those convs (157 MB for a 52 MB slice) is a cold-cache artefact of the serialised capture.  LDCONV_C2F_DUAL_STORE=1 enables.
-_DUAL_STORE = os.environ.get("LDCONV_C2F_DUAL_STORE", "0") == "1"
-
-
-# A/B switch: C2f outputs that also feed a later Concat are written into its buffer by the C2f's last conv (second output)
-_C2F_DUAL_OUT = os.environ.get("LDCONV_C2F_DUAL_OUT", "1") != "0"
-_SCALSEQ_FUSE = os.environ.get("LDCONV_SCALSEQ_FUSE", "1") != "0"     # A/B switch: SSFF maximum + Add in the finest level's GEMM
-# narrow dense 1x1 convs run with P pixels per GEMM row (block-diagonal weights): LDCONV_GEMM_PACK=0 switches it off,
-# LDCONV_GEMM_PACK_MAX_K bounds P * Cin
-_GEMM_PACK = os.environ.get("LDCONV_GEMM_PACK", "1") != "0"
-_GEMM_PACK_MAX_K = int(os.environ.get("LDCONV_GEMM_PACK_MAX_K", "256"))
-# widest input that is packed: stand-alone the packing gains 19-25 % at Cin = 32 / 48 and nothing at 64, where the plain kernel's
-# warp-staged stores gain 10 % instead (profiles/r1_gemm_pack_ab_s4.jsonl)
-_GEMM_PACK_MAX_C = int(os.environ.get("LDCONV_GEMM_PACK_MAX_C", "48"))
-_CAT_VIA_UP = os.environ.get("LDCONV_CAT_VIA_UP", "1") != "0"
-_DETECT_FUSE = os.environ.get("LDCONV_DETECT_FUSE", "1") != "0"      # A/B switch: stacked first conv of the Detect branches
+# Settled by measurement in round 1 (the A/B environment switches are gone):
+#   * C2f.cv1 does NOT also store the first Bottleneck's chunk densely (0.7 % slower in the step: the slice is L2-resident);
+#   * a C2f whose output also feeds a later Concat writes that slice from its last conv (second output of the GEMM);
+#   * the SSFF maximum + Add run in the epilogue of the finest level's point-wise GEMM;
+#   * an LDConv whose other consumers are up-samplings writes straight into the Concat buffer (they read the slice);
+#   * the first convs of the two Detect branches of a level run as one stacked conv;
+#   * narrow dense 1x1 convs (Cin <= 48) run with P pixels per GEMM row and block-diagonal weights: -19...-25 % stand-alone at
+#     Cin = 32 / 48, nothing at 64 where the plain kernel's warp-staged stores gain 10 % (profiles/r1_gemm_pack_ab_s4.jsonl).
+_GEMM_PACK_MAX_K = 256
+_GEMM_PACK_MAX_C = 48
 
 
 class _C2f:
-    def __init__(self, m: dealyolo.C2f):
+    def __init__(self, m):
         self.c = m.c
         self.n = len(m.m)
-        self.cv1 = _Folded(m.cv1.conv, m.cv1.bn)
-        self.cv2 = _Folded(m.cv2.conv, m.cv2.bn)
-        self.blocks = [(_Folded(b.cv1.conv, b.cv1.bn), _Folded(b.cv2.conv, b.cv2.bn), b.add) for b in m.m]
+        self.cv1 = _fold(m.cv1)
+        self.cv2 = _fold(m.cv2)
+        self.blocks = [(_fold(b.cv1), _fold(b.cv2), b.add) for b in m.m]
 
     def __call__(self, x, out2=None):
         """out2: optional NHWC slice (of a later Concat's buffer) that receives a second copy of the output in the same pass"""
         B, H, W, _ = x.shape
         c, n = self.c, self.n
         cat = _new(x, B, H, W, (2 + n) * c)
-        # optional: the chunk the first Bottleneck reads is also written densely by cv1 (see _DUAL_STORE)
-        y1 = _new(x, B, H, W, c) if (c % 16 == 0 and (2 * c) % 16 == 0 and _DUAL_STORE) else None
-        conv1x1(x, self.cv1, cat[..., : 2 * c], out2=y1, c2_lo=c)
+        conv1x1(x, self.cv1, cat[..., : 2 * c])
         tmp = _new(x, B, H, W, c)
         for i, (p1, p2, add) in enumerate(self.blocks):
-            src = y1 if (i == 0 and y1 is not None) else cat[..., (1 + i) * c: (2 + i) * c]
+            src = cat[..., (1 + i) * c: (2 + i) * c]
             conv3x3(src, p1, tmp)
             conv3x3(tmp, p2, cat[..., (2 + i) * c: (3 + i) * c], residual=src if add else None)
         return conv1x1(cat, self.cv2, _new(x, B, H, W, self.cv2.cout), out2=out2, c2_lo=0)
 
 
 class _SPPF:
-    def __init__(self, m: dealyolo.SPPF):
-        self.cv1 = _Folded(m.cv1.conv, m.cv1.bn)
-        self.cv2 = _Folded(m.cv2.conv, m.cv2.bn)
+    def __init__(self, m):
+        self.cv1 = _fold(m.cv1)
+        self.cv2 = _fold(m.cv2)
         self.k = m.m.kernel_size
 
     def __call__(self, x):
@@ -212,11 +211,29 @@ def upsample_into(x: torch.Tensor, out: torch.Tensor, factor: int):
     return out
 
 
+def add_nhwc(xs):
+    """`Add` row: the sum of ALL its inputs (NHWC tensors / channel slices), fp32 accumulation, one rounding per launch
+    (up to four inputs per launch; longer lists chain through the running sum)."""
+    import ctypes
+    pending = list(xs)
+    B, H, W, C, _ = _nhwc_geometry(pending[0])
+    while True:
+        part, pending = pending[:4], pending[4:]
+        srcs = (ctypes.c_void_p * len(part))(*[t.data_ptr() for t in part])
+        lds = (ctypes.c_int * len(part))(*[_nhwc_geometry(t)[4] for t in part])
+        out = _new(part[0], B, H, W, C)
+        _lib.check(_lib.load().ldconv_add_nhwc(srcs, lds, len(part), out.data_ptr(), C, B * H * W, C, _lib.BF16, _stream()),
+                   "ldconv_add_nhwc")
+        if not pending:
+            return out
+        pending.insert(0, out)
+
+
 class _ScalSeq:
-    def __init__(self, m: dealyolo.ScalSeq):
-        self.conv0 = _Folded(m.conv0.conv, m.conv0.bn) if hasattr(m, "conv0") else None
-        self.conv1 = _Folded(m.conv1.conv, m.conv1.bn)
-        self.conv2 = _Folded(m.conv2.conv, m.conv2.bn)
+    def __init__(self, m):
+        self.conv0 = _fold(m.conv0) if hasattr(m, "conv0") else None
+        self.conv1 = _fold(m.conv1)
+        self.conv2 = _fold(m.conv2)
         self.mix = _Folded(m.conv3d, m.bn)          # Conv3d(1x1x1) + BatchNorm3d, point-wise per level
 
     def __call__(self, xs, addend=None):
@@ -228,7 +245,7 @@ class _ScalSeq:
         coarse = conv1x1(coarse, self.conv2, _new(coarse, *coarse.shape[:3], ch))
         B, H, W, _ = fine.shape
         out = _new(fine, B, H, W, ch)
-        if _SCALSEQ_FUSE and ch % 16 == 0:
+        if ch % 16 == 0:
             # the finest level's point-wise GEMM takes the maximum over the levels (and the Add) in its epilogue: its own
             # (B,H,W,ch) map (105 MB at P2, batch 64) never reaches HBM and the tail kernel disappears
             z1 = conv1x1(mid, self.mix, _new(mid, *mid.shape[:3], ch), act="leaky")
@@ -257,11 +274,11 @@ class _Detect:
     # before the fork, the side streams only launch kernels, and the join precedes any reuse.
     parallel_branches = True
 
-    def __init__(self, m: dealyolo.Detect):
+    def __init__(self, m):
         self.nc, self.reg_max, self.no = m.nc, m.reg_max, m.no
         self.stride = [float(s) for s in m.stride]
-        self.box = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv2]
-        self.cls = [[_Folded(s[0].conv, s[0].bn), _Folded(s[1].conv, s[1].bn), _Folded(s[2])] for s in m.cv3]
+        self.box = [[_fold(s[0]), _fold(s[1]), _Folded(s[2])] for s in m.cv2]
+        self.cls = [[_fold(s[0]), _fold(s[1]), _Folded(s[2])] for s in m.cv3]
         self.streams = None
         # The first convs of the two branches of a level read the same input (nn/modules/head.py:43-52: cv2[i][0] ch -> 64, cv3[i][0]
         # ch -> 32).  As ONE conv with the weights stacked (Cout = 96) the input is read once and the MMAs run at N = 96: the wide
@@ -271,7 +288,7 @@ class _Detect:
         self.first = []
         for b, c in zip(self.box, self.cls):
             f = None
-            if _DETECT_FUSE and b[0].cin <= 64 and (b[0].cout + c[0].cout) % 16 == 0 and b[0].cout % 16 == 0:
+            if b[0].cin <= 64 and (b[0].cout + c[0].cout) % 16 == 0 and b[0].cout % 16 == 0:
                 f = object.__new__(_Folded)
                 f.w = torch.cat([b[0].w, c[0].w], 0).contiguous()
                 f.scale = torch.cat([b[0].scale, c[0].scale]).contiguous()
@@ -356,34 +373,26 @@ class FusedDealYolo:
     """Inference executor: `y, feats = FusedDealYolo(model)(images)` with `images` (B,3,H,W) bf16 (any memory format).
     `y` is the decoded (B, 4+nc, anchors) tensor of the reference's Detect head in eval mode."""
 
-    def __init__(self, model: dealyolo.DealYolo):
+    def __init__(self, model):
         p = next(model.parameters())
         if not p.is_cuda:
             raise RuntimeError("FusedDealYolo needs the model on a CUDA device (sm_100a); there is no CPU path")
         _lib.check(_lib.load().ldconv_device_check(), "ldconv_device_check")
         if model.training:
             raise RuntimeError("FusedDealYolo is an inference executor: call model.eval() first")
+        convert(model)      # reference LDConv rows -> this package's class, in place (parameters / state_dict untouched)
         self.model = model
         self.layers = []
-        for layer in model.model:
-            if isinstance(layer, LDConv):
+        builders = {"c2f": _C2f, "sppf": _SPPF, "scalseq": _ScalSeq, "detect": _Detect}
+        for layer, kind in zip(model.model, self.recognise(model)):
+            if kind in builders:
+                op = ("fn", builders[kind](layer))
+            elif kind == "ldconv":
                 op = ("ldconv", layer)
-            elif isinstance(layer, dealyolo.C2f):
-                op = ("fn", _C2f(layer))
-            elif isinstance(layer, dealyolo.SPPF):
-                op = ("fn", _SPPF(layer))
-            elif isinstance(layer, dealyolo.ScalSeq):
-                op = ("fn", _ScalSeq(layer))
-            elif isinstance(layer, dealyolo.Detect):
-                op = ("fn", _Detect(layer))
-            elif isinstance(layer, dealyolo.Concat):
-                op = ("cat", None)
-            elif isinstance(layer, dealyolo.Add):
-                op = ("add", None)
-            elif isinstance(layer, nn.Upsample):
+            elif kind == "up":
                 op = ("up", int(layer.scale_factor))
             else:
-                raise NotImplementedError(f"FusedDealYolo: no fused executor for {type(layer).__name__}")
+                op = (kind, None)
             self.layers.append((op, layer.f, layer.i))
         self.save = set(model.save)
         # LDConv whose ONLY consumer is a Concat writes its output straight into that Concat's buffer
@@ -420,9 +429,9 @@ class FusedDealYolo:
                 # other consumers may be up-samplings: they read the slice through its pixel stride (yaml row 8 -> 9 and 22)
                 others_up = all(self.layers[cj][0][0] == "up" for cj in consumers.get(sidx, []) if cj != i)
                 if k2 == "ldconv" and c0 % 8 == 0 and sidx not in self.cat_plan and (
-                        consumers.get(sidx) == [i] or (_CAT_VIA_UP and others_up)):
+                        consumers.get(sidx) == [i] or others_up):
                     self.cat_plan[sidx] = (i, c0, sum(widths))
-                elif (_C2F_DUAL_OUT and k2 == "fn" and isinstance(a2, _C2f) and c0 % 8 == 0 and wd % 16 == 0
+                elif (k2 == "fn" and isinstance(a2, _C2f) and c0 % 8 == 0 and wd % 16 == 0
                       and sidx not in self.dual_plan):
                     # a C2f with further consumers (yaml row 12 -> 13 and 19): its last 1x1 conv writes the dense output AND the
                     # Concat's slice in one pass instead of a strided copy_ later (62 us for 52 MB at P3)
@@ -435,6 +444,35 @@ class FusedDealYolo:
                 other = [j for j in f2 if j != -1][0]
                 self.layers[n] = (("scalseq_add", (arg, other)), f, i)
                 self.layers[n + 1] = (("identity", None), -1, self.layers[n + 1][2])
+
+    @staticmethod
+    def recognise(model):
+        """Row kinds of a yolov8-LD-P2-style graph.  Rows are recognised by class NAME and structure, not by type: the
+        reference's own `DetectionModel` (nn/tasks.py:275; modules from nn/modules/{conv,block,head}.py and
+        nn/extra_modules/block.py) has the same attribute names as this package's dealyolo graph, so either can be handed
+        in.  Needs no device (tests/test_host_cpu.py runs it on the real reference model)."""
+        kinds = []
+        for layer in model.model:
+            name = type(layer).__name__
+            if name == "LDConv" and hasattr(layer, "p_conv") and hasattr(layer, "p_n"):
+                kinds.append("ldconv")
+            elif name == "C2f" and _is_conv_block(layer.cv1) and all(type(b).__name__ == "Bottleneck" for b in layer.m):
+                kinds.append("c2f")
+            elif name == "SPPF" and _is_conv_block(layer.cv1):
+                kinds.append("sppf")
+            elif name == "ScalSeq" and hasattr(layer, "conv3d"):
+                kinds.append("scalseq")
+            elif name == "Detect" and hasattr(layer, "cv2") and hasattr(layer, "cv3") and hasattr(layer, "dfl"):
+                kinds.append("detect")
+            elif name == "Concat" and getattr(layer, "d", 1) == 1:
+                kinds.append("cat")
+            elif name == "Add":
+                kinds.append("add")
+            elif isinstance(layer, nn.Upsample) and layer.mode == "nearest" and float(layer.scale_factor).is_integer():
+                kinds.append("up")
+            else:
+                raise NotImplementedError(f"FusedDealYolo: no fused executor for {name}")
+        return kinds
 
     def _out_channels(self, idx):
         kind, arg = self.layers[idx][0]
@@ -465,7 +503,7 @@ class FusedDealYolo:
             if isinstance(t, _Deferred):
                 upsample_into(t.src, dst, t.factor)
             elif t.data_ptr() != dst.data_ptr():
-                dst.copy_(t)
+                upsample_into(t, dst, 1)          # factor 1 = a strided slice copy
             c0 += c
         return out
 
@@ -534,7 +572,7 @@ class FusedDealYolo:
                         x[pos] = buf[..., plan[1]:plan[1] + x[pos].shape[3]]
                 x = self._concat(x, buf)
             elif kind == "add":
-                x = x[0] + x[1]
+                x = add_nhwc(x)
             elif kind == "up":
                 x = _Deferred(x, arg)        # materialised by the consumer (Concat writes it straight into its buffer)
             elif kind == "identity":
@@ -552,7 +590,7 @@ class PipelinedPredictor:
     rotated so that the upload of batch i+1 and the download of batch i-1 overlap the compute of batch i on separate
     streams.  Results come back in submission order."""
 
-    def __init__(self, model: dealyolo.DealYolo, batch: int, imgsz: int, channels: int = 3, slots: int = 2):
+    def __init__(self, model, batch: int, imgsz: int, channels: int = 3, slots: int = 2):
         self.exec = FusedDealYolo(model)
         dev = next(model.parameters()).device
         self.dev, self.slots = dev, slots

@@ -26,6 +26,20 @@ from . import _lib
 __all__ = ["LDConv", "install", "ldconv_function", "base_grid"]
 
 _DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+# float16 (the reference's only reduced-precision mode: `model.half()` in get_FPS.py:59-61 / engine/validator.py:113-115 and
+# fp16 autocast in engine/trainer.py:800) is accepted at the module boundary and computed by the fp32 kernels: fp16 -> fp32 is
+# exact, the result is rounded to fp16 once on the way out, gradients come back in the parameter dtype.  Parity: the fp32
+# reference on fp16-rounded tensors (tests/test_gpu_parity.py::test_module_half_*).
+_COMPUTE_AS = {torch.float16: torch.float32}
+
+
+def _ver(t: Optional[torch.Tensor]):
+    """cache-key component of a tensor: (address, version counter).  Inference tensors have no version counter
+    (`_version` raises): they are keyed by address and a marker, and never shared with a grad-mode forward (see
+    LDConv._prepared)."""
+    if t is None:
+        return None
+    return (t.data_ptr(), -1 if t.is_inference() else t._version)
 
 
 def base_grid(num_param: int) -> torch.Tensor:
@@ -51,7 +65,7 @@ def _check_input(x: torch.Tensor) -> int:
             "experiment_yolo_b200.LDConv runs on sm_100a only and needs a CUDA tensor "
             f"(got a {x.device.type} tensor); there is no CPU fallback")
     if x.dtype not in _DTYPES:
-        raise TypeError(f"experiment_yolo_b200.LDConv supports float32 and bfloat16 activations, got {x.dtype}")
+        raise TypeError(f"experiment_yolo_b200.LDConv supports float32, bfloat16 and float16 activations, got {x.dtype}")
     if x.dim() != 4:
         raise ValueError(f"LDConv expects a (B,C,H,W) tensor, got shape {tuple(x.shape)}")
     return _DTYPES[x.dtype]
@@ -97,6 +111,27 @@ def _prepare(p_w, p_b, c_w, p_n, dtype: torch.dtype, need_wt_t: bool) -> _Prepar
     return pr
 
 
+def offset_conv_nhwc(xh: torch.Tensor, pr: _Prepared, N: int, s: int) -> torch.Tensor:
+    """conv.py:356,368 `offset = p_conv(x)` on a dense NHWC tensor -> (B,h,w,2N) fp32 offsets, rows then columns.  Picks the
+    kernel the shape allows: zero-copy tcgen05 on the space-to-depth view (stride 2), tcgen05 implicit GEMM, CUDA cores."""
+    L = _lib.load()
+    B, H, W, C = xh.shape
+    dt = _DTYPES[xh.dtype]
+    st = _stream()
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    off = torch.empty((B, h, w, 2 * N), device=xh.device, dtype=torch.float32)
+    if s == 2 and pr.w_off_s2d is not None and L.ldconv_offset_conv_s2d_supported(C, N, H, W, dt):
+        _lib.check(L.ldconv_offset_conv_s2d_fwd(_ptr(xh), _ptr(pr.w_off_s2d), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, dt, st),
+                   "ldconv_offset_conv_s2d_fwd")
+    elif pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
+        _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(xh), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
+                   "ldconv_offset_conv_tc_fwd")
+    else:
+        _lib.check(L.ldconv_offset_conv_fwd(_ptr(xh), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
+                   "ldconv_offset_conv_fwd")
+    return off
+
+
 class _LDConvFunction(torch.autograd.Function):
     """Forward = offset conv -> fused grid+gather -> GEMM (+BN statistics) -> BN/SiLU; backward = the closed form of
     SURVEY.md Appendix A.  Every step is one C-ABI call."""
@@ -119,16 +154,7 @@ class _LDConvFunction(torch.autograd.Function):
             pr.wt_t = pr.wt.t().contiguous()
 
         xh = _nhwc(x)
-        off = torch.empty((B, h, w, 2 * N), device=dev, dtype=torch.float32)
-        if s == 2 and pr.w_off_s2d is not None and L.ldconv_offset_conv_s2d_supported(C, N, H, W, dt):
-            _lib.check(L.ldconv_offset_conv_s2d_fwd(_ptr(xh), _ptr(pr.w_off_s2d), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, dt, st),
-                       "ldconv_offset_conv_s2d_fwd")
-        elif pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
-            _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(xh), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt,
-                                                   st), "ldconv_offset_conv_tc_fwd")
-        else:
-            _lib.check(L.ldconv_offset_conv_fwd(_ptr(xh), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
-                       "ldconv_offset_conv_fwd")
+        off = offset_conv_nhwc(xh, pr, N, s)
         operand = torch.empty((M, K), device=dev, dtype=x.dtype)
         _lib.check(L.ldconv_gather_fwd(_ptr(xh), _ptr(off), _ptr(pr.pn), _ptr(operand), None, None, B, C, H, W, N, s, dt, st),
                    "ldconv_gather_fwd")
@@ -299,9 +325,10 @@ class LDConv(nn.Module):
 
     def _prepared(self, dtype: torch.dtype, need_wt_t: bool):
         conv, pconv = self.conv[0], self.p_conv
-        key = (dtype, conv.weight.data_ptr(), conv.weight._version, pconv.weight.data_ptr(), pconv.weight._version,
-               None if pconv.bias is None else (pconv.bias.data_ptr(), pconv.bias._version), self.p_n._version,
-               conv.weight.device)
+        # torch.is_inference_mode_enabled(): operands built under inference_mode are inference tensors and cannot be saved for
+        # backward, so a grad-mode forward never reuses them (the reference's smart_inference_mode validates between epochs)
+        key = (dtype, _ver(conv.weight), _ver(pconv.weight), _ver(pconv.bias), _ver(self.p_n), conv.weight.device,
+               torch.is_inference_mode_enabled())
         c = self._prep_cache
         if c is None or c.key != key:
             c = _prepare(pconv.weight, pconv.bias, conv.weight, self.p_n, dtype, need_wt_t)
@@ -310,6 +337,12 @@ class LDConv(nn.Module):
         elif need_wt_t and c.wt_t is None:
             c.wt_t = c.wt.t().contiguous()
         return c
+
+    def invalidate(self):
+        """Drop the cached operand forms of the parameters and the folded BatchNorm.  Needed only after an in-place update
+        that bypasses the version counter (`param.data.op_()`); `optimizer.step()`, `load_state_dict`, `.to()` bump it."""
+        self._prep_cache = None
+        self.conv[1].__dict__.pop(_FOLD_CACHE_ATTR, None)
 
     def _fused_ok(self, x) -> bool:
         if not self.use_fused_inference:
@@ -324,13 +357,23 @@ class LDConv(nn.Module):
                                                        self.conv[0].out_channels, _DTYPES[x.dtype]))
 
     def forward(self, x):
-        # Under bf16 autocast (the reference trainer runs the forward under torch.cuda.amp.autocast, engine/trainer.py:693)
-        # the reference's own convs inside LDConv run in the low-precision dtype; an fp32 input (the image, layer 0) is cast
-        # here so that the layer takes the bf16 tensor-core kernels instead of the fp32 CUDA-core ones.  fp16 autocast is not
-        # covered by the kernels and keeps fp32.
-        if x.is_cuda and x.dtype == torch.float32 and torch.is_autocast_enabled() \
-                and torch.get_autocast_gpu_dtype() == torch.bfloat16:
-            x = x.to(torch.bfloat16)
+        # Reduced precision at the boundary (the reference trainer runs the forward under torch.cuda.amp.autocast,
+        # engine/trainer.py:693,800; validator / get_FPS.py call model.half()):
+        #   bf16 autocast + fp32 input (the image, layer 0)  -> cast to bf16: the layer takes the bf16 tensor-core kernels
+        #   fp16 input, or fp16 autocast + fp32 input          -> exact up-cast to fp32, fp32 kernels, fp16 result (what the
+        #                                                        reference's own convs return under fp16 autocast)
+        out_dtype = None
+        if x.is_cuda:
+            ac = torch.get_autocast_gpu_dtype() if torch.is_autocast_enabled() else None
+            if x.dtype == torch.float32 and ac == torch.bfloat16:
+                x = x.to(torch.bfloat16)
+            elif x.dtype in _COMPUTE_AS or (x.dtype == torch.float32 and ac in _COMPUTE_AS):
+                out_dtype = x.dtype if x.dtype in _COMPUTE_AS else ac
+                x = x.to(_COMPUTE_AS[out_dtype])
+        y = self._forward(x)
+        return y if out_dtype is None else y.to(out_dtype)
+
+    def _forward(self, x):
         _check_input(x)
         conv, bn = self.conv[0], self.conv[1]
         training = self.training
@@ -380,16 +423,7 @@ def infer_nhwc(mod: "LDConv", x: torch.Tensor, out: Optional[torch.Tensor] = Non
                    "ldconv_fused_fwd")
         return out
     M, K = B * h * w, N * C
-    off = torch.empty((B, h, w, 2 * N), device=x.device, dtype=torch.float32)
-    if s == 2 and pr.w_off_s2d is not None and L.ldconv_offset_conv_s2d_supported(C, N, H, W, dt):
-        _lib.check(L.ldconv_offset_conv_s2d_fwd(_ptr(x), _ptr(pr.w_off_s2d), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, dt, st),
-                   "ldconv_offset_conv_s2d_fwd")
-    elif pr.w_off_tc is not None and L.ldconv_offset_conv_tc_supported(C, N, s, dt):
-        _lib.check(L.ldconv_offset_conv_tc_fwd(_ptr(x), _ptr(pr.w_off_tc), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
-                   "ldconv_offset_conv_tc_fwd")
-    else:
-        _lib.check(L.ldconv_offset_conv_fwd(_ptr(x), _ptr(pr.w_off), _ptr(pr.b_off), _ptr(off), B, C, H, W, N, s, dt, st),
-                   "ldconv_offset_conv_fwd")
+    off = offset_conv_nhwc(x, pr, N, s)
     if out is None:
         out = torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
     ldo = out.stride(2)
@@ -416,9 +450,8 @@ def infer_nhwc(mod: "LDConv", x: torch.Tensor, out: Optional[torch.Tensor] = Non
 def _folded_bn(bn: nn.BatchNorm2d, device):
     """Eval-mode BatchNorm folded to per-channel scale/shift through the C ABI (eps read from the module).  Cached on the
     BatchNorm module while its parameters / statistics / eps are unchanged (the fold is five tiny launches otherwise)."""
-    key = (bn.eps, bn.running_mean.data_ptr(), bn.running_mean._version, bn.running_var._version,
-           None if bn.weight is None else (bn.weight.data_ptr(), bn.weight._version),
-           None if bn.bias is None else bn.bias._version, str(device))
+    key = (bn.eps, _ver(bn.running_mean), _ver(bn.running_var), _ver(bn.weight), _ver(bn.bias), str(device),
+           torch.is_inference_mode_enabled())
     cached = bn.__dict__.get(_FOLD_CACHE_ATTR)
     if cached is not None and cached[0] == key:
         return cached[1], cached[2]

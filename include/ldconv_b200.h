@@ -248,6 +248,10 @@ int ldconv_tal_assign(const long long* topk_idx, const float* anchors, const flo
  * :3479-3484); SPPF's three chained k x k max-pools (nn/modules/block.py:166-171) as the k, 2k-1, 3k-2 window maxima. */
 int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, int H, int W, int C, int factor, int dtype,
                             void* stream);
+/* `Add` rows (nn/extra_modules/block.py:3479-3484, torch.sum(torch.stack(x), 0)): out = sum of n <= 4 NHWC tensors / channel
+ * slices (host arrays of device pointers and pixel strides), fp32 accumulation, one rounding. */
+int ldconv_add_nhwc(const void* const* srcs, const int* lds, int n, void* out, int ldo, long long pixels, int C, int dtype,
+                    void* stream);
 int ldconv_scalseq_tail(const void* z0, const void* z1, const void* z2, const void* addend, int ld_add, void* out, int ldo,
                         int B, int H, int W, int H1, int W1, int H2, int W2, int C, int dtype, void* stream);
 /* uint8 NCHW image batch -> `scale`-normalised bf16 NHWC (the predictor's `im.half(); im /= 255`, engine/predictor.py:120-131,

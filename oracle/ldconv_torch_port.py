@@ -9,8 +9,8 @@ p_0 every call (conv.py:435-444), ~a dozen element-wise passes for floor / clamp
 `torch.gather` calls over an int64 index expanded across channels (:456-489), the weighted sum (:402-405), the
 rearrange copy (:494-503) and the (N,1) Conv2d + BatchNorm2d + SiLU (:355,408).  tests/test_torch_port.py checks that
 it reproduces the golden vectors bit-for-bit in the forward pass and that its state_dict layout equals the
-reference's; oracle/check_port_vs_reference.py (authoring container only) compares outputs and wall-clock time with
-the real reference module.
+reference's; oracle/gen_model_golden.py (authoring container only) asserts that the whole graph built on this port equals the
+real reference DetectionModel bit for bit and records both wall-clock times.
 """
 from __future__ import annotations
 

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from experiment_yolo_b200 import dealyolo
+from experiment_yolo_b200.ldconv import LDConv as E_LDConv
 from tests import _golden
 
 pytestmark = pytest.mark.gpu
@@ -124,3 +125,40 @@ def test_pipelined_predictor_host_buffers_round_trip():
     # the uint8 path equals the float path on the normalised images
     y_f, _ = eng((batches[0].to(DEV).float() / 255.0).bfloat16())
     assert float((y_f.float().cpu() - outs[0].float()).abs().max()) <= 0.5
+
+
+def test_fused_engine_accepts_a_model_built_with_foreign_ldconv_rows():
+    """the executor recognises rows by class name / structure and converts reference-style LDConv rows in
+    place (ldconv.convert): a graph whose LDConv rows are instances of ANOTHER class named `LDConv` with the reference's
+    children (here: the eager CPU port under that name) gives the same output as the native graph."""
+    from experiment_yolo_b200 import engine
+    from oracle.ldconv_torch_port import LDConvTorchPort
+    Foreign = type("LDConv", (LDConvTorchPort,), {})          # class name `LDConv`, not experiment_yolo_b200's type
+    z, model = _load()
+    foreign = dealyolo.DealYolo(nc=6, ldconv_cls=Foreign)
+    foreign.load_state_dict(model.state_dict(), strict=True)
+    assert not any(isinstance(m, E_LDConv) for m in foreign.modules())
+    foreign = foreign.to(DEV).bfloat16().eval()
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
+    x = torch.from_numpy(z["x"]).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    y_native, _ = engine.FusedDealYolo(model)(x)
+    eng = engine.FusedDealYolo(foreign)
+    assert sum(isinstance(m, E_LDConv) for m in foreign.modules()) == 10
+    y_foreign, _ = eng(x)
+    torch.cuda.synchronize()
+    assert torch.equal(y_native, y_foreign)
+
+
+def test_engine_add_row_sums_all_inputs_through_the_library():
+    from experiment_yolo_b200 import engine
+    g = torch.Generator(device=DEV).manual_seed(3)
+    wide = torch.randn((2, 12, 20, 64), device=DEV, generator=g).bfloat16()
+    xs = [torch.randn((2, 12, 20, 32), device=DEV, generator=g).bfloat16(), wide[..., 16:48],
+          torch.randn((2, 12, 20, 32), device=DEV, generator=g).bfloat16()]
+    for n in (2, 3):
+        y = engine.add_nhwc(xs[:n])
+        want = torch.stack([t.float() for t in xs[:n]]).sum(0).bfloat16()
+        assert torch.equal(y, want)
+    five = xs + xs[:2]
+    y = engine.add_nhwc(five)
+    assert float((y.float() - torch.stack([t.float() for t in five]).sum(0)).abs().max()) <= 0.07

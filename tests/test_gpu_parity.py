@@ -425,6 +425,95 @@ def test_module_train_bf16(name):
     assert _rel(mod.p_conv.weight.grad.float().cpu().numpy(), g["p_conv.weight"]) <= 5e-2
 
 
+# ------------------------------------------------------------------------------------------------- float16 boundary ----
+def _fp16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).half().float().numpy()
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if not c.endswith("_far")])
+def test_module_half_vs_fp32_reference_on_fp16_rounded_tensors(name):
+    """`model.half()` (get_FPS.py:59-61, engine/validator.py:113-115): fp16 parameters and activations.  Parity definition
+    as for bf16: the fp32 reference algorithm on fp16-rounded x / parameters; the module's result is that value rounded to
+    fp16 once, gradients come back in fp16."""
+    import copy
+    z, prm, m = _golden.load(name)
+    p = copy.deepcopy(prm)
+    for f_ in ("p_conv_weight", "p_conv_bias", "conv_weight", "bn_weight", "bn_bias", "running_mean", "running_var"):
+        setattr(p, f_, _fp16_round(getattr(p, f_)))
+    x = _fp16_round(z["x"])
+    mod = _module_from_golden(z, prm, m, torch.float16)
+    for training in (False, True):
+        f = oracle.forward(x, p, training=training, update_running=False)
+        g = oracle.backward(x, p, f, _fp16_round(z["grad_out"]), training=training)
+        mod.train(training)
+        mod.zero_grad()
+        xt = _t(x, torch.float16).requires_grad_(True)
+        y = mod(xt)
+        assert y.dtype == torch.float16 and tuple(y.shape) == tuple(f["out"].shape)
+        yn = y.float().detach().cpu().numpy()
+        assert np.abs(yn - f["out"]).max() <= 1e-3 * max(1.0, np.abs(f["out"]).max())      # one fp16 rounding (2^-11)
+        assert _rel(yn, f["out"]) <= 5e-4
+        if name.endswith("_zero"):
+            continue
+        y.backward(_t(z["grad_out"], torch.float16))
+        assert xt.grad.dtype == torch.float16 and mod.p_conv.weight.grad.dtype == torch.float16
+        assert _rel(xt.grad.float().cpu().numpy(), g["x"]) <= 2e-3
+        assert _rel(mod.conv[0].weight.grad.float().cpu().numpy(), g["conv.0.weight"]) <= 2e-3
+        assert _rel(mod.p_conv.weight.grad.float().cpu().numpy(), g["p_conv.weight"]) <= 4e-3
+
+
+def test_module_under_fp16_autocast_like_the_reference_trainer():
+    """engine/trainer.py:800: the forward runs under torch.cuda.amp.autocast(fp16) with fp32 parameters.  Row 0 of the YAML
+    sees the fp32 image, row 3 the fp16 output of an autocast conv; both must run, return fp16 (what the reference's own
+    convs return under autocast) and give scaled gradients in fp32 to the fp32 parameters."""
+    torch.manual_seed(5)
+    first = E.LDConv(3, 16, 3, 2).to(DEV)
+    mid = torch.nn.Conv2d(16, 32, 3, padding=1).to(DEV)
+    third = E.LDConv(32, 64, 3, 2).to(DEV)
+    with torch.no_grad():
+        first.p_conv.weight.normal_(0, 0.05)
+        third.p_conv.weight.normal_(0, 0.05)
+    x = torch.rand(2, 3, 64, 64, device=DEV)
+    with torch.autocast("cuda", dtype=torch.float16):
+        a = first(x)
+        b = mid(a)
+        c = third(b)
+        loss = c.float().square().mean() * 1024.0      # GradScaler-style scaling
+    assert a.dtype == torch.float16 and b.dtype == torch.float16 and c.dtype == torch.float16
+    loss.backward()
+    for mod in (first, third):
+        for n_, p_ in mod.named_parameters():
+            assert p_.grad is not None and p_.grad.dtype == torch.float32 and bool(torch.isfinite(p_.grad).all()), n_
+    # numbers: the fp32 oracle on the same fp32 tensors, rounded to fp16
+    rnd = lambda t: t.detach().float().cpu().numpy()
+    prm = oracle.LDConvParams(rnd(first.p_conv.weight), rnd(first.p_conv.bias), rnd(first.conv[0].weight), rnd(first.conv[1].weight),
+                              rnd(first.conv[1].bias), np.zeros(16, np.float32), np.ones(16, np.float32), 3, 2,
+                              first.conv[1].eps, first.conv[1].momentum)
+    f = oracle.forward(rnd(x), prm, training=True, update_running=False)
+    assert _rel(rnd(a), f["out"]) <= 5e-4
+
+
+def test_prepared_cache_survives_inference_mode_then_training():
+    """a cache built under torch.inference_mode() holds inference tensors; the next grad-mode forward must
+    rebuild it instead of handing them to save_for_backward."""
+    mod = E.LDConv(16, 32, 3, 2).to(DEV)
+    x = torch.randn(2, 16, 24, 24, device=DEV)
+    mod.eval()
+    with torch.inference_mode():
+        y0 = mod(x)
+    mod.train()
+    y1 = mod(x.clone().requires_grad_(True))
+    y1.sum().backward()
+    assert mod.conv[0].weight.grad is not None
+    with torch.no_grad():
+        mod.p_conv.weight.data.add_(0.25)       # bypasses the version counter ...
+    mod.invalidate()                            # ... so the documented hook is needed
+    mod.eval()
+    with torch.no_grad():
+        y2 = mod(x)
+    assert not torch.equal(y2, y0)
+
+
 # ------------------------------------------------------------------------------------------- one-kernel inference ----
 @pytest.mark.parametrize("C,O,N,s,H,W,B,sigma", [
     (16, 32, 3, 2, 64, 80, 2, 0.05), (16, 32, 3, 2, 37, 53, 2, 0.3), (32, 64, 3, 2, 40, 40, 2, 0.05), (64, 128, 3, 2, 24, 40, 2, 0.05),

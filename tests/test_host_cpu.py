@@ -169,3 +169,69 @@ def test_engine_pixel_packing_rule_and_block_diagonal_weights():
     packed = (x.reshape(2, 64) @ wp.float().t()) * sc + sh                                          # (2 rows, 4 x 32)
     # (the CPU matmul blocks K = 64 and K = 16 differently, so this host-side statement is equal up to fp32 rounding)
     assert torch.allclose(packed.reshape(8, 32), plain, rtol=0, atol=1e-5)
+
+
+_REAL_INSTALL_SCRIPT = r'''
+import json, sys, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, {root!r})
+import torch
+from oracle.gen_model_golden import load_reference_tasks, REF_YAML
+T = load_reference_tasks()                                  # the unmodified reference, third-party roots stubbed
+import experiment_yolo_b200 as E
+from experiment_yolo_b200 import ldconv
+ref_cls = T.LDConv
+torch.manual_seed(0)
+ref_model, _ = T.parse_model(T.yaml_model_load(REF_YAML) | {{"nc": 6}}, ch=3, verbose=False)
+patched = E.install()
+torch.manual_seed(0)
+new_model, save = T.parse_model(T.yaml_model_load(REF_YAML) | {{"nc": 6}}, ch=3, verbose=False)
+rows = [type(m).__module__ + "." + type(m).__name__ for m in new_model if type(m).__name__ == "LDConv"]
+ref_sd, new_sd = ref_model.state_dict(), new_model.state_dict()
+same_keys = list(ref_sd) == list(new_sd)
+same_vals = same_keys and all(torch.equal(ref_sd[k], new_sd[k]) for k in ref_sd)
+probe = ""
+try:
+    new_model[0](torch.zeros(2, 3, 64, 64))
+except RuntimeError as e:
+    probe = str(e)
+from experiment_yolo_b200 import engine
+det = T.DetectionModel.__new__(T.DetectionModel)           # the executor's row recognition on the REAL reference modules
+torch.nn.Module.__init__(det)
+det.model = ref_model
+kinds = engine.FusedDealYolo.recognise(det)
+import ultralytics.nn.modules.block as RB
+bott = RB.Bottleneck_LDConv(16, 16)                        # block.py:628-629 picks the rebound name up too
+print(json.dumps({{"patched": patched, "rows": rows, "same_keys": same_keys, "same_vals": same_vals, "probe": probe,
+                  "params": sum(p.numel() for p in new_model.parameters()),
+                  "ref_is_other_class": ref_cls is not E.LDConv, "kinds": kinds,
+                  "bottleneck": [type(bott.cv1).__module__, type(bott.cv2).__module__]}}))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ultralytics"), reason="the reference tree only exists in the authoring container")
+def test_install_against_the_real_reference_parse_model(tmp_path):
+    """VERDICT r1 item 3: `install()` on the REAL `ultralytics.nn.tasks` (stub importer of SURVEY.md App. D for the absent
+    third-party roots), in a subprocess so the reference import cannot leak into the other tests: `parse_model`
+    (nn/tasks.py:813-864) builds all ten LDConv rows of yolov8-LD-P2.yaml with this class, the state_dict equals the
+    reference-built model's under the same seed (keys, order, values), and a CPU tensor raises the 'CUDA tensor' error the
+    stride probe retries on (nn/tasks.py:317-321)."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, YOLO_CONFIG_DIR=str(tmp_path), PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-c", _REAL_INSTALL_SCRIPT.format(root=root)], capture_output=True, text=True, env=env,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert sorted(out["patched"]) == sorted(ldconv._REF_MODULES)
+    assert out["ref_is_other_class"]
+    assert out["rows"] == ["experiment_yolo_b200.ldconv.LDConv"] * 10
+    assert out["same_keys"] and out["same_vals"]
+    assert out["params"] == 918304                            # SURVEY.md Appendix D
+    assert "CUDA tensor" in out["probe"]
+    assert out["bottleneck"] == ["experiment_yolo_b200.ldconv"] * 2
+    # engine.FusedDealYolo recognises every row of the reference-built graph (yolov8-LD-P2.yaml:14-52)
+    assert out["kinds"] == ["ldconv", "ldconv", "c2f", "ldconv", "c2f", "ldconv", "c2f", "sppf", "ldconv", "up", "ldconv", "cat",
+                            "c2f", "ldconv", "up", "ldconv", "cat", "c2f", "ldconv", "cat", "c2f", "ldconv", "cat", "c2f",
+                            "scalseq", "add", "detect"]
