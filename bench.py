@@ -1,15 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- DEAL-YOLO-LD 640x640 images/s on B200 (BASELINE.json metric), with the LDConv roofline beside it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A step = one full forward of DEAL-YOLO-LD (cfg/deal-yolo-ld-p2.yaml = the reference's yolov8-LD-P2.yaml, 918,304
 parameters, random-init seeded weights) over one synthetic batch of 64 bf16 640x640 images per GPU, inference mode,
 channels_last; the batch is sharded over ranks with no collective (every LDConv sample depends on its own image only).
   value     images/s with the batch already resident in HBM (CUDA-graph replay of the forward), max over ranks
-  e2e       images/s through the public call `engine.FusedDealYolo(model)(images)` with HOST buffers: every step copies its uint8 batch from
-            pinned host memory, normalises on the device, runs the forward and reads the detections back to the host
+  e2e       images/s through the public call `engine.PipelinedPredictor.submit()/result()` with HOST buffers: every step copies its
+            uint8 batch from pinned host memory, normalises on the device, runs the forward and reads the result back to the host
   roofline  the LDConv gather+GEMM kernel at its largest launch of the step (and `roofline_gather`: the stand-alone gather
             kernel): algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the eager CPU port of the reference path (oracle/ldconv_torch_port.py inside the same
@@ -143,6 +143,77 @@ def cpu_port_images_per_s(batch: int, iters: int, warmup: int = 1):
     return batch / min(times), batch / (sum(times) / len(times)), sum(times) / len(times), cores
 
 
+def gpu_eager_leg(dtype_name: str, batch: int, iters: int, local: int):
+    """one dtype of the GPU eager baseline, in its OWN process (see gpu_eager_images_per_s); prints one JSON object"""
+    import torch
+    from experiment_yolo_b200 import dealyolo
+    from oracle.ldconv_torch_port import LDConvTorchPort
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[dtype_name]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    model = dealyolo.DealYolo(nc=NC, ldconv_cls=LDConvTorchPort)
+    model.load_state_dict(dealyolo.seeded_state(model, 0))
+    model = dealyolo.channels_last_(model.to(dev).to(dtype).eval())
+    x = torch.rand((batch, 3, IMG, IMG), device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
+    with torch.inference_mode():
+        for _ in range(2):
+            model(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            model(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    _emit({"value": round(batch / (ms / 1e3), 1), "ms_per_step": round(ms, 2)})
+    return 0
+
+
+def gpu_eager_images_per_s(local: int, batch: int, iters: int = 3):
+    """SURVEY.md 8d's second, fairer baseline: the eager reference algorithm ON THE GPU -- the same graph with the eager
+    port of the reference LDConv (its ATen op sequence, host-built p_0 and int64 gathers included), cuDNN convs around it,
+    get_FPS.py:63-88 protocol (warm-up, timed loop, synchronize) under inference_mode, in fp32 and in the reference's own
+    low-precision style (coordinates computed in the low precision too; timing only, its numbers are not used).  Each dtype
+    runs in a subprocess: the low-precision coordinate arithmetic of the reference can produce an out-of-range gather index
+    (a device-side assert, which would poison this process's CUDA context)."""
+    out = {}
+    for name in ("fp32", "bf16", "fp16"):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--eager-leg", name, "--eager-batch", str(batch),
+                                "--eager-iters", str(iters), "--eager-device", str(local)], capture_output=True, text=True, timeout=240)
+            if r.returncode == 0 and r.stdout.strip():
+                out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+            else:
+                err = [l for l in r.stderr.splitlines() if "Error" in l or "assert" in l.lower()]
+                out[name] = {"error": (err[-1] if err else f"exit code {r.returncode}")[:160]}
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+    out.update({"unit": "images/s", "batch": batch, "iters": iters,
+                "what": "eager port of the reference LDConv + torch/cuDNN graph on this GPU, inference_mode, channels_last"})
+    return out
+
+
+def lib_sha16() -> str:
+    import hashlib
+    from experiment_yolo_b200 import _lib
+    with open(_lib.LIB_PATH, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
+def committed_traffic():
+    """ncu DRAM byte counts captured on a build of the library (profiles/r2_ncu_traffic.json, written by
+    scripts/ncu_traffic.py from `ncu --set full` reports); only used when its lib_sha16 equals the library being timed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+    except Exception:
+        return {}, "no profiles/r2_ncu_traffic.json"
+    sha = lib_sha16()
+    if t.get("lib_sha16") != sha:
+        return {}, f"profiles/r2_ncu_traffic.json was captured on library {t.get('lib_sha16')}, this run times {sha}: not reported"
+    return t, f"ncu --set full capture of this exact library build ({sha}), profiles/r2_ncu_traffic.json"
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -152,7 +223,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "images_per_sec", "value": round(mean, 3), "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": dict(workload_config(args.gpus), timed_batch=CPU_SAMPLE_BATCH, engine="eager CPU port",
+                           note=f"each step times a bounded sample of the workload: batch {CPU_SAMPLE_BATCH} of the "
+                                f"{PER_GPU_BATCH}-image batch (the CPU port's images/s at batch 64 and batch 8 agree, DESIGN.md 6)"),
             "cpu_baseline": {"value": round(mean, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(mean, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -160,11 +233,23 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(n_gpus: int, engine: str = "fused"):
+def per_gpu_batch(n_gpus: int, scaling: str = "weak") -> int:
+    """weak: 64 images per GPU (global 64 N); strong: SURVEY.md 8d config 3, one 64-image batch split 64/32/16/8"""
+    return PER_GPU_BATCH if scaling == "weak" else max(1, PER_GPU_BATCH // n_gpus)
+
+
+def n_input_buffers(batch: int) -> int:
+    return max(2, -(-300_000_000 // (batch * 3 * IMG * IMG * 2)))
+
+
+def workload_config(n_gpus: int, engine: str = "fused", scaling: str = "weak"):
+    pgb = per_gpu_batch(n_gpus, scaling)
     return {"engine": engine, "workload": "DEAL-YOLO-LD (yolov8-LD-P2 graph, 10 LDConv + SSFF, nc=6) full forward, 640x640, inference",
-            "global_batch": PER_GPU_BATCH * n_gpus, "per_gpu_batch": PER_GPU_BATCH, "imgsz": IMG,
+            "global_batch": pgb * n_gpus, "per_gpu_batch": pgb, "imgsz": IMG,
             "layout": "channels_last", "parallelism": f"batch-sharded x{n_gpus}, no collective",
-            "l2_policy": "inputs_exceed_l2 (157 MB bf16 batch, two alternating input buffers; activations of one step are GBs)",
+            "l2_policy": f"inputs_exceed_l2 ({pgb * 3 * IMG * IMG * 2 / 1e6:.0f} MB bf16 batch, {n_input_buffers(pgb)} rotating input buffers "
+                         f"= {n_input_buffers(pgb) * pgb * 3 * IMG * IMG * 2 / 1e6:.0f} MB > 126 MB L2; the activations of one step are "
+                         f"{7.9 * pgb / 64:.1f} GB)",
             "weights": "seeded random init (dealyolo.seeded_state(0)), p_conv.weight ~ N(0,0.05)"}
 
 
@@ -188,10 +273,12 @@ def ldconv_roofline(model, x, peaks, iters: int):
     for h in hooks:
         h.remove()
     st = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, device=x.device, dtype=torch.uint8)      # > the 126 MB L2
 
     def timed(fn):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters + 1)]
         for a, b in ev:
+            flush.zero_()            # L2 flush between the timed launches: every launch reads its input from HBM
             a.record(st)
             fn()
             b.record(st)
@@ -236,11 +323,7 @@ def ldconv_roofline(model, x, peaks, iters: int):
         per_layer.append(row)
     peak = peaks.get("hbm_gbs", 6650.0)
     src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 (of fallback)"
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-    except Exception:
-        pass
+    traffic, traffic_note = committed_traffic()
     big = max((r for r in per_layer if "gg_us" in r), key=lambda r: r["gg_MB"], default=None)
     roof = None
     if big is not None:
@@ -248,8 +331,10 @@ def ldconv_roofline(model, x, peaks, iters: int):
         roof = {"bound": "hbm", "kernel": f"ldconv_gg2_kernel (LDConv gather + GEMM + BN + SiLU, layer {big['layer']}: the largest "
                 "LDConv launch of the step)", "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "frac_of_8TBs_nominal": round(ach / 8000.0, 4),
-                "traffic": traffic.get("ldconv_gg_kernel_layer1_bytes"), "algorithmic_bytes_per_launch": round(big["gg_MB"] * 1e6),
-                "us_per_launch": big["gg_us"], "timing": "CUDA events on the launching stream, median of %d" % iters,
+                "traffic": traffic.get("roofline_kernel_bytes"), "traffic_source": traffic_note,
+                "algorithmic_bytes_per_launch": round(big["gg_MB"] * 1e6),
+                "us_per_launch": big["gg_us"], "timing": "CUDA events on the launching stream, median of %d, L2 flushed (256 MB "
+                "memset) before every timed launch" % iters,
                 "all_gg_launches": {"GBps": round(tot["gg"][0] / max(tot["gg"][1], 1e-9) / 1e6, 1),
                                     "us_per_step": round(tot["gg"][1] * 1e3, 1)},
                 "per_layer": per_layer}
@@ -257,7 +342,7 @@ def ldconv_roofline(model, x, peaks, iters: int):
     roof_gather = {"bound": "hbm", "kernel": "gather_fwd_tiled_kernel (stand-alone LDConv resampling, training path; the 9 launches "
                    "with C >= 16 of one step)", "achieved": round(g_ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
                    "frac": round(g_ach / peak, 4), "frac_of_8TBs_nominal": round(g_ach / 8000.0, 4),
-                   "traffic": traffic.get("gather_fwd_tiled_kernel_layer1_bytes"),
+                   "traffic": traffic.get("gather_kernel_bytes"),
                    "us_per_step": round(tot["gather"][1] * 1e3, 1)}
     return roof, roof_gather
 
@@ -299,10 +384,11 @@ def run_gpu_arm(args):
         engine._Detect.parallel_branches = False
     run = engine.FusedDealYolo(model) if args.engine == "fused" else model
 
-    B = PER_GPU_BATCH
+    B = per_gpu_batch(world, args.scaling)
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    n_in = n_input_buffers(B)      # the rotating set of input batches exceeds the 126 MB L2 at every per-GPU batch
     xs = [torch.rand((B, 3, IMG, IMG), device=dev, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
-          for _ in range(2)]
+          for _ in range(n_in)]
 
     # ---- device-resident throughput: CUDA-graph replay of the whole forward ----------------------------------------------
     static_x = xs[0].clone()
@@ -321,7 +407,7 @@ def run_gpu_arm(args):
         launches_per_step = sum(_lib.call_counts.values())
 
         def step(i):
-            static_x.copy_(xs[i & 1], non_blocking=True)
+            static_x.copy_(xs[i % n_in], non_blocking=True)
             graph.replay()
 
         for i in range(max(3, args.warmup)):
@@ -395,16 +481,27 @@ def run_gpu_arm(args):
     if rank == 0:
         roof, roof_gather = ldconv_roofline(model, xs[0], peaks, iters=7)
         cpu_best, cpu_mean, cpu_sec, cores = cpu_port_images_per_s(CPU_SAMPLE_BATCH, 3, 1) if world == 1 else (None,) * 4
+        eager = gpu_eager_images_per_s(local, B) if world == 1 else None
+        traffic, traffic_note = committed_traffic()
+        step_bytes = traffic.get("step_dram_bytes")
+        peak = peaks.get("hbm_gbs", 6650.0)
         line = {"metric": "images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(world, args.engine),
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world, args.engine, args.scaling), "lib_sha16": lib_sha16(),
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "api": "engine.PipelinedPredictor.submit()/result()" if args.engine == "fused"
                         else "DealYolo.forward", "input": "uint8 NCHW batch in pinned host memory, normalised on device",
                         "result": "decoded detections (B,10,33600) bf16 copied to pinned host memory"},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "clocks": clk.summary(), "roofline": roof, "roofline_gather": roof_gather}
+        if step_bytes and B == PER_GPU_BATCH:
+            # whole-step roofline: DRAM bytes of one step (sum over the ncu launch list of this library build) / step time
+            line["step_roofline"] = {"bound": "hbm", "dram_bytes_per_step": step_bytes, "achieved": round(step_bytes / ms_per_step / 1e6, 1),
+                                     "peak": peak, "unit": "GB/s", "frac": round(step_bytes / ms_per_step / 1e6 / peak, 4),
+                                     "source": traffic_note}
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         if cpu_mean is not None:
             line["cpu_baseline"] = {"value": round(cpu_mean, 3), "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"batch {CPU_SAMPLE_BATCH} x 3 forwards of the same graph in fp32 (eager CPU port "
@@ -436,8 +533,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default="fused", choices=["fused", "eager"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 64 images per GPU; strong: one 64-image batch split over the ranks (SURVEY.md 8d config 3)")
     ap.add_argument("--micro-batch", type=int, default=0, help="images per pass of the fused executor (0 = its default)")
+    ap.add_argument("--eager-leg", default=None, help=argparse.SUPPRESS)      # internal: one dtype of gpu_eager_baseline
+    ap.add_argument("--eager-batch", type=int, default=PER_GPU_BATCH, help=argparse.SUPPRESS)
+    ap.add_argument("--eager-iters", type=int, default=3, help=argparse.SUPPRESS)
+    ap.add_argument("--eager-device", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.eager_leg:
+        return gpu_eager_leg(args.eager_leg, args.eager_batch, args.eager_iters, args.eager_device)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

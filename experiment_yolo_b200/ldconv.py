@@ -364,7 +364,7 @@ class LDConv(nn.Module):
         #                                                        reference's own convs return under fp16 autocast)
         out_dtype = None
         if x.is_cuda:
-            ac = torch.get_autocast_gpu_dtype() if torch.is_autocast_enabled() else None
+            ac = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
             if x.dtype == torch.float32 and ac == torch.bfloat16:
                 x = x.to(torch.bfloat16)
             elif x.dtype in _COMPUTE_AS or (x.dtype == torch.float32 and ac in _COMPUTE_AS):

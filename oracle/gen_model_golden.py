@@ -89,6 +89,19 @@ def main():
     print(f"params {n_params}  out {tuple(y_ref.shape)}  |ref - harness(port)| max = {diff:.3e}")
     assert diff == 0.0, "the benchmark graph + eager port must reproduce the reference bit for bit on the CPU"
 
+    # BASELINE config 1 at its real size: torch.rand(1,3,640,640, seed 0), fp32, eval (SURVEY.md 8d).  The input is regenerated
+    # from the seed by the tests (a checksum and a strided sample are stored to catch a generator change); only the decoded
+    # head output and the three LDConv-heavy feature statistics are stored.
+    g0 = torch.Generator().manual_seed(0)
+    x640 = torch.rand(1, 3, 640, 640, generator=g0)
+    with torch.no_grad():
+        y640, f640 = ref(x640)
+        y640_mine, _ = mine(x640)
+    assert float((y640 - y640_mine).abs().max()) == 0.0
+    np.savez_compressed(OUT640, y=y640.numpy(), x_sum=np.float64(x640.double().sum().item()),
+                        x_probe=x640.reshape(-1)[::4099].numpy(), feat_absmean=np.array([float(f.abs().mean()) for f in f640]))
+    print("wrote", OUT640, os.path.getsize(OUT640) // 1024, "KiB")
+
     # train-mode outputs (raw head maps, batch statistics) for the training-step harness
     ref.train(); mine.train()
     x2 = torch.rand(2, 3, 64, 64, generator=g)
@@ -110,19 +123,6 @@ def main():
             times[name] = best
     print(f"CPU forward 1x3x640x640, {torch.get_num_threads()} threads: reference {times['reference']*1e3:.1f} ms, "
           f"port {times['port']*1e3:.1f} ms")
-
-    # BASELINE config 1 at its real size: torch.rand(1,3,640,640, seed 0), fp32, eval (SURVEY.md 8d).  The input is regenerated
-    # from the seed by the tests (a checksum and a strided sample are stored to catch a generator change); only the decoded
-    # head output and the three LDConv-heavy feature statistics are stored.
-    g0 = torch.Generator().manual_seed(0)
-    x640 = torch.rand(1, 3, 640, 640, generator=g0)
-    with torch.no_grad():
-        y640, f640 = ref(x640)
-        y640_mine, _ = mine(x640)
-    assert float((y640 - y640_mine).abs().max()) == 0.0
-    np.savez_compressed(OUT640, y=y640.numpy(), x_sum=np.float64(x640.double().sum().item()),
-                        x_probe=x640.reshape(-1)[::4099].numpy(), feat_absmean=np.array([float(f.abs().mean()) for f in f640]))
-    print("wrote", OUT640, os.path.getsize(OUT640) // 1024, "KiB")
 
     np.savez_compressed(OUT, x=x.numpy(), y=y_ref.numpy(), feat0=feats_ref[0].numpy(), n_params=np.int64(n_params),
                         strides=np.array([float(v) for v in ref.stride]),

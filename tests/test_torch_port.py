@@ -75,3 +75,21 @@ def test_strides_agree_with_a_probe_forward():
     with torch.no_grad():
         feats = model(torch.zeros(2, 3, 64, 64))
     assert [64 / f.shape[-2] for f in feats] == [4.0, 8.0, 16.0]
+
+
+def test_port_graph_reproduces_the_640_fixture_of_the_reference_model():
+    """BASELINE config 1 at its real size: the benchmark graph + eager port on the CPU equals the fixture minted from the
+    reference DetectionModel (oracle/gen_model_golden.py; bit for bit there, with the generator's thread count -- the CPU
+    conv kernels partition by thread count, so here: boxes to 1e-3 of 640 pixels, scores to 1e-6) -- the fixture the GPU tests of
+    tests/test_gpu_fullsize.py compare with, and the model `--impl reference` / `cpu_baseline` time."""
+    import os
+    z = np.load(os.path.join(_golden.GOLDEN_DIR, "model_deal_yolo_ld_640.npz"))
+    x = torch.rand(1, 3, 640, 640, generator=torch.Generator().manual_seed(0))
+    assert np.array_equal(x.reshape(-1)[::4099].numpy(), z["x_probe"])
+    model = dealyolo.DealYolo(nc=6, ldconv_cls=LDConvTorchPort)
+    model.load_state_dict(dealyolo.seeded_state(model, seed=0), strict=True)
+    model.eval()
+    with torch.no_grad():
+        y, _ = model(x)
+    d = np.abs(y.numpy() - z["y"])
+    assert d[:, :4].max() <= 1e-3 and d[:, 4:].max() <= 1e-6
