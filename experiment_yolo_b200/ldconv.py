@@ -300,6 +300,9 @@ class LDConv(nn.Module):
     fused_tcgen05 = False
     # inference: gather + GEMM + BN + SiLU as one persistent kernel after the tensor-core offset conv (ldconv_gather_gemm_fwd)
     use_gather_gemm = True
+    # inference: the whole forward in one kernel, offset conv on the tensor cores over the gather's own staged tile
+    # (ldconv_onepass_fwd; the yolov8-LD-P2 shapes).  A/B switch for the tests, which compare the two paths bit for bit
+    use_onepass = True
 
     def __init__(self, inc, outc, num_param, stride=1, bias=None):
         super().__init__()
@@ -423,10 +426,16 @@ def infer_nhwc(mod: "LDConv", x: torch.Tensor, out: Optional[torch.Tensor] = Non
                    "ldconv_fused_fwd")
         return out
     M, K = B * h * w, N * C
-    off = offset_conv_nhwc(x, pr, N, s)
     if out is None:
         out = torch.empty((B, h, w, O), device=x.device, dtype=x.dtype)
     ldo = out.stride(2)
+    w_conv = pr.w_off_tc if s == 1 else pr.w_off_s2d
+    if mod.use_onepass and w_conv is not None and L.ldconv_onepass_supported(B, C, H, W, N, s, O, ldo, dt):
+        # one kernel, x read once: offsets never reach HBM
+        _lib.check(L.ldconv_onepass_fwd(_ptr(x), _ptr(w_conv), _ptr(pr.b_off), _ptr(pr.pn), _ptr(pr.wt), _ptr(scale), _ptr(shift),
+                                        _ptr(out), ldo, None, B, C, H, W, N, s, O, _lib.ACT_SILU, dt, st), "ldconv_onepass_fwd")
+        return out
+    off = offset_conv_nhwc(x, pr, N, s)
     if mod.use_gather_gemm and L.ldconv_gather_gemm_supported(B, C, H, W, N, s, O, ldo, dt):
         # gather + GEMM + BN + SiLU in one persistent kernel: the (M, N*C) operand never reaches HBM
         _lib.check(L.ldconv_gather_gemm_fwd(_ptr(x), _ptr(off), _ptr(pr.pn), _ptr(pr.wt), _ptr(scale), _ptr(shift), _ptr(out), ldo,

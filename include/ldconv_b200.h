@@ -176,6 +176,20 @@ int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, cons
                      const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W,
                      int N, int s, int O, int act, int dtype, void* stream);
 
+/* The WHOLE eval-mode forward of conv.py:366-410 in one persistent kernel, x read once (bf16): the 3x3 offset conv (:356,:368)
+ * runs as a zero-copy tcgen05 implicit GEMM on the same TMA-staged tile the gather samples from (stride 2: on the
+ * space-to-depth view), its 2N offsets go TMEM -> registers -> sampling grid, never to HBM; then as ldconv_gather_gemm_fwd.
+ *   x (B,H,W,C) bf16 dense NHWC; w_offconv bf16: stride 1 (2N, 9C) with k = (ky*3+kx)*C + c, stride 2 (2N, 16C) in the
+ *   space-to-depth order of ldconv_offset_conv_s2d_fwd; b_off (2N) fp32 or NULL; p_n (2N) int32; wt (O, N*C) bf16;
+ *   scale / shift (O) fp32; out (B,h,w,O) bf16 with pixel stride ldo; off_out (B,h,w,2N) fp32 or NULL (debug / tests: the
+ *   offsets the kernel used, bit-identical to ldconv_offset_conv_{tc,s2d}_fwd).
+ * Covered: the yolov8-LD-P2 shapes (num_param 1 / stride 1 / C in {32,64,128}; num_param 3 / stride 2 / C in {16,32,64},
+ * even H and W), O % 16 == 0, O <= 256; ldconv_onepass_supported returns 1 for them, else use the entry points below. */
+int ldconv_onepass_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype);
+int ldconv_onepass_fwd(const void* x, const void* w_offconv, const float* b_off, const int32_t* p_n, const void* wt,
+                       const float* scale, const float* shift, void* out, int ldo, float* off_out, int B, int C, int H, int W,
+                       int N, int s, int O, int act, int dtype, void* stream);
+
 /* Everything AFTER the offset conv in one persistent kernel (conv.py:369-408, eval mode, bf16): sampling grid, clamps,
  * bilinear gather (TMA-staged tile + halo, L2 beyond it), the rearrange, the (N,1) conv as a tcgen05 GEMM whose operand tile
  * is written by the gather warps straight into shared memory (never to HBM), folded BatchNorm + activation.

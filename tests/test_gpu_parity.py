@@ -812,6 +812,74 @@ def test_gather_gemm_kernel_matches_gather_then_gemm(C, O, N, s, H, W, B, sigma,
     assert _rel(a, (z * torch.sigmoid(z)).cpu().numpy()) <= 6e-3
 
 
+# ---------------------------------------------------------------------------------------------- one-pass kernel ----
+@pytest.mark.parametrize("C,O,N,s,H,W,B,sigma,bias_sigma,pad", [
+    (32, 32, 1, 1, 48, 48, 2, 0.05, 0.0, 0), (32, 32, 1, 1, 33, 21, 1, 0.3, 2.0, 0), (64, 64, 1, 1, 40, 24, 2, 0.05, 0.0, 0),
+    (64, 32, 1, 1, 17, 19, 2, 0.1, 1.0, 32), (128, 64, 1, 1, 20, 20, 2, 0.05, 0.0, 0), (128, 64, 1, 1, 40, 40, 3, 0.02, 3.0, 64),
+    (16, 32, 3, 2, 64, 80, 2, 0.05, 0.0, 0), (16, 32, 3, 2, 38, 54, 3, 0.3, 2.0, 0), (32, 64, 3, 2, 40, 40, 2, 0.05, 0.0, 64),
+    (32, 32, 3, 2, 160, 160, 9, 0.05, 1.0, 0), (64, 128, 3, 2, 24, 40, 2, 0.05, 0.0, 0), (64, 64, 3, 2, 80, 80, 3, 0.1, 4.0, 0),
+    (16, 32, 3, 2, 2, 2, 1, 0.05, 0.0, 0), (32, 32, 1, 1, 2, 3, 2, 0.05, 0.5, 0), (16, 16, 3, 2, 320, 320, 4, 0.05, 0.5, 0)])
+def test_onepass_kernel_equals_offset_conv_plus_gather_gemm_bit_for_bit(C, O, N, s, H, W, B, sigma, bias_sigma, pad):
+    """ldconv_onepass_fwd (offset conv on the tensor cores over the gather's own staged tile, offsets TMEM -> registers)
+    against ldconv_offset_conv_{tc,s2d}_fwd + ldconv_gather_gemm_fwd: same MMA order and the same device functions, so
+    the OFFSETS it used (off_out) and the OUTPUT are bit-identical; and against the fp32 oracle on bf16-rounded tensors
+    (rel-L2 <= 1e-2).  Cases: every yolov8-LD-P2 shape family, partial tiles, far offsets (L2 path, clamp quirk), a channel
+    slice of a wider buffer, more tiles than CTAs."""
+    L = _lib.load()
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    M = B * h * w
+    ldo = O + pad
+    assert L.ldconv_onepass_supported(B, C, H, W, N, s, O, ldo, _lib.BF16) == 1
+    torch.manual_seed(C * 13 + O + N + H)
+    mod = E.LDConv(C, O, N, s)
+    with torch.no_grad():
+        mod.p_conv.weight.normal_(0, sigma)
+        mod.p_conv.bias.normal_(0, bias_sigma) if bias_sigma > 0 else mod.p_conv.bias.zero_()
+        mod.conv[1].running_mean.normal_(0, 0.3)
+        mod.conv[1].running_var.uniform_(0.5, 1.5)
+        mod.conv[1].weight.uniform_(0.5, 1.5)
+        mod.conv[1].bias.normal_(0, 0.2)
+    mod.conv[1].eps = 1e-3
+    x = torch.randn(B, C, H, W)
+    rnd = lambda t: t.detach().bfloat16().float().numpy()
+    prm = oracle.LDConvParams(rnd(mod.p_conv.weight), rnd(mod.p_conv.bias), rnd(mod.conv[0].weight), rnd(mod.conv[1].weight),
+                              rnd(mod.conv[1].bias), rnd(mod.conv[1].running_mean), rnd(mod.conv[1].running_var), N, s, 1e-3, 0.1)
+    f = oracle.forward(rnd(x), prm, training=False)
+    dmod = mod.to(DEV).bfloat16().eval()
+    xh = x.to(DEV).bfloat16().permute(0, 2, 3, 1).contiguous()
+    pr = dmod._prepared(torch.bfloat16, False)
+    from experiment_yolo_b200.ldconv import _folded_bn, offset_conv_nhwc
+    scale, shift = _folded_bn(dmod.conv[1], xh.device)
+    # reference path: separate tensor-core offset conv, then the gather+GEMM kernel
+    off_ref = offset_conv_nhwc(xh, pr, N, s)
+    buf_ref = torch.full((M, ldo), 7.0, device=DEV, dtype=torch.bfloat16)
+    out_ref = buf_ref[:, pad:] if pad else buf_ref
+    _lib.check(L.ldconv_gather_gemm_fwd(_ptr(xh), _ptr(off_ref), _ptr(pr.pn), _ptr(pr.wt), _ptr(scale), _ptr(shift), _ptr(out_ref), ldo,
+                                        B, C, H, W, N, s, O, _lib.ACT_SILU, _lib.BF16, _stream()), "ldconv_gather_gemm_fwd")
+    # one-pass kernel
+    off_one = torch.full((B, h, w, 2 * N), float("nan"), device=DEV, dtype=torch.float32)
+    buf_one = torch.full((M, ldo), 7.0, device=DEV, dtype=torch.bfloat16)
+    out_one = buf_one[:, pad:] if pad else buf_one
+    w_conv = pr.w_off_tc if s == 1 else pr.w_off_s2d
+    _lib.check(L.ldconv_onepass_fwd(_ptr(xh), _ptr(w_conv), _ptr(pr.b_off), _ptr(pr.pn), _ptr(pr.wt), _ptr(scale), _ptr(shift),
+                                    _ptr(out_one), ldo, _ptr(off_one), B, C, H, W, N, s, O, _lib.ACT_SILU, _lib.BF16, _stream()),
+               "ldconv_onepass_fwd")
+    torch.cuda.synchronize()
+    assert torch.equal(off_one, off_ref), float((off_one - off_ref).abs().max())
+    assert torch.equal(buf_one, buf_ref)
+    if pad:
+        assert float((buf_one[:, :pad].float() - 7.0).abs().max()) == 0.0
+    y = out_one.float().reshape(B, h, w, O).permute(0, 3, 1, 2).cpu().numpy()
+    if sigma * (9 * C) ** 0.5 + bias_sigma < 6.0:      # far-offset cases sit on the p = H-1 discontinuity: bit-equality above covers them
+        assert _rel(y, f["out"]) <= 1e-2
+    # and the module's inference path takes this kernel
+    _lib.call_counts.clear()
+    with torch.no_grad():
+        ym = dmod(x.to(DEV).bfloat16().contiguous(memory_format=torch.channels_last))
+    assert "ldconv_onepass_fwd" in _lib.call_counts
+    assert torch.equal(ym.permute(0, 2, 3, 1).reshape(M, O), out_one)
+
+
 # ------------------------------------------------------------------------------------- larger seeded cases vs oracle ----
 @pytest.mark.parametrize("C,O,N,s,H,W,B", [(16, 32, 3, 2, 40, 40, 2), (64, 64, 1, 1, 20, 20, 2), (32, 32, 5, 1, 16, 24, 2),
                                            (128, 64, 1, 1, 10, 10, 2), (3, 16, 3, 2, 64, 64, 2), (64, 128, 3, 2, 20, 20, 2)])
