@@ -228,6 +228,21 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     }
                 }
             };
+            // L2 prefetch of a tile one step before its TMA: with a single input buffer the load can only be issued once the workers
+            // have consumed the previous tile, and its latency sits on the tile's critical path (TMA -> offset conv -> phase 1);
+            // measured: 693 -> 677 us over the nine yolov8-LD-P2 layers at batch 64
+            auto prefetch_x_tile = [&](int tile) {
+                const TC t = tile_coords(tile);
+#pragma unroll
+                for (int hf = 0; hf < S::HALVES; ++hf) {
+                    if constexpr (TS == 1)
+                        tma_prefetch_4d(&tmX, hf * 64, t.j0 - S::ORG, t.i0 - S::ORG, t.b);
+                    else {
+                        constexpr int per_sy = S::HALVES / 2;
+                        tma_prefetch_5d(&tmX, (hf % per_sy) * (S::PB / 2), hf / per_sy, t.j0 - 1, t.i0 - 1, t.b);
+                    }
+                }
+            };
             const uint32_t idesc_c = make_idesc_bf16(128, 16);
             const uint32_t idesc_m = make_idesc_bf16(128, g.ON);
             const uint64_t descA_hi = op_desc(0, (uint32_t)(S::TWs * S::PB), S::LAYOUT) & ~0x3fffull;
@@ -277,6 +292,7 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 if (!S::blk_zero(kb)) tma_load_2d(smem + g.ofs_bc + (size_t)S::slot(kb) * 2048, &tmWc, w_full, kb * 64, 0);
             for (int k = 0; k < g.XB; ++k)
                 if ((int)blockIdx.x + k * (int)gridDim.x < g.num_tiles) issue_x_tile(blockIdx.x + k * gridDim.x, k);
+            if ((int)blockIdx.x + g.XB * (int)gridDim.x < g.num_tiles) prefetch_x_tile(blockIdx.x + g.XB * gridDim.x);
             if ((int)blockIdx.x < g.num_tiles) {
                 mbar_wait_sleep(w_full, 0);
                 mbar_wait_sleep(&x_full[0], 0);
@@ -298,8 +314,10 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     }
                     main_mma(ab, tb);
                     if (tile + 2 * (int)gridDim.x < g.num_tiles) issue_x_tile(tile + 2 * gridDim.x, xb);
+                    if (tile + 3 * (int)gridDim.x < g.num_tiles) prefetch_x_tile(tile + 3 * gridDim.x);
                 } else {
                     if (more) issue_x_tile(tile + gridDim.x, 0);      // the only input buffer is free again: refill first (latency)
+                    if (tile + 2 * (int)gridDim.x < g.num_tiles) prefetch_x_tile(tile + 2 * gridDim.x);
                     main_mma(ab, tb);
                     if (more) {
                         mbar_wait_sleep(&x_full[0], (uint32_t)(it + 1) & 1u);

@@ -97,7 +97,7 @@ def _check_layer(C, O, N, s, H, W, B, sigma, bias_sigma=None):
         y = dmod(xd)
     torch.cuda.synchronize()
     used = set(_lib.call_counts)
-    assert used & {"ldconv_fused_fwd", "ldconv_gather_gemm_fwd", "ldconv_ldconv_fwd"}, used      # not the training fallback
+    assert used & {"ldconv_fused_fwd", "ldconv_gather_gemm_fwd", "ldconv_onepass_fwd"}, used      # not the training fallback
     y = y.float().cpu().numpy()
     assert y.shape == f["out"].shape
     rel = _rel(y, f["out"])
