@@ -24,6 +24,8 @@ the golden output of the reference DetectionModel.
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn as nn
 
@@ -584,16 +586,22 @@ class FusedDealYolo:
 class PipelinedPredictor:
     """The end-to-end inference call on HOST buffers: `submit(u8_batch_in_pinned_memory)` / `result()`.
 
-    Mirrors what the reference's predictor does per batch (upload uint8 images, normalise on the device, forward, read
-    detections back; engine/predictor.py:120-140,266-300) with the B200-side plumbing around the fused executor: the whole
-    forward (uint8 -> bf16 NHWC conversion included) is captured once per input slot in a CUDA graph, and two slots are
-    rotated so that the upload of batch i+1 and the download of batch i-1 overlap the compute of batch i on separate
-    streams.  Results come back in submission order."""
+    Mirrors what the reference's predictor does per batch (upload uint8 images, normalise on the device, forward,
+    non_max_suppression, read detections back; engine/predictor.py:120-140,266-300, utils/ops.py:292) with the B200-side
+    plumbing around the fused executor: the whole forward (uint8 -> bf16 NHWC conversion and, with `nms=`, the device-side
+    NMS included) is captured once per input slot in a CUDA graph, and the slots are rotated so that the upload of batch i+1
+    and the download of batch i-1 overlap the compute of batch i on separate streams.  Results come back in submission order.
 
-    def __init__(self, model, batch: int, imgsz: int, channels: int = 3, slots: int = 2):
+    nms=None: `result()` is the decoded head output (B, 4+nc, anchors) bf16 (43 MB per 64 images at 640x640).
+    nms=dict(conf_thres=..., iou_thres=..., agnostic=..., max_det=...): `result()` is (detections (B, max_det, 6) fp32 rows
+    (x1, y1, x2, y2, conf, cls), counts (B,) int32) -- 0.46 MB per 64 images; `detections()` slices them per image."""
+
+    def __init__(self, model, batch: int, imgsz: int, channels: int = 3, slots: int = 2, nms: Optional[dict] = None):
+        from . import nms as _nms
         self.exec = FusedDealYolo(model)
         dev = next(model.parameters()).device
         self.dev, self.slots = dev, slots
+        self.nms = dict(nms) if nms is not None else None
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.u8 = [torch.zeros((batch, channels, imgsz, imgsz), device=dev, dtype=torch.uint8) for _ in range(slots)]
         self.graphs, self.y_dev, self.y_host = [], [], []
@@ -602,23 +610,29 @@ class PipelinedPredictor:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.exec(self.u8[0])
+                y, _ = self.exec(self.u8[0])
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
+        ws = None
+        if self.nms is not None:
+            ws = _nms.nms_workspace(batch, y.shape[2], int(self.nms.get("max_nms", 30000)), dev)      # shared: graphs run in stream order
         for k in range(slots):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 y, _ = self.exec(self.u8[k])
+                if self.nms is not None:
+                    y = _nms.nms_padded(y, workspace=ws, **self.nms)
             self.graphs.append(g)
-            self.y_dev.append(y)
-            self.y_host.append(torch.empty(tuple(y.shape), dtype=y.dtype).pin_memory())
+            ys = y if isinstance(y, tuple) else (y,)
+            self.y_dev.append(ys)
+            self.y_host.append(tuple(torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in ys))
         self.ev_in = [torch.cuda.Event() for _ in range(slots)]
         self.ev_comp = [torch.cuda.Event() for _ in range(slots)]
         self.ev_out = [torch.cuda.Event() for _ in range(slots)]
         self.n_submitted = 0
         self.n_returned = 0
         self.h2d_bytes = self.u8[0].numel()
-        self.d2h_bytes = self.y_host[0].numel() * self.y_host[0].element_size()
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.y_host[0])
 
     def submit(self, host_u8: torch.Tensor):
         """host_u8: (B,C,H,W) uint8 in pinned host memory.  Asynchronous."""
@@ -638,22 +652,32 @@ class PipelinedPredictor:
         self.ev_comp[k].record(comp)
         self.s_out.wait_event(self.ev_comp[k])
         with torch.cuda.stream(self.s_out):
-            self.y_host[k].copy_(self.y_dev[k], non_blocking=True)
+            for h, d in zip(self.y_host[k], self.y_dev[k]):
+                h.copy_(d, non_blocking=True)
             self.ev_out[k].record(self.s_out)
         self.n_submitted += 1
 
-    def result(self) -> torch.Tensor:
-        """Blocks until the oldest outstanding batch's detections are in host memory and returns them (a pinned buffer that
-        is reused `slots` submissions later)."""
+    def result(self):
+        """Blocks until the oldest outstanding batch's result is in host memory and returns it (pinned buffers that are
+        reused `slots` submissions later): the decoded head output, or (detections, counts) with `nms=`."""
         assert self.n_returned < self.n_submitted, "no outstanding batch"
         k = self.n_returned % self.slots
         self.ev_out[k].synchronize()
         self.n_returned += 1
-        return self.y_host[k]
+        return self.y_host[k][0] if self.nms is None else self.y_host[k]
+
+    @staticmethod
+    def detections(result):
+        """(detections, counts) of `result()` -> list of (n_i, 6) tensors, the return value of the reference's
+        non_max_suppression (utils/ops.py:427)"""
+        det, cnt = result
+        cnt = cnt.tolist()
+        if any(c < 0 for c in cnt):
+            raise RuntimeError("nms: more candidates than max_nms in an image; raise conf_thres")
+        return [det[b, :c] for b, c in enumerate(cnt)]
 
     def drain_to(self, stream=None):
         """make `stream` (default: current) wait for every outstanding download (for device-side timing)"""
         stream = stream or torch.cuda.current_stream(self.dev)
         for k in range(min(self.slots, self.n_submitted)):
             stream.wait_event(self.ev_out[k])
-

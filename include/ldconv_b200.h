@@ -242,6 +242,17 @@ int ldconv_conv3x3_bn_act_fwd(const void* x, int ldx, const void* wt, const floa
 int ldconv_detect_decode(const void* box, const void* cls, void* y, int B, int H, int W, int nc, int reg_max, float stride,
                          int anchor_offset, int total_anchors, int dtype, void* stream);
 
+/* Post-processing of the predictor / validator on the device (utils/ops.py:292-427 `non_max_suppression`, single label, no
+ * masks, not rotated, with the fork's own `soft_nms`, ops.py:260-290, that line 407 calls): confidence filter in anchor order,
+ * class-offset boxes, sequential soft-NMS with in-place score decay, max_det cut.  One CTA per image, one launch.
+ *   y (B, 4+nc, A) bf16 / fp32 decoded head output (xywh pixels, class scores); out (B, max_det, 6) fp32 rows
+ *   (x1, y1, x2, y2, conf, cls) in keep order; out_count (B) int32, negative = -(candidates) when an image has more than
+ *   max_nms candidates (the confidence-sorted truncation of ops.py:395-396 is not implemented);
+ *   workspace: ldconv_nms_workspace_bytes(B, min(A, max_nms)) bytes, 16-byte aligned. */
+size_t ldconv_nms_workspace_bytes(int B, int max_nms);
+int ldconv_nms(const void* y, void* out, int32_t* out_count, void* workspace, size_t workspace_bytes, int B, int A, int nc,
+               float conf_thres, float iou_thres, int agnostic, int max_det, int max_nms, float max_wh, int dtype, void* stream);
+
 /* Task-aligned assigner of the training criterion (utils/tal.py:13-290), dense part, fp32:
  * ldconv_tal_metric: scores (B,na,nc) in [0,1], boxes (B,na,4) xyxy px, anchors (na,2) px, gt_labels (B,n) int32, gt_boxes (B,n,4)
  *   xyxy px, gt_valid (B,n) bytes -> align = score[label]^alpha * max(CIoU, 0)^beta and overlaps = max(CIoU, 0) on anchors
