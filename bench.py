@@ -255,16 +255,18 @@ def workload_config(n_gpus: int, engine: str = "fused", scaling: str = "weak"):
 
 # --------------------------------------------------------------------------------------------------------------- GPU arm
 def ldconv_roofline(model, x, peaks, iters: int):
-    """Time the LDConv kernels of one step at this step's shapes with CUDA events on the launching stream, feeding them the
-    real layer inputs and offsets.  Two kernels are reported (SURVEY.md 8d formulas for the algorithmic bytes):
-      gather+GEMM  ldconv_gather_gemm_fwd, the kernel the inference step runs after the offset conv: x + offsets + out
+    """Time the LDConv kernels of one step at this step's shapes with CUDA events on the launching stream (L2 flushed before
+    every timed launch), feeding them the real layer inputs.  Kernels (SURVEY.md 8d formulas for the algorithmic bytes):
+      one-pass     ldconv_onepass_fwd, THE kernel the inference step runs per LDConv row with C >= 16: x + out
+                   (offsets and the resampled operand never reach HBM)
+      two-kernel   the round-1 path for comparison: tensor-core offset conv (x + offsets) + ldconv_gather_gemm_fwd (x + offsets + out)
       gather       ldconv_gather_fwd, the stand-alone resampling kernel of the training path: x + offsets + operand
-    `roofline` (the contract's key) is the gather+GEMM kernel at its largest launch (layer 1: 16->32 channels, 3 samples,
-    stride 2, 320x320 -> 160x160, batch 64); `traffic` is that launch's dram__bytes_read + dram__bytes_write from the
-    committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)."""
+    `roofline` (the contract's key) is the one-pass kernel at its largest launch (layer 1: 16->32 channels, 3 samples,
+    stride 2, 320x320 -> 160x160, batch 64); `traffic` is that launch's dram__bytes_read + dram__bytes_write from an
+    `ncu --set full` capture of the same library build (profiles/r2_ncu_traffic.json), else null."""
     import torch
     from experiment_yolo_b200 import _lib
-    from experiment_yolo_b200.ldconv import _folded_bn
+    from experiment_yolo_b200.ldconv import _folded_bn, offset_conv_nhwc
     L = _lib.load()
     feats = {}
     hooks = [m.register_forward_pre_hook(lambda mod, inp, i=m.i: feats.__setitem__(i, inp[0])) for m in model.ldconv_layers()]
@@ -286,7 +288,7 @@ def ldconv_roofline(model, x, peaks, iters: int):
         ms = sorted(a.elapsed_time(b) for a, b in ev[1:])
         return ms[len(ms) // 2]
 
-    per_layer, tot = [], {"gg": [0.0, 0.0], "gather": [0.0, 0.0]}
+    per_layer, tot = [], {"one": [0.0, 0.0], "two": [0.0, 0.0], "gather": [0.0, 0.0]}
     for m in model.ldconv_layers():
         xin = feats[m.i]
         B, C, H, W = xin.shape
@@ -296,47 +298,59 @@ def ldconv_roofline(model, x, peaks, iters: int):
         xh = xin.permute(0, 2, 3, 1).contiguous()
         pr = m._prepared(xin.dtype, False)
         scale, shift = _folded_bn(m.conv[1], xin.device)
-        off = torch.empty((B, h, w, 2 * N), device=xin.device, dtype=torch.float32)
         dt = _lib.BF16 if xin.dtype == torch.bfloat16 else _lib.F32
-        _lib.check(L.ldconv_offset_conv_fwd(xh.data_ptr(), pr.w_off.data_ptr(), pr.b_off.data_ptr(), off.data_ptr(), B, C, H,
-                                            W, N, s, dt, st.cuda_stream), "ldconv_offset_conv_fwd")
+        sv = st.cuda_stream
+        off = offset_conv_nhwc(xh, pr, N, s)
         row = {"layer": m.i, "C": C, "O": O, "N": N, "s": s, "hw": [h, w]}
+        x_bytes, off_bytes, out_bytes = e * B * C * H * W, 4 * B * 2 * N * h * w, e * B * h * w * O
         operand = torch.empty((B * h * w, N * C), device=xin.device, dtype=xin.dtype)
         ms = timed(lambda: _lib.check(L.ldconv_gather_fwd(xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(), operand.data_ptr(),
-                                                          None, None, B, C, H, W, N, s, dt, st.cuda_stream), "ldconv_gather_fwd"))
-        nbytes = e * B * C * H * W + 4 * B * 2 * N * h * w + e * B * h * w * N * C
+                                                          None, None, B, C, H, W, N, s, dt, sv), "ldconv_gather_fwd"))
+        nbytes = x_bytes + off_bytes + e * B * h * w * N * C
         row.update({"gather_MB": round(nbytes / 1e6, 1), "gather_us": round(ms * 1e3, 1), "gather_GBps": round(nbytes / ms / 1e6, 1)})
         if C >= 8:          # layer 0 (C = 3) runs the one-kernel small-C path in the step, not these kernels
             tot["gather"][0] += nbytes
             tot["gather"][1] += ms
-        if L.ldconv_gather_gemm_supported(B, C, H, W, N, s, O, O, dt):
-            out = torch.empty((B, h, w, O), device=xin.device, dtype=xin.dtype)
-            ms = timed(lambda: _lib.check(L.ldconv_gather_gemm_fwd(xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(),
-                                                                   pr.wt.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                                                   out.data_ptr(), O, B, C, H, W, N, s, O, _lib.ACT_SILU, dt,
-                                                                   st.cuda_stream), "ldconv_gather_gemm_fwd"))
-            nb = e * B * C * H * W + 4 * B * 2 * N * h * w + e * B * h * w * O
-            row.update({"gg_MB": round(nb / 1e6, 1), "gg_us": round(ms * 1e3, 1), "gg_GBps": round(nb / ms / 1e6, 1),
-                        "gg_TFLOPs": round(2.0 * B * h * w * N * C * O / ms / 1e9, 1)})
-            tot["gg"][0] += nb
-            tot["gg"][1] += ms
+        out = torch.empty((B, h, w, O), device=xin.device, dtype=xin.dtype)
+        w_conv = pr.w_off_tc if s == 1 else pr.w_off_s2d
+        if w_conv is not None and L.ldconv_onepass_supported(B, C, H, W, N, s, O, O, dt):
+            ms = timed(lambda: _lib.check(L.ldconv_onepass_fwd(xh.data_ptr(), w_conv.data_ptr(), pr.b_off.data_ptr(), pr.pn.data_ptr(),
+                                                               pr.wt.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(), O, None,
+                                                               B, C, H, W, N, s, O, _lib.ACT_SILU, dt, sv), "ldconv_onepass_fwd"))
+            nb = x_bytes + out_bytes
+            row.update({"onepass_MB": round(nb / 1e6, 1), "onepass_us": round(ms * 1e3, 1), "onepass_GBps": round(nb / ms / 1e6, 1),
+                        "onepass_TFLOPs": round(2.0 * B * h * w * (N * C * O + 9 * C * 2 * N) / ms / 1e9, 1)})
+            tot["one"][0] += nb
+            tot["one"][1] += ms
+            # the round-1 path on the same input: offset conv, then gather + GEMM
+            t_off = timed(lambda: offset_conv_nhwc(xh, pr, N, s))
+            t_gg = timed(lambda: _lib.check(L.ldconv_gather_gemm_fwd(xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(), pr.wt.data_ptr(),
+                                                                     scale.data_ptr(), shift.data_ptr(), out.data_ptr(), O, B, C, H, W, N,
+                                                                     s, O, _lib.ACT_SILU, dt, sv), "ldconv_gather_gemm_fwd"))
+            row.update({"offconv_us": round(t_off * 1e3, 1), "gg_us": round(t_gg * 1e3, 1),
+                        "gg_GBps": round((x_bytes + off_bytes + out_bytes) / t_gg / 1e6, 1)})
+            tot["two"][0] += 2 * x_bytes + 2 * off_bytes + out_bytes
+            tot["two"][1] += t_off + t_gg
         per_layer.append(row)
     peak = peaks.get("hbm_gbs", 6650.0)
     src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 (of fallback)"
     traffic, traffic_note = committed_traffic()
-    big = max((r for r in per_layer if "gg_us" in r), key=lambda r: r["gg_MB"], default=None)
+    big = max((r for r in per_layer if "onepass_us" in r), key=lambda r: r["onepass_MB"], default=None)
     roof = None
     if big is not None:
-        ach = big["gg_MB"] * 1e3 / big["gg_us"]
-        roof = {"bound": "hbm", "kernel": f"ldconv_gg2_kernel (LDConv gather + GEMM + BN + SiLU, layer {big['layer']}: the largest "
-                "LDConv launch of the step)", "achieved": round(ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "frac_of_8TBs_nominal": round(ach / 8000.0, 4),
+        ach = big["onepass_MB"] * 1e3 / big["onepass_us"]
+        roof = {"bound": "hbm", "kernel": f"ldconv_onepass_kernel (whole LDConv forward: offset conv + sampling grid + gather + GEMM + BN + "
+                f"SiLU, x read once; layer {big['layer']}: the largest LDConv launch of the step)", "achieved": round(ach, 1),
+                "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(ach / peak, 4), "frac_of_8TBs_nominal": round(ach / 8000.0, 4),
                 "traffic": traffic.get("roofline_kernel_bytes"), "traffic_source": traffic_note,
-                "algorithmic_bytes_per_launch": round(big["gg_MB"] * 1e6),
-                "us_per_launch": big["gg_us"], "timing": "CUDA events on the launching stream, median of %d, L2 flushed (256 MB "
+                "algorithmic_bytes_per_launch": round(big["onepass_MB"] * 1e6),
+                "algorithmic_bytes": "e*B*C*H*W (x once) + e*B*h*w*O (out); offsets and the resampled operand stay on chip",
+                "us_per_launch": big["onepass_us"], "timing": "CUDA events on the launching stream, median of %d, L2 flushed (256 MB "
                 "memset) before every timed launch" % iters,
-                "all_gg_launches": {"GBps": round(tot["gg"][0] / max(tot["gg"][1], 1e-9) / 1e6, 1),
-                                    "us_per_step": round(tot["gg"][1] * 1e3, 1)},
+                "all_onepass_launches": {"GBps": round(tot["one"][0] / max(tot["one"][1], 1e-9) / 1e6, 1),
+                                         "us_per_step": round(tot["one"][1] * 1e3, 1)},
+                "round1_two_kernel_path": {"us_per_step": round(tot["two"][1] * 1e3, 1),
+                                           "what": "offset conv (tcgen05) + ldconv_gather_gemm_fwd on the same inputs, for comparison"},
                 "per_layer": per_layer}
     g_ach = tot["gather"][0] / max(tot["gather"][1], 1e-9) / 1e6
     roof_gather = {"bound": "hbm", "kernel": "gather_fwd_tiled_kernel (stand-alone LDConv resampling, training path; the 9 launches "
@@ -438,16 +452,57 @@ def run_gpu_arm(args):
         # captured forward (uint8 -> bf16 NHWC conversion included) and downloads the detections to pinned host memory;
         # uploads / downloads of neighbouring steps overlap the compute on side streams, every result is waited for.
         host_u8 = [torch.randint(0, 256, (B, 3, IMG, IMG), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        if args.engine == "fused":
-            pred = engine.PipelinedPredictor(model, B, IMG)
-            h2d, d2h = pred.h2d_bytes, pred.d2h_bytes
 
-            def e2e_run(n):
-                for i in range(n):
-                    pred.submit(host_u8[i & 1])
-                    if i >= 1:
-                        pred.result()
-                pred.result()
+        def timed_e2e(e2e_run, drain=None):
+            e2e_run(max(3, args.warmup))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            e2e_run(args.steps)                      # returns only after the last result is in host memory
+            if drain is not None:
+                drain()
+            e3.record()
+            torch.cuda.synchronize()
+            t2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            return B * world * args.steps / (float(t2.item()) / 1e3)
+
+        e2e_extra = {}
+        if args.engine == "fused":
+            def make_run(pred):
+                def e2e_run(n):
+                    for i in range(n):
+                        pred.submit(host_u8[i & 1])
+                        if i >= 1:
+                            pred.result()
+                    pred.result()
+                return e2e_run
+
+            # (1) what the reference's predictor returns: detections after non_max_suppression (utils/ops.py:292, device-side
+            # here).  The weights are random, so the class scores carry no objects: the confidence threshold is set once,
+            # untimed, to the 99th percentile of the best-class scores of one batch (~336 candidates per image, a realistic load
+            # for UAV scenes; at the default 0.25 every anchor of a random-init head is a candidate).
+            probe = (host_u8[0].to(dev).float() / 255.0).bfloat16().contiguous(memory_format=torch.channels_last)
+            y_probe, _ = run(probe)
+            conf_thr = float(y_probe[:, 4:].float().amax(1).flatten().quantile(0.99))
+            nms_kw = dict(conf_thres=conf_thr, iou_thres=0.45, max_det=300)
+            pred = engine.PipelinedPredictor(model, B, IMG, nms=nms_kw)
+            h2d, d2h = pred.h2d_bytes, pred.d2h_bytes
+            e2e_value = timed_e2e(make_run(pred), pred.drain_to)
+            det, cnt = pred.y_host[0]
+            e2e_extra["nms"] = {"conf_thres": round(conf_thr, 5), "iou_thres": 0.45, "max_det": 300,
+                                "kept_per_image_mean": round(float(cnt.float().mean()), 1),
+                                "note": "conf_thres = 99th percentile of the best-class score (random-init weights), chosen untimed"}
+            del pred
+            # (2) the round-1 variant for comparison: the raw decoded head output (B, 4+nc, anchors) copied to the host
+            pred_raw = engine.PipelinedPredictor(model, B, IMG)
+            e2e_extra["raw_head_output"] = {"value": round(timed_e2e(make_run(pred_raw), pred_raw.drain_to), 2), "unit": "images/s",
+                                            "d2h_bytes_per_step": pred_raw.d2h_bytes}
+            del pred_raw
         else:
             host_out = torch.empty(tuple(static_y.shape), dtype=static_y.dtype).pin_memory()
             h2d, d2h = host_u8[0].numel(), host_out.numel() * host_out.element_size()
@@ -459,27 +514,26 @@ def run_gpu_arm(args):
                     y, _ = run(xb)
                     host_out.copy_(y, non_blocking=True)
                 torch.cuda.synchronize()
+            e2e_value = timed_e2e(e2e_run)
 
-        e2e_run(max(3, args.warmup))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        e2e_run(args.steps)                      # returns only after the last result is in host memory
-        if args.engine == "fused":
-            pred.drain_to()
-        e3.record()
-        torch.cuda.synchronize()
-        t2 = torch.tensor([e2.elapsed_time(e3)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_value = B * world * args.steps / (float(t2.item()) / 1e3)
+    # ---- BASELINE config 4 beside it: the training step (batch 128 split over the ranks, NCCL gradient all-reduce), so that the
+    # driver's 1 / 2 / 4 / 8-GPU runs of this file also give the training curve.  Every rank takes part; a failure is reported,
+    # it does not void the inference line.
+    train = None
+    if args.train_steps > 0 and args.scaling == "weak":
+        try:
+            del graph, static_y, static_x, xs
+            torch.cuda.empty_cache()
+            from benchmarks.train_step import run_train
+            train = run_train(128, args.train_steps, 3, rank, world, dev)
+        except Exception as e:
+            train = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
 
     line = None
     if rank == 0:
-        roof, roof_gather = ldconv_roofline(model, xs[0], peaks, iters=7)
+        roof, roof_gather = ldconv_roofline(model, host_u8[0].to(dev).float().div_(255.0).bfloat16().contiguous(memory_format=torch.channels_last),
+                                            peaks, iters=7)
         cpu_best, cpu_mean, cpu_sec, cores = cpu_port_images_per_s(CPU_SAMPLE_BATCH, 3, 1) if world == 1 else (None,) * 4
         eager = gpu_eager_images_per_s(local, B) if world == 1 else None
         traffic, traffic_note = committed_traffic()
@@ -492,7 +546,9 @@ def run_gpu_arm(args):
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "api": "engine.PipelinedPredictor.submit()/result()" if args.engine == "fused"
                         else "DealYolo.forward", "input": "uint8 NCHW batch in pinned host memory, normalised on device",
-                        "result": "decoded detections (B,10,33600) bf16 copied to pinned host memory"},
+                        "result": "detections after device-side non_max_suppression, (B,300,6) fp32 + counts, copied to pinned host "
+                                  "memory" if args.engine == "fused" else "decoded head output (B,10,33600) bf16 copied to pinned host memory",
+                        **e2e_extra},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "clocks": clk.summary(), "roofline": roof, "roofline_gather": roof_gather}
         if step_bytes and B == PER_GPU_BATCH:
@@ -500,6 +556,8 @@ def run_gpu_arm(args):
             line["step_roofline"] = {"bound": "hbm", "dram_bytes_per_step": step_bytes, "achieved": round(step_bytes / ms_per_step / 1e6, 1),
                                      "peak": peak, "unit": "GB/s", "frac": round(step_bytes / ms_per_step / 1e6 / peak, 4),
                                      "source": traffic_note}
+        if train is not None:
+            line["config4_train"] = train
         if eager is not None:
             line["gpu_eager_baseline"] = eager
         if cpu_mean is not None:
@@ -536,6 +594,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 64 images per GPU; strong: one 64-image batch split over the ranks (SURVEY.md 8d config 3)")
     ap.add_argument("--micro-batch", type=int, default=0, help="images per pass of the fused executor (0 = its default)")
+    ap.add_argument("--train-steps", type=int, default=6, help="timed steps of the config-4 training leg (0 = skip)")
     ap.add_argument("--eager-leg", default=None, help=argparse.SUPPRESS)      # internal: one dtype of gpu_eager_baseline
     ap.add_argument("--eager-batch", type=int, default=PER_GPU_BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--eager-iters", type=int, default=3, help=argparse.SUPPRESS)

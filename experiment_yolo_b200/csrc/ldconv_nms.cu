@@ -18,7 +18,7 @@
 
 namespace ldc {
 
-static constexpr int kNmsThreads = 256;
+static constexpr int kNmsThreads = 512;
 
 __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int& total)
 {
@@ -69,20 +69,40 @@ nms_soft_kernel(const T* __restrict__ y, int A, int nc, float conf_thres, float 
     float* ob = out + (size_t)b * max_det * 6;
 
     // ---- candidates: best class score > conf_thres, in anchor order (ops.py:347,363,384-385) ------------------------------------
-    int n = 0;
-    for (int a0 = 0; a0 < A; a0 += kNmsThreads) {
-        const int a = a0 + tid;
-        float best = -1.f;
-        int bj = 0;
-        if (a < A) {
+    // Each warp owns a contiguous range of anchors: pass 1 counts its candidates (ballot + popc, no block barrier inside the
+    // loop), one block scan over the warp totals gives every warp its first slot, pass 2 writes them -- a stable compaction
+    // with three block barriers in total instead of three per 256 anchors.
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = kNmsThreads / 32;
+    const int per_warp = ((A + NWARP - 1) / NWARP + 31) & ~31;
+    const int a_begin = warp * per_warp, a_end = min(A, a_begin + per_warp);
+    auto best_of = [&](int a, float& best, int& bj) {
+        best = -1.f;
+        bj = 0;
+        if (a < a_end) {
             for (int j = 0; j < nc; ++j) {      // torch.max: first maximal index
                 const float v = Elem<T>::to_f(yb[(size_t)(4 + j) * A + a]);
                 if (v > best) { best = v; bj = j; }
             }
         }
-        const int flag = (a < A && best > conf_thres) ? 1 : 0;
-        int total;
-        const int pos = n + block_excl_scan(flag, s_warp, total);
+        return (a < a_end && best > conf_thres) ? 1 : 0;
+    };
+    int wcount = 0;
+    for (int a0 = a_begin; a0 < a_end; a0 += 32) {
+        float best;
+        int bj;
+        wcount += __popc(__ballot_sync(0xffffffffu, best_of(a0 + lane, best, bj)));
+    }
+    int n;
+    const int wbase = block_excl_scan(lane == 0 ? wcount : 0, s_warp, n);      // lane 0 of every warp: exclusive sum of the warp totals
+    int pos0 = __shfl_sync(0xffffffffu, wbase, 0);
+    for (int a0 = a_begin; a0 < a_end; a0 += 32) {
+        const int a = a0 + lane;
+        float best;
+        int bj;
+        const int flag = best_of(a, best, bj);
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        const int pos = pos0 + __popc(bal & ((1u << lane) - 1u));
         if (flag && pos < cap) {
             const float cx = Elem<T>::to_f(yb[a]), cy = Elem<T>::to_f(yb[(size_t)A + a]);
             const float w = Elem<T>::to_f(yb[(size_t)2 * A + a]), h = Elem<T>::to_f(yb[(size_t)3 * A + a]);
@@ -92,7 +112,7 @@ nms_soft_kernel(const T* __restrict__ y, int A, int nc, float conf_thres, float 
             cls[pos] = bj;
             order0[pos] = pos;
         }
-        n += total;
+        pos0 += __popc(bal);
     }
     if (n > cap) {      // more candidates than max_nms: the reference sorts by confidence and truncates (ops.py:395-396); not covered
         if (tid == 0) out_count[b] = -n;

@@ -30,48 +30,97 @@ def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 
 class FlatGradAllReduce:
-    """Packs the gradients of `params` into one flat fp32 buffer, all-reduces it once (sum) and scatters it back."""
+    """ONE flat fp32 gradient buffer for the whole model, reduced with all-reduce(sum).
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    The parameters' `.grad` tensors ARE views of the flat buffer, so there is no pack / unpack copy per parameter: autograd
+    accumulates in place, `zero()` is one memset and the optimizer reads the reduced values where they lie.  The buffer is
+    cut into `buckets` contiguous slices in reverse parameter order (backward produces the last layers' gradients first); a
+    post-accumulate hook counts the gradients of a slice and launches its all-reduce asynchronously the moment the last one
+    has landed -- i.e. right after that slice's last weight-gradient kernel, overlapped with the rest of backward.  `__call__()`
+    after `backward()` launches whatever has not been launched (parameters that received no gradient) and waits.
+    Per-GPU BatchNorm statistics and plain sum like the reference's DDP step (engine/trainer.py:695,803-804)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], buckets: int = 2):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-
-    def __call__(self, async_op: bool = False):
-        ofs = 0
+        self.views, ofs = [], 0
         for p in self.params:
             n = p.numel()
-            if p.grad is None:
-                self.flat[ofs:ofs + n].zero_()
-            else:
-                self.flat[ofs:ofs + n].copy_(p.grad.reshape(-1))
+            self.views.append(self.flat[ofs:ofs + n].view_as(p))
             ofs += n
-        work = None
+        # bucket k covers parameters [cut[k], cut[k+1]); bucket len-1 (the last layers) is complete first during backward
+        buckets = max(1, min(int(buckets), len(self.params) or 1))
+        target, self.cut, acc = self.numel / buckets, [0], 0
+        for i, p in enumerate(self.params):
+            acc += p.numel()
+            if acc >= target * len(self.cut) and len(self.cut) < buckets and i + 1 < len(self.params):
+                self.cut.append(i + 1)
+        self.cut.append(len(self.params))
+        self.bucket_of = {}
+        for k in range(len(self.cut) - 1):
+            for i in range(self.cut[k], self.cut[k + 1]):
+                self.bucket_of[id(self.params[i])] = (k, i)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.works, self.launched, self.pending = [], [], []
+        self.zero()
+
+    # ---- per step -----------------------------------------------------------------------------------------------------------
+    def zero(self):
+        """replaces optimizer.zero_grad(): one memset, gradients stay views of the flat buffer"""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+        self.pending = [self.cut[k + 1] - self.cut[k] for k in range(len(self.cut) - 1)]
+        self.launched = [False] * (len(self.cut) - 1)
+        self.works = []
+
+    def _on_grad(self, p: torch.nn.Parameter):
+        k, i = self.bucket_of[id(p)]
+        v = self.views[i]
+        if p.grad is not None and p.grad.data_ptr() != v.data_ptr():      # someone reset .grad (zero_grad(set_to_none=True)): adopt
+            v.copy_(p.grad.reshape(v.shape))
+            p.grad = v
+        self.pending[k] -= 1
+        if self.pending[k] == 0:
+            self._launch(k)
+
+    def _slice(self, k: int) -> torch.Tensor:
+        lo = sum(p.numel() for p in self.params[: self.cut[k]])
+        hi = lo + sum(p.numel() for p in self.params[self.cut[k]: self.cut[k + 1]])
+        return self.flat[lo:hi]
+
+    def _launch(self, k: int):
+        if self.launched[k]:
+            return
+        self.launched[k] = True
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
-        if async_op and work is not None:
-            return work
-        self.unpack()
+            self.works.append(dist.all_reduce(self._slice(k), op=dist.ReduceOp.SUM, async_op=True))
+
+    def __call__(self):
+        """after backward(): reduce what is still local, wait for every slice; `.grad` then holds the summed gradients"""
+        for p, v in zip(self.params, self.views):      # parameters autograd never touched keep their zero view
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad.reshape(v.shape))
+                p.grad = v
+        for k in range(len(self.cut) - 1):
+            self._launch(k)
+        for w in self.works:
+            w.wait()
+        self.works = []
         return None
 
-    def unpack(self):
-        ofs = 0
-        for p in self.params:
-            n = p.numel()
-            g = self.flat[ofs:ofs + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.to(p.dtype).clone()
-            else:
-                p.grad.copy_(g)
-            ofs += n
+    def unpack(self):      # kept for callers of the first version: gradients already are views of the buffer
+        return None
 
 
 def surrogate_detection_loss(outs: List[torch.Tensor], targets: List[torch.Tensor]) -> torch.Tensor:
     """Stand-in for the reference's v8DetectionLoss in the synthetic training-step harness: a dense regression of the raw
     head maps (train-mode Detect output, nn/modules/head.py:47-48) onto synthetic targets, summed over the local batch
-    like the reference loss (`loss.sum() * batch_size`, utils/loss.py:361).  The TAL / WIoU / NWD loss itself is a
-    "next" row and is not re-implemented."""
+    like the reference loss (`loss.sum() * batch_size`, utils/loss.py:361).  The reference criterion itself (TAL + Wise-IoU +
+    NWD + DFL) is experiment_yolo_b200/loss.py; this stand-in stays for A/B runs and the gloo test."""
     total = outs[0].new_zeros((), dtype=torch.float32)
     for o, t in zip(outs, targets):
         total = total + (o.float() - t.float()).square().mean(dim=(1, 2, 3)).sum()
@@ -82,7 +131,7 @@ def train_step(model: torch.nn.Module, images: torch.Tensor, targets: List[torch
                optimizer: torch.optim.Optimizer, reducer: FlatGradAllReduce) -> torch.Tensor:
     """One data-parallel step on this rank's shard: forward (train-mode BN, per-GPU statistics), backward through the
     CUDA LDConv kernels, ONE flat gradient all-reduce, optimizer step."""
-    optimizer.zero_grad(set_to_none=True)
+    reducer.zero()
     outs = model(images)
     loss = surrogate_detection_loss(outs, targets)
     loss.backward()

@@ -613,17 +613,25 @@ class PipelinedPredictor:
                 y, _ = self.exec(self.u8[0])
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        ws = None
+        # The NMS launch is NOT part of the captured forward: it runs on the download stream, so the 64 one-CTA-per-image
+        # sequential loops of batch i overlap the forward of batch i+1 instead of holding 84 SMs idle at the tail of every graph
+        # (inside the graph the end-to-end rate was 5 % below the raw-output variant)
+        self._nms_fn = _nms.nms_padded
+        self.nms_ws = None
         if self.nms is not None:
-            ws = _nms.nms_workspace(batch, y.shape[2], int(self.nms.get("max_nms", 30000)), dev)      # shared: graphs run in stream order
+            self.nms_ws = _nms.nms_workspace(batch, y.shape[2], int(self.nms.get("max_nms", 30000)), dev)      # launches are ordered on s_out
+        self.y_raw = []
         for k in range(slots):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 y, _ = self.exec(self.u8[k])
-                if self.nms is not None:
-                    y = _nms.nms_padded(y, workspace=ws, **self.nms)
             self.graphs.append(g)
-            ys = y if isinstance(y, tuple) else (y,)
+            self.y_raw.append(y)
+            if self.nms is not None:
+                md = int(self.nms.get("max_det", 300))
+                ys = (torch.zeros((batch, md, 6), device=dev, dtype=torch.float32), torch.zeros((batch,), device=dev, dtype=torch.int32))
+            else:
+                ys = (y,)
             self.y_dev.append(ys)
             self.y_host.append(tuple(torch.empty(tuple(t.shape), dtype=t.dtype).pin_memory() for t in ys))
         self.ev_in = [torch.cuda.Event() for _ in range(slots)]
@@ -652,6 +660,8 @@ class PipelinedPredictor:
         self.ev_comp[k].record(comp)
         self.s_out.wait_event(self.ev_comp[k])
         with torch.cuda.stream(self.s_out):
+            if self.nms is not None:
+                self._nms_fn(self.y_raw[k], out=self.y_dev[k][0], count=self.y_dev[k][1], workspace=self.nms_ws, **self.nms)
             for h, d in zip(self.y_host[k], self.y_dev[k]):
                 h.copy_(d, non_blocking=True)
             self.ev_out[k].record(self.s_out)

@@ -57,8 +57,16 @@ def _worker(rank, world, port, q):
         red = xdist.FlatGradAllReduce(model.parameters())
         outs = model(images[lo:hi])
         xdist.surrogate_detection_loss(outs, targets).backward()
+        assert all(red.launched), "every slice's all-reduce is launched from the gradient hooks, during backward"
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views)), "gradients are views of the flat buffer"
         red()
         flat = red.flat.clone()
+        # a second step on the same reducer: zero() resets the buffer (no double counting), same result
+        red.zero()
+        outs = model(images[lo:hi])
+        xdist.surrogate_detection_loss(outs, targets).backward()
+        red()
+        assert torch.allclose(red.flat, flat, rtol=1e-5, atol=1e-7)
         if rank == 0:
             model.zero_grad()
             outs = model(images)
