@@ -65,6 +65,7 @@ SIGNATURES = {
     "ldconv_sppf_pools": (_i, [_vp, _vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "ldconv_gather_gemm_supported": (_i, [_i] * 9),
     "ldconv_gather_gemm_fwd": (_i, [_vp] * 7 + [_i] * 10 + [_vp]),
+    "ldconv_debug_onepass_trace": (_i, [_vp]),
     "ldconv_onepass_supported": (_i, [_i] * 9),
     "ldconv_onepass_fwd": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 9 + [_vp]),
     "ldconv_fused_supported": (_i, [_i] * 8),

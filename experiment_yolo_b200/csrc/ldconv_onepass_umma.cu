@@ -38,12 +38,24 @@ struct OPGeom {
     int N, H, W, h, w, O, ON, K, num_kb, ksteps;
     int tiles_h, tiles_w, num_tiles, ldo, act, per_sm;
     int XB, AB, xb_mask, xb_shift, ab_mask;
+    int tstore, st_rowb;               // TMA-store epilogue: bytes per staged output row (min(O, 64) * 2), 0 = direct stores
     float hm, wm;
     unsigned long long img_bytes;
     unsigned inv_img, inv_tw;
-    uint32_t ofs_a, ofs_b, ofs_bc, ofs_x, ofs_rec, ofs_aff, ofs_bias, ofs_bar;
+    uint32_t ofs_a, ofs_b, ofs_bc, ofs_x, ofs_rec, ofs_aff, ofs_bias, ofs_bar, ofs_stage;
     uint32_t a_bytes, b_bytes, x_bytes, x_tx_bytes, tmem_cols;
 };
+
+// debug timeline (ldconv_debug_onepass_trace): clock64 stamps of CTA 0's first worker thread and issuer thread for tile iterations
+// 6..9; two uniform branches per stamp, not inside the unrolled loops
+static constexpr int kOpTraceN = 64;
+struct OpTracer {
+    long long* buf; int n; bool on;
+    __device__ __forceinline__ void operator()(int it, int tag) {
+        if (on && it >= 6 && it < 10 && n < kOpTraceN) { buf[2 * n] = (long long)it * 100 + tag; buf[2 * n + 1] = clock64(); ++n; }
+    }
+};
+static thread_local long long* g_op_trace = nullptr;
 
 static constexpr int kOpTH = 16, kOpTW = 8;       // output tile: MMA row group (8 rows) = 8 consecutive pixels of one row
 
@@ -140,10 +152,11 @@ template <int TCVS, int TS> struct OPShape {
 template <int TN, int TCVS, int TS, int TG, int MINB>
 __global__ void __launch_bounds__(128 * TG + 32, MINB)
 ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                      const __grid_constant__ CUtensorMap tmWc, const __nv_bfloat16* __restrict__ x,
+                      const __grid_constant__ CUtensorMap tmWc, const __grid_constant__ CUtensorMap tmO,
+                      const __nv_bfloat16* __restrict__ x,
                       const float* __restrict__ bias, const int* __restrict__ pn, const float* __restrict__ scale,
                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, float* __restrict__ off_dbg,
-                      const OPGeom g)
+                      long long* __restrict__ trace, const OPGeom g)
 {
     using S = OPShape<TCVS, TS>;
     extern __shared__ uint8_t smem_raw[];
@@ -155,7 +168,9 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint64_t* off_done = bars + 4;       // offset-conv MMAs of a tile are complete (and have released nothing: the tile stays)
     uint64_t* b_done = bars + 5;         // the workers have passed barrier B of a tile (operand complete, input tile consumed)
     uint64_t* w_full = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);       // [0] main accumulators, [1] offset accumulator
+    uint64_t* e_done = bars + 7;         // every worker warp has parked its part of a tile's output in the staging tile (TMA-store epilogue)
+    uint64_t* s_free = bars + 8;         // the TMA store of the staged tile has read it: the next epilogue may overwrite
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);       // [0] main accumulators, [1] offset accumulator
     float* sAff = reinterpret_cast<float*>(smem + g.ofs_aff);          // [0, ON) scale, [ON, 2 ON) shift (halved for SiLU)
     float* sBias = reinterpret_cast<float*>(smem + g.ofs_bias);        // [16] offset-conv bias
     const uint32_t aff_s = smem_s + g.ofs_aff;
@@ -184,10 +199,13 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmWc);
+        if (g.tstore) tma_prefetch_desc(&tmO);
         for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&mma_done[i], 1); }
         mbar_init(off_done, 1);
         mbar_init(b_done, 1);
         mbar_init(w_full, 1);
+        mbar_init(e_done, 4 * TG);
+        mbar_init(s_free, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -210,11 +228,17 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const uint32_t tmem_base = tmem_slot[0];
     const uint32_t tmem_off = tmem_slot[1];
 
+    OpTracer tr{trace ? trace + (warp == 4 * TG ? 2 * kOpTraceN + 2 : 0) : nullptr, 0,
+                trace != nullptr && blockIdx.x == 0 && (tid == 0 || tid == NW)};
     if (warp == 4 * TG) {
-        // ================================================ issuer warp: one thread ================================================
-        if (lane == 0) {
-            auto issue_x_tile = [&](int tile, int xb) {
-                const TC t = tile_coords(tile);
+        // ===================================== issuer warp: warp-uniform control flow, one elected lane issues =====================
+        // (under `if (lane == 0)` the compiler wraps every uniform-datapath instruction -- UTCHMMA, UTMALDG -- in an ELECT /
+        // BRA.U.ANY loop over the active lanes: ~10 dependent instructions and ~85 cycles per MMA with 27 warps sharing the SM,
+        // 1500 cycles for the 18 offset-conv MMAs of a 32-channel tile -- benchmarks/trace_onepass.py)
+        const bool leader = elect_one();
+        {
+            auto issue_x_tile_at = [&](const TC& t, int xb) {
+                if (!leader) return;
                 mbar_arrive_expect_tx(&x_full[xb], S::X_TX);
                 uint8_t* dst = smem + g.ofs_x + (size_t)xb * S::X_BYTES;
 #pragma unroll
@@ -231,8 +255,9 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             // L2 prefetch of a tile one step before its TMA: with a single input buffer the load can only be issued once the workers
             // have consumed the previous tile, and its latency sits on the tile's critical path (TMA -> offset conv -> phase 1);
             // measured: 693 -> 677 us over the nine yolov8-LD-P2 layers at batch 64
-            auto prefetch_x_tile = [&](int tile) {
-                const TC t = tile_coords(tile);
+            auto issue_x_tile = [&](int tile, int xb) { issue_x_tile_at(tile_coords(tile), xb); };
+            auto prefetch_x_tile_at = [&](const TC& t) {
+                if (!leader) return;
 #pragma unroll
                 for (int hf = 0; hf < S::HALVES; ++hf) {
                     if constexpr (TS == 1)
@@ -242,6 +267,19 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                         tma_prefetch_5d(&tmX, (hf % per_sy) * (S::PB / 2), hf / per_sy, t.j0 - 1, t.i0 - 1, t.b);
                     }
                 }
+            };
+            auto prefetch_x_tile = [&](int tile) { prefetch_x_tile_at(tile_coords(tile)); };
+            // TMA store of the staged output tile of iteration `eit` once every worker warp has parked its part: coordinates (channel,
+            // column, row, image), pixels beyond the map are clipped by the tensor map; then the staging tile is handed back
+            auto store_tile = [&](int eit, bool last) {
+                mbar_wait_sleep(e_done, (uint32_t)eit & 1u);
+                const TC t = tile_coords((int)blockIdx.x + eit * (int)gridDim.x);
+                if (!leader) return;
+                for (int cb = 0; cb * 64 < g.O; ++cb)
+                    tma_store_4d(&tmO, smem + g.ofs_stage + (size_t)cb * (128 * 128), cb * 64, t.j0, t.i0, t.b);
+                tma_store_commit();
+                if (last) tma_store_wait_all(); else tma_store_wait_read();
+                mbar_arrive(s_free);
             };
             const uint32_t idesc_c = make_idesc_bf16(128, 16);
             const uint32_t idesc_m = make_idesc_bf16(128, g.ON);
@@ -253,6 +291,7 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             // conv3x3_zc_kernel so the fp32 accumulation is bit-identical to ldconv_offset_conv_{tc,s2d}_fwd
             auto offset_conv_mma = [&](int xb) {
                 const uint64_t descA = descA_hi | (uint64_t)(((smem_s + g.ofs_x + (uint32_t)xb * S::X_BYTES) >> 4) & 0x3fffu);
+                if (!leader) return;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int tap = 0; tap < S::TAPS; ++tap) {
@@ -277,6 +316,7 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             auto main_mma = [&](int ab, int tb) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(tb * g.ON);
                 const uint64_t da = make_desc_k_sw128(smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes);
+                if (!leader) return;
                 for (int st = 0; st < g.ksteps; ++st) {
                     const uint32_t kb = (uint32_t)st >> 2, kk = (uint32_t)st & 3;
                     mma_bf16_ss(d_tmem, da + (uint64_t)(kb * 1024u + kk * 2u), descBm0 + (uint64_t)(kb * (g.b_bytes >> 4) + kk * 2u),
@@ -285,11 +325,13 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                 mma_commit(&mma_done[tb]);
             };
 
-            mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes + (uint32_t)S::NZ_KB * 2048u);
-            for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(smem + g.ofs_b + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+            if (leader) {
+                mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes + (uint32_t)S::NZ_KB * 2048u);
+                for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(smem + g.ofs_b + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
 #pragma unroll
-            for (int kb = 0; kb < S::KC_KB; ++kb)
-                if (!S::blk_zero(kb)) tma_load_2d(smem + g.ofs_bc + (size_t)S::slot(kb) * 2048, &tmWc, w_full, kb * 64, 0);
+                for (int kb = 0; kb < S::KC_KB; ++kb)
+                    if (!S::blk_zero(kb)) tma_load_2d(smem + g.ofs_bc + (size_t)S::slot(kb) * 2048, &tmWc, w_full, kb * 64, 0);
+            }
             for (int k = 0; k < g.XB; ++k)
                 if ((int)blockIdx.x + k * (int)gridDim.x < g.num_tiles) issue_x_tile(blockIdx.x + k * gridDim.x, k);
             if ((int)blockIdx.x + g.XB * (int)gridDim.x < g.num_tiles) prefetch_x_tile(blockIdx.x + g.XB * gridDim.x);
@@ -303,8 +345,15 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
                 const int xb = it & g.xb_mask, ab = it & g.ab_mask, tb = it & 1;
                 const bool more = tile + (int)gridDim.x < g.num_tiles;
+                // everything that does not depend on the workers is computed before the wait: this thread's instruction stream after
+                // barrier B is the critical path of the next tile (TMA -> offset conv -> phase 1)
+                const TC t_next = tile_coords(more ? tile + (int)gridDim.x : tile);
+                const bool more2 = tile + 2 * (int)gridDim.x < g.num_tiles;
+                const TC t_pf = tile_coords(more2 ? tile + 2 * (int)gridDim.x : tile);
+                tr(it, 50);
                 mbar_wait_sleep(b_done, (uint32_t)it & 1u);      // operand tile of `it` complete, its input tile consumed, epilogue(it - 2) done
                 tc_fence_after_sync();
+                tr(it, 51);
                 if (g.XB == 2) {
                     // the next tile is already staged: its offsets first (phase 1 of the workers waits for them), then this tile's GEMM
                     if (more) {
@@ -316,16 +365,23 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     if (tile + 2 * (int)gridDim.x < g.num_tiles) issue_x_tile(tile + 2 * gridDim.x, xb);
                     if (tile + 3 * (int)gridDim.x < g.num_tiles) prefetch_x_tile(tile + 3 * gridDim.x);
                 } else {
-                    if (more) issue_x_tile(tile + gridDim.x, 0);      // the only input buffer is free again: refill first (latency)
-                    if (tile + 2 * (int)gridDim.x < g.num_tiles) prefetch_x_tile(tile + 2 * gridDim.x);
+                    if (more) issue_x_tile_at(t_next, 0);      // the only input buffer is free again: refill first (latency)
+                    tr(it, 52);
                     main_mma(ab, tb);
+                    tr(it, 53);
                     if (more) {
                         mbar_wait_sleep(&x_full[0], (uint32_t)(it + 1) & 1u);
                         tc_fence_after_sync();
+                        tr(it, 54);
                         offset_conv_mma(0);
+                        tr(it, 55);
                     }
+                    if (more2) prefetch_x_tile_at(t_pf);
                 }
+                // epilogue(it - 1) runs right after barrier B of this tile: its output is parked soon
+                if (g.tstore && it > 0) store_tile(it - 1, false);
             }
+            if (g.tstore && it > 0) store_tile(it - 1, true);
         }
     } else {
         // ===================================================== worker warps =====================================================
@@ -351,6 +407,7 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t cx = (uint32_t)(cv & (S::PB / 16 - 1)) << 4;
         const uint32_t hoff = (TS == 1 && TCVS == 4) ? (uint32_t)(cv >> 3) * S::HALF_BYTES : 0u;
         const int grp = warp >> 2;
+        const uint32_t stage_s = smem_s + g.ofs_stage;
         const int chunks = g.ON / 16;
         const int ch_begin = chunks * grp / TG, ch_end = chunks * (grp + 1) / TG;
 
@@ -359,6 +416,7 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const int tb = eit & 1;
             mbar_wait(&mma_done[tb], (eit >> 1) & 1);
             tc_fence_after_sync();
+            if (g.tstore && eit > 0) mbar_wait(s_free, (uint32_t)(eit - 1) & 1u);      // the previous tile's store has read the staging tile
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tb * g.ON);
             for (int ch = ch_begin; ch < ch_end; ++ch) {
                 const int c0 = ch * 16;
@@ -395,13 +453,29 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[e >> 1]) : "f"(a1), "f"(a0));
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[(e >> 1) + 1]) : "f"(a3), "f"(a2));
                 }
-                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m_out * (size_t)g.ldo + c0);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                if (g.tstore) {
+                    // park the 32 bytes in the staging tile [64-channel block][128 pixels][row] at the tensor map's swizzle: the 8
+                    // lanes of a quarter-warp (8 consecutive pixels) land on 8 different 16-byte bank slots, and ONE TMA store per tile
+                    // writes whole lines (a thread's own 16-byte global stores cost an L1 request each and half-filled L2 sectors)
+                    const uint32_t rowb = (uint32_t)g.st_rowb;
+                    const uint32_t row = stage_s + (uint32_t)(c0 >> 6) * (128u * 128u) + (uint32_t)p * rowb;
+                    const uint32_t key = ((uint32_t)p * rowb >> 7) & (rowb / 16u - 1u);
+                    const uint32_t cc = (uint32_t)(c0 & 63) >> 3;
+                    op_sts128(row + (((cc) ^ key) << 4), w[0], w[1], w[2], w[3]);
+                    op_sts128(row + (((cc + 1u) ^ key) << 4), w[4], w[5], w[6], w[7]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m_out * (size_t)g.ldo + c0);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            }
+            if (g.tstore) {
+                fence_proxy_async_smem();      // staged rows -> visible to the TMA store the issuer warp launches once every warp has arrived
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(e_done);
             }
             tc_fence_before_sync();       // ordered before the barrier that precedes the next MMA into this buffer
         };
-
         // ---- phase 1 of one tile: offsets from TMEM, one record per sample (n-major: sample = n * 128 + pixel); returns this
         // thread's output pixel index ((b h + i) w + j), -1 outside the map
         auto phase1 = [&](const TC& t, uint32_t rec_s, uint32_t x_s, int it) -> int {
@@ -416,6 +490,7 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             tmem_ld_32x32b_x16(tmem_off + ((uint32_t)((warp & 3) * 32) << 16), v);
             tmem_ld_wait();
             tc_fence_before_sync();      // the accumulator may be overwritten by the next tile's offset conv after barrier B
+            tr(it, 1);
             float o[2 * N];
 #pragma unroll
             for (int e = 0; e < 2 * N; ++e) o[e] = __uint_as_float(v[e]) + sBias[e];
@@ -471,13 +546,17 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
             const int xb = it & g.xb_mask, ab = it & g.ab_mask;
             const TC cur = tile_coords(tile);
+            tr(it, 0);
             const uint32_t rec_s = smem_s + g.ofs_rec;
             const uint32_t x_s = smem_s + g.ofs_x + (uint32_t)xb * S::X_BYTES;
             cur_m = phase1(cur, rec_s, x_s, it);
+            tr(it, 2);
             op_bar_sync(1, NW);                                           // (A) records of this tile are visible
+            tr(it, 3);
             mbar_wait(&x_full[xb], (uint32_t)(it >> g.xb_shift) & 1u);   // the staged input tile has landed (acquire for the generic loads)
             if (g.ab_mask == 0 && it > 0) mbar_wait(&mma_done[(it - 1) & 1], ((it - 1) >> 1) & 1);   // operand buffer free again
 
+            tr(it, 4);
             // ---- phase 2: bilinear resampling into the swizzled operand tile; IF items in flight, loads first ------------------------
             {
                 const uint32_t a_s = smem_s + g.ofs_a + (uint32_t)ab * g.a_bytes;
@@ -530,14 +609,18 @@ ldconv_onepass_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
                         if (k + u < R) store_item(sx0 + (k + u) * spr, gw[u], q[u]);
                 }
             }
+            tr(it, 5);
             fence_proxy_async_smem();      // generic-proxy stores of the operand tile -> visible to tcgen05 (async proxy)
             op_bar_sync(2, NW);            // (B) operand tile complete, input tile consumed, epilogue(it - 2) done by every warp
             if (tid == 0) mbar_arrive(b_done);
+            tr(it, 6);
             if (it > 0) epilogue(prev_m, it - 1);      // the previous tile's MMAs ran during this tile's phases
+            tr(it, 7);
             prev_m = cur_m;
         }
         if (it > 0) epilogue(prev_m, it - 1);
     }
+    if (tr.on) tr.buf[2 * kOpTraceN] = tr.n;
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 1) {
@@ -600,28 +683,44 @@ static int op_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     const int tmem_cap = (int)(512u / (g.tmem_cols + 32u));
     // candidate plans (input-tile buffers, operand buffers): most CTAs per SM first, then the deeper buffering
     static const int cfg[4][2] = {{2, 2}, {2, 1}, {1, 2}, {1, 1}};
+    static int env_ts = -1;      // A/B switch while the TMA-store epilogue is being measured
+    if (env_ts < 0) { const char* e = getenv("LDCONV_OP_TSTORE"); env_ts = e ? atoi(e) : 1; }
     int best_ctas = 0;
     OPGeom best = g;
     size_t best_smem = 0;
-    for (int ci = 0; ci < 4; ++ci) {
-        OPGeom q = g;
-        q.XB = cfg[ci][0]; q.AB = cfg[ci][1];
-        uint32_t ofs = 0;
-        q.ofs_a = ofs; ofs += (uint32_t)q.AB * q.a_bytes;
-        q.ofs_b = ofs; ofs += (uint32_t)q.num_kb * q.b_bytes;
-        q.ofs_bc = ofs; ofs += (uint32_t)pl->kc_kb * 2048u;
-        q.ofs_x = ofs; ofs += (uint32_t)q.XB * q.x_bytes;
-        q.ofs_rec = ofs; ofs += (uint32_t)(128 * N * 32);
-        q.ofs_aff = ofs; ofs += (uint32_t)q.ON * 8u;
-        q.ofs_bias = ofs; ofs += 64u;
-        ofs = (ofs + 7u) & ~7u;
-        q.ofs_bar = ofs; ofs += 7u * 8u + 16u;
-        const size_t need = (size_t)ofs + 1024;
-        if (need > 225 * 1024) continue;
-        int ctas = (int)((227 * 1024) / (need + 1024));
-        if (ctas > reg_cap) ctas = reg_cap;
-        if (ctas > tmem_cap) ctas = tmem_cap;
-        if (ctas > best_ctas) { best_ctas = ctas; best = q; best_smem = need; }
+    const bool ts_shape = env_ts && (O == 16 || O == 32 || O == 64 || O == 128);
+    // with the TMA-store staging tile first; without it only when that costs a CTA per SM or does not fit (64 -> 128 channels)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ts = pass == 0 ? 1 : 0;
+        if (ts && !ts_shape) continue;
+        for (int ci = 0; ci < 4; ++ci) {
+            OPGeom q = g;
+            q.XB = cfg[ci][0]; q.AB = cfg[ci][1];
+            uint32_t ofs = 0;
+            q.ofs_a = ofs; ofs += (uint32_t)q.AB * q.a_bytes;
+            q.ofs_b = ofs; ofs += (uint32_t)q.num_kb * q.b_bytes;
+            q.ofs_bc = ofs; ofs += (uint32_t)pl->kc_kb * 2048u;
+            q.ofs_x = ofs; ofs += (uint32_t)q.XB * q.x_bytes;
+            q.ofs_rec = ofs; ofs += (uint32_t)(128 * N * 32);
+            q.tstore = ts;
+            q.st_rowb = (O < 64 ? O : 64) * 2;
+            q.ofs_stage = 0;
+            if (ts) {      // staging tile of the TMA-store epilogue: [64-channel block][128 pixels][row], 1024-aligned (swizzled rows)
+                ofs = (ofs + 1023u) & ~1023u;
+                q.ofs_stage = ofs;
+                ofs += (uint32_t)((O + 63) / 64) * 128u * 128u;
+            }
+            q.ofs_aff = ofs; ofs += (uint32_t)q.ON * 8u;
+            q.ofs_bias = ofs; ofs += 64u;
+            ofs = (ofs + 7u) & ~7u;
+            q.ofs_bar = ofs; ofs += 9u * 8u + 16u;
+            const size_t need = (size_t)ofs + 1024;
+            if (need > 225 * 1024) continue;
+            int ctas = (int)((227 * 1024) / (need + 1024));
+            if (ctas > reg_cap) ctas = reg_cap;
+            if (ctas > tmem_cap) ctas = tmem_cap;
+            if (ctas > best_ctas) { best_ctas = ctas; best = q; best_smem = need; }
+        }
     }
     if (best_ctas == 0) return 0;
     g = best;
@@ -661,7 +760,7 @@ int onepass_fwd(const void* x, const void* w_conv, const float* bias, const int*
         return fail(LDCONV_E_ARG, "one-pass LDConv kernel: shape not covered (C=%d N=%d s=%d O=%d ldo=%d H=%d W=%d)", C, N, s, O, ldo, H, W);
     if (!aligned16(x) || !aligned16(wt) || !aligned16(w_conv) || !aligned16(out))
         return fail(LDCONV_E_ALIGN, "one-pass LDConv kernel: x / weights / out must be 16-byte aligned");
-    CUtensorMap tmX, tmW, tmWc;
+    CUtensorMap tmX, tmW, tmWc, tmO;
     if (s == 1) {
         const int cb = C >= 64 ? 64 : C;
         cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -691,8 +790,17 @@ int onepass_fwd(const void* x, const void* w_conv, const float* bias, const int*
         cuuint32_t box[2] = {64, 16};
         if (int e = encode_map(&tmWc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_conv, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
     }
-    using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, const __nv_bfloat16*, const float*, const int*, const float*,
-                          const float*, __nv_bfloat16*, float*, OPGeom);
+    tmO = tmW;      // placeholder when the epilogue stores directly
+    if (g.tstore) {      // out (B, h, w, O | ldo): box = (one row of <= 64 channels, 8 columns, 16 rows) = the staging tile's order
+        const int cb = O < 64 ? O : 64;
+        cuuint64_t gdim[4] = {(cuuint64_t)O, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ldo * 2, (cuuint64_t)g.w * ldo * 2, (cuuint64_t)g.h * g.w * ldo * 2};
+        cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)kOpTW, (cuuint32_t)kOpTH, 1};
+        const CUtensorMapSwizzle sw = cb * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        if (int e = encode_map(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, sw)) return e;
+    }
+    using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const __nv_bfloat16*, const float*, const int*, const float*,
+                          const float*, __nv_bfloat16*, float*, long long*, OPGeom);
     Kern kern = nullptr;
     const int key = ((N * 10 + pl.cvs) * 10 + s) * 10 + g.per_sm;
     switch (key) {
@@ -714,14 +822,23 @@ int onepass_fwd(const void* x, const void* w_conv, const float* bias, const int*
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * g.per_sm;
     if (grid > g.num_tiles) grid = g.num_tiles;
-    LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(128 * pl.TG + 32), smem, st, tmX, tmW, tmWc, (const __nv_bfloat16*)x, bias, pn, scale,
-                        shift, (__nv_bfloat16*)out, off_dbg, g));
+    LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(128 * pl.TG + 32), smem, st, tmX, tmW, tmWc, tmO, (const __nv_bfloat16*)x, bias, pn, scale,
+                        shift, (__nv_bfloat16*)out, off_dbg, g_op_trace, g));
+    g_op_trace = nullptr;
     LDC_LAUNCH_CHECK("ldconv_onepass_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     return LDCONV_OK;
 }
 
 }  // namespace ldc
+
+// debug: the NEXT ldconv_onepass_fwd call of this thread writes its timeline into `device_buf` (2 x (2 * 64 + 2) long long: per
+// role (worker thread 0, issuer thread) pairs (iteration * 100 + tag, clock64) and the pair count)
+LDC_API int ldconv_debug_onepass_trace(void* device_buf)
+{
+    ldc::g_op_trace = (long long*)device_buf;
+    return LDCONV_OK;
+}
 
 LDC_API int ldconv_onepass_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype)
 {

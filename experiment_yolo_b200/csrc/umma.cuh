@@ -139,6 +139,18 @@ __device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, in
                  : "memory");
 }
 
+// TMA store of a shared-memory box into a tensor map (bulk async-group completion): the writers of the box must have executed
+// fence.proxy.async.shared::cta and synchronised with the issuing thread first
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
 // ---- TMEM --------------------------------------------------------------------------------------------------------------
 // one full warp allocates; the base address lands in shared memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols)
