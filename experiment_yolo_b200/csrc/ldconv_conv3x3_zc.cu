@@ -119,10 +119,16 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int tiles_per_img = g.tiles_h * g.tiles_w;
     const uint32_t half_bytes = g.x_bytes / (uint32_t)g.halves;
 
+    // Control warps: warp-uniform loops, one ELECTED lane issues.  Under `if (lane == 0)` every uniform-datapath instruction
+    // (UTMALDG, UTCHMMA, commits) is wrapped in an ELECT / BRA.U.ANY loop over the active lanes -- ~10 dependent instructions per
+    // MMA on the thread the whole CTA waits for (652 UTCHMMA / 918 such loops in this file's SASS before the change).
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes);
-            for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(sB + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+        const bool leader = elect_one();
+        {
+            if (leader) {
+                mbar_arrive_expect_tx(w_full, (uint32_t)g.num_kb * g.b_bytes);
+                for (int kb = 0; kb < g.num_kb; ++kb) tma_load_2d(sB + (size_t)kb * g.b_bytes, &tmW, w_full, kb * 64, 0);
+            }
             int it = 0;
             for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
                 const int buf = it % g.xbufs;
@@ -130,6 +136,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const int b = tile / tiles_per_img, rem = tile % tiles_per_img;
                 const int ti = rem / g.tiles_w, tj = rem % g.tiles_w;
                 tr(it, 100000 + it * 100);
+                if (!leader) continue;
                 mbar_arrive_expect_tx(&x_full[buf], g.x_tx_bytes);
                 for (int hf = 0; hf < g.halves; ++hf) {
                     if (TAPS == 4) {    // space-to-depth view: dims (2C [sx, c], sy, W/2, H/2, B); halves = 2 (block = one sy row of
@@ -145,7 +152,8 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         }
     } else if (warp == 1 || (ISSUERS == 2 && warp == 10)) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             const int q = warp == 1 ? 0 : 1;          // this issuer's tiles: it = q, q + ISSUERS, ...
             // The single issuing thread is the serial resource of this kernel (profiles/r1_conv3x3_timeline.txt: ~230 cycles
             // per MMA when the descriptors are rebuilt with run-time arithmetic), so everything that depends only on the
@@ -175,6 +183,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * g.ON);
                 const uint64_t descA = descA_hi | (uint64_t)(x0 + (uint32_t)xb * xstep);
+                if (leader) {
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
@@ -193,6 +202,8 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
                 mma_commit(&x_empty[xb]);     // the tile slot is free once these MMAs have read it
                 mma_commit(&t_full[buf]);
+                }
+                __syncwarp();
                 tr(it, 300000 + it * 100);
             }
         }

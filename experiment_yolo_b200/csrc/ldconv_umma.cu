@@ -211,20 +211,27 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The two control warps run their loops WARP-UNIFORMLY and one elected lane issues: under `if (lane == 0)` the compiler wraps
+    // every uniform-datapath instruction (UTMALDG, UTCHMMA, the commits) in an ELECT / BRA.U.ANY loop over the active lanes, ~10
+    // dependent instructions per MMA on the one thread the whole CTA waits for (benchmarks/trace_onepass.py, round 2).
     if (warp == 0) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    if (dbg & 1) {          // experiment: no operand traffic (results are garbage)
-                        mbar_arrive(&full[s]);
-                    } else {
-                        mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
-                        tma_load_2d(sA + (size_t)s * kABytes, &tmA, &full[s], kb * kBlockK, tile * kTileM);
-                        tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], kb * kBlockK, 0);
+                    if (leader) {
+                        if (dbg & 1) {          // experiment: no operand traffic (results are garbage)
+                            mbar_arrive(&full[s]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+                            tma_load_2d(sA + (size_t)s * kABytes, &tmA, &full[s], kb * kBlockK, tile * kTileM);
+                            tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], kb * kBlockK, 0);
+                        }
                     }
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -233,7 +240,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // (three issuing warps on alternate tiles were tried: the pure hand-off time fell from 31 to 20 us at layer 1, the full
         // kernel did not move -- it is bound by the TMA box-row rate of the operand loads, ~1 row per 10 cycles per SM whatever
         // the row width, scripts/gemm_dbg.sh -- and sharing the stage ring between issuers needs per-issuer sub-rings)
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             const uint32_t idesc = make_idesc_bf16(kTileM, ON);
             int s = 0;
             uint32_t ph = 0;
@@ -249,15 +257,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc_fence_after_sync();
                     const uint32_t a_addr = smem_u32(sA + (size_t)s * kABytes);
                     const uint32_t b_addr = smem_u32(sB + (size_t)s * b_bytes);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
-                                    (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            mma_bf16_ss(d_tmem, make_desc_k_sw128(a_addr + k * 32), make_desc_k_sw128(b_addr + k * 32), idesc,
+                                        (uint32_t)((kb | k) != 0));
+                        }
+                        mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
                     }
-                    mma_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1; }
                 }
-                mma_commit(&tfull[buf]);
+                if (leader) mma_commit(&tfull[buf]);
+                __syncwarp();
             }
         }
     } else {
