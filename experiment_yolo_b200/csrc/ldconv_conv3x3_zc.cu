@@ -266,19 +266,8 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
-static int zc_enabled()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LDCONV_CONV_ZC"); v = e ? atoi(e) : 1; }
-    return v;
-}
-
-static int zc_two_issuers()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LDCONV_ZC_ISSUERS"); v = e ? (atoi(e) >= 2) : 1; }
-    return v;
-}
+static constexpr int zc_enabled() { return 1; }
+static constexpr int zc_two_issuers() { return 1; }      // one CTA per SM: a second issuing warp takes the odd tiles
 
 int conv3x3_zc_supported(int Cin, int Cout, int s, int mode)
 {
@@ -319,8 +308,8 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
     g.x_bytes = half_pitch * g.halves;
     g.ldo = ldo; g.ldr = ldr;
     // measured on B200: the swizzle XOR uses absolute shared-memory address bits, so the descriptor's matrix-base-offset
-    // stays 0 even for starts that are not aligned to the swizzle pattern (LDCONV_ZC_BASE=1 is the experiment that fails)
-    { const char* e = getenv("LDCONV_ZC_BASE"); g.base_mode = e ? atoi(e) : 0; }
+    // stays 0 even for starts that are not aligned to the swizzle pattern
+    g.base_mode = 0;
     { const char* e = getenv("LDCONV_DBG"); g.dbg = e ? atoi(e) : 0; }
     const size_t wbytes = (size_t)g.num_kb * g.b_bytes;
     // two CTAs (two MMA issuers) per SM when the weights + a useful tile ring fit in half the shared memory
@@ -394,9 +383,6 @@ int conv3x3_zc(const void* x, int ldx, const void* wt, const float* scale, const
 int conv3x3_zc_s2d_supported(int C, int N, int H, int W)
 {
     if (!zc_enabled()) return 0;
-    static int en = -1;
-    if (en < 0) { const char* e = getenv("LDCONV_CONV_S2D"); en = e ? atoi(e) : 1; }
-    if (!en) return 0;
     return (C == 16 || C == 32 || C == 64) && N >= 1 && 2 * N <= 16 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2;
 }
 

@@ -496,8 +496,7 @@ l0_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w_
 
 static bool l0_rows_applicable(const void* x, int B, int C, int H, int W, int N, int s, int O)
 {
-    static const int enabled = getenv("LDCONV_L0_ROWS") ? atoi(getenv("LDCONV_L0_ROWS")) : 1;
-    return enabled && C == 3 && N == 3 && O == 16 && s == 2 && H % 2 == 0 && W % 2 == 0 && ((uintptr_t)x & 3) == 0 &&
+    return C == 3 && N == 3 && O == 16 && s == 2 && H % 2 == 0 && W % 2 == 0 && ((uintptr_t)x & 3) == 0 &&
            (long long)H * W * C < (1ll << 31) && (long long)B * (H / 2) < (1ll << 31);
 }
 
@@ -510,8 +509,6 @@ static int l0_slot(int dev, int act, const void* w_off, const void* b_off, const
     static std::mutex mu;
     static L0Slot table[64];
     static int used = 0;
-    static const int enabled = getenv("LDCONV_L0_CONST") ? atoi(getenv("LDCONV_L0_CONST")) : 1;
-    if (!enabled) return -1;
     std::lock_guard<std::mutex> lock(mu);
     int on_dev = 0;
     for (int t = 0; t < used; ++t) {
@@ -542,7 +539,7 @@ static int launch_l0_rows(const __nv_bfloat16* x, const float* w_off, const floa
     const int h = H / 2, w = W / 2, rows = B * h;
     const int threads = w % 160 == 0 ? 160 : (w >= 128 ? 128 : ((w + 31) / 32) * 32);
     // CTAs per SM the register budget is compiled for: 6 (64 registers) or 5 (80 registers)
-    static const int minb = getenv("LDCONV_L0_MINB") ? atoi(getenv("LDCONV_L0_MINB")) : 6;
+    constexpr int minb = 6;      // measured: the 64-register build with six CTAs per SM (profiles/r1_l0_ab_s4.jsonl)
     int dev = 0;
     LDC_CUDA(cudaGetDevice(&dev));
     L0Weights* slot_addr = nullptr;
@@ -593,7 +590,7 @@ static int launch_smallc(const T* x, const float* w_off, const float* b_off, con
     const int O2P = (2 * N + 3) & ~3;
     const size_t smem = (size_t)(((THin * TWin * C + 3) & ~3) + 9 * C * O2P + N * C * O + 2 * O) * sizeof(float);
     const long long ctas = (long long)B * tiles_h * tiles_w;
-    static const int use_tiled = getenv("LDCONV_SMALLC_TILED") ? atoi(getenv("LDCONV_SMALLC_TILED")) : 0;   // measured slower (1448 vs 1124 us on layer 0)
+    constexpr int use_tiled = 0;      // the tiled variant measured slower (1448 vs 1124 us on layer 0); kept for C = 4 experiments
     if (use_tiled && smem <= 96 * 1024 && ctas <= 0x7fffffffll) {
         auto kern = smallc_tiled_kernel<T, C, 9>;
         LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -633,11 +630,6 @@ static int dispatch_smallc(const void* x, const float* w_off, const float* b_off
     }
 }
 
-int umma_fused_supported(int B, int C, int H, int W, int N, int s, int O, int dtype);
-int umma_fused_fwd(const void* x, const float* w_off, const float* b_off, const int* pn, const void* wt,
-                   const float* scale, const float* shift, void* out, float* off_out, int B, int C, int H, int W, int N,
-                   int s, int O, int act, cudaStream_t st);
-
 }  // namespace ldc
 
 using namespace ldc;
@@ -647,8 +639,8 @@ LDC_API int ldconv_fused_supported(int B, int C, int H, int W, int N, int s, int
     if (B < 0 || C < 1 || H < 1 || W < 1 || N < 1 || s < 1 || O < 1) return 0;
     if (dtype != LDCONV_F32 && dtype != LDCONV_BF16) return 0;
     const int V = dtype == LDCONV_BF16 ? 8 : 4;
-    if (C <= 4 && N <= 9 && O <= 32 && O % V == 0) return 1;
-    return umma_fused_supported(B, C, H, W, N, s, O, dtype);
+    // small-C layers only (the model's first row); wider layers take ldconv_onepass_fwd (offset conv on the tensor cores)
+    return (C <= 4 && N <= 9 && O <= 32 && O % V == 0) ? 1 : 0;
 }
 
 LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, const int32_t* p_n, const void* wt,
@@ -664,14 +656,10 @@ LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_o
     if (B == 0) return LDCONV_OK;
     LDC_REQUIRE(aligned16(out), "ldconv_fused_fwd: out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (C <= 4) {
-        if (dtype == LDCONV_BF16 && l0_rows_applicable(x, B, C, H, W, N, s, O))
-            return launch_l0_rows((const __nv_bfloat16*)x, w_off, b_off, p_n, (const __nv_bfloat16*)wt, scale, shift,
-                                  (__nv_bfloat16*)out, off_out, B, H, W, act, st);
-        if (dtype == LDCONV_BF16)
-            return dispatch_smallc<__nv_bfloat16>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O,
-                                                  act, st);
-        return dispatch_smallc<float>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
-    }
-    return umma_fused_fwd(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
+    if (dtype == LDCONV_BF16 && l0_rows_applicable(x, B, C, H, W, N, s, O))
+        return launch_l0_rows((const __nv_bfloat16*)x, w_off, b_off, p_n, (const __nv_bfloat16*)wt, scale, shift,
+                              (__nv_bfloat16*)out, off_out, B, H, W, act, st);
+    if (dtype == LDCONV_BF16)
+        return dispatch_smallc<__nv_bfloat16>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
+    return dispatch_smallc<float>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
 }

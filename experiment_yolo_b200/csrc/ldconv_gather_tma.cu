@@ -297,9 +297,7 @@ static int gather_tiled_t(const T* x, const float* off, const int* pn, T* operan
 
     const size_t smem = smem_of(g) + 16 + rec_bytes(g) + 128;
     if constexpr (sizeof(T) == 2) {      // shape-specialised instances (yolov8-LD-P2, 8 x 16 tile, no debug outputs, 32-bit indices)
-        static int env_v = -1;           // LDCONV_GATHER_V=1: the generic kernel everywhere (A/B partner)
-        if (env_v < 0) { const char* e = getenv("LDCONV_GATHER_V"); env_v = e ? atoi(e) : 2; }
-        if (env_v >= 2 && g.TH == 8 && g.TW == 16 && g.cv_shift >= 0 && !dbg_idx && !dbg_coord && !g_miss_counter &&
+        if (g.TH == 8 && g.TW == 16 && g.cv_shift >= 0 && !dbg_idx && !dbg_coord && !g_miss_counter &&
             (long long)B * h * w * N * C < 0x7fffffffll && (long long)H * W * C * 2 < 0x7fffffffll) {
             using K2 = void (*)(CUtensorMap, const __nv_bfloat16*, const float*, const int*, __nv_bfloat16*, int, int, int, int, float,
                                 float, TileGeom);

@@ -345,12 +345,7 @@ thin_tn_kernel(const T* __restrict__ G, const T* __restrict__ A, float* __restri
     for (int t = tid; t < O * K; t += blockDim.x) atomicAdd(dW + t, sAcc[t / K][t % K]);
 }
 
-static int thin_enabled()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LDCONV_THIN_GEMM"); v = e ? atoi(e) : 1; }
-    return v;
-}
+static constexpr int thin_enabled() { return 1; }      // K <= 16, O <= 16: thread-per-row kernels (145.8 vs 149.8 ms per training step)
 
 template <typename T>
 static int gemm_nt_t(const T* a, const T* wt, const float* scale, const float* shift, T* out, T* pre, double* stat_sum,

@@ -679,12 +679,7 @@ ldconv_gg2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
-static int gg_v2_enabled()      // LDCONV_GG_V=1: the generic kernel everywhere (A/B partner); 3: v2 without shape specialisation
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LDCONV_GG_V"); v = e ? atoi(e) : 2; }
-    return v >= 2 ? v : 0;
-}
+static constexpr int gg_v2_enabled() { return 2; }      // v2 kernel with the shape-specialised instances (settled in round 1)
 
 static void gg_pn_extent(int N, int* max_r, int* max_k)
 {
@@ -737,22 +732,13 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     g.split = 0;
     GGGeom best = g;
     size_t best_smem = 0;
-    static int env_plan = -2, env_ctas = -2, env_tg = -2;      // experiments: LDCONV_GG_PLAN=<plan index>, LDCONV_GG_CTAS=<CTAs per SM>
-    if (env_tg == -2) { const char* e = getenv("LDCONV_GG_TG"); env_tg = e ? atoi(e) : -1; }
     // N = 3 (every strided LDConv of yolov8-LD-P2): 384 samples per tile -> 384 threads make phase 1 one balanced round
     // (profiles/r1_ncu_ggL1v4.txt: 17 % of the stall samples were warps 4-7 waiting at barrier A for the second round of warps 0-3)
     // measured (B = 64, bf16): C = 32 / 64 gain 3-7 % with 384 threads (shared memory limits them to 1-2 CTAs per SM, so the extra
     // warps are free); C = 16 (layer 1) loses 9 % (two CTAs of 12 warps instead of three of 8) and keeps 256 threads
     g.TG = (gg_v2_enabled() && g.cv_shift >= 2 && N % 3 == 0) ? 3 : 2;
-    if (env_tg == 2 || env_tg == 3) g.TG = (env_tg == 3 && (N * g.CV) % 3 != 0) ? 2 : env_tg;
     const int reg_cap = g.TG == 3 ? 2 : 3;      // CTAs per SM the register file allows at 80 registers per thread
-    if (env_plan == -2) { const char* e = getenv("LDCONV_GG_PLAN"); env_plan = e ? atoi(e) : -1; }
-    if (env_ctas == -2) { const char* e = getenv("LDCONV_GG_CTAS"); env_ctas = e ? atoi(e) : -1; }
-    static int env_merge = -2;
-    if (env_merge == -2) { const char* e = getenv("LDCONV_GG_MERGE"); env_merge = e ? atoi(e) : -1; }
-    static int env_split = -2;
-    if (env_split == -2) { const char* e = getenv("LDCONV_GG_SPLIT"); env_split = e ? atoi(e) : 1; }
-    const bool split_ok = env_split != 0 && gg_v2_enabled() && g.cv_shift >= 0 && s == 2 && W % 2 == 0 && C <= 32;
+    const bool split_ok = gg_v2_enabled() && g.cv_shift >= 0 && s == 2 && W % 2 == 0 && C <= 32;
     // shared-memory layout of plan ci with (mg + 1) record buffers -> CTAs per SM (0: does not fit)
     auto layout = [&](int ci, int mg, GGGeom& q, size_t& need) {
         q.halo = cfg[ci][0]; q.XB = cfg[ci][1]; q.AB = cfg[ci][2];
@@ -780,13 +766,11 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
         int ctas = (int)((227 * 1024) / (need + 1024));          // + the per-CTA reservation of the driver
         if (ctas > reg_cap) ctas = reg_cap;
         if (ctas > (int)(512u / q.tmem_cols)) ctas = (int)(512u / q.tmem_cols);
-        if (env_ctas >= 1 && ctas > env_ctas) ctas = env_ctas;
         q.merge = mg;
         return ctas;
     };
     int best_ci = -1;
     for (int ci = 0; ci < 5; ++ci) {
-        if (env_plan >= 0 && ci != env_plan) continue;
         size_t need = 0;
         const int ctas = layout(ci, 0, g, need);
         if (ctas > best_ctas) { best_ctas = ctas; best = g; best_smem = need; best_ci = ci; }
@@ -794,7 +778,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     // One-barrier flow (phase 1 of the next tile shares the barrier interval of phase 2; two record buffers): measured to pay
     // for N = 1 (layer 15: 95 -> 86 us; phase 1 occupies half the warps there) and not for N = 3 (layer 1: 127 -> 134 us), and
     // only taken when the SAME buffering plan keeps its CTAs per SM with the second record buffer.
-    if (best_ci >= 0 && gg_v2_enabled() && g.cv_shift >= 0 && (env_merge == 1 || (env_merge != 0 && N == 1))) {
+    if (best_ci >= 0 && gg_v2_enabled() && g.cv_shift >= 0 && N == 1) {
         size_t need = 0;
         GGGeom q = g;
         if (layout(best_ci, 1, q, need) == best_ctas) { best = q; best_smem = need; }
@@ -808,7 +792,7 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     const long long nt = (long long)B * g.tiles_h * g.tiles_w;
     if (nt > 0x7fffffffll || (long long)B * g.h * g.w > 0x7fffffffll) return 0;
     g.num_tiles = (int)nt;
-    { static int d = -1; if (d < 0) { const char* e = getenv("LDCONV_GG_DBG"); d = e ? atoi(e) : 0; } g.dbg = d; }
+    g.dbg = 0;
     // tile / tiles_per_img and rem / tiles_w as __umulhi(x, ceil(2^32 / d)): exact while x * d < 2^32
     const unsigned tpi = (unsigned)(g.tiles_h * g.tiles_w);
     if (nt * tpi >= 0xffffffffll) return 0;
@@ -819,16 +803,10 @@ static int gg_geometry(int B, int C, int H, int W, int N, int s, int O, int ldo,
     return 1;
 }
 
-static int gg_enabled()
-{
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LDCONV_GG"); v = e ? atoi(e) : 1; }
-    return v;
-}
 
 int gather_gemm_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype)
 {
-    if (!gg_enabled() || dtype != LDCONV_BF16) return 0;
+    if (dtype != LDCONV_BF16) return 0;
     GGGeom g;
     size_t smem;
     return gg_geometry(B, C, H, W, N, s, O, ldo, LDCONV_ACT_SILU, &g, &smem);

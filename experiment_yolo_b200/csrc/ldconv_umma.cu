@@ -365,7 +365,7 @@ int umma_set_force_ffma(int v)
 int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                      const void* residual, int ldr, int ldo, double* stat_sum, double* stat_sqsum, int M, int K, int O, int act,
                      cudaStream_t st);
-static thread_local GemmOut2 g_out2 = {nullptr, 0, 0, 0};      // consumed (and cleared) by the next umma_gemm_fwd_ld of this thread
+static thread_local GemmOut2 g_out2 = {nullptr, 0, 0, 0};      // snapshotted and cleared at the entry of the next umma_gemm_fwd_ld of this thread
 static thread_local GemmMaxUp g_maxup = {nullptr, nullptr, 0, 0, 0, 0, 0, 0};      // likewise
 static thread_local GemmPack g_pack = {1, 0};                                       // likewise
 
@@ -379,6 +379,15 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
                      const void* residual, int ldr, int ldo, double* stat_sum, double* stat_sqsum, int M, int K, int O, int act,
                      cudaStream_t st)
 {
+    // The epilogue extensions arrive through thread-local side channels set by the C entry points right before this call: they are
+    // snapshotted AND cleared here, before any return path, so a failed call can never leak a stale second-output pointer / packing
+    // factor into the next, unrelated GEMM of this thread.
+    const GemmOut2 o2 = g_out2;
+    const GemmMaxUp mu = g_maxup;
+    const GemmPack pk = g_pack;
+    g_out2 = GemmOut2{nullptr, 0, 0, 0};
+    g_maxup = GemmMaxUp{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+    g_pack = GemmPack{1, 0};
     if (stat_sum && !pre) return fail(LDCONV_E_ARG, "tcgen05 GEMM: batch statistics need the `pre` output");
     const int ON = (O + 15) / 16 * 16;
     const int num_kb = (K + kBlockK - 1) / kBlockK;
@@ -390,14 +399,9 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     // accumulator buffers: as many as fit 256 TMEM columns (two CTAs per SM), at most 8, a power of two
     int NB = 8;
     while (NB > 2 && NB * ON > 256) NB >>= 1;
-    static int g_env_nb = -2;
-    if (g_env_nb == -2) { const char* e = getenv("LDCONV_GEMM_NB"); g_env_nb = e ? atoi(e) : -1; }
-    if ((g_env_nb == 2 || g_env_nb == 4 || g_env_nb == 8) && g_env_nb <= NB) NB = g_env_nb;
     // warp-staged stores: plain outputs (no pre / residual / second output / max-up / packing) with rows of 64 or 128 bytes
-    static int env_stage = -2;
-    if (env_stage == -2) { const char* e = getenv("LDCONV_GEMM_STAGE"); env_stage = e ? atoi(e) : 1; }
     int stage_rb = 0;
-    if (env_stage && out && !pre && !residual && !g_out2.ptr && !g_maxup.z1 && g_pack.P == 1 && (O == 32 || O == 64) && ldo % 8 == 0 &&
+    if (out && !pre && !residual && !o2.ptr && !mu.z1 && pk.P == 1 && (O == 32 || O == 64) && ldo % 8 == 0 &&
         aligned16(out))
         stage_rb = O * 2;
     const int stage_bytes = stage_rb ? 8 * 32 * stage_rb + 16 : 0;
@@ -413,19 +417,13 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     if (int e = make_map_2d(&tmA, a, M, K, kTileM, lda)) return e;
     if (int e = make_map_2d(&tmB, wt, O, K, ON, K)) return e;
 
-    const GemmMaxUp mu = g_maxup;
-    g_maxup = GemmMaxUp{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
-    const GemmPack pk = g_pack;
-    g_pack = GemmPack{1, 0};
-    if (pk.P > 1 && (mu.z1 || g_out2.ptr || residual || pre || stat_sum))
+    if (pk.P > 1 && (mu.z1 || o2.ptr || residual || pre || stat_sum))
         return fail(LDCONV_E_ARG, "tcgen05 GEMM: pixel packing takes no residual / second output / statistics");
     auto kern = mu.z1 ? umma_gemm_kernel<true> : umma_gemm_kernel<false>;
     LDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = num_sms() * (two_per_sm ? 2 : 1);
     if (grid > num_tiles) grid = num_tiles;
     const int vec_store = (O % 8 == 0) && (ldo % 8 == 0) && (!out || aligned16(out)) && (!pre || aligned16(pre));
-    const GemmOut2 o2 = g_out2;
-    g_out2 = GemmOut2{nullptr, 0, 0, 0};
     if (o2.ptr && (!vec_store || !out || O % 16 != 0))
         return fail(LDCONV_E_ARG, "tcgen05 GEMM: the second output needs 16-byte stores and Cout %% 16 == 0");
     if (mu.z1 && (!vec_store || !out || pre || O % 16 != 0))

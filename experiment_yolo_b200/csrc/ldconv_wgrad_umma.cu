@@ -130,9 +130,6 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 
 int wgrad_umma_supported(int M, int K, int O, const void* g, const void* a)
 {
-    static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("LDCONV_WGRAD_TC"); enabled = e ? atoi(e) : 1; }
-    if (!enabled) return 0;
     return M >= 1 && O >= 1 && O <= 128 && K % 8 == 0 && O % 8 == 0 && aligned16(g) && aligned16(a);
 }
 

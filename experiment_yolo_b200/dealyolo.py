@@ -252,7 +252,7 @@ class DealYolo(nn.Module):
         self.save = sorted(save)
         head = self.model[-1]
         # the reference discovers these with a 2x3x640x640 probe forward (nn/tasks.py:309-324); they are the P2/P3/P4
-        # strides of this graph, so they are set directly and checked by tests/test_model_cpu.py against a probe
+        # strides of this graph, so they are set directly and checked by tests/test_torch_port.py::test_strides_agree_with_a_probe_forward against a probe
         head.stride = torch.tensor(strides)
         self.stride = head.stride
         head.bias_init()

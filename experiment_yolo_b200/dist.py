@@ -48,7 +48,11 @@ class FlatGradAllReduce:
         self.views, ofs = [], 0
         for p in self.params:
             n = p.numel()
-            self.views.append(self.flat[ofs:ofs + n].view_as(p))
+            chunk = self.flat[ofs:ofs + n]
+            # same strides as the parameter (autograd's gradient layout contract): channels_last weights get a channels_last view
+            # of their slice, so AccumulateGrad adds in place without a layout-converting copy
+            dense_cl = p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last)
+            self.views.append(chunk.as_strided(p.size(), p.stride()) if dense_cl else chunk.view_as(p))
             ofs += n
         # bucket k covers parameters [cut[k], cut[k+1]); bucket len-1 (the last layers) is complete first during backward
         buckets = max(1, min(int(buckets), len(self.params) or 1))
@@ -81,7 +85,7 @@ class FlatGradAllReduce:
         k, i = self.bucket_of[id(p)]
         v = self.views[i]
         if p.grad is not None and p.grad.data_ptr() != v.data_ptr():      # someone reset .grad (zero_grad(set_to_none=True)): adopt
-            v.copy_(p.grad.reshape(v.shape))
+            v.copy_(p.grad)
             p.grad = v
         self.pending[k] -= 1
         if self.pending[k] == 0:
@@ -103,7 +107,7 @@ class FlatGradAllReduce:
         """after backward(): reduce what is still local, wait for every slice; `.grad` then holds the summed gradients"""
         for p, v in zip(self.params, self.views):      # parameters autograd never touched keep their zero view
             if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad.reshape(v.shape))
+                v.copy_(p.grad)
                 p.grad = v
         for k in range(len(self.cut) - 1):
             self._launch(k)

@@ -292,12 +292,8 @@ def ldconv_fused_inference(x, prepared: _Prepared, scale, shift, C, O, N, s):
 class LDConv(nn.Module):
     """B200-native LDConv.  Signature, children, buffer and state_dict layout: conv.py:350-359."""
 
-    # one-kernel inference path (tcgen05) when shapes allow; class-level switch so tests can A/B it
+    # small-C one-kernel inference path (the model's first row, C <= 4: ldconv_fused_fwd); class-level switch so tests can A/B it
     use_fused_inference = True
-    # the tcgen05 one-kernel path (C % 16 == 0) is correct but, until its offset-conv phase moves to the tensor cores, slower
-    # than offset-conv(tcgen05) -> gather -> GEMM(tcgen05) on the YAML's shapes (profiles/r1_layers_*.jsonl); the small-C
-    # one-kernel path (layer 0) is always used
-    fused_tcgen05 = False
     # inference: gather + GEMM + BN + SiLU as one persistent kernel after the tensor-core offset conv (ldconv_gather_gemm_fwd)
     use_gather_gemm = True
     # inference: the whole forward in one kernel, offset conv on the tensor cores over the gather's own staged tile
@@ -354,8 +350,6 @@ class LDConv(nn.Module):
         if bn.running_mean is None or self.conv[0].bias is not None:
             return False
         B, C, H, W = x.shape
-        if C > 4 and not self.fused_tcgen05:
-            return False
         return bool(_lib.load().ldconv_fused_supported(B, C, H, W, self.num_param, int(self.stride),
                                                        self.conv[0].out_channels, _DTYPES[x.dtype]))
 

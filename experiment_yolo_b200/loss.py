@@ -227,7 +227,13 @@ class DealYoloLoss(nn.Module):
         start = torch.cumsum(counts, 0) - counts
         pos = torch.arange(t, device=device) - start[idx[order]]
         out = torch.zeros((b, n_max, 5), device=device)
-        out[idx[order], pos] = rows[order]
+        if self.max_boxes is not None:
+            # a fixed `max_boxes` avoids the host sync of counts.max(); targets beyond it are dropped by a mask (an unchecked
+            # `out[idx, pos] = ...` with pos >= n_max is a device-side assert that poisons the CUDA context)
+            keep = pos < n_max
+            out[idx[order][keep], pos[keep]] = rows[order][keep]
+        else:
+            out[idx[order], pos] = rows[order]
         h, w = imgsz_hw
         xywh = out[..., 1:5] * torch.tensor([w, h, w, h], device=device, dtype=out.dtype)
         half = xywh[..., 2:] / 2

@@ -525,11 +525,14 @@ def test_prepared_cache_survives_inference_mode_then_training():
     (3, 16, 3, 2, 16, 320, 2, 0.05), (3, 16, 3, 2, 24, 400, 1, 0.1), (3, 16, 3, 2, 30, 50, 3, 0.3), (3, 16, 3, 2, 2, 2, 1, 0.05),
     (3, 16, 3, 2, 31, 50, 2, 0.05), (3, 16, 3, 2, 30, 51, 2, 0.05)])
 def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s, H, W, B, sigma):
-    """ldconv_fused_fwd (small-C CUDA-core kernel / tcgen05 kernel) against (a) the offset_conv -> gather -> gemm path on
-    the same inputs and (b) the fp32 oracle on bf16-rounded tensors (rel-L2 <= 1e-2).  sigma scales p_conv.weight: large
-    values push samples outside the staged halo (L2 path) and outside the image (clamp quirk)."""
+    """The one-kernel inference paths -- ldconv_fused_fwd (C <= 4: first-layer rows kernel / thread-per-pixel kernel) and
+    ldconv_onepass_fwd (the yolov8-LD-P2 shapes with C >= 16) -- against (a) the offset_conv -> gather -> gemm path on the same
+    inputs and (b) the fp32 oracle on bf16-rounded tensors (rel-L2 <= 1e-2).  sigma scales p_conv.weight: large values push
+    samples outside the staged halo (L2 path) and outside the image (clamp quirk).  Shapes neither kernel covers take the
+    gather+GEMM kernel in both runs."""
     L = _lib.load()
-    assert L.ldconv_fused_supported(B, C, H, W, N, s, O, _lib.BF16) == 1
+    small_c = C <= 4
+    assert L.ldconv_fused_supported(B, C, H, W, N, s, O, _lib.BF16) == int(small_c)
     torch.manual_seed(C * 7 + O + N)
     mod = E.LDConv(C, O, N, s)
     with torch.no_grad():
@@ -549,15 +552,16 @@ def test_fused_inference_kernel_matches_three_kernel_path_and_oracle(C, O, N, s,
     outs = {}
     for fused in (True, False):
         E.LDConv.use_fused_inference = fused
-        E.LDConv.fused_tcgen05 = True
+        E.LDConv.use_onepass = fused
         try:
             _lib.call_counts.clear()
             with torch.no_grad():
                 outs[fused] = dmod(xd).float().cpu().numpy()
-            assert ("ldconv_fused_fwd" in _lib.call_counts) == fused
+            assert ("ldconv_fused_fwd" in _lib.call_counts) == (fused and small_c)
+            assert not ("ldconv_onepass_fwd" in _lib.call_counts and not fused)
         finally:
             E.LDConv.use_fused_inference = True
-            E.LDConv.fused_tcgen05 = False
+            E.LDConv.use_onepass = True
     assert _rel(outs[True], f["out"]) <= 1e-2
     assert _rel(outs[True], outs[False]) <= 6e-3
     if sigma <= 0.1:

@@ -78,3 +78,14 @@ def test_assigner_invariants_on_uav_targets():
     assert float(ts.max()) <= 1.0 + 1e-6 and float(ts.min()) >= 0.0
     assert bool(((ts > 0).sum(-1) <= 1).all()) and float(ts[~fg].abs().max()) == 0.0
     assert bool((ts[fg].argmax(-1) == tl[fg]).logical_or(ts[fg].sum(-1) == 0).all())
+
+
+def test_max_boxes_smaller_than_an_images_target_count_drops_the_excess_instead_of_indexing_out_of_range():
+    """with a fixed `max_boxes` (no host sync) an image with more targets must not index past the padded tensor."""
+    from experiment_yolo_b200.loss import DealYoloLoss
+    crit = DealYoloLoss(nc=6, max_boxes=3, fused_assigner=False)
+    batch = {"batch_idx": torch.tensor([0, 0, 0, 0, 0, 1]), "cls": torch.zeros(6), "bboxes": torch.rand(6, 4) * 0.5 + 0.1}
+    out = crit.preprocess(batch, 2, (64, 64), torch.device("cpu"))
+    assert tuple(out.shape) == (2, 3, 5)
+    full = DealYoloLoss(nc=6, fused_assigner=False).preprocess(batch, 2, (64, 64), torch.device("cpu"))
+    assert torch.equal(out[0], full[0, :3]) and torch.equal(out[1, :1], full[1, :1])
