@@ -51,6 +51,7 @@ SIGNATURES = {
     "ldconv_conv1x1_bn_act_fwd2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _ll, _i, _i, _i, _i, _vp]),
     "ldconv_conv3x3_supported": (_i, [_i] * 4),
     "ldconv_conv3x3_bn_act_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 8 + [_vp]),
+    "ldconv_conv1x1_detect_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "ldconv_detect_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "ldconv_nms_workspace_bytes": (ctypes.c_size_t, [_i, _i]),
     "ldconv_nms": (_i, [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _i, _i, _f, _f, _i, _i, _i, _f, _i, _vp]),

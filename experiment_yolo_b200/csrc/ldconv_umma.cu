@@ -72,6 +72,40 @@ struct GemmPack {
     int P, o_shift;
 };
 
+// Detect head in the epilogue (nn/modules/head.py:55-77): the LAST 1x1 conv of a branch decodes its own accumulator rows instead of
+// writing logits that a decode kernel reads back.  mode 1 (box branch, Cout = 4 x 16 DFL bins): per side softmax-expectation over
+// the 16 bins (DFL, nn/modules/block.py:37-56), dist2bbox around the cell-centre anchor (utils/tal.py:309-319), times the level
+// stride -> rows 0..3 of y (B, 4+nc, total) at column a0 + pixel.  mode 2 (class branch, Cout = nc <= 16): sigmoid -> rows 4..4+nc.
+// The logits are rounded to bf16 first, exactly like the plain epilogue's store, and the arithmetic is detect_decode_kernel's: y is
+// bit-identical to conv1x1 -> ldconv_detect_decode, minus a 275 MB round trip of logits per 64 images.
+struct GemmDetect {
+    __nv_bfloat16* y;
+    int mode, H, W, nc, a0, total;
+    float stride;
+};
+
+__device__ __forceinline__ void detect_logits16(const uint32_t (&v)[16], uint32_t sc_addr, uint32_t sh_addr, float (&z)[16])
+{
+    affine_act16(v, sc_addr, sh_addr, LDCONV_ACT_NONE, z);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) z[e] = __bfloat162float(__float2bfloat16_rn(z[e]));      // what the unfused path stores and reloads
+}
+
+__device__ __forceinline__ float dfl_expectation16(const float (&v)[16])
+{
+    float mx = v[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) mx = fmaxf(mx, v[k]);
+    float den = 0.f, num = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float e = __expf(v[k] - mx);
+        den += e;
+        num = fmaf(e, (float)k, num);
+    }
+    return num / den;
+}
+
 // aff_s = shared-space address of the scale of column c0, aff_s + sh_ofs = of its shift (explicit LDS: the generic loads this replaces were
 // the top stall of the kernel, profiles/r1_ncu_gemmL1b.txt).
 __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], long long m, int c0, int O, uint32_t aff_s, int act,
@@ -164,7 +198,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                  __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ residual, int M, int O, int ON, int num_kb,
                  int num_tiles, int stages, int act, uint32_t tmem_cols, int vec_store, int ldo, int ldr, int NB, int dbg,
-                 GemmOut2 o2, GemmMaxUp mu, GemmPack pk, int stage_rb)
+                 GemmOut2 o2, GemmMaxUp mu, GemmPack pk, int stage_rb, GemmDetect det)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space: LDS / STS, not generic LD / ST
@@ -296,6 +330,48 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mx1 = mu.z1 + (((long long)b * mu.H1 + i1) * mu.W1 + j1) * O;
                 mx2 = mu.z2 + (((long long)b * mu.H2 + i2) * mu.W2 + j2) * O;
             }
+            if (det.mode) {
+                // ---- Detect decode in the epilogue (see GemmDetect) ----------------------------------------------------------------
+                const uint32_t sh_ofs = (uint32_t)ON * 4u;
+                const long long per_img = (long long)det.H * det.W;
+                const int b = (int)(m / per_img), a = (int)(m - (long long)b * per_img);
+                __nv_bfloat16* yp = det.y + (size_t)b * (size_t)(4 + det.nc) * det.total + det.a0 + a;
+                if (det.mode == 1) {
+                    float d[4];
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        uint32_t v0[16], v1[16];
+                        tmem_ld_32x32b_x16(taddr + (uint32_t)pr * 32u, v0);
+                        tmem_ld_32x32b_x16(taddr + (uint32_t)pr * 32u + 16u, v1);
+                        tmem_ld_wait();
+                        float z[16];
+                        detect_logits16(v0, aff_s + (uint32_t)(2 * pr) * 64u, aff_s + (uint32_t)(2 * pr) * 64u + sh_ofs, z);
+                        d[2 * pr] = dfl_expectation16(z);
+                        detect_logits16(v1, aff_s + (uint32_t)(2 * pr + 1) * 64u, aff_s + (uint32_t)(2 * pr + 1) * 64u + sh_ofs, z);
+                        d[2 * pr + 1] = dfl_expectation16(z);
+                    }
+                    if (m < M) {
+                        const int ai = a / det.W, aj = a - ai * det.W;
+                        const float ax = (float)aj + 0.5f, ay = (float)ai + 0.5f;
+                        const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+                        yp[0] = __float2bfloat16_rn(0.5f * (x1 + x2) * det.stride);
+                        yp[(size_t)det.total] = __float2bfloat16_rn(0.5f * (y1 + y2) * det.stride);
+                        yp[2 * (size_t)det.total] = __float2bfloat16_rn((x2 - x1) * det.stride);
+                        yp[3 * (size_t)det.total] = __float2bfloat16_rn((y2 - y1) * det.stride);
+                    }
+                } else {
+                    uint32_t v0[16];
+                    tmem_ld_32x32b_x16(taddr, v0);
+                    tmem_ld_wait();
+                    float z[16];
+                    detect_logits16(v0, aff_s, aff_s + sh_ofs, z);
+                    if (m < M) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (c < det.nc) yp[(size_t)(4 + c) * det.total] = __float2bfloat16_rn(1.f / (1.f + __expf(-z[c])));
+                    }
+                }
+            } else
             for (int ch = 0; ch < chunks; ch += 2) {
                 const bool two = ch + 1 < chunks;
                 uint32_t v0[16], v1[16];
@@ -367,7 +443,8 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
                      cudaStream_t st);
 static thread_local GemmOut2 g_out2 = {nullptr, 0, 0, 0};      // snapshotted and cleared at the entry of the next umma_gemm_fwd_ld of this thread
 static thread_local GemmMaxUp g_maxup = {nullptr, nullptr, 0, 0, 0, 0, 0, 0};      // likewise
-static thread_local GemmPack g_pack = {1, 0};                                       // likewise
+static thread_local GemmPack g_pack = {1, 0};
+static thread_local GemmDetect g_detect = {nullptr, 0, 0, 0, 0, 0, 0, 0.f};                                       // likewise
 
 int umma_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                   double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, cudaStream_t st)
@@ -388,6 +465,10 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
     g_out2 = GemmOut2{nullptr, 0, 0, 0};
     g_maxup = GemmMaxUp{nullptr, nullptr, 0, 0, 0, 0, 0, 0};
     g_pack = GemmPack{1, 0};
+    const GemmDetect det = g_detect;
+    g_detect = GemmDetect{nullptr, 0, 0, 0, 0, 0, 0, 0.f};
+    if (det.mode && (out || pre || residual || o2.ptr || mu.z1 || pk.P != 1 || stat_sum))
+        return fail(LDCONV_E_ARG, "tcgen05 GEMM: the Detect-decode epilogue takes no other output");
     if (stat_sum && !pre) return fail(LDCONV_E_ARG, "tcgen05 GEMM: batch statistics need the `pre` output");
     const int ON = (O + 15) / 16 * 16;
     const int num_kb = (K + kBlockK - 1) / kBlockK;
@@ -430,7 +511,7 @@ int umma_gemm_fwd_ld(const void* a, int lda, const void* wt, const float* scale,
         return fail(LDCONV_E_ARG, "tcgen05 GEMM: the max-with-coarser-levels epilogue needs 16-byte stores and Cout %% 16 == 0");
     LDC_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, st, tmA, tmB, scale, shift, (__nv_bfloat16*)out,
                         (__nv_bfloat16*)pre, (const __nv_bfloat16*)residual, M, O, ON, num_kb, num_tiles, stages, act, tmem_cols,
-                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu, pk, stage_rb));
+                        vec_store, ldo, ldr, NB, gemm_dbg(), o2, mu, pk, stage_rb, det));
     LDC_LAUNCH_CHECK("umma_gemm_kernel");
     set_impl(LDCONV_IMPL_TCGEN05);
     if (stat_sum) {
@@ -482,6 +563,25 @@ LDC_API int ldconv_conv1x1_bn_act_maxup_fwd(const void* x, int ldx, const void* 
     g_maxup = GemmMaxUp{(const __nv_bfloat16*)z1, (const __nv_bfloat16*)z2, H, W, H1, W1, H2, W2};
     return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, out, nullptr, residual, ldr, ldo, nullptr, nullptr, B * H * W, Cin, Cout, act,
                             (cudaStream_t)stream);
+}
+
+// Last 1x1 conv of a Detect branch with the decode in its epilogue (see GemmDetect): x (B*H*W, Cin | ldx) bf16, wt (Cout, Cin);
+// mode 1: Cout = 64 (4 sides x 16 DFL bins) -> y rows 0..3 (xywh * stride); mode 2: Cout = nc <= 16 -> y rows 4..4+nc (sigmoid).
+// y (B, 4+nc, total) bf16; this level's anchors occupy columns [a0, a0 + H*W).  Bit-identical to ldconv_conv1x1_bn_act_fwd (no
+// activation) followed by ldconv_detect_decode.
+LDC_API int ldconv_conv1x1_detect_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift, void* y, int mode,
+                                      int B, int H, int W, int Cin, int Cout, int nc, float stride, int a0, int total, int dtype,
+                                      void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_conv1x1_detect_fwd: bf16 only");
+    LDC_REQUIRE(x && wt && y && B >= 0 && H >= 1 && W >= 1 && nc >= 1 && nc <= 16, "ldconv_conv1x1_detect_fwd: bad arguments");
+    LDC_REQUIRE((mode == 1 && Cout == 64) || (mode == 2 && Cout == nc), "ldconv_conv1x1_detect_fwd: mode 1 needs Cout = 64, mode 2 Cout = nc");
+    LDC_REQUIRE(Cin % 8 == 0 && ldx % 8 == 0 && ldx >= Cin && aligned16(x) && aligned16(wt), "ldconv_conv1x1_detect_fwd: Cin / ldx / alignment");
+    LDC_REQUIRE(a0 >= 0 && (long long)a0 + (long long)H * W <= total && (long long)B * H * W < (1ll << 31), "ldconv_conv1x1_detect_fwd: anchor range");
+    if (B == 0) return LDCONV_OK;
+    g_detect = GemmDetect{(__nv_bfloat16*)y, mode, H, W, nc, a0, total, stride};
+    return umma_gemm_fwd_ld(x, ldx, wt, scale, shift, nullptr, nullptr, nullptr, 0, Cout, nullptr, nullptr, B * H * W, Cin, Cout,
+                            LDCONV_ACT_NONE, (cudaStream_t)stream);
 }
 
 // The 1x1 `Conv` block on P consecutive pixels per operand row (see GemmPack): x (rows, Cin) dense, wt_packed (P Cout, P Cin) =

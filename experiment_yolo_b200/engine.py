@@ -269,12 +269,26 @@ class _ScalSeq:
         return out
 
 
+def conv1x1_detect(x: torch.Tensor, p: _Folded, y: torch.Tensor, mode: int, nc: int, stride: float, a0: int):
+    """last 1x1 conv of a Detect branch with the decode in its epilogue (ldconv_conv1x1_detect_fwd): mode 1 = box branch -> rows
+    0..3 of y (B, 4+nc, anchors), mode 2 = class branch -> rows 4..4+nc; this level's anchors start at column a0"""
+    B, H, W, C, ldx = _nhwc_geometry(x)
+    assert C == p.cin and y.is_contiguous() and y.shape[1] == 4 + nc
+    _lib.check(_lib.load().ldconv_conv1x1_detect_fwd(x.data_ptr(), ldx, p.w.data_ptr(), p.scale.data_ptr(), p.shift.data_ptr(),
+                                                      y.data_ptr(), mode, B, H, W, C, p.cout, nc, float(stride), a0, y.shape[2],
+                                                      _lib.BF16, _stream()), "ldconv_conv1x1_detect_fwd")
+
+
 class _Detect:
     # The six conv chains of the head (3 pyramid levels x {box, class} branch) are independent until the decode: they are forked
     # onto side streams (captured as parallel branches of the CUDA graph) so that the small P3 / P4 kernels and the two
     # branches of a level share the GPU instead of running back to back.  Every buffer is allocated on the calling stream
     # before the fork, the side streams only launch kernels, and the join precedes any reuse.
     parallel_branches = True
+    # The last 1x1 conv of every branch decodes its own accumulator rows (DFL expectation + dist2bbox + stride / sigmoid) straight
+    # into y: no logits in HBM, no decode launches; bit-identical to the unfused sequence.  The raw head maps (`feats`, what the
+    # reference returns beside y in eval mode) are then not produced: set False when they are needed.
+    decode_in_epilogue = True
 
     def __init__(self, m):
         self.nc, self.reg_max, self.no = m.nc, m.reg_max, m.no
@@ -299,9 +313,11 @@ class _Detect:
             self.first.append(f)
 
     @staticmethod
-    def _chain(x, ps, bufs, skip_first=False):
+    def _chain(x, ps, bufs, skip_first=False, det=None):
         t = x if skip_first else conv3x3(x, ps[0], bufs[0])
         t = conv3x3(t, ps[1], bufs[1])
+        if det is not None:
+            return conv1x1_detect(t, ps[2], *det)
         return conv1x1(t, ps[2], bufs[2], act="none")
 
     def __call__(self, xs):
@@ -309,6 +325,13 @@ class _Detect:
         B = xs[0].shape[0]
         total = sum(x.shape[1] * x.shape[2] for x in xs)
         y = torch.empty((B, 4 + self.nc, total), device=xs[0].device, dtype=torch.bfloat16)
+        fuse_dec = self.decode_in_epilogue and self.reg_max == 16 and self.nc <= 16 and all(b[2].cin % 8 == 0 for b in self.box + self.cls)
+        a0s, acc = [], 0
+        for x in xs:
+            a0s.append(acc)
+            acc += x.shape[1] * x.shape[2]
+        dets = [((y, 1, self.nc, self.stride[lvl], a0s[lvl]), (y, 2, self.nc, self.stride[lvl], a0s[lvl])) if fuse_dec else (None, None)
+                for lvl in range(len(xs))]
         bufs = []
         for lvl, x in enumerate(xs):
             _, H, W, _ = x.shape
@@ -317,8 +340,8 @@ class _Detect:
                 b0, c0 = both[..., : self.box[lvl][0].cout], both[..., self.box[lvl][0].cout:]
             else:
                 both, b0, c0 = None, _new(x, B, H, W, self.box[lvl][0].cout), _new(x, B, H, W, self.cls[lvl][0].cout)
-            bb = [b0, _new(x, B, H, W, self.box[lvl][1].cout), _new(x, B, H, W, 4 * self.reg_max)]
-            cb = [c0, _new(x, B, H, W, self.cls[lvl][1].cout), _new(x, B, H, W, self.nc)]
+            bb = [b0, _new(x, B, H, W, self.box[lvl][1].cout), None if fuse_dec else _new(x, B, H, W, 4 * self.reg_max)]
+            cb = [c0, _new(x, B, H, W, self.cls[lvl][1].cout), None if fuse_dec else _new(x, B, H, W, self.nc)]
             bufs.append((bb, cb, both))
         cur = torch.cuda.current_stream(xs[0].device)
         if self.parallel_branches:
@@ -335,14 +358,14 @@ class _Detect:
                             conv3x3(xs[lvl], self.first[lvl], bufs[lvl][2])
                             stacked_done[lvl] = torch.cuda.Event()
                             stacked_done[lvl].record(st)      # the class branch starts here, not after the whole box chain
-                        self._chain(bufs[lvl][0][0] if fused else xs[lvl], self.box[lvl], bufs[lvl][0], skip_first=fused)
+                        self._chain(bufs[lvl][0][0] if fused else xs[lvl], self.box[lvl], bufs[lvl][0], skip_first=fused, det=dets[lvl][0])
                 else:
                     if fused:
                         st.wait_event(stacked_done[lvl])
                     else:
                         st.wait_stream(cur)
                     with torch.cuda.stream(st):
-                        self._chain(bufs[lvl][1][0] if fused else xs[lvl], self.cls[lvl], bufs[lvl][1], skip_first=fused)
+                        self._chain(bufs[lvl][1][0] if fused else xs[lvl], self.cls[lvl], bufs[lvl][1], skip_first=fused, det=dets[lvl][1])
             for st in self.streams:
                 cur.wait_stream(st)
         else:
@@ -350,8 +373,10 @@ class _Detect:
                 fused = self.first[lvl] is not None
                 if fused:
                     conv3x3(x, self.first[lvl], bufs[lvl][2])
-                self._chain(bufs[lvl][0][0] if fused else x, self.box[lvl], bufs[lvl][0], skip_first=fused)
-                self._chain(bufs[lvl][1][0] if fused else x, self.cls[lvl], bufs[lvl][1], skip_first=fused)
+                self._chain(bufs[lvl][0][0] if fused else x, self.box[lvl], bufs[lvl][0], skip_first=fused, det=dets[lvl][0])
+                self._chain(bufs[lvl][1][0] if fused else x, self.cls[lvl], bufs[lvl][1], skip_first=fused, det=dets[lvl][1])
+        if fuse_dec:
+            return y, None
         feats, a0 = [], 0
         for lvl, x in enumerate(xs):
             _, H, W, _ = x.shape

@@ -254,6 +254,14 @@ size_t ldconv_nms_workspace_bytes(int B, int max_nms);
 int ldconv_nms(const void* y, void* out, int32_t* out_count, void* workspace, size_t workspace_bytes, int B, int A, int nc,
                float conf_thres, float iou_thres, int agnostic, int max_det, int max_nms, float max_wh, int dtype, void* stream);
 
+/* The LAST 1x1 conv of a Detect branch with the decode in its epilogue (head.py:55-77, DFL block.py:37-56, dist2bbox tal.py:309-319):
+ * mode 1 = box branch (Cout = 64 = 4 sides x 16 bins) -> y rows 0..3 (xywh * stride); mode 2 = class branch (Cout = nc <= 16) ->
+ * y rows 4..4+nc (sigmoid).  x (B*H*W, Cin | ldx) bf16; y (B, 4+nc, total) bf16, this level at columns [a0, a0 + H*W).  Bit-identical
+ * to ldconv_conv1x1_bn_act_fwd (act none) + ldconv_detect_decode; the logits never reach HBM. */
+int ldconv_conv1x1_detect_fwd(const void* x, int ldx, const void* wt, const float* scale, const float* shift, void* y, int mode,
+                              int B, int H, int W, int Cin, int Cout, int nc, float stride, int a0, int total, int dtype,
+                              void* stream);
+
 /* Task-aligned assigner of the training criterion (utils/tal.py:13-290), dense part, fp32:
  * ldconv_tal_metric: scores (B,na,nc) in [0,1], boxes (B,na,4) xyxy px, anchors (na,2) px, gt_labels (B,n) int32, gt_boxes (B,n,4)
  *   xyxy px, gt_valid (B,n) bytes -> align = score[label]^alpha * max(CIoU, 0)^beta and overlaps = max(CIoU, 0) on anchors

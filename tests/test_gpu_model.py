@@ -162,3 +162,27 @@ def test_engine_add_row_sums_all_inputs_through_the_library():
     five = xs + xs[:2]
     y = engine.add_nhwc(five)
     assert float((y.float() - torch.stack([t.float() for t in five]).sum(0)).abs().max()) <= 0.07
+
+
+def test_detect_decode_in_the_gemm_epilogue_is_bit_identical_to_conv_then_decode():
+    """engine._Detect.decode_in_epilogue: the last 1x1 conv of every Detect branch decodes its own accumulator rows
+    (ldconv_conv1x1_detect_fwd) -- same logits rounding, same DFL / dist2bbox / sigmoid arithmetic as ldconv_conv1x1_bn_act_fwd +
+    ldconv_detect_decode (head.py:55-77), so the decoded output is bit-identical; non-square maps, batch 3."""
+    from experiment_yolo_b200 import _lib, engine
+    z, model = _load()
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
+    x = torch.rand(3, 3, 96, 160, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    eng = engine.FusedDealYolo(model)
+    try:
+        engine._Detect.decode_in_epilogue = False
+        _lib.call_counts.clear()
+        y_ref, feats = eng(x)
+        assert "ldconv_detect_decode" in _lib.call_counts and feats is not None
+        engine._Detect.decode_in_epilogue = True
+        _lib.call_counts.clear()
+        y, none = eng(x)
+        assert "ldconv_detect_decode" not in _lib.call_counts and _lib.call_counts["ldconv_conv1x1_detect_fwd"] == 6 and none is None
+    finally:
+        engine._Detect.decode_in_epilogue = True
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
