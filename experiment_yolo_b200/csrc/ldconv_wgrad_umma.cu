@@ -69,23 +69,29 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     // chunks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int my_chunks = chunks_total > (int)blockIdx.x ? (chunks_total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
+    // control warps: warp-uniform loops, one elected lane issues (no ELECT / BRA.U.ANY loop around every UTMALDG / UTCHMMA)
     if (warp == 0) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             int s = 0;
             uint32_t ph = 0;
             for (int c = 0; c < my_chunks; ++c) {
                 const int row0 = (blockIdx.x + c * gridDim.x) * kWgRows;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full[s], stage_bytes);
-                uint8_t* st = smem + (size_t)s * stage_bytes;
-                tma_load_2d(st, &tmG, &full[s], 0, row0);
-                tma_load_2d(st + kWgRows * 128, &tmG, &full[s], 64, row0);
-                for (int j = 0; j < nb; ++j) tma_load_2d(st + g_bytes + (size_t)j * kWgRows * 128, &tmA, &full[s], k_tile0 + j * 64, row0);
+                if (leader) {
+                    mbar_arrive_expect_tx(&full[s], stage_bytes);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    tma_load_2d(st, &tmG, &full[s], 0, row0);
+                    tma_load_2d(st + kWgRows * 128, &tmG, &full[s], 64, row0);
+                    for (int j = 0; j < nb; ++j) tma_load_2d(st + g_bytes + (size_t)j * kWgRows * 128, &tmA, &full[s], k_tile0 + j * 64, row0);
+                }
+                __syncwarp();
                 if (++s == kWgStages) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             // D format F32, A/B BF16, both operands MN-major (bits 15, 16), M_ = 128, N_ = nb*64
             const uint32_t idesc = make_idesc_bf16(128, N_) | (1u << 15) | (1u << 16);
             int s = 0;
@@ -95,14 +101,18 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                 tc_fence_after_sync();
                 const uint32_t g_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t a_addr = g_addr + g_bytes;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < kWgRows / 16; ++k)
-                    mma_bf16_ss(tmem_base, wg_desc_mn(g_addr + k * 2048, kWgRows * 128), wg_desc_mn(a_addr + k * 2048, kWgRows * 128),
-                                idesc, (uint32_t)((c | k) != 0));
-                mma_commit(&empty[s]);
+                    for (int k = 0; k < kWgRows / 16; ++k)
+                        mma_bf16_ss(tmem_base, wg_desc_mn(g_addr + k * 2048, kWgRows * 128), wg_desc_mn(a_addr + k * 2048, kWgRows * 128),
+                                    idesc, (uint32_t)((c | k) != 0));
+                    mma_commit(&empty[s]);
+                }
+                __syncwarp();
                 if (++s == kWgStages) { s = 0; ph ^= 1; }
             }
-            mma_commit(done);
+            if (leader) mma_commit(done);
+            __syncwarp();
         }
     } else if (my_chunks > 0) {
         mbar_wait(done, 0);
