@@ -328,6 +328,45 @@ __device__ __forceinline__ void affine_act16(const uint32_t (&v)[16], uint32_t s
     }
 }
 
+// The same epilogue with the 16 scales / shifts already in registers: affine_load16 issues the eight LDS.128 BEFORE the caller's
+// tcgen05.wait::ld, so their latency (through an L1 data pipe that the epilogue's own 16-byte global stores keep busy: every FFMA2
+// of affine_act16 sat on the short scoreboard behind them, 32 % of conv3x3_zc_kernel's stall samples, profiles/r2_ncu_zc32_64.txt)
+// hides behind the TMEM load instead of following it.  Bit-identical to affine_act16.
+__device__ __forceinline__ void affine_load16(uint32_t sc_addr, uint32_t sh_addr, float4 (&sc)[4], float4 (&sh)[4])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sc[q].x), "=f"(sc[q].y), "=f"(sc[q].z), "=f"(sc[q].w) : "r"(sc_addr + q * 16));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sh[q].x), "=f"(sh[q].y), "=f"(sh[q].z), "=f"(sh[q].w) : "r"(sh_addr + q * 16));
+    }
+}
+
+__device__ __forceinline__ void affine_act16_r(const uint32_t (&v)[16], const float4 (&scv)[4], const float4 (&shv)[4], int act, float (&z)[16])
+{
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+        const float4 sc = scv[e >> 2], sh = shv[e >> 2];
+        uint64_t z0 = f2_fma(f2_pack(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), f2_pack(sc.x, sc.y), f2_pack(sh.x, sh.y));
+        uint64_t z1 = f2_fma(f2_pack(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])), f2_pack(sc.z, sc.w), f2_pack(sh.z, sh.w));
+        float a0, a1, a2, a3;
+        f2_unpack(z0, a0, a1);
+        f2_unpack(z1, a2, a3);
+        if (act == LDCONV_ACT_SILU) {
+            float t0, t1, t2, t3;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t2) : "f"(a2));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t3) : "f"(a3));
+            f2_unpack(f2_fma(z0, f2_pack(t0, t1), z0), a0, a1);
+            f2_unpack(f2_fma(z1, f2_pack(t2, t3), z1), a2, a3);
+        } else if (act == LDCONV_ACT_LEAKY01) {
+            a0 = a0 > 0.f ? a0 : 0.1f * a0; a1 = a1 > 0.f ? a1 : 0.1f * a1;
+            a2 = a2 > 0.f ? a2 : 0.1f * a2; a3 = a3 > 0.f ? a3 : 0.1f * a3;
+        }
+        z[e] = a0; z[e + 1] = a1; z[e + 2] = a2; z[e + 3] = a3;
+    }
+}
+
 // 16 fp32 values -> 16 bf16 as two 16-byte vectors
 __device__ __forceinline__ void pack16_bf16(const float (&z)[16], uint4& lo, uint4& hi)
 {

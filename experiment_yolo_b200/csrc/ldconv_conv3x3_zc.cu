@@ -228,6 +228,8 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * g.ON);
             for (int ch = ch_begin; ch < ch_end; ++ch) {
                 const int c0 = ch * 16;
+                float4 sc4[4], sh4[4];
+                if (MODE != ZC_MODE_OFFSETS) affine_load16(aff_s + (uint32_t)c0 * 4u, aff_s + (uint32_t)(g.ON + c0) * 4u, sc4, sh4);
                 uint32_t v[16];
                 tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
                 tmem_ld_wait();
@@ -239,7 +241,7 @@ conv3x3_zc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         if (c0 + e < g.Cout) dst[e] = __uint_as_float(v[e]) + sAff[g.ON + c0 + e];
                 } else {
                     float z[16];
-                    affine_act16(v, aff_s + (uint32_t)c0 * 4u, aff_s + (uint32_t)(g.ON + c0) * 4u, act, z);
+                    affine_act16_r(v, sc4, sh4, act, z);
                     if (residual) {
                         float r0[8], r1[8];
                         Vec16<T>::load(residual + m * g.ldr + c0, r0);

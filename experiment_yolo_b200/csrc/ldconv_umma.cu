@@ -113,7 +113,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
                                                     const __nv_bfloat16* __restrict__ residual, int ldo, int ldr, bool vec_store,
                                                     const GemmOut2& o2, uint32_t sh_ofs, const __nv_bfloat16* mx1 = nullptr,
                                                     const __nv_bfloat16* mx2 = nullptr, GemmPack pk = GemmPack{1, 0},
-                                                    uint32_t stage_row_s = 0, uint32_t stage_swz = 0)
+                                                    uint32_t stage_row_s = 0, uint32_t stage_swz = 0, const float4* pre_sc = nullptr,
+                                                    const float4* pre_sh = nullptr)
 {
     const bool full16 = vec_store && (c0 + 16 <= O);
     if (pre) {
@@ -132,7 +133,13 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&v)[16], lon
     }
     if (out) {
         float z[16];
-        affine_act16(v, aff_s, aff_s + sh_ofs, act, z);
+        if (pre_sc) {      // scales / shifts already in registers (requested before the caller's tcgen05.wait::ld)
+            const float4 (&scr)[4] = *reinterpret_cast<const float4 (*)[4]>(pre_sc);
+            const float4 (&shr)[4] = *reinterpret_cast<const float4 (*)[4]>(pre_sh);
+            affine_act16_r(v, scr, shr, act, z);
+        } else {
+            affine_act16(v, aff_s, aff_s + sh_ofs, act, z);
+        }
         if (mx1) {      // host: O % 16 == 0, z1 / z2 dense and 16-byte aligned.  The level's own output is a bf16 tensor in the reference
             float a1[8], a2[8], b1[8], b2[8];
             Vec16<__nv_bfloat16>::load(mx1 + c0, a1);
@@ -374,6 +381,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             } else
             for (int ch = 0; ch < chunks; ch += 2) {
                 const bool two = ch + 1 < chunks;
+                float4 sc0[4], sh0[4];      // first chunk's scales / shifts: requested before the TMEM loads are waited for
+                affine_load16(aff_s + (uint32_t)ch * 64u, aff_s + (uint32_t)ch * 64u + (uint32_t)ON * 4u, sc0, sh0);
                 uint32_t v0[16], v1[16];
                 tmem_ld_32x32b_x16(taddr + (uint32_t)ch * 16u, v0);
                 if (two) tmem_ld_32x32b_x16(taddr + (uint32_t)(ch + 1) * 16u, v1);
@@ -381,7 +390,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (m < M && !(dbg & 2)) {
                     if (ch * 16 < O)
                         gemm_epilogue_chunk(v0, m, ch * 16, O, aff_s + (uint32_t)ch * 64u, act, out, pre, residual, ldo, ldr,
-                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk, stage_row_s, stage_swz);
+                                            vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk, stage_row_s, stage_swz, sc0, sh0);
                     if (two && (ch + 1) * 16 < O)
                         gemm_epilogue_chunk(v1, m, (ch + 1) * 16, O, aff_s + (uint32_t)(ch + 1) * 64u, act, out, pre, residual,
                                             ldo, ldr, vec_store != 0, o2, (uint32_t)ON * 4u, mx1, mx2, pk, stage_row_s, stage_swz);
