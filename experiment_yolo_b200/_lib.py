@@ -38,6 +38,7 @@ SIGNATURES = {
     "ldconv_offset_conv_s2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 6 + [_vp]),
     "ldconv_gather_fwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_gemm_fwd": (_i, [_vp] * 8 + [_i] * 5 + [_vp]),
+    "ldconv_col_stats": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
     "ldconv_bn_finalize": (_i, [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "ldconv_bn_act_apply": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "ldconv_bn_act_bwd_reduce": (_i, [_vp] * 7 + [_ll, _i, _i, _i, _vp]),

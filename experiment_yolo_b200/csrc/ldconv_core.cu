@@ -998,6 +998,16 @@ LDC_API int ldconv_gather_fwd(const void* x, const float* off, const int32_t* p_
                                             dbg_coord, B, C, H, W, N, s, st);
 }
 
+// Column sums / sums of squares of an existing (M, O) bf16 tensor (fp64 accumulators, caller zero-inits): the batch statistics of a
+// Conv block's pre-activation when the conv itself ran elsewhere (cuDNN 3x3); the GEMM entry points produce them in their epilogue.
+LDC_API int ldconv_col_stats(const void* pre, double* stat_sum, double* stat_sqsum, long long M, int O, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_col_stats: bf16 only");
+    LDC_REQUIRE(pre && stat_sum && stat_sqsum && M >= 0 && O >= 1, "ldconv_col_stats: bad arguments");
+    if (M == 0) return LDCONV_OK;
+    return col_stats_bf16((const __nv_bfloat16*)pre, M, O, stat_sum, stat_sqsum, (cudaStream_t)stream);
+}
+
 LDC_API int ldconv_bn_finalize(const double* stat_sum, const double* stat_sqsum, long long count, const float* gamma,
                                const float* beta, float* running_mean, float* running_var, float eps, float momentum,
                                int training, float* scale, float* shift, float* save_mean, float* save_invstd, int O,

@@ -39,8 +39,19 @@ class Conv(nn.Module):
         self.bn = nn.BatchNorm2d(c2)
         self.act = nn.SiLU() if act is True else (act if isinstance(act, nn.Module) else nn.Identity())
 
+    # training on the GPU under bf16 autocast: batch-stat BatchNorm + SiLU run as four passes of the library's kernels
+    # (ldconv.bn_silu_train) instead of ATen's batch_norm + SiLU forward / backward; class switch for A/B and tests
+    fused_bn_silu_train = True
+
     def forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        y = self.conv(x)
+        if self.training and self.fused_bn_silu_train and y.is_cuda and y.dtype == torch.bfloat16 and isinstance(self.act, nn.SiLU) \
+                and torch.is_grad_enabled():
+            from .ldconv import bn_silu_train
+            z = bn_silu_train(y, self.bn)
+            if z is not None:
+                return z
+        return self.act(self.bn(y))
 
 
 class Bottleneck(nn.Module):

@@ -476,6 +476,71 @@ def _fold_bn_uncached(bn: nn.BatchNorm2d, device):
     return scale, shift
 
 
+# ---- training-mode BatchNorm2d + SiLU of a `Conv` block through the library's kernels -------------------------------------------
+class _BNSiLUTrainFunction(torch.autograd.Function):
+    """act(BatchNorm2d(pre)) in TRAINING mode for a bf16 channels_last pre-activation (the `Conv` block of the reference,
+    nn/modules/conv.py:41-59, after its convolution): batch statistics (fp64 sums) -> scale / shift + running statistics ->
+    one apply pass; backward = one reduction pass + one apply pass.  Four passes over the tensor instead of ATen's batch_norm
+    (collect, transform, backward reduce, backward elementwise) + SiLU forward / backward (28 % of the config-4 step)."""
+
+    @staticmethod
+    def forward(ctx, pre, gamma, beta, running_mean, running_var, eps, momentum):
+        L = _lib.load()
+        st = _stream()
+        B, O, H, W = pre.shape
+        M = B * H * W
+        ph = _nhwc(pre)                                   # (B,H,W,O) dense: zero-copy for channels_last
+        dev = pre.device
+        stats = torch.zeros((2, O), device=dev, dtype=torch.float64)
+        _lib.check(L.ldconv_col_stats(_ptr(ph), _ptr(stats[0]), _ptr(stats[1]), M, O, _lib.BF16, st), "ldconv_col_stats")
+        scale = torch.empty(O, device=dev, dtype=torch.float32)
+        shift = torch.empty(O, device=dev, dtype=torch.float32)
+        mean = torch.empty(O, device=dev, dtype=torch.float32)
+        invstd = torch.empty(O, device=dev, dtype=torch.float32)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _lib.check(L.ldconv_bn_finalize(_ptr(stats[0]), _ptr(stats[1]), M, _ptr(g32), _ptr(b32), _ptr(running_mean), _ptr(running_var),
+                                        float(eps), float(momentum), 1, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), O, st),
+                   "ldconv_bn_finalize")
+        out = torch.empty((B, H, W, O), device=dev, dtype=pre.dtype)
+        _lib.check(L.ldconv_bn_act_apply(_ptr(ph), _ptr(scale), _ptr(shift), _ptr(out), M, O, _lib.ACT_SILU, _lib.BF16, st),
+                   "ldconv_bn_act_apply")
+        ctx.save_for_backward(ph, scale, shift, mean, invstd)
+        ctx.gdtype = gamma.dtype
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        L = _lib.load()
+        st = _stream()
+        ph, scale, shift, mean, invstd = ctx.saved_tensors
+        B, H, W, O = ph.shape
+        M = B * H * W
+        go = _nhwc(grad_out.to(ph.dtype))
+        red = torch.zeros((2, O), device=ph.device, dtype=torch.float64)
+        _lib.check(L.ldconv_bn_act_bwd_reduce(_ptr(ph), _ptr(go), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(red), M, O,
+                                              _lib.ACT_SILU, _lib.BF16, st), "ldconv_bn_act_bwd_reduce")
+        gpre = torch.empty_like(ph)
+        _lib.check(L.ldconv_bn_act_bwd_apply(_ptr(ph), _ptr(go), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(red), _ptr(gpre),
+                                             M, O, _lib.ACT_SILU, 1, _lib.BF16, st), "ldconv_bn_act_bwd_apply")
+        return gpre.permute(0, 3, 1, 2), red[1].to(ctx.gdtype), red[0].to(ctx.gdtype), None, None, None, None
+
+
+def bn_silu_train(pre: torch.Tensor, bn: nn.BatchNorm2d) -> torch.Tensor:
+    """Training-mode `SiLU(bn(pre))` through the library (see _BNSiLUTrainFunction), or None when the case is not covered (the
+    caller then runs the torch modules): needs a CUDA bf16 tensor, affine BatchNorm2d with fp32 running statistics, > 1 value
+    per channel."""
+    if not (pre.is_cuda and pre.dtype == torch.bfloat16 and pre.dim() == 4 and bn.training and bn.affine and bn.track_running_stats
+            and bn.running_mean is not None and bn.running_mean.dtype == torch.float32 and pre.numel() > pre.shape[1]):
+        return None
+    momentum = bn.momentum
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return _BNSiLUTrainFunction.apply(pre, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, momentum)
+
+
 # ---- the reference's plugin hook -------------------------------------------------------------------------------------------
 _REF_MODULES = ("ultralytics.nn.modules.conv", "ultralytics.nn.modules", "ultralytics.nn.modules.block",
                 "ultralytics.nn.tasks")

@@ -114,6 +114,10 @@ int ldconv_gather_fwd(const void* x, const float* off, const int32_t* p_n, void*
 int ldconv_gemm_fwd(const void* a, const void* wt, const float* scale, const float* shift, void* out, void* pre,
                     double* stat_sum, double* stat_sqsum, int M, int K, int O, int act, int dtype, void* stream);
 
+/* Batch statistics of an existing (M, O) bf16 pre-activation (fp64 column sums / sums of squares, caller zero-inits): first pass of
+ * the training forward of a `Conv` block (nn/modules/conv.py:41-59) whose convolution ran elsewhere. */
+int ldconv_col_stats(const void* pre, double* stat_sum, double* stat_sqsum, long long M, int O, int dtype, void* stream);
+
 /* torch.nn.BatchNorm2d bookkeeping of conv.py:355 (eps / momentum come from the module, never hard-coded).
  * training != 0: mean/var from stat_sum/stat_sqsum over `count` rows; running <- (1-momentum)*running +
  *   momentum*(mean, unbiased var) (running_* may be NULL); training == 0: mean/var = running_*.

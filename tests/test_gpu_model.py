@@ -186,3 +186,32 @@ def test_detect_decode_in_the_gemm_epilogue_is_bit_identical_to_conv_then_decode
         engine._Detect.decode_in_epilogue = True
     torch.cuda.synchronize()
     assert torch.equal(y, y_ref)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(4, 32, 24, 40), (2, 16, 33, 17), (3, 96, 10, 10), (2, 64, 160, 160)])
+def test_fused_bn_silu_training_op_vs_torch(B, C, H, W):
+    """ldconv.bn_silu_train (col_stats -> bn_finalize -> bn_act_apply; backward reduce + apply) against torch's BatchNorm2d + SiLU in
+    fp32 on the same bf16 pre-activation: output, running statistics, and the gradients of the input / gamma / beta."""
+    from experiment_yolo_b200.ldconv import bn_silu_train
+    torch.manual_seed(C + H)
+    pre = (torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).bfloat16().contiguous(memory_format=torch.channels_last)
+    gout = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(C, eps=1e-3, momentum=0.03).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.2)
+    ref_bn = torch.nn.BatchNorm2d(C, eps=1e-3, momentum=0.03).to(DEV).train()
+    ref_bn.load_state_dict(bn.state_dict())
+    x1 = pre.clone().requires_grad_(True)
+    y1 = bn_silu_train(x1, bn)
+    assert y1 is not None and y1.dtype == torch.bfloat16 and y1.is_contiguous(memory_format=torch.channels_last)
+    y1.backward(gout)
+    x2 = pre.float().clone().requires_grad_(True)
+    y2 = torch.nn.functional.silu(ref_bn(x2))
+    y2.backward(gout.float())
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    assert rel(y1, y2) <= 4e-3
+    assert rel(x1.grad, x2.grad) <= 1e-2
+    assert rel(bn.weight.grad, ref_bn.weight.grad) <= 2e-3 and rel(bn.bias.grad, ref_bn.bias.grad) <= 2e-3
+    assert torch.allclose(bn.running_mean, ref_bn.running_mean, atol=1e-5) and torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-4, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 1
