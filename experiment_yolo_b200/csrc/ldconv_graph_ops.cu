@@ -245,6 +245,35 @@ image_u8_to_nhwc_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, int 
     for (int c = 0; c < C; ++c) dst[c] = __float2bfloat16_rn((float)src[(long long)c * hw] * scale);
 }
 
+// C = 3, 8 pixels per thread: one 8-byte load per colour plane, 48 contiguous output bytes as three 16-byte stores (the per-pixel
+// kernel above issues three 1-byte loads and three 2-byte stores per pixel)
+__global__ void __launch_bounds__(256)
+image_u8_to_nhwc3_x8_kernel(const uint8_t* __restrict__ x, T* __restrict__ out, long long hw, float scale, long long groups)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= groups) return;
+    const long long gpi = hw >> 3;                       // groups of 8 pixels per image
+    const long long b = t / gpi, p = (t - b * gpi) << 3;
+    const uint8_t* src = x + b * 3 * hw + p;
+    const uint2 r = *reinterpret_cast<const uint2*>(src), g = *reinterpret_cast<const uint2*>(src + hw),
+                bl = *reinterpret_cast<const uint2*>(src + 2 * hw);
+    const uint32_t rw[2] = {r.x, r.y}, gw[2] = {g.x, g.y}, bw[2] = {bl.x, bl.y};
+    uint32_t w[12];                                       // 8 pixels x 3 channels bf16 = 24 values = 12 words
+    float v[24];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[3 * k] = (float)((rw[k >> 2] >> (8 * (k & 3))) & 0xffu) * scale;
+        v[3 * k + 1] = (float)((gw[k >> 2] >> (8 * (k & 3))) & 0xffu) * scale;
+        v[3 * k + 2] = (float)((bw[k >> 2] >> (8 * (k & 3))) & 0xffu) * scale;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+    uint4* dst = reinterpret_cast<uint4*>(out + (b * hw + p) * 3);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+}
+
 }  // namespace ldc
 
 using namespace ldc;
@@ -256,6 +285,13 @@ LDC_API int ldconv_image_u8_to_nhwc(const void* x_u8, void* out, int B, int C, i
     LDC_REQUIRE(x_u8 && out && C >= 1 && C <= 16, "ldconv_image_u8_to_nhwc: bad arguments");
     const long long total = (long long)B * H * W;
     if (total == 0) return LDCONV_OK;
+    if (C == 3 && ((long long)H * W) % 8 == 0 && (reinterpret_cast<uintptr_t>(x_u8) & 7) == 0 && aligned16(out)) {
+        const long long groups = total / 8;
+        image_u8_to_nhwc3_x8_kernel<<<cdiv(groups, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x_u8, (T*)out, (long long)H * W,
+                                                                                       scale, groups);
+        LDC_LAUNCH_CHECK("image_u8_to_nhwc3_x8_kernel");
+        return LDCONV_OK;
+    }
     image_u8_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x_u8, (T*)out, C,
                                                                                (long long)H * W, scale, total);
     LDC_LAUNCH_CHECK("image_u8_to_nhwc_kernel");

@@ -286,3 +286,17 @@ def test_conv1x1_pixel_packed_matches_plain_kernel(Cin, Cout, P, rows, ldo, act)
     assert _rel(got[:, :Cout].float().cpu().numpy(), ref.cpu().numpy()) <= 6e-3
     if ldo > Cout:
         assert bool((got[:, Cout:] == 5.0).all())
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 64, 96), (2, 17, 23), (1, 640, 640)])
+def test_image_u8_to_nhwc_bit_exact(B, H, W):
+    """uint8 NCHW batch -> bf16 NHWC in [0, 1] (the reference predictor's `im.half(); im /= 255` + layout change,
+    engine/predictor.py:120-131): the 8-pixels-per-thread kernel (H*W % 8 == 0) and the per-pixel fallback, bit for bit."""
+    from experiment_yolo_b200 import _lib
+    g = torch.Generator().manual_seed(H)
+    u8 = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).to(DEV)
+    out = torch.empty((B, H, W, 3), device=DEV, dtype=torch.bfloat16)
+    _lib.check(_lib.load().ldconv_image_u8_to_nhwc(u8.data_ptr(), out.data_ptr(), B, 3, H, W, 1.0 / 255.0, _lib.BF16,
+                                                   torch.cuda.current_stream().cuda_stream), "ldconv_image_u8_to_nhwc")
+    want = (u8.float() * torch.tensor(1.0 / 255.0, dtype=torch.float32)).bfloat16().permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(out, want)
