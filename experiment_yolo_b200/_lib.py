@@ -56,6 +56,7 @@ SIGNATURES = {
     "ldconv_detect_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _vp]),
     "ldconv_nms_workspace_bytes": (ctypes.c_size_t, [_i, _i]),
     "ldconv_nms": (_i, [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _i, _i, _f, _f, _i, _i, _i, _f, _i, _vp]),
+    "ldconv_head_decode_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp]),
     "ldconv_tal_metric": (_i, [_vp] * 8 + [_i] * 4 + [_f] * 3 + [_vp]),
     "ldconv_tal_assign": (_i, [_vp] * 12 + [_i] * 4 + [_f, _vp]),
     "ldconv_conv1x1_bn_act_maxup_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i] + [_i] * 7 + [_vp]),

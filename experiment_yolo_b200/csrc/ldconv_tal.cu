@@ -34,6 +34,43 @@ __device__ __forceinline__ float tal_ciou(float ax1, float ay1, float ax2, float
     return iou - (rho2 / c2 + v * alpha);
 }
 
+// Dense, gradient-free decode of the raw head outputs for the assigner (utils/loss.py:347-354 `bbox_decode` = DFL softmax-expectation
+// (nn/modules/block.py:37-56) + dist2bbox in grid units, utils/tal.py:309-318; and `pred_scores.sigmoid()`, loss.py:388-394): one
+// thread per anchor row of x (rows, 4*16 + nc).  The criterion itself differentiates only through the (few) foreground rows, so the
+// reference's dense softmax / matmul / their backward over all 33600 anchors are not needed.
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_decode_rows_kernel(const T* __restrict__ x, const float* __restrict__ anc, float* __restrict__ boxes, float* __restrict__ scores,
+                        long long rows, int na, int nc)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int no = 64 + nc;
+    const T* xr = x + r * no;
+    const int a = (int)(r % na);
+    const float ax = anc[2 * a], ay = anc[2 * a + 1];
+    float d[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = Elem<T>::to_f(xr[side * 16 + k]);
+        float mx = v[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) mx = fmaxf(mx, v[k]);
+        float den = 0.f, num = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float e = expf(v[k] - mx);
+            den += e;
+            num = fmaf(e, (float)k, num);
+        }
+        d[side] = num / den;
+    }
+    reinterpret_cast<float4*>(boxes)[r] = make_float4(ax - d[0], ay - d[1], ax + d[2], ay + d[3]);
+    for (int c = 0; c < nc; ++c) scores[r * nc + c] = 1.f / (1.f + expf(-Elem<T>::to_f(xr[64 + c])));
+}
+
 constexpr int kTalMaxGt = 256;
 
 __global__ void __launch_bounds__(256)
@@ -153,5 +190,25 @@ LDC_API int ldconv_tal_assign(const long long* topk_idx, const float* anchors, c
     LDC_LAUNCH_CHECK("tal_topk_mask_kernel");
     tal_resolve_kernel<<<dim3(cdiv(na, 256), B), 256, 0, st>>>(mask_ws, align, overlaps, fg, gt_idx, align_sel, pos_align, pos_over, na, n);
     LDC_LAUNCH_CHECK("tal_resolve_kernel");
+    return LDCONV_OK;
+}
+
+// x (rows = b * na, 64 + nc) bf16 / fp32 raw head rows (4 sides x 16 DFL bins, then nc class logits); anc (na, 2) fp32 anchor centres in
+// grid units -> boxes (rows, 4) fp32 xyxy in grid units, scores (rows, nc) fp32 = sigmoid(logits).  No gradient: assigner inputs.
+LDC_API int ldconv_head_decode_rows(const void* x, const float* anc, float* boxes, float* scores, long long rows, int na, int nc,
+                                    int reg_max, int dtype, void* stream)
+{
+    using namespace ldc;
+    LDC_REQUIRE(x && anc && boxes && scores && rows >= 0 && na >= 1 && nc >= 1, "ldconv_head_decode_rows: bad arguments");
+    LDC_REQUIRE(reg_max == 16, "ldconv_head_decode_rows: reg_max %d not supported (16)", reg_max);
+    LDC_REQUIRE(dtype == LDCONV_BF16 || dtype == LDCONV_F32, "ldconv_head_decode_rows: unsupported dtype %d", dtype);
+    LDC_REQUIRE(aligned16(boxes), "ldconv_head_decode_rows: boxes must be 16-byte aligned");
+    if (rows == 0) return LDCONV_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == LDCONV_BF16)
+        head_decode_rows_kernel<__nv_bfloat16><<<cdiv(rows, 256), 256, 0, st>>>((const __nv_bfloat16*)x, anc, boxes, scores, rows, na, nc);
+    else
+        head_decode_rows_kernel<float><<<cdiv(rows, 256), 256, 0, st>>>((const float*)x, anc, boxes, scores, rows, na, nc);
+    LDC_LAUNCH_CHECK("head_decode_rows_kernel");
     return LDCONV_OK;
 }

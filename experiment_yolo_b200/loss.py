@@ -212,6 +212,7 @@ class DealYoloLoss(nn.Module):
         self.use_wiseiou, self.nwd_loss, self.iou_ratio = use_wiseiou, nwd_loss, iou_ratio
         self.wiou_loss = WiseIoU()
         self.max_boxes = max_boxes
+        self.sparse_head = True      # CUDA: dense no-grad decode kernel + foreground-row decode (see forward); False = the dense torch path
         self.register_buffer("proj", torch.arange(reg_max, dtype=torch.float32), persistent=False)
 
     # ---- targets: (t, 6) rows -> (b, n_max, 5) padded [cls, xyxy px]  (loss.py:329-345) ---------------------------------
@@ -244,27 +245,44 @@ class DealYoloLoss(nn.Module):
         feats = list(feats[:len(self.strides)])
         b = feats[0].shape[0]
         dev = feats[0].device
-        # one concatenation in the maps' own dtype (bf16 under autocast), one fp32 conversion fused with the transposition
-        x = torch.cat([f.reshape(b, self.no, -1) for f in feats], 2)
-        pred_distri, pred_scores = x.split((self.reg_max * 4, self.nc), 1)
-        pred_scores = pred_scores.permute(0, 2, 1).float().contiguous()                    # (b,na,nc)
-        pred_distri = pred_distri.permute(0, 2, 1).float().contiguous()                    # (b,na,4*reg_max)
-        na = pred_scores.shape[1]
         shapes = [tuple(f.shape[2:]) for f in feats]
         imgsz = (shapes[0][0] * self.strides[0], shapes[0][1] * self.strides[0])
         anchor_points, stride_tensor = make_anchors(shapes, self.strides, 0.5, device=dev)
-
         targets = self.preprocess(batch, b, imgsz, dev)
         gt_labels, gt_bboxes = targets.split((1, 4), 2)
         mask_gt = gt_bboxes.sum(2, keepdim=True) > 0
-
-        # decode: DFL expectation -> ltrb -> xyxy in grid units (loss.py:347-354, tal.py:309-318)
-        dist = pred_distri.view(b, na, 4, self.reg_max).softmax(3).matmul(self.proj)
-        pred_bboxes = torch.cat((anchor_points - dist[..., :2], anchor_points + dist[..., 2:]), -1)
+        sparse = self.sparse_head and feats[0].is_cuda and self.reg_max == 16 and feats[0].dtype in (torch.bfloat16, torch.float32)
+        if sparse:
+            # CUDA path: ONE anchor-major concatenation of the maps in their own dtype (zero-copy NHWC views of channels_last maps in,
+            # (b, na, no) out).  The assigner's inputs -- decoded boxes and sigmoid scores of ALL anchors, which carry no gradient --
+            # come from one kernel (ldconv_head_decode_rows); the criterion differentiates through the foreground rows only, so the
+            # dense fp32 copies, softmax, matmul and their backward over 33600 anchors per image disappear (~14 -> ~7 ms at batch 128).
+            from . import _lib
+            x = torch.cat([f.permute(0, 2, 3, 1).reshape(b, -1, self.no) for f in feats], 1)          # (b, na, no)
+            na = x.shape[1]
+            pred_scores = x[..., self.reg_max * 4:].float()                                          # (b, na, nc), differentiable
+            boxes_all = torch.empty((b, na, 4), device=dev, dtype=torch.float32)
+            scores_sig = torch.empty((b, na, self.nc), device=dev, dtype=torch.float32)
+            xd = x.detach()
+            _lib.check(_lib.load().ldconv_head_decode_rows(
+                xd.data_ptr(), anchor_points.contiguous().data_ptr(), boxes_all.data_ptr(), scores_sig.data_ptr(), b * na, na, self.nc,
+                self.reg_max, _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32, torch.cuda.current_stream(dev).cuda_stream),
+                "ldconv_head_decode_rows")
+            pred_distri = pred_bboxes = None
+        else:
+            # one concatenation in the maps' own dtype (bf16 under autocast), one fp32 conversion fused with the transposition
+            x = torch.cat([f.reshape(b, self.no, -1) for f in feats], 2)
+            pred_distri, pred_scores = x.split((self.reg_max * 4, self.nc), 1)
+            pred_scores = pred_scores.permute(0, 2, 1).float().contiguous()                    # (b,na,nc)
+            pred_distri = pred_distri.permute(0, 2, 1).float().contiguous()                    # (b,na,4*reg_max)
+            na = pred_scores.shape[1]
+            # decode: DFL expectation -> ltrb -> xyxy in grid units (loss.py:347-354, tal.py:309-318)
+            dist = pred_distri.view(b, na, 4, self.reg_max).softmax(3).matmul(self.proj)
+            pred_bboxes = torch.cat((anchor_points - dist[..., :2], anchor_points + dist[..., 2:]), -1)
+            boxes_all, scores_sig = pred_bboxes.detach(), pred_scores.detach().sigmoid()
 
         _, target_bboxes, target_scores, fg_mask, _ = self.assigner(
-            pred_scores.detach().sigmoid(), pred_bboxes.detach() * stride_tensor, anchor_points * stride_tensor,
-            gt_labels, gt_bboxes, mask_gt.to(gt_bboxes.dtype))
+            scores_sig, boxes_all * stride_tensor, anchor_points * stride_tensor, gt_labels, gt_bboxes, mask_gt.to(gt_bboxes.dtype))
         tss = target_scores.sum().clamp(min=1)
 
         loss = torch.zeros(3, device=dev)
@@ -278,7 +296,15 @@ class DealYoloLoss(nn.Module):
         take = lambda t: torch.gather(t, 1, sel.unsqueeze(-1).expand(-1, -1, t.shape[-1])).reshape(b * cap, t.shape[-1])
         unit = torch.tensor([0.0, 0.0, 1.0, 1.0], device=dev)
         vcol = valid.unsqueeze(-1)
-        pb = torch.where(vcol, take(pred_bboxes), unit)
+        ap = anchor_points.unsqueeze(0).expand(b, -1, -1)
+        apc = take(ap)
+        if sparse:      # decode the foreground rows only (same arithmetic as the dense decode, row by row)
+            pd_rows = take(x[..., : self.reg_max * 4]).float()                                       # (b*cap, 4*reg_max)
+            dist = pd_rows.view(-1, 4, self.reg_max).softmax(-1).matmul(self.proj)
+            pb_rows = torch.cat((apc - dist[:, :2], apc + dist[:, 2:]), -1)
+        else:
+            pd_rows, pb_rows = take(pred_distri), take(pred_bboxes)
+        pb = torch.where(vcol, pb_rows, unit)
         tb = torch.where(vcol, take(target_bboxes / stride_tensor), unit)
         weight = torch.where(valid, take(target_scores).sum(-1), torch.zeros((), device=dev))
         if self.use_wiseiou:
@@ -290,11 +316,9 @@ class DealYoloLoss(nn.Module):
             loss_nwd = ((1.0 - nwd(pb, tb)) * weight).sum() / tss
             loss_iou = self.iou_ratio * loss_iou + (1 - self.iou_ratio) * loss_nwd
         # DFL (loss.py:226-250, tal.py:321-324)
-        ap = anchor_points.unsqueeze(0).expand(b, -1, -1)
-        apc = take(ap)
         ltrb = torch.cat((apc - tb[:, :2], tb[:, 2:] - apc), -1).clamp(0, self.reg_max - 1 - 0.01)
         ltrb = torch.where(vcol, ltrb, torch.zeros((), device=dev))
-        logp = F.log_softmax(take(pred_distri).view(-1, 4, self.reg_max), -1)
+        logp = F.log_softmax(pd_rows.view(-1, 4, self.reg_max), -1)
         tl = ltrb.long()
         wl = (tl + 1).to(ltrb.dtype) - ltrb
         ce_l = -logp.gather(-1, tl.unsqueeze(-1)).squeeze(-1)

@@ -280,6 +280,11 @@ int ldconv_tal_assign(const long long* topk_idx, const float* anchors, const flo
                       const float* align, const float* overlaps, unsigned char* mask_ws, unsigned char* fg, long long* gt_idx,
                       float* align_sel, float* pos_align, float* pos_over, int B, int na, int n, int k, float eps, void* stream);
 
+/* Dense gradient-free decode of the raw head rows for the assigner (utils/loss.py:347-354 bbox_decode + pred_scores.sigmoid()):
+ * x (rows = b*na, 64 + nc) bf16 / fp32; anc (na, 2) fp32 grid units -> boxes (rows, 4) fp32 xyxy grid units, scores (rows, nc) fp32. */
+int ldconv_head_decode_rows(const void* x, const float* anc, float* boxes, float* scores, long long rows, int na, int nc,
+                            int reg_max, int dtype, void* stream);
+
 /* Glue ops of the graph (bf16 NHWC, channel-slice aware through the pixel strides ld*):
  * nearest up-sampling by an integer factor (yolov8-LD-P2.yaml:26,33); the SSFF tail = max over the three pyramid levels,
  * coarser levels indexed like torch's nearest interpolation, + optional residual (nn/extra_modules/block.py:3432-3443,
