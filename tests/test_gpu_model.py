@@ -215,3 +215,37 @@ def test_fused_bn_silu_training_op_vs_torch(B, C, H, W):
     assert rel(bn.weight.grad, ref_bn.weight.grad) <= 2e-3 and rel(bn.bias.grad, ref_bn.bias.grad) <= 2e-3
     assert torch.allclose(bn.running_mean, ref_bn.running_mean, atol=1e-5) and torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-4, atol=1e-6)
     assert int(bn.num_batches_tracked) == 1
+
+
+def test_fused_engine_on_a_model_whose_conv_blocks_were_fused_like_model_fuse():
+    """The reference's `model.fuse()` (nn/tasks.py:168-195) folds BatchNorm into every `Conv` block's convolution and deletes `bn`;
+    the executor must take such blocks too (Conv2d with bias + SiLU).  Folding here is done in fp32 exactly like
+    `fuse_conv_and_bn` (utils/torch_utils.py), so the executor's own fold of the unfused model agrees to bf16 rounding of the weights."""
+    from experiment_yolo_b200 import engine
+    z, model = _load()
+    fused = copy_model(model)
+    for m in fused.modules():
+        if type(m).__name__ == "Conv" and hasattr(m, "bn"):
+            conv, bn = m.conv, m.bn
+            w = conv.weight.detach().clone()
+            scale = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+            new = torch.nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, bias=True)
+            new.weight.data = w * scale.view(-1, 1, 1, 1)
+            new.bias.data = bn.bias.detach() - bn.running_mean.detach() * scale
+            m.conv = new
+            del m.bn
+    model = dealyolo.channels_last_(model.to(DEV).bfloat16().eval())
+    fused = fused.to(DEV).eval()      # fp32 parameters: the executor rounds the folded weights itself
+    x = torch.from_numpy(z["x"]).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    y0, _ = engine.FusedDealYolo(model)(x)
+    y1, _ = engine.FusedDealYolo(fused)(x)
+    torch.cuda.synchronize()
+    a, b = y1.float().cpu().numpy(), y0.float().cpu().numpy()
+    assert np.isfinite(a).all()
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 2e-2
+    assert np.linalg.norm(a - z["y"]) / np.linalg.norm(z["y"]) <= 5e-2
+
+
+def copy_model(model):
+    import copy
+    return copy.deepcopy(model)
