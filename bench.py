@@ -249,7 +249,7 @@ def workload_config(n_gpus: int, engine: str = "fused", scaling: str = "weak"):
             "layout": "channels_last", "parallelism": f"batch-sharded x{n_gpus}, no collective",
             "l2_policy": f"inputs_exceed_l2 ({pgb * 3 * IMG * IMG * 2 / 1e6:.0f} MB bf16 batch, {n_input_buffers(pgb)} rotating input buffers "
                          f"= {n_input_buffers(pgb) * pgb * 3 * IMG * IMG * 2 / 1e6:.0f} MB > 126 MB L2; the activations of one step are "
-                         f"{7.9 * pgb / 64:.1f} GB)",
+                         f"{6.5 * pgb / 64:.1f} GB of DRAM traffic)",
             "weights": "seeded random init (dealyolo.seeded_state(0)), p_conv.weight ~ N(0,0.05)"}
 
 
