@@ -139,6 +139,14 @@ def main():
                                                               grad_x.data_ptr(), grad_off.data_ptr(), B, C, H, W, N, s, dt, st)),
                        args.iters, flush)
             rec("gather_bwd", "atomics", ms, bytes_s)
+            if dtype == torch.bfloat16 and L.ldconv_bwd_acc16_supported(B, C, H, W, N, s):
+                grad_x16 = torch.zeros((B, H, W, C), device=dev, dtype=torch.bfloat16)
+                bytes_16 = e * M * K + e * B * C * H * W + 4 * B * 2 * N * h * w + 2 * B * C * H * W + 4 * B * 2 * N * h * w
+                ms = timed(lambda: _lib.check(L.ldconv_gather_bwd_acc16(gop.data_ptr(), x.data_ptr(), off.data_ptr(), pn.data_ptr(),
+                                                                        grad_x16.data_ptr(), grad_off.data_ptr(), B, C, H, W, N, s, st)),
+                           args.iters, flush)
+                rec("gather_bwd", "atomics_bf16_accumulator", ms, bytes_16)
+                del grad_x16
             gpre = torch.randn((M, O), device=dev, generator=g).to(dtype)
             gw = torch.zeros((O, K), device=dev)
             ms = timed(lambda: _lib.check(L.ldconv_gemm_bwd_weight(gpre.data_ptr(), operand.data_ptr(), gw.data_ptr(), M, K, O,

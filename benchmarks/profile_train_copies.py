@@ -50,8 +50,12 @@ def main():
     agg = collections.defaultdict(lambda: [0, 0.0, ""])
     for e in prof.events():
         if e.name in ("aten::copy_",) and e.device_time_total > 0:
-            stack = [s for s in (e.stack or []) if "experiment_yolo_b200" in s or "benchmarks" in s or "torch/nn/modules" in s or "torch/optim" in s]
-            key = (str(e.input_shapes), stack[0][-90:] if stack else "?")
+            # the chain of enclosing ops (backward copies have no Python stack: the autograd node's name is the attribution)
+            chain, par = [], e.cpu_parent
+            while par is not None and len(chain) < 6:
+                chain.append(par.name.replace("autograd::engine::evaluate_function: ", "bwd:"))
+                par = par.cpu_parent
+            key = (str(e.input_shapes), " < ".join(chain)[-110:] if chain else "?")
             agg[key][0] += 1
             agg[key][1] += e.device_time_total
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])

@@ -45,9 +45,12 @@ SIGNATURES = {
     "ldconv_bn_act_bwd_apply": (_i, [_vp] * 8 + [_ll, _i, _i, _i, _i, _vp]),
     "ldconv_gemm_bwd_weight": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ldconv_gather_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "ldconv_bwd_acc16_supported": (_i, [_i] * 6),
+    "ldconv_gather_bwd_acc16": (_i, [_vp] * 6 + [_i] * 6 + [_vp]),
     "ldconv_offset_conv_bwd": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
     "ldconv_offset_conv_bwd_workspace_bytes": (ctypes.c_size_t, [_i] * 7),
     "ldconv_offset_conv_bwd_tc": (_i, [_vp] * 7 + [ctypes.c_size_t] + [_i] * 7 + [_vp]),
+    "ldconv_offset_conv_bwd_tc_acc16": (_i, [_vp] * 7 + [ctypes.c_size_t] + [_i] * 6 + [_vp]),
     "ldconv_conv1x1_bn_act_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _ll, _i, _i, _i, _i, _vp]),
     "ldconv_conv1x1_bn_act_fwd2": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _ll, _i, _i, _i, _i, _vp]),
     "ldconv_conv3x3_supported": (_i, [_i] * 4),

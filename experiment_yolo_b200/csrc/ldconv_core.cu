@@ -502,12 +502,30 @@ __device__ __forceinline__ void red_add_vec(float* dst, const float* v, int n)
     for (int e = 0; e < n; ++e) atomicAdd(dst + e, v[e]);
 }
 
+// bf16 accumulator (ldconv_gather_bwd_acc16): eight channels per 16-byte reduction -- half the L2 reduction requests of the fp32
+// accumulator, which is what bounds the scatter (1.3-1.7 cycles per lane request, profiles/r1_ncu_scatterL1.txt).  The product
+// g * weight is formed in fp32 and rounded to bf16 once; the accumulator rounds after every addition (what autograd's own
+// scatter_add_ does for a reduced-precision model), so its tolerance is stated separately (tests/test_gpu_parity.py).
+__device__ __forceinline__ void red_add_vec(__nv_bfloat16* dst, const float* v, int n)
+{
+    if (n == 8) {
+        uint32_t p0, p1, p2, p3;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(v[1]), "f"(v[0]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v[3]), "f"(v[2]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(v[5]), "f"(v[4]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(v[7]), "f"(v[6]));
+        asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+        return;
+    }
+    for (int e = 0; e < n; ++e) atomicAdd(dst + e, __float2bfloat16_rn(v[e]));
+}
+
 // IDX: the integer type of the item decomposition -- unsigned 32-bit whenever the item count fits (always at the benchmark
 // sizes); the 64-bit divisions of the general case cost several hundred instructions per item
-template <typename T, bool VECX, typename IDX>
+template <typename T, bool VECX, typename IDX, typename ACC = float>
 __global__ void __launch_bounds__(256, 5)      // <= 51 registers: 40 warps per SM instead of 24
 gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const float* __restrict__ off,
-                  const int* __restrict__ pn, float* __restrict__ grad_x, float* __restrict__ grad_off, int C, int H,
+                  const int* __restrict__ pn, ACC* __restrict__ grad_x, float* __restrict__ grad_off, int C, int H,
                   int W, int h, int w, int N, int s, int CV, int group, long long total)
 {
     constexpr int V = VECX ? Vec16<T>::N : 1;
@@ -592,8 +610,9 @@ gather_bwd_kernel(const T* __restrict__ gop, const T* __restrict__ x, const floa
                         for (int e = 0; e < V; ++e) v[e] = acc[e];
                     }
                 }
+                constexpr int PER = sizeof(ACC) == 2 ? 8 : 4;     // values per 16-byte reduction
 #pragma unroll
-                for (int e0 = 0; e0 < V; e0 += 4) red_add_vec(grad_x + o + e0, v + e0, V - e0 < 4 ? V - e0 : 4);
+                for (int e0 = 0; e0 < V; e0 += PER) red_add_vec(grad_x + o + e0, v + e0, V - e0 < PER ? V - e0 : PER);
             };
             auto corner = [&](size_t o, float wgt, bool clamped) {
                 float v[V];
@@ -931,6 +950,8 @@ int gather_set_direct(int v);
 int gather_set_miss_counter(void* p);
 int gather_fwd_tiled(const void* x, const float* off, const int* pn, void* operand, int* dbg_idx, float* dbg_coord, int B,
                      int C, int H, int W, int N, int s, int dtype, cudaStream_t st);
+int scatter_bwd_tiled(const __nv_bfloat16* x, const float* off, const int* pn, const __nv_bfloat16* gop, __nv_bfloat16* grad_x,
+                      float* grad_off, int B, int C, int H, int W, int N, int s, cudaStream_t st);
 }
 
 LDC_API int ldconv_set_flag(int flag, int value)
@@ -1132,13 +1153,15 @@ LDC_API int ldconv_bn_act_bwd_apply(const void* pre, const void* grad_out, const
 }
 
 
-template <typename T>
-static int gather_bwd_t(const T* gop, const T* x, const float* off, const int* pn, float* grad_x, float* grad_off, int B,
+template <typename T, typename ACC>
+static int gather_bwd_t(const T* gop, const T* x, const float* off, const int* pn, ACC* grad_x, float* grad_off, int B,
                         int C, int H, int W, int N, int s, cudaStream_t st)
 {
     const int h = out_size(H, s), w = out_size(W, s);
     constexpr int V = Vec16<T>::N;
     const bool vec = (C % V == 0) && aligned16(x) && aligned16(gop) && (!grad_x || aligned16(grad_x));
+    if (sizeof(ACC) == 2 && !vec)
+        return fail(LDCONV_E_ARG, "ldconv_gather_bwd_acc16: needs C %% 8 == 0 and 16-byte aligned tensors (C=%d)", C);
     const int CV = vec ? C / V : C;
     const long long total = (long long)B * h * w * N * CV;
     LDC_CUDA(cudaMemsetAsync(grad_off, 0, (size_t)B * h * w * 2 * N * sizeof(float), st));
@@ -1147,17 +1170,17 @@ static int gather_bwd_t(const T* gop, const T* x, const float* off, const int* p
     const unsigned blocks = cdiv(total, 256);
     const bool small = total + 256 < 0xffffffffll;      // the last block's thread ids must not wrap
     if (vec && small)
-        gather_bwd_kernel<T, true, unsigned><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV, group,
-                                                                     total);
+        gather_bwd_kernel<T, true, unsigned, ACC><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
+                                                                          group, total);
     else if (vec)
-        gather_bwd_kernel<T, true, long long><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV, group,
-                                                                      total);
+        gather_bwd_kernel<T, true, long long, ACC><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
+                                                                           group, total);
     else if (small)
-        gather_bwd_kernel<T, false, unsigned><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
-                                                                      group, total);
+        gather_bwd_kernel<T, false, unsigned, ACC><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
+                                                                           group, total);
     else
-        gather_bwd_kernel<T, false, long long><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
-                                                                       group, total);
+        gather_bwd_kernel<T, false, long long, ACC><<<blocks, 256, 0, st>>>(gop, x, off, pn, grad_x, grad_off, C, H, W, h, w, N, s, CV,
+                                                                            group, total);
     LDC_LAUNCH_CHECK("gather_bwd_kernel");
     return LDCONV_OK;
 }
@@ -1172,10 +1195,25 @@ LDC_API int ldconv_gather_bwd(const void* grad_operand, const void* x, const flo
     if (B == 0) return LDCONV_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == LDCONV_F32)
-        return gather_bwd_t<float>((const float*)grad_operand, (const float*)x, off, p_n, grad_x, grad_off, B, C, H, W, N, s,
-                                   st);
-    return gather_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)grad_operand, (const __nv_bfloat16*)x, off, p_n, grad_x,
-                                       grad_off, B, C, H, W, N, s, st);
+        return gather_bwd_t<float, float>((const float*)grad_operand, (const float*)x, off, p_n, grad_x, grad_off, B, C, H, W, N, s,
+                                          st);
+    return gather_bwd_t<__nv_bfloat16, float>((const __nv_bfloat16*)grad_operand, (const __nv_bfloat16*)x, off, p_n, grad_x,
+                                              grad_off, B, C, H, W, N, s, st);
+}
+
+LDC_API int ldconv_gather_bwd_acc16(const void* grad_operand, const void* x, const float* off, const int32_t* p_n, void* grad_x,
+                                    float* grad_off, int B, int C, int H, int W, int N, int s, void* stream)
+{
+    if (int e = check_dims("ldconv_gather_bwd_acc16", B, C, H, W, N, s)) return e;
+    LDC_REQUIRE(grad_operand && x && off && p_n && grad_off, "ldconv_gather_bwd_acc16: null pointer");
+    if (B == 0) return LDCONV_OK;
+    {   // TMA-tiled kernel for the model's shapes (ldconv_gather_tma.cu); 1 = no instance for this shape
+        const int e = scatter_bwd_tiled((const __nv_bfloat16*)x, off, p_n, (const __nv_bfloat16*)grad_operand, (__nv_bfloat16*)grad_x,
+                                        grad_off, B, C, H, W, N, s, (cudaStream_t)stream);
+        if (e != 1) return e;
+    }
+    return gather_bwd_t<__nv_bfloat16, __nv_bfloat16>((const __nv_bfloat16*)grad_operand, (const __nv_bfloat16*)x, off, p_n,
+                                                      (__nv_bfloat16*)grad_x, grad_off, B, C, H, W, N, s, (cudaStream_t)stream);
 }
 
 LDC_API int ldconv_offset_conv_bwd(const float* grad_off, const void* x, const float* w, float* grad_x, float* grad_w,

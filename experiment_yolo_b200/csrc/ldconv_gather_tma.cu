@@ -245,6 +245,260 @@ gather_fwd_tiled2_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfl
     }
 }
 
+// ---- backward scatter on the same tiles (bf16 activations, bf16 grad_x accumulator) -----------------------------------------------
+// autograd of conv.py:386-405 like gather_bwd_kernel (ldconv_core.cu), restructured like the forward kernel above: that kernel ran
+// 512 instructions per (sample, 16-byte vector) item -- eight 32-bit divisions to decompose the item index, make_point per item --
+// and fetched the four corner vectors of x through L1 / L2 (profiles/r2_ncu_scatterL1_acc16.txt: l1tex 76 %, 9.3 cycles of long
+// scoreboard per issue).  Here the tile of x is TMA-staged, phase 1 computes one record per SAMPLE (interpolation factors, corner
+// offsets in the tile and in the image), and phase 2 maps (sample, channel vector) items onto the contiguous run of grad_operand
+// a tile row is: one coalesced 16-byte load of the gradient, four shared-memory corner loads, four dot products for the offset
+// gradient (reduced over the channel lanes with shuffles, ONE plain store per sample and axis: every sample has exactly one owner,
+// no atomics and no memset for grad_off), and one 16-byte bf16x8 reduction per distinct corner for grad_x.
+__device__ __forceinline__ void red_bf16x8(uint8_t* dst, const float (&v)[8])
+{
+    uint32_t p0, p1, p2, p3;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(v[7]), "f"(v[6]));
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8])
+{
+    f[0] = __uint_as_float(q.x << 16); f[1] = __uint_as_float(q.x & 0xffff0000u);
+    f[2] = __uint_as_float(q.y << 16); f[3] = __uint_as_float(q.y & 0xffff0000u);
+    f[4] = __uint_as_float(q.z << 16); f[5] = __uint_as_float(q.z & 0xffff0000u);
+    f[6] = __uint_as_float(q.w << 16); f[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+
+__device__ __forceinline__ float dot_bf16x8(const float (&g)[8], const uint4& q)
+{
+    float f[8];
+    unpack_bf16x8(q, f);
+    float a = g[0] * f[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) a = fmaf(g[e], f[e], a);
+    return a;
+}
+
+template <int TN, int TCVS, int TS>
+__global__ void __launch_bounds__(256)
+scatter_bwd_tiled2_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ x, const float* __restrict__ off,
+                          const int* __restrict__ pn, const __nv_bfloat16* __restrict__ gop, __nv_bfloat16* __restrict__ grad_x,
+                          float* __restrict__ grad_off, int H, int W, int h, int w, float hm, float wm, TileGeom g)
+{
+    constexpr int CV = 1 << TCVS, C = CV * 8, TW = 16, TH = 8;
+    constexpr int SAMPLES = TH * TW * TN, ROW_ITEMS = TW * TN * CV, ITEMS = TH * ROW_ITEMS;
+    static_assert(ITEMS % 256 == 0, "whole rounds of the CTA (the shuffles below need converged warps)");
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const uint32_t tile_bytes = ((uint32_t)(g.THin * g.TWin * C * 2) + 15u) & ~15u;
+    const uint32_t tile_s = smem_u32(sm);
+    // per sample: rec_o = corner byte offsets in the staged tile (.x = 0xffffffff: pixel outside the map; bit 31 of .x: a corner
+    // lies outside tile + halo, read x from the image), rec_d = corner byte offsets in the image (bit 31 of .x / .y = the clamp
+    // indicators in_r / in_k), rec_w = (ar0, ar1, ak0, ak1)
+    const uint32_t rec_o = tile_s + tile_bytes, rec_d = rec_o + SAMPLES * 16u, rec_w = rec_d + SAMPLES * 16u;
+
+    const unsigned bid = blockIdx.x;
+    const unsigned tpi = (unsigned)(g.tiles_w * g.tiles_h);
+    const int b = (int)(bid / tpi);
+    const unsigned rem = bid - (unsigned)b * tpi;
+    const int ti = (int)(rem / (unsigned)g.tiles_w), tj = (int)(rem - (unsigned)ti * (unsigned)g.tiles_w);
+    const int i0 = ti * TH, j0 = tj * TW;
+    const int r_org = i0 * TS - g.halo, k_org = j0 * TS - g.halo;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&bar, (uint32_t)(g.THin * g.TWin * C * 2));
+        tma_load_4d(sm, &tmX, &bar, 0, k_org, r_org, b);
+    }
+
+    const int rowB = g.TWin * (C * 2), imgRowB = W * (C * 2);
+    const int m0 = (b * h + i0) * w + j0;
+#pragma unroll
+    for (int r = 0; r < (SAMPLES + 255) / 256; ++r) {
+        const int sidx = tid + r * 256;
+        if (SAMPLES % 256 != 0 && sidx >= SAMPLES) break;
+        const int p = sidx / TN, n = sidx - p * TN;
+        const int di = p >> 4, dj = p & 15;
+        if (i0 + di >= h || j0 + dj >= w) {
+            sts128(rec_o + sidx * 16, 0xffffffffu, 0, 0, 0);
+            continue;
+        }
+        const float* op = off + (size_t)(unsigned)((m0 + di * w + dj) * (2 * TN));
+        const SamplePoint q = make_point_grid((i0 + di) * TS + pn[n], (j0 + dj) * TS + pn[TN + n], op[n], op[TN + n], hm, wm);
+        sts128(rec_w + sidx * 16, __float_as_uint(q.ar0), __float_as_uint(q.ar1), __float_as_uint(q.ak0), __float_as_uint(q.ak1));
+        {
+            const int a0 = q.r0 * imgRowB, a1 = q.r1 * imgRowB, b0 = q.k0 * (C * 2), b1 = q.k1 * (C * 2);
+            sts128(rec_d + sidx * 16, (uint32_t)(a0 + b0) | (q.in_r ? 0x80000000u : 0u), (uint32_t)(a1 + b1) | (q.in_k ? 0x80000000u : 0u),
+                   (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
+        }
+        const int t0 = q.r0 - r_org, t1 = q.r1 - r_org, u0 = q.k0 - k_org, u1 = q.k1 - k_org;
+        const bool inside = (unsigned)t0 < (unsigned)g.THin && (unsigned)t1 < (unsigned)g.THin &&
+                            (unsigned)u0 < (unsigned)g.TWin && (unsigned)u1 < (unsigned)g.TWin;
+        if (inside) {
+            const int a0 = t0 * rowB, a1 = t1 * rowB, b0 = u0 * (C * 2), b1 = u1 * (C * 2);
+            sts128(rec_o + sidx * 16, (uint32_t)(a0 + b0), (uint32_t)(a1 + b1), (uint32_t)(a0 + b1), (uint32_t)(a1 + b0));
+        } else {
+            sts128(rec_o + sidx * 16, 0x80000000u, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const uint8_t* xg = reinterpret_cast<const uint8_t*>(x) + (size_t)b * H * W * (C * 2);
+    uint8_t* gxb = grad_x ? reinterpret_cast<uint8_t*>(grad_x) + (size_t)b * H * W * (C * 2) : nullptr;
+    const uint4* gop4 = reinterpret_cast<const uint4*>(gop) + (size_t)(unsigned)(m0 * (TN * CV));
+    const int row_stride = w * (TN * CV);
+#pragma unroll 1
+    for (int r = 0; r < ITEMS / 256; ++r) {
+        const int it = tid + r * 256;
+        const int sidx = it >> TCVS, cv = it & (CV - 1);
+        const uint4 o = lds128(rec_o + sidx * 16);
+        const bool valid = o.x != 0xffffffffu;
+        float acc_r = 0.f, acc_k = 0.f;
+        uint4 d = make_uint4(0, 0, 0, 0);
+        float gv[8];
+        float ar0 = 0.f, ar1 = 0.f, ak0 = 0.f, ak1 = 0.f;
+        if (valid) {
+            const int pi = it / ROW_ITEMS;
+            const uint4 gq = __ldg(gop4 + pi * row_stride + (it - pi * ROW_ITEMS));
+            d = lds128(rec_d + sidx * 16);
+            const uint4 wq = lds128(rec_w + sidx * 16);
+            ar0 = __uint_as_float(wq.x); ar1 = __uint_as_float(wq.y); ak0 = __uint_as_float(wq.z); ak1 = __uint_as_float(wq.w);
+            uint4 q00, q11, q01, q10;
+            if ((int)o.x >= 0) {
+                const uint32_t t0 = tile_s + (uint32_t)cv * 16u;
+                q00 = lds128(t0 + o.x); q11 = lds128(t0 + o.y); q01 = lds128(t0 + o.z); q10 = lds128(t0 + o.w);
+            } else {
+                const uint8_t* g0 = xg + cv * 16;
+                q00 = __ldg(reinterpret_cast<const uint4*>(g0 + (d.x & 0x7fffffffu))); q11 = __ldg(reinterpret_cast<const uint4*>(g0 + (d.y & 0x7fffffffu)));
+                q01 = __ldg(reinterpret_cast<const uint4*>(g0 + d.z)); q10 = __ldg(reinterpret_cast<const uint4*>(g0 + d.w));
+            }
+            unpack_bf16x8(gq, gv);
+            const float s00 = dot_bf16x8(gv, q00), s11 = dot_bf16x8(gv, q11), s01 = dot_bf16x8(gv, q01), s10 = dot_bf16x8(gv, q10);
+            acc_r = fmaf(ak0, s10 - s00, ak1 * (s11 - s01));
+            acc_k = fmaf(ar0, s01 - s00, ar1 * (s11 - s10));
+        }
+#pragma unroll
+        for (int sh = CV >> 1; sh > 0; sh >>= 1) {
+            acc_r += __shfl_xor_sync(0xffffffffu, acc_r, sh);
+            acc_k += __shfl_xor_sync(0xffffffffu, acc_k, sh);
+        }
+        if (!valid) continue;
+        if (cv == 0) {
+            const int p = sidx / TN, n = sidx - p * TN;
+            float* gp = grad_off + (size_t)(unsigned)((m0 + (p >> 4) * w + (p & 15)) * (2 * TN));
+            gp[n] = (d.x >> 31) ? acc_r : 0.f;
+            gp[TN + n] = (d.y >> 31) ? acc_k : 0.f;
+        }
+        if (gxb == nullptr) continue;
+        const uint32_t d00 = d.x & 0x7fffffffu, d11 = d.y & 0x7fffffffu, d01 = d.z, d10 = d.w;
+        const float g_lt = ar0 * ak0, g_rb = ar1 * ak1, g_lb = ar0 * ak1, g_rt = ar1 * ak0;
+        const bool same_r = d00 == d10, same_k = d00 == d01;
+        uint8_t* base = gxb + cv * 16;
+        auto corner = [&](uint32_t dofs, float wgt, bool clamped) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = gv[e] * wgt;
+            if (clamped) {          // border pixels collect many samples: lanes of the warp that hit the same address add up first
+                const unsigned act = __activemask();
+                const unsigned peers = __match_any_sync(act, dofs + (uint32_t)cv * 16u);
+                if (__any_sync(act, (peers & (peers - 1)) != 0)) {
+                    const int lane = tid & 31;
+                    const int leader = __ffs(peers) - 1;
+                    float acc[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                    for (unsigned mk = act; mk; mk &= mk - 1) {
+                        const int src = __ffs(mk) - 1;
+                        const bool take = (peers >> src) & 1u;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float t = __shfl_sync(act, v[e], src);
+                            if (take) acc[e] += t;
+                        }
+                    }
+                    if (lane != leader) return;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = acc[e];
+                }
+            }
+            red_bf16x8(base + dofs, v);
+        };
+        if (same_r && same_k) {
+            corner(d00, (g_lt + g_rb) + (g_lb + g_rt), true);
+        } else if (same_r) {
+            corner(d00, g_lt + g_rt, true);
+            corner(d01, g_lb + g_rb, true);
+        } else if (same_k) {
+            corner(d00, g_lt + g_lb, true);
+            corner(d10, g_rt + g_rb, true);
+        } else {
+            corner(d00, g_lt, false);
+            corner(d11, g_rb, false);
+            corner(d01, g_lb, false);
+            corner(d10, g_rt, false);
+        }
+    }
+}
+
+// returns LDCONV_OK when launched, 1 when the shape has no instance (caller: gather_bwd_kernel of ldconv_core.cu)
+int scatter_bwd_tiled(const __nv_bfloat16* x, const float* off, const int* pn, const __nv_bfloat16* gop, __nv_bfloat16* grad_x,
+                      float* grad_off, int B, int C, int H, int W, int N, int s, cudaStream_t st)
+{
+    if (C % 8 != 0 || C > 128 || N > 16 || !aligned16(x) || !aligned16(gop) || (grad_x && !aligned16(grad_x))) return 1;
+    int32_t table[64];
+    if (int e = ldconv_p_n(N, table)) return e;
+    int max_r = 0, max_k = 0;
+    for (int n = 0; n < N; ++n) {
+        if (table[n] > max_r) max_r = table[n];
+        if (table[N + n] > max_k) max_k = table[N + n];
+    }
+    const int h = out_size(H, s), w = out_size(W, s);
+    TileGeom g = {};
+    g.halo = 2;
+    g.TH = 8;
+    g.TW = 16;
+    g.THin = (g.TH - 1) * s + 2 + max_r + 2 * g.halo;
+    g.TWin = (g.TW - 1) * s + 2 + max_k + 2 * g.halo;
+    const size_t tile = ((size_t)g.THin * g.TWin * C * 2 + 15) & ~(size_t)15;
+    // larger tiles (C = 64 at stride 2: 99 KB, two CTAs per SM) measured slower than the direct kernel: 105 vs 77 us at layer 5
+    if (tile > 64 * 1024 || g.THin > 256 || g.TWin > 256) return 1;
+    if ((long long)B * h * w * N * C >= 0x7fffffffll || (long long)H * W * C * 2 >= 0x7fffffffll) return 1;
+    g.tiles_h = (h + g.TH - 1) / g.TH;
+    g.tiles_w = (w + g.TW - 1) / g.TW;
+    const long long ctas = (long long)B * g.tiles_h * g.tiles_w;
+    if (ctas > 0x7fffffffll) return 1;
+    int cvs = -1;
+    for (int sh = 0; sh < 8; ++sh)
+        if ((8 << sh) == C) cvs = sh;
+    using K2 = void (*)(CUtensorMap, const __nv_bfloat16*, const float*, const int*, const __nv_bfloat16*, __nv_bfloat16*, float*, int, int,
+                        int, int, float, float, TileGeom);
+    K2 k2 = nullptr;
+    switch (N * 100 + cvs * 10 + s) {
+        case 312: k2 = scatter_bwd_tiled2_kernel<3, 1, 2>; break;      // C = 16 (layer 1)
+        case 322: k2 = scatter_bwd_tiled2_kernel<3, 2, 2>; break;      // C = 32 (layers 3, 18)
+        case 121: k2 = scatter_bwd_tiled2_kernel<1, 2, 1>; break;      // C = 32 (layer 15)
+        case 131: k2 = scatter_bwd_tiled2_kernel<1, 3, 1>; break;      // C = 64 (layers 10, 13)
+        default: return 1;
+    }
+    CUtensorMap tm;
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)g.TWin, (cuuint32_t)g.THin, 1};
+    if (int e = encode_map(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    const size_t smem = tile + 16 + (size_t)g.TH * g.TW * N * 48 + 128;
+    LDC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k2<<<(unsigned)ctas, 256, smem, st>>>(tm, x, off, pn, gop, grad_x, grad_off, H, W, h, w, (float)(H - 1), (float)(W - 1), g);
+    LDC_LAUNCH_CHECK("scatter_bwd_tiled2_kernel");
+    return LDCONV_OK;
+}
+
 static thread_local int g_gather_direct = 0;
 static thread_local unsigned long long* g_miss_counter = nullptr;
 

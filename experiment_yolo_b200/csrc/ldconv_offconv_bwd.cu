@@ -109,9 +109,11 @@ __global__ void dw_scatter_kernel(const float* __restrict__ dW, float* __restric
 
 // ---- data gradient ------------------------------------------------------------------------------------------------------
 // S = 1 / 2: compile-time stride (the model's values) so the tap validity test is a bit test; S = 0: any stride
-template <int NMAX, int S>
+// ACC: the type of grad_x (read-modify-write: it already holds the scatter's part) -- fp32, or bf16 for the 16-bit accumulator of
+// ldconv_gather_bwd_acc16 (C % 4 == 0 there: one 8-byte access per thread)
+template <int NMAX, int S, typename ACC>
 __global__ void __launch_bounds__(256)
-offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict__ w, float* __restrict__ grad_x, int B, int C,
+offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict__ w, ACC* __restrict__ grad_x, int B, int C,
                         int H, int W, int h, int wo, int N, int s_rt, long long total)
 {
     extern __shared__ __align__(16) float s_w[];            // [9][2N][C4*4]: w (3,3,C,2N) transposed to channel-fastest
@@ -156,8 +158,16 @@ offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict_
                 }
             }
         }
-        float* dst = grad_x + pix * C + cg * 4;
-        if ((C & 3) == 0) {
+        ACC* dst = grad_x + pix * C + cg * 4;
+        if constexpr (sizeof(ACC) == 2) {
+            const uint2 old = *reinterpret_cast<const uint2*>(dst);
+            uint2 nw;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(nw.x) : "f"(__uint_as_float(old.x & 0xffff0000u) + acc[1]),
+                "f"(__uint_as_float(old.x << 16) + acc[0]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(nw.y) : "f"(__uint_as_float(old.y & 0xffff0000u) + acc[3]),
+                "f"(__uint_as_float(old.y << 16) + acc[2]));
+            *reinterpret_cast<uint2*>(dst) = nw;
+        } else if ((C & 3) == 0) {
             float4 v = *reinterpret_cast<float4*>(dst);
             v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
             *reinterpret_cast<float4*>(dst) = v;
@@ -170,8 +180,9 @@ offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict_
 }
 
 // returns 1 when launched, 0 when the shape is outside the kernel's range (caller uses the generic kernel)
-int offconv_bwd_data_fast(const float* goff, const float* w, float* grad_x, int B, int C, int H, int W, int N, int s,
-                          cudaStream_t st)
+template <typename ACC>
+static int offconv_bwd_data_fast_t(const float* goff, const float* w, ACC* grad_x, int B, int C, int H, int W, int N, int s,
+                                 cudaStream_t st)
 {
     const int C4 = (C + 3) / 4;
     const size_t smem = (size_t)9 * 2 * N * C4 * 4 * sizeof(float);
@@ -185,9 +196,9 @@ int offconv_bwd_data_fast(const float* goff, const float* w, float* grad_x, int 
     };
 #define LDC_BWD_DATA(NM)                                                          \
     do {                                                                          \
-        if (s == 1) launch(offconv_bwd_data_kernel<NM, 1>);                       \
-        else if (s == 2) launch(offconv_bwd_data_kernel<NM, 2>);                  \
-        else launch(offconv_bwd_data_kernel<NM, 0>);                              \
+        if (s == 1) launch(offconv_bwd_data_kernel<NM, 1, ACC>);                  \
+        else if (s == 2) launch(offconv_bwd_data_kernel<NM, 2, ACC>);             \
+        else launch(offconv_bwd_data_kernel<NM, 0, ACC>);                         \
     } while (0)
     if (N <= 1) LDC_BWD_DATA(1);
     else if (N <= 3) LDC_BWD_DATA(3);
@@ -196,6 +207,11 @@ int offconv_bwd_data_fast(const float* goff, const float* w, float* grad_x, int 
     else LDC_BWD_DATA(16);
 #undef LDC_BWD_DATA
     return 1;
+}
+
+int offconv_bwd_data_fast(const float* goff, const float* w, float* grad_x, int B, int C, int H, int W, int N, int s, cudaStream_t st)
+{
+    return offconv_bwd_data_fast_t<float>(goff, w, grad_x, B, C, H, W, N, s, st);
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -220,8 +236,9 @@ size_t offconv_bwd_tc_workspace(int B, int C, int H, int W, int N, int s)
     return g16 + col + dw + 256;
 }
 
-int offconv_bwd_tc(const float* goff, const __nv_bfloat16* x, const float* w, float* grad_x, float* grad_w, float* grad_b,
-                   void* workspace, size_t workspace_bytes, int B, int C, int H, int W, int N, int s, cudaStream_t st)
+// grad_x (fp32) or grad_x16 (bf16 accumulator), at most one of them
+int offconv_bwd_tc(const float* goff, const __nv_bfloat16* x, const float* w, float* grad_x, __nv_bfloat16* grad_x16, float* grad_w,
+                   float* grad_b, void* workspace, size_t workspace_bytes, int B, int C, int H, int W, int N, int s, cudaStream_t st)
 {
     const int h = out_size(H, s), wo = out_size(W, s);
     const long long M = (long long)B * h * wo;
@@ -237,8 +254,13 @@ int offconv_bwd_tc(const float* goff, const __nv_bfloat16* x, const float* w, fl
     const size_t col_bytes = (rows_chunk * (size_t)Kp * 2 + 255) & ~(size_t)255;
     float* dW = reinterpret_cast<float*>(ws + g16_bytes + col_bytes);
 
+    if (grad_x16) {
+        if ((C & 3) != 0 || !offconv_bwd_data_fast_t<__nv_bfloat16>(goff, w, grad_x16, B, C, H, W, N, s, st))
+            return fail(LDCONV_E_ARG, "ldconv_offset_conv_bwd_tc_acc16: shape outside the 16-bit accumulator kernel (C=%d, N=%d)", C, N);
+        LDC_LAUNCH_CHECK("offconv_bwd_data_kernel");
+    }
     if (grad_x) {       // data gradient first: it only needs grad_off
-        if (offconv_bwd_data_fast(goff, w, grad_x, B, C, H, W, N, s, st)) {
+        if (offconv_bwd_data_fast_t<float>(goff, w, grad_x, B, C, H, W, N, s, st)) {
             LDC_LAUNCH_CHECK("offconv_bwd_data_kernel");
         } else {        // weights do not fit shared memory (e.g. C=256, N=9): the generic kernel of ldconv_core.cu
             if (int e = ldconv_offset_conv_bwd(goff, x, w, grad_x, nullptr, nullptr, B, C, H, W, N, s, LDCONV_BF16, (void*)st)) return e;
@@ -292,6 +314,24 @@ LDC_API int ldconv_offset_conv_bwd_tc(const float* grad_off, const void* x, cons
     LDC_REQUIRE(grad_off && x && w && workspace, "ldconv_offset_conv_bwd_tc: null pointer");
     LDC_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1 && N >= 1 && N <= 16 && s >= 1, "ldconv_offset_conv_bwd_tc: bad dims");
     if (B == 0) return LDCONV_OK;
-    return offconv_bwd_tc(grad_off, (const __nv_bfloat16*)x, w, grad_x, grad_w, grad_b, workspace, workspace_bytes, B, C, H, W,
-                          N, s, (cudaStream_t)stream);
+    return offconv_bwd_tc(grad_off, (const __nv_bfloat16*)x, w, grad_x, nullptr, grad_w, grad_b, workspace, workspace_bytes, B, C, H,
+                          W, N, s, (cudaStream_t)stream);
+}
+
+LDC_API int ldconv_bwd_acc16_supported(int B, int C, int H, int W, int N, int s)
+{
+    // gather_bwd: 16-byte bf16 vectors (C % 8 == 0); data gradient: the offset conv's weights must fit its shared-memory copy
+    const size_t smem = (size_t)9 * 2 * N * ((C + 3) / 4) * 4 * sizeof(float);
+    return B >= 1 && C >= 8 && C % 8 == 0 && H >= 1 && W >= 1 && N >= 1 && N <= 16 && s >= 1 && smem <= 96 * 1024;
+}
+
+LDC_API int ldconv_offset_conv_bwd_tc_acc16(const float* grad_off, const void* x, const float* w, void* grad_x, float* grad_w,
+                                            float* grad_b, void* workspace, size_t workspace_bytes, int B, int C, int H, int W,
+                                            int N, int s, void* stream)
+{
+    LDC_REQUIRE(grad_off && x && w && workspace, "ldconv_offset_conv_bwd_tc_acc16: null pointer");
+    LDC_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1 && N >= 1 && N <= 16 && s >= 1, "ldconv_offset_conv_bwd_tc_acc16: bad dims");
+    if (B == 0) return LDCONV_OK;
+    return offconv_bwd_tc(grad_off, (const __nv_bfloat16*)x, w, nullptr, (__nv_bfloat16*)grad_x, grad_w, grad_b, workspace,
+                          workspace_bytes, B, C, H, W, N, s, (cudaStream_t)stream);
 }

@@ -136,6 +136,9 @@ class _LDConvFunction(torch.autograd.Function):
     """Forward = offset conv -> fused grid+gather -> GEMM (+BN statistics) -> BN/SiLU; backward = the closed form of
     SURVEY.md Appendix A.  Every step is one C-ABI call."""
 
+    # bf16 activations: accumulate grad_x in bf16 (ldconv_gather_bwd_acc16); False = the fp32 accumulator + cast pass (A/B, tests)
+    bf16_accumulator = True
+
     @staticmethod
     def forward(ctx, x, p_w, p_b, c_w, c_b, bn_w, bn_b, running_mean, running_var, p_n, stride, eps, momentum, training,
                 prepared):
@@ -242,22 +245,36 @@ class _LDConvFunction(torch.autograd.Function):
         grad_operand = torch.empty((M, K), device=dev, dtype=xdtype)
         _lib.check(L.ldconv_gemm_fwd(_ptr(grad_pre), _ptr(wt_t), None, None, _ptr(grad_operand), None, None, None, M, O, K,
                                      _lib.ACT_NONE, dt, st), "ldconv_gemm_fwd(data grad)")
-        grad_x32 = torch.zeros((B, H, W, C), device=dev, dtype=torch.float32) if need_x else None
+        # grad_x accumulator: bf16 for the bf16 path (eight channels per reduction request instead of four, no fp32 buffer and
+        # no cast pass; include/ldconv_b200.h states its tolerance), fp32 otherwise
+        acc16 = bool(need_x and dt == _lib.BF16 and _LDConvFunction.bf16_accumulator
+                     and L.ldconv_bwd_acc16_supported(B, C, H, W, N, s))
         grad_off = torch.empty((B, h, w, 2 * N), device=dev, dtype=torch.float32)
-        _lib.check(L.ldconv_gather_bwd(_ptr(grad_operand), _ptr(xh), _ptr(off), _ptr(pn), _ptr(grad_x32), _ptr(grad_off),
-                                       B, C, H, W, N, s, dt, st), "ldconv_gather_bwd")
         grad_w_off = torch.zeros((3, 3, C, 2 * N), device=dev, dtype=torch.float32)
         grad_b_off = torch.zeros((2 * N,), device=dev, dtype=torch.float32)
         ws_bytes = int(L.ldconv_offset_conv_bwd_workspace_bytes(B, C, H, W, N, s, dt)) if dt == _lib.BF16 else 0
-        if ws_bytes > 0:      # bf16: weight gradient as a tensor-core reduction over an L2-resident im2col workspace
+        if acc16:
+            grad_xa = torch.zeros((B, H, W, C), device=dev, dtype=torch.bfloat16)
+            _lib.check(L.ldconv_gather_bwd_acc16(_ptr(grad_operand), _ptr(xh), _ptr(off), _ptr(pn), _ptr(grad_xa), _ptr(grad_off),
+                                                 B, C, H, W, N, s, st), "ldconv_gather_bwd_acc16")
             ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-            _lib.check(L.ldconv_offset_conv_bwd_tc(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
-                                                   _ptr(grad_b_off), _ptr(ws), ws_bytes, B, C, H, W, N, s, dt, st),
-                       "ldconv_offset_conv_bwd_tc")
+            _lib.check(L.ldconv_offset_conv_bwd_tc_acc16(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_xa), _ptr(grad_w_off),
+                                                         _ptr(grad_b_off), _ptr(ws), ws_bytes, B, C, H, W, N, s, st),
+                       "ldconv_offset_conv_bwd_tc_acc16")
+            grad_x = grad_xa.permute(0, 3, 1, 2)
         else:
-            _lib.check(L.ldconv_offset_conv_bwd(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
-                                                _ptr(grad_b_off), B, C, H, W, N, s, dt, st), "ldconv_offset_conv_bwd")
-        grad_x = grad_x32.to(xdtype).permute(0, 3, 1, 2) if need_x else None
+            grad_x32 = torch.zeros((B, H, W, C), device=dev, dtype=torch.float32) if need_x else None
+            _lib.check(L.ldconv_gather_bwd(_ptr(grad_operand), _ptr(xh), _ptr(off), _ptr(pn), _ptr(grad_x32), _ptr(grad_off),
+                                           B, C, H, W, N, s, dt, st), "ldconv_gather_bwd")
+            if ws_bytes > 0:      # bf16: weight gradient as a tensor-core reduction over an L2-resident im2col workspace
+                ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+                _lib.check(L.ldconv_offset_conv_bwd_tc(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
+                                                       _ptr(grad_b_off), _ptr(ws), ws_bytes, B, C, H, W, N, s, dt, st),
+                           "ldconv_offset_conv_bwd_tc")
+            else:
+                _lib.check(L.ldconv_offset_conv_bwd(_ptr(grad_off), _ptr(xh), _ptr(w_off), _ptr(grad_x32), _ptr(grad_w_off),
+                                                    _ptr(grad_b_off), B, C, H, W, N, s, dt, st), "ldconv_offset_conv_bwd")
+            grad_x = grad_x32.to(xdtype).permute(0, 3, 1, 2) if need_x else None
         grad_p_w = grad_w_off.permute(3, 2, 0, 1).contiguous().to(pw_dtype)
         grad_p_b = grad_b_off.to(pw_dtype)
         grad_gamma = red[1].to(bn_dtype) if bn_dtype is not None else None

@@ -169,6 +169,22 @@ int ldconv_offset_conv_bwd_tc(const float* grad_off, const void* x, const float*
                               void* workspace, size_t workspace_bytes, int B, int C, int H, int W, int N, int s, int dtype,
                               void* stream);
 
+/* The same two backward steps with a 16-BIT accumulator for grad_x (bf16 activations only; C % 8 == 0): grad_x (B,H,W,C) bf16,
+ * zero-initialised by the caller.  ldconv_gather_bwd_acc16 = ldconv_gather_bwd with eight channels per 16-byte reduction
+ * (red.global.add.noftz.v4.bf16x2) instead of four -- half the L2 reduction requests, which bound the scatter -- and
+ * ldconv_offset_conv_bwd_tc_acc16 adds the offset conv's data gradient onto the same bf16 tensor, so the fp32 buffer, half of its
+ * memset and the fp32 -> bf16 cast pass of the fp32 route disappear.  The accumulator rounds to bf16 after every addition (what
+ * autograd's scatter_add_ does for a reduced-precision model, conv.py:456-489 backward): parity bound rel-L2 <= 1e-2 against the
+ * fp32 reference on bf16-rounded tensors in the benchmark regime (tests/test_gpu_parity.py); samples that pile onto one pixel
+ * by the hundreds (a diverged offset conv) lose low-order bits -- use the fp32 entry points there.  Shapes outside the
+ * kernels' range (ldconv_bwd_acc16_supported returns 0) return LDCONV_E_ARG. */
+int ldconv_bwd_acc16_supported(int B, int C, int H, int W, int N, int s);
+int ldconv_gather_bwd_acc16(const void* grad_operand, const void* x, const float* off, const int32_t* p_n, void* grad_x,
+                            float* grad_off, int B, int C, int H, int W, int N, int s, void* stream);
+int ldconv_offset_conv_bwd_tc_acc16(const float* grad_off, const void* x, const float* w, void* grad_x, float* grad_w,
+                                    float* grad_b, void* workspace, size_t workspace_bytes, int B, int C, int H, int W, int N,
+                                    int s, void* stream);
+
 /* Inference forward of the whole module (conv.py:366-410, eval mode) in ONE kernel; the resampled operand never touches
  * HBM.  Two kernels behind it: C <= 4 (the first layer) runs one thread per output pixel on CUDA cores; C % 16 == 0 with
  * bf16 runs offset conv + grid + gather into shared memory in the tcgen05 operand layout + UMMA with TMEM accumulators +

@@ -769,6 +769,105 @@ def test_offset_conv_backward_tensor_core_path(C, N, s, H, W, B):
         assert _rel(gw.cpu().numpy(), ref_gw.cpu().numpy()) <= (4e-3 if tc else 1e-4)
 
 
+# --------------------------------------------------------------------- backward with the 16-bit grad_x accumulator ----
+@pytest.mark.parametrize("scale", [0.5, 3.0])
+@pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 37, 53, 2), (32, 3, 2, 40, 24, 2), (64, 3, 2, 18, 34, 1), (32, 1, 1, 21, 40, 2),
+                                         (64, 1, 1, 19, 17, 2), (128, 1, 1, 12, 20, 1), (8, 5, 1, 16, 18, 2), (16, 9, 2, 21, 23, 1)])
+def test_scatter_backward_bf16_accumulator_vs_oracle(C, N, s, H, W, B, scale):
+    """ldconv_gather_bwd_acc16 (red.global.add.noftz.v4.bf16x2: grad_x accumulated in bf16) against the oracle's fp64-free scatter
+    (autograd of conv.py:386-405) on bf16-rounded tensors.  Stated tolerance of the 16-bit accumulator: rel-L2 <= 1e-2 in the
+    benchmark regime (offsets of 0.5 - 3 px: a pixel receives ~4 N / s^2 contributions, each addition rounds to 8 mantissa bits);
+    grad_offset does not go through the accumulator and keeps the fp32 bound."""
+    L = _lib.load()
+    assert L.ldconv_bwd_acc16_supported(B, C, H, W, N, s) == 1
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    rng = np.random.default_rng(int(scale * 10) + C + N)
+    x = _bf16_round(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    off = (rng.standard_normal((B, 2 * N, h, w)) * scale).astype(np.float32)
+    g = _bf16_round(rng.standard_normal((B, C, N, h, w)).astype(np.float32))
+    gx_ref, goff_ref = oracle.sample_bwd(np.ascontiguousarray(g.transpose(0, 1, 3, 2, 4)).reshape(B, C, h * N, w), x, off, N, s)
+    M = B * h * w
+    xd = _t(_nhwc(x), torch.bfloat16)
+    offd = _t(_nhwc(off))
+    gop = _t(np.ascontiguousarray(g.transpose(0, 3, 4, 2, 1)).reshape(M, N * C), torch.bfloat16)
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    gx = torch.zeros((B, H, W, C), device=DEV, dtype=torch.bfloat16)
+    goff = torch.full((B, h, w, 2 * N), 123.0, device=DEV)
+    _lib.check(L.ldconv_gather_bwd_acc16(_ptr(gop), _ptr(xd), _ptr(offd), _ptr(pn), _ptr(gx), _ptr(goff), B, C, H, W, N, s, _stream()),
+               "ldconv_gather_bwd_acc16")
+    torch.cuda.synchronize()
+    assert _rel(gx.float().cpu().numpy().transpose(0, 3, 1, 2), gx_ref) <= 1e-2
+    got_off = goff.cpu().numpy().transpose(0, 3, 1, 2)
+    assert np.abs(got_off - goff_ref).max() <= 2e-4 * max(1.0, float(np.abs(goff_ref).max()))
+
+
+def test_backward_bf16_accumulator_rejects_uncovered_shapes():
+    """C % 8 != 0 (the first layer's C = 3) has no 16-byte bf16 vectors: the query says no and the entry point fails loudly."""
+    L = _lib.load()
+    assert L.ldconv_bwd_acc16_supported(2, 3, 16, 16, 3, 2) == 0
+    assert L.ldconv_bwd_acc16_supported(2, 20, 16, 16, 3, 2) == 0
+    B, C, H, W, N, s = 1, 3, 8, 8, 3, 2
+    x = torch.zeros((B, H, W, C), device=DEV, dtype=torch.bfloat16)
+    off = torch.zeros((B, 4, 4, 2 * N), device=DEV)
+    gop = torch.zeros((B * 16, N * C), device=DEV, dtype=torch.bfloat16)
+    pn = torch.tensor(_lib.p_n_table(N), dtype=torch.int32, device=DEV)
+    gx = torch.zeros((B, H, W, C), device=DEV, dtype=torch.bfloat16)
+    goff = torch.zeros_like(off)
+    assert L.ldconv_gather_bwd_acc16(_ptr(gop), _ptr(x), _ptr(off), _ptr(pn), _ptr(gx), _ptr(goff), B, C, H, W, N, s, _stream()) != 0
+
+
+@pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 1, 1, 24, 24, 2), (64, 3, 2, 21, 33, 2), (128, 9, 2, 20, 20, 1)])
+def test_offset_conv_backward_bf16_accumulator(C, N, s, H, W, B):
+    """ldconv_offset_conv_bwd_tc_acc16 adds the offset conv's data gradient (conv.py:356 backward) onto a bf16 grad_x: equal to the
+    fp32 route's result rounded to bf16 (one rounding of the sum: rel-L2 <= 3e-3), weight / bias gradients identical."""
+    L = _lib.load()
+    h, w = (H - 1) // s + 1, (W - 1) // s + 1
+    g = torch.Generator(device=DEV).manual_seed(C * 17 + N + H)
+    x = torch.randn((B, H, W, C), device=DEV, generator=g).bfloat16()
+    goff = torch.randn((B, h, w, 2 * N), device=DEV, generator=g)
+    wk = torch.randn((3, 3, C, 2 * N), device=DEV, generator=g) * 0.1
+    gx0 = torch.randn((B, H, W, C), device=DEV, generator=g).bfloat16()
+    nbytes = int(L.ldconv_offset_conv_bwd_workspace_bytes(B, C, H, W, N, s, _lib.BF16))
+    ws = torch.empty(nbytes, device=DEV, dtype=torch.uint8)
+    gx32, gw32, gb32 = gx0.float(), torch.zeros((3, 3, C, 2 * N), device=DEV), torch.zeros((2 * N,), device=DEV)
+    _lib.check(L.ldconv_offset_conv_bwd_tc(_ptr(goff), _ptr(x), _ptr(wk), _ptr(gx32), _ptr(gw32), _ptr(gb32), _ptr(ws), nbytes,
+                                           B, C, H, W, N, s, _lib.BF16, _stream()), "ldconv_offset_conv_bwd_tc")
+    gx16, gw16, gb16 = gx0.clone(), torch.zeros_like(gw32), torch.zeros_like(gb32)
+    _lib.check(L.ldconv_offset_conv_bwd_tc_acc16(_ptr(goff), _ptr(x), _ptr(wk), _ptr(gx16), _ptr(gw16), _ptr(gb16), _ptr(ws), nbytes,
+                                                 B, C, H, W, N, s, _stream()), "ldconv_offset_conv_bwd_tc_acc16")
+    torch.cuda.synchronize()
+    assert torch.equal(gx16, gx32.bfloat16())                      # same fp32 sum, rounded once
+    assert _rel(gw16.cpu().numpy(), gw32.cpu().numpy()) <= 1e-5    # fp32 atomics: order only
+    assert _rel(gb16.cpu().numpy(), gb32.cpu().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if not c.endswith(("_far", "_zero"))])
+def test_module_train_bf16_accumulator_ab(name):
+    """The module's bf16 backward with the 16-bit accumulator (default where ldconv_bwd_acc16_supported) and with the fp32
+    accumulator + cast pass: both inside the bf16 gradient bound against the oracle, and close to each other."""
+    from experiment_yolo_b200.ldconv import _LDConvFunction
+    z, prm, m = _golden.load(name)
+    x, p, f = _oracle_on_bf16_rounded(z, prm, training=True)
+    g = oracle.backward(x, p, f, _bf16_round(z["grad_out"]), training=True)
+    grads = {}
+    for acc16 in (True, False):
+        old = _LDConvFunction.bf16_accumulator
+        _LDConvFunction.bf16_accumulator = acc16
+        try:
+            _lib.call_counts.clear()
+            mod = _module_from_golden(z, prm, m, torch.bfloat16).train()
+            xt = _t(x, torch.bfloat16).requires_grad_(True)
+            mod(xt).backward(_t(z["grad_out"], torch.bfloat16))
+            B, C, H, W = xt.shape
+            used16 = "ldconv_gather_bwd_acc16" in _lib.call_counts
+            assert used16 == bool(acc16 and _lib.load().ldconv_bwd_acc16_supported(B, C, H, W, mod.num_param, int(mod.stride)))
+        finally:
+            _LDConvFunction.bf16_accumulator = old
+        grads[acc16] = xt.grad.float().cpu().numpy()
+        assert _rel(grads[acc16], g["x"]) <= 3e-2
+    assert _rel(grads[True], grads[False]) <= 1e-2
+
+
 # ------------------------------------------------------------------------------- gather + GEMM in one kernel ----
 @pytest.mark.parametrize("C,O,N,s,H,W,B,sigma,pad", [
     (16, 32, 3, 2, 64, 80, 2, 0.5, 0), (16, 32, 3, 2, 37, 53, 3, 3.0, 0), (32, 64, 3, 2, 40, 40, 2, 0.5, 64), (32, 32, 1, 1, 48, 48, 1, 0.5, 0),
