@@ -280,6 +280,143 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stat_sum, const do
     if (save_invstd) save_invstd[o] = (float)invstd;
 }
 
+// ---- column-invariant streaming kernels (the vector path of the four BatchNorm / activation passes) -----------------------------
+// The generic kernels below redo `(t * V) % O` in 64 bits and reload scale / shift / mean / invstd / the pass-1 sums for every
+// element (up to six global loads per value): they were instruction / LSU-bound at 1.5-2.7 TB/s (profiles/r2_bwd_launches_L1_before.csv)
+// and, with the training-mode Conv blocks going through them too, 21 % of the config-4 step.  Here the CTA size and the grid stride
+// are multiples of the column-vector count CVn = O / V, so a thread keeps ONE column vector for its whole grid-stride loop: the
+// per-column constants live in registers, the loop body is loads -> arithmetic -> store, unrolled UN times with the loads issued
+// first (UN independent 16-byte requests in flight per thread).
+constexpr int kColUnroll = 4;
+
+__device__ __forceinline__ float sigmoid_t(float z, float)            // fp32 tensors: the reference's own formula
+{
+    return 1.f / (1.f + __expf(-z));
+}
+__device__ __forceinline__ float sigmoid_t(float z, __nv_bfloat16)    // bf16 tensors: MUFU.EX2 + MUFU.RCP (2 ulp, far below 2^-9)
+{
+    return __fdividef(1.f, 1.f + __expf(-z));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_apply_cols_kernel(const T* __restrict__ pre, const float* __restrict__ scale, const float* __restrict__ shift,
+                         T* __restrict__ out, long long nvec, int CVn, int act)
+{
+    constexpr int V = Vec16<T>::N;
+    const unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o0 = (int)(t0 % (unsigned)CVn) * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { sc[e] = scale[o0 + e]; sh[e] = shift[o0 + e]; }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = t0; t < nvec; t += kColUnroll * stride) {
+        uint4 raw[kColUnroll];
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u)
+            if (t + u * stride < nvec) raw[u] = *reinterpret_cast<const uint4*>(pre + (t + u * stride) * V);
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u) {
+            if (t + u * stride >= nvec) break;
+            float v[V];
+            Vec16<T>::unpack(raw[u], v);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float z = fmaf(v[e], sc[e], sh[e]);
+                v[e] = act == LDCONV_ACT_SILU ? z * sigmoid_t(z, T()) : z;
+            }
+            *reinterpret_cast<uint4*>(out + (t + u * stride) * V) = Vec16<T>::pack(v);
+        }
+    }
+}
+
+// d(pre) = scale * (dz - (sum dz + xhat * sum dz xhat) / M) with dz = g * act'(z): folded per column into
+//   scale * dz + c0 + c1 * (pre - mean),   c1 = -scale * invstd * red1 / M,   c0 = -scale * red0 / M      (training)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_cols_kernel(const T* __restrict__ pre, const T* __restrict__ gout, const float* __restrict__ scale,
+                             const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                             const double* __restrict__ red, T* __restrict__ gpre, long long nvec, long long M, int O, int CVn,
+                             int act, int training)
+{
+    constexpr int V = Vec16<T>::N;
+    const unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o0 = (int)(t0 % (unsigned)CVn) * V;
+    float sc[V], sh[V], mu[V], c0[V], c1[V];
+    const float invM = 1.f / (float)M;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        sc[e] = scale[o0 + e];
+        sh[e] = shift[o0 + e];
+        mu[e] = mean[o0 + e];
+        if (training) {
+            c1[e] = -sc[e] * invstd[o0 + e] * (float)red[O + o0 + e] * invM;
+            c0[e] = -sc[e] * (float)red[o0 + e] * invM;
+        } else {
+            c1[e] = 0.f;
+            c0[e] = 0.f;
+        }
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = t0; t < nvec; t += kColUnroll * stride) {
+        uint4 rp[kColUnroll], rg[kColUnroll];
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u)
+            if (t + u * stride < nvec) {
+                rp[u] = *reinterpret_cast<const uint4*>(pre + (t + u * stride) * V);
+                rg[u] = *reinterpret_cast<const uint4*>(gout + (t + u * stride) * V);
+            }
+#pragma unroll
+        for (int u = 0; u < kColUnroll; ++u) {
+            if (t + u * stride >= nvec) break;
+            float pv[V], g[V];
+            Vec16<T>::unpack(rp[u], pv);
+            Vec16<T>::unpack(rg[u], g);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                float dz = g[e];
+                if (act == LDCONV_ACT_SILU) {
+                    const float z = fmaf(pv[e], sc[e], sh[e]);
+                    const float sg = sigmoid_t(z, T());
+                    dz *= sg * (1.f + z * (1.f - sg));
+                }
+                pv[e] = fmaf(sc[e], dz, fmaf(c1[e], pv[e] - mu[e], c0[e]));
+            }
+            *reinterpret_cast<uint4*>(gpre + (t + u * stride) * V) = Vec16<T>::pack(pv);
+        }
+    }
+}
+
+// fold the per-thread partial sums of the two column reductions below: tree over the row phases in shared memory, then one fp64
+// atomic per column and quantity (the first version let `tile` threads walk all phases serially in fp64: up to 1024 dependent
+// additions at O = 32, the tail of every small launch)
+template <int V>
+__device__ __forceinline__ void fold_phases(float (&a)[V], float (&b)[V], float* s_a, float* s_b, int tile, int phases,
+                                            double* dst_a, double* dst_b, bool live)
+{
+    const int L = threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < V; ++e) { s_a[L * V + e] = a[e]; s_b[L * V + e] = b[e]; }
+    __syncthreads();
+    for (int half = phases >> 1; half >= 1; half >>= 1) {
+        if (L < half * tile) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                s_a[L * V + e] += s_a[(L + half * tile) * V + e];
+                s_b[L * V + e] += s_b[(L + half * tile) * V + e];
+            }
+        }
+        __syncthreads();
+    }
+    if (L < tile && live) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            atomicAdd(dst_a + e, (double)s_a[L * V + e]);
+            atomicAdd(dst_b + e, (double)s_b[L * V + e]);
+        }
+    }
+}
+
 template <typename T, bool VECX>
 __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const T* __restrict__ pre, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -333,39 +470,46 @@ bn_act_bwd_reduce_kernel(const T* __restrict__ pre, const T* __restrict__ gout, 
         for (int e = 0; e < V; ++e) {
             sc[e] = scale[o0 + e]; sh[e] = shift[o0 + e]; mu[e] = mean[o0 + e]; is[e] = invstd[o0 + e];
         }
-        for (long long r = (long long)blockIdx.x * phases + phase; r < M; r += (long long)gridDim.x * phases) {
-            float p[V], g[V];
-            if constexpr (VECX) {
-                Vec16<T>::load(pre + r * O + o0, p);
-                Vec16<T>::load(gout + r * O + o0, g);
-            } else {
-                p[0] = Elem<T>::to_f(pre[r * O + o0]);
-                g[0] = Elem<T>::to_f(gout[r * O + o0]);
-            }
+        const long long rstride = (long long)gridDim.x * phases;
+        if constexpr (VECX) {
+            for (long long r = (long long)blockIdx.x * phases + phase; r < M; r += kColUnroll * rstride) {
+                uint4 rp[kColUnroll], rg[kColUnroll];
 #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const float z = fmaf(p[e], sc[e], sh[e]);
-                const float dz = act == LDCONV_ACT_SILU ? g[e] * silu_grad(z) : g[e];
-                a[e] += dz;
-                bsum[e] = fmaf(dz, (p[e] - mu[e]) * is[e], bsum[e]);
+                for (int u = 0; u < kColUnroll; ++u)
+                    if (r + u * rstride < M) {
+                        rp[u] = *reinterpret_cast<const uint4*>(pre + (r + u * rstride) * O + o0);
+                        rg[u] = *reinterpret_cast<const uint4*>(gout + (r + u * rstride) * O + o0);
+                    }
+#pragma unroll
+                for (int u = 0; u < kColUnroll; ++u) {
+                    if (r + u * rstride >= M) break;
+                    float p[V], g[V];
+                    Vec16<T>::unpack(rp[u], p);
+                    Vec16<T>::unpack(rg[u], g);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        float dz = g[e];
+                        if (act == LDCONV_ACT_SILU) {
+                            const float z = fmaf(p[e], sc[e], sh[e]);
+                            const float sg = sigmoid_t(z, T());
+                            dz *= sg * (1.f + z * (1.f - sg));
+                        }
+                        a[e] += dz;
+                        bsum[e] = fmaf(dz, (p[e] - mu[e]) * is[e], bsum[e]);
+                    }
+                }
+            }
+        } else {
+            for (long long r = (long long)blockIdx.x * phases + phase; r < M; r += rstride) {
+                const float p = Elem<T>::to_f(pre[r * O + o0]), g = Elem<T>::to_f(gout[r * O + o0]);
+                const float z = fmaf(p, sc[0], sh[0]);
+                const float dz = act == LDCONV_ACT_SILU ? g * silu_grad(z) : g;
+                a[0] += dz;
+                bsum[0] = fmaf(dz, (p - mu[0]) * is[0], bsum[0]);
             }
         }
     }
-#pragma unroll
-    for (int e = 0; e < V; ++e) { s_a[L * V + e] = a[e]; s_b[L * V + e] = bsum[e]; }
-    __syncthreads();
-    if (phase == 0 && o0 < O) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            double ta = 0.0, tb = 0.0;
-            for (int ph = 0; ph < phases; ++ph) {
-                ta += (double)s_a[(ph * tile + cv) * V + e];
-                tb += (double)s_b[(ph * tile + cv) * V + e];
-            }
-            atomicAdd(red + o0 + e, ta);
-            atomicAdd(red + O + o0 + e, tb);
-        }
-    }
+    fold_phases<V>(a, bsum, s_a, s_b, tile, phases, red + o0, red + O + o0, o0 < O);
 }
 
 template <typename T, bool VECX>
@@ -426,32 +570,31 @@ col_stats_kernel(const T* __restrict__ pre, double* __restrict__ sum, double* __
 #pragma unroll
     for (int e = 0; e < V; ++e) { a[e] = 0.f; b[e] = 0.f; }
     if (o0 < O) {
-        for (long long r = (long long)blockIdx.x * phases + phase; r < M; r += (long long)gridDim.x * phases) {
-            float p[V];
-            if constexpr (VECX) {
-                Vec16<T>::load(pre + r * O + o0, p);
-            } else {
-                p[0] = Elem<T>::to_f(pre[r * O + o0]);
-            }
+        const long long rstride = (long long)gridDim.x * phases;
+        if constexpr (VECX) {
+            for (long long r = (long long)blockIdx.x * phases + phase; r < M; r += kColUnroll * rstride) {
+                uint4 rp[kColUnroll];
 #pragma unroll
-            for (int e = 0; e < V; ++e) { a[e] += p[e]; b[e] = fmaf(p[e], p[e], b[e]); }
+                for (int u = 0; u < kColUnroll; ++u)
+                    if (r + u * rstride < M) rp[u] = *reinterpret_cast<const uint4*>(pre + (r + u * rstride) * O + o0);
+#pragma unroll
+                for (int u = 0; u < kColUnroll; ++u) {
+                    if (r + u * rstride >= M) break;
+                    float p[V];
+                    Vec16<T>::unpack(rp[u], p);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) { a[e] += p[e]; b[e] = fmaf(p[e], p[e], b[e]); }
+                }
+            }
+        } else {
+            for (long long r = (long long)blockIdx.x * phases + phase; r < M; r += rstride) {
+                const float p = Elem<T>::to_f(pre[r * O + o0]);
+                a[0] += p;
+                b[0] = fmaf(p, p, b[0]);
+            }
         }
     }
-#pragma unroll
-    for (int e = 0; e < V; ++e) { s_a[L * V + e] = a[e]; s_b[L * V + e] = b[e]; }
-    __syncthreads();
-    if (phase == 0 && o0 < O) {
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            double ta = 0.0, tb = 0.0;
-            for (int ph = 0; ph < phases; ++ph) {
-                ta += (double)s_a[(ph * tile + cv) * V + e];
-                tb += (double)s_b[(ph * tile + cv) * V + e];
-            }
-            atomicAdd(sum + o0 + e, ta);
-            atomicAdd(sqsum + o0 + e, tb);
-        }
-    }
+    fold_phases<V>(a, b, s_a, s_b, tile, phases, sum + o0, sqsum + o0, o0 < O);
 }
 
 static int pow2_at_least(int v);
@@ -1057,7 +1200,13 @@ static int bn_act_apply_t(const T* pre, const float* scale, const float* shift, 
     long long want = (nvec + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
-    if (vec)
+    const int CVn = vec ? O / V : 0;
+    if (vec && CVn <= 256) {      // threads and grid stride are multiples of CVn: a thread keeps its column vector
+        const int threads = 256 / CVn * CVn;
+        long long nb = (nvec + (long long)threads * kColUnroll - 1) / ((long long)threads * kColUnroll);
+        if (nb > cap) nb = cap;
+        bn_act_apply_cols_kernel<T><<<(unsigned)nb, threads, 0, st>>>(pre, scale, shift, out, nvec, CVn, act);
+    } else if (vec)
         bn_act_apply_kernel<T, true><<<blocks, 256, 0, st>>>(pre, scale, shift, out, nvec, O, act);
     else
         bn_act_apply_kernel<T, false><<<blocks, 256, 0, st>>>(pre, scale, shift, out, nvec, O, act);
@@ -1126,7 +1275,14 @@ static int bn_act_bwd_apply_t(const T* pre, const T* gout, const float* scale, c
     long long want = (nvec + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
     const unsigned blocks = (unsigned)(want < cap ? want : cap);
-    if (vec)
+    const int CVn = vec ? O / V : 0;
+    if (vec && CVn <= 256) {
+        const int threads = 256 / CVn * CVn;
+        long long nb = (nvec + (long long)threads * kColUnroll - 1) / ((long long)threads * kColUnroll);
+        if (nb > cap) nb = cap;
+        bn_act_bwd_apply_cols_kernel<T><<<(unsigned)nb, threads, 0, st>>>(pre, gout, scale, shift, mean, invstd, red, gpre, nvec, M, O,
+                                                                           CVn, act, training);
+    } else if (vec)
         bn_act_bwd_apply_kernel<T, true><<<blocks, 256, 0, st>>>(pre, gout, scale, shift, mean, invstd, red, gpre, nvec, M,
                                                                  O, act, training);
     else

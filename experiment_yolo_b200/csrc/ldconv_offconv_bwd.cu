@@ -108,73 +108,92 @@ __global__ void dw_scatter_kernel(const float* __restrict__ dW, float* __restric
 }
 
 // ---- data gradient ------------------------------------------------------------------------------------------------------
-// S = 1 / 2: compile-time stride (the model's values) so the tap validity test is a bit test; S = 0: any stride
-// ACC: the type of grad_x (read-modify-write: it already holds the scatter's part) -- fp32, or bf16 for the 16-bit accumulator of
-// ldconv_gather_bwd_acc16 (C % 4 == 0 there: one 8-byte access per thread)
+// grad_x[b, r, k, c] += sum over taps (ky, kx) with (r + 1 - ky, k + 1 - kx) = s * (i, j):  sum_o grad_off[b, i, j, o] * w[ky, kx, c, o]
+// (conv_transpose of conv.py:356 in gather form).  Thread = (column k, CG channels), a CTA walks `rows` rows of one image: grid
+// (column segments, row chunks, B), no index division per element.  The sum is ADDED with one 16-byte reduction per thread and row
+// (red.global.add: v4.f32, or v4.bf16x2 for the 16-bit accumulator of ldconv_gather_bwd_acc16) instead of a read-modify-write:
+// the first versions loaded the old value, one 8 / 16-byte request in flight per thread, and ran at 0.75-0.85 TB/s however the
+// index arithmetic was written (532 / 467 us for 399 MB at layer 1, batch 64: latency-bound); a reduction returns nothing, so
+// nothing waits for DRAM.  fp32: the same rounding as load-add-store.  bf16: the sum is rounded to bf16 before it is added.
+// S = 1 / 2: compile-time stride (the model's values) so the tap validity test is a bit test; S = 0: any stride.
 template <int NMAX, int S, typename ACC>
 __global__ void __launch_bounds__(256)
-offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict__ w, ACC* __restrict__ grad_x, int B, int C,
-                        int H, int W, int h, int wo, int N, int s_rt, long long total)
+offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict__ w, ACC* __restrict__ grad_x, int C, int H, int W,
+                        int h, int wo, int N, int s_rt, int rows)
 {
-    extern __shared__ __align__(16) float s_w[];            // [9][2N][C4*4]: w (3,3,C,2N) transposed to channel-fastest
+    constexpr bool V16 = sizeof(ACC) == 2;
+    constexpr int CG = V16 ? 8 : 4;                         // channels per thread: one 16-byte reduction
+    extern __shared__ __align__(16) float s_w[];            // [9][2N][Cp]: w (3,3,C,2N) transposed to channel-fastest, Cp = C rounded up to CG
     const int s = S ? S : s_rt;
     const int O2 = 2 * N;
-    const int C4 = (C + 3) / 4;
-    for (int t = threadIdx.x; t < 9 * O2 * C4 * 4; t += blockDim.x) {
-        const int c = t % (C4 * 4), o = (t / (C4 * 4)) % O2, tap = t / (C4 * 4 * O2);
+    const int CGn = (C + CG - 1) / CG, Cp = CGn * CG;
+    for (int t = threadIdx.x; t < 9 * O2 * Cp; t += blockDim.x) {
+        const int c = t % Cp, o = (t / Cp) % O2, tap = t / (Cp * O2);
         s_w[t] = c < C ? w[((size_t)tap * C + c) * O2 + o] : 0.f;
     }
     __syncthreads();
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(t % C4);
-        const long long pix = t / C4;
-        const int k = (int)(pix % W);
-        const int r = (int)((pix / W) % H);
-        const long long b = pix / ((long long)W * H);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)(W * CGn)) return;
+    const int k = (int)(t / (unsigned)CGn), cg = (int)(t - (unsigned)k * (unsigned)CGn);
+    const int b = blockIdx.z;
+    // the (at most three) taps of this column: kx valid iff k + 1 - kx = s * j with 0 <= j < wo
+    int jx[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+        const int kj = k + 1 - kx;
+        const bool ok = kj >= 0 && (S == 2 ? (kj & 1) : (S == 1 ? 0 : kj % s)) == 0;
+        const int j = S == 2 ? (kj >> 1) : (S == 1 ? kj : kj / s);
+        jx[kx] = (ok && j < wo) ? j : -1;
+    }
+    const int r_begin = blockIdx.y * rows, r_end = min(H, r_begin + rows);
+    for (int r = r_begin; r < r_end; ++r) {
+        float acc[CG];
+#pragma unroll
+        for (int e = 0; e < CG; ++e) acc[e] = 0.f;
+        bool any = false;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int ri = r + 1 - ky;
             if (ri < 0 || (S == 2 ? (ri & 1) : (S == 1 ? 0 : ri % s)) != 0) continue;
             const int i = S == 2 ? (ri >> 1) : (S == 1 ? ri : ri / s);
             if (i >= h) continue;
+            const float* grow = goff + ((size_t)b * h + i) * wo * O2;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int kj = k + 1 - kx;
-                if (kj < 0 || (S == 2 ? (kj & 1) : (S == 1 ? 0 : kj % s)) != 0) continue;
-                const int j = S == 2 ? (kj >> 1) : (S == 1 ? kj : kj / s);
-                if (j >= wo) continue;
-                const float2* gp = reinterpret_cast<const float2*>(goff + ((b * h + i) * wo + j) * O2);
-                const float4* wp = reinterpret_cast<const float4*>(s_w + (size_t)(ky * 3 + kx) * O2 * C4 * 4) + cg;
+                if (jx[kx] < 0) continue;
+                any = true;
+                const float2* gp = reinterpret_cast<const float2*>(grow + (size_t)jx[kx] * O2);
+                const float4* wp = reinterpret_cast<const float4*>(s_w + ((size_t)(ky * 3 + kx) * O2) * Cp + cg * CG);
 #pragma unroll
                 for (int n = 0; n < NMAX; ++n) {
                     if (n >= N) break;
                     const float2 g = __ldg(gp + n);
-                    const float4 w0 = wp[(size_t)(2 * n) * C4], w1 = wp[(size_t)(2 * n + 1) * C4];
-                    acc[0] = fmaf(g.x, w0.x, acc[0]); acc[1] = fmaf(g.x, w0.y, acc[1]);
-                    acc[2] = fmaf(g.x, w0.z, acc[2]); acc[3] = fmaf(g.x, w0.w, acc[3]);
-                    acc[0] = fmaf(g.y, w1.x, acc[0]); acc[1] = fmaf(g.y, w1.y, acc[1]);
-                    acc[2] = fmaf(g.y, w1.z, acc[2]); acc[3] = fmaf(g.y, w1.w, acc[3]);
+#pragma unroll
+                    for (int q = 0; q < CG / 4; ++q) {
+                        const float4 w0 = wp[(size_t)(2 * n) * (Cp / 4) + q], w1 = wp[(size_t)(2 * n + 1) * (Cp / 4) + q];
+                        acc[4 * q + 0] = fmaf(g.x, w0.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(g.x, w0.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(g.x, w0.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(g.x, w0.w, acc[4 * q + 3]);
+                        acc[4 * q + 0] = fmaf(g.y, w1.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(g.y, w1.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(g.y, w1.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(g.y, w1.w, acc[4 * q + 3]);
+                    }
                 }
             }
         }
-        ACC* dst = grad_x + pix * C + cg * 4;
-        if constexpr (sizeof(ACC) == 2) {
-            const uint2 old = *reinterpret_cast<const uint2*>(dst);
-            uint2 nw;
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(nw.x) : "f"(__uint_as_float(old.x & 0xffff0000u) + acc[1]),
-                "f"(__uint_as_float(old.x << 16) + acc[0]));
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(nw.y) : "f"(__uint_as_float(old.y & 0xffff0000u) + acc[3]),
-                "f"(__uint_as_float(old.y << 16) + acc[2]));
-            *reinterpret_cast<uint2*>(dst) = nw;
+        if (!any) continue;
+        ACC* dst = grad_x + (((size_t)b * H + r) * W + k) * C + cg * CG;
+        if constexpr (V16) {
+            uint32_t p0, p1, p2, p3;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(acc[1]), "f"(acc[0]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(acc[3]), "f"(acc[2]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(acc[5]), "f"(acc[4]));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(acc[7]), "f"(acc[6]));
+            asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
         } else if ((C & 3) == 0) {
-            float4 v = *reinterpret_cast<float4*>(dst);
-            v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
-            *reinterpret_cast<float4*>(dst) = v;
+            atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (cg * 4 + e < C) dst[e] += acc[e];
+                if (cg * 4 + e < C) atomicAdd(dst + e, acc[e]);
         }
     }
 }
@@ -182,17 +201,23 @@ offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict_
 // returns 1 when launched, 0 when the shape is outside the kernel's range (caller uses the generic kernel)
 template <typename ACC>
 static int offconv_bwd_data_fast_t(const float* goff, const float* w, ACC* grad_x, int B, int C, int H, int W, int N, int s,
-                                 cudaStream_t st)
+                                   cudaStream_t st)
 {
-    const int C4 = (C + 3) / 4;
-    const size_t smem = (size_t)9 * 2 * N * C4 * 4 * sizeof(float);
-    if (smem > 96 * 1024 || N > 16) return 0;
+    constexpr int CG = sizeof(ACC) == 2 ? 8 : 4;
+    const int CGn = (C + CG - 1) / CG;
+    const size_t smem = (size_t)9 * 2 * N * CGn * CG * sizeof(float);
+    if (smem > 96 * 1024 || N > 16 || B > 65535 || (long long)W * CGn > 0x7fffffffll) return 0;
+    if (sizeof(ACC) == 2 && C % 8 != 0) return 0;
     const int h = out_size(H, s), wo = out_size(W, s);
-    const long long total = (long long)B * H * W * C4;
-    const unsigned blocks = (unsigned)min((long long)num_sms() * 8, (total + 255) / 256);     // persistent: weights staged once per CTA
+    const unsigned gx = (unsigned)(((long long)W * CGn + 255) / 256);
+    // rows per CTA: enough CTAs to fill the machine a few times over, at most 16 rows (the weights are re-staged per CTA)
+    int rows = 16;
+    while (rows > 1 && (long long)gx * ((H + rows - 1) / rows) * B < (long long)num_sms() * 16) rows >>= 1;
+    const unsigned gy = (unsigned)((H + rows - 1) / rows);
+    if (gy > 65535) return 0;
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<blocks, 256, smem, st>>>(goff, w, grad_x, B, C, H, W, h, wo, N, s, total);
+        kern<<<dim3(gx, gy, (unsigned)B), 256, smem, st>>>(goff, w, grad_x, C, H, W, h, wo, N, s, rows);
     };
 #define LDC_BWD_DATA(NM)                                                          \
     do {                                                                          \
@@ -255,7 +280,7 @@ int offconv_bwd_tc(const float* goff, const __nv_bfloat16* x, const float* w, fl
     float* dW = reinterpret_cast<float*>(ws + g16_bytes + col_bytes);
 
     if (grad_x16) {
-        if ((C & 3) != 0 || !offconv_bwd_data_fast_t<__nv_bfloat16>(goff, w, grad_x16, B, C, H, W, N, s, st))
+        if (!offconv_bwd_data_fast_t<__nv_bfloat16>(goff, w, grad_x16, B, C, H, W, N, s, st))
             return fail(LDCONV_E_ARG, "ldconv_offset_conv_bwd_tc_acc16: shape outside the 16-bit accumulator kernel (C=%d, N=%d)", C, N);
         LDC_LAUNCH_CHECK("offconv_bwd_data_kernel");
     }

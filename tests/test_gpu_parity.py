@@ -818,8 +818,9 @@ def test_backward_bf16_accumulator_rejects_uncovered_shapes():
 
 @pytest.mark.parametrize("C,N,s,H,W,B", [(16, 3, 2, 40, 56, 2), (32, 1, 1, 24, 24, 2), (64, 3, 2, 21, 33, 2), (128, 9, 2, 20, 20, 1)])
 def test_offset_conv_backward_bf16_accumulator(C, N, s, H, W, B):
-    """ldconv_offset_conv_bwd_tc_acc16 adds the offset conv's data gradient (conv.py:356 backward) onto a bf16 grad_x: equal to the
-    fp32 route's result rounded to bf16 (one rounding of the sum: rel-L2 <= 3e-3), weight / bias gradients identical."""
+    """ldconv_offset_conv_bwd_tc_acc16 adds the offset conv's data gradient (conv.py:356 backward) onto a bf16 grad_x with bf16
+    reductions: the fp32 route's result up to two bf16 roundings (of the added sum, and of the total: rel-L2 <= 3e-3), weight /
+    bias gradients identical."""
     L = _lib.load()
     h, w = (H - 1) // s + 1, (W - 1) // s + 1
     g = torch.Generator(device=DEV).manual_seed(C * 17 + N + H)
@@ -836,7 +837,7 @@ def test_offset_conv_backward_bf16_accumulator(C, N, s, H, W, B):
     _lib.check(L.ldconv_offset_conv_bwd_tc_acc16(_ptr(goff), _ptr(x), _ptr(wk), _ptr(gx16), _ptr(gw16), _ptr(gb16), _ptr(ws), nbytes,
                                                  B, C, H, W, N, s, _stream()), "ldconv_offset_conv_bwd_tc_acc16")
     torch.cuda.synchronize()
-    assert torch.equal(gx16, gx32.bfloat16())                      # same fp32 sum, rounded once
+    assert _rel(gx16.float().cpu().numpy(), gx32.cpu().numpy()) <= 3e-3
     assert _rel(gw16.cpu().numpy(), gw32.cpu().numpy()) <= 1e-5    # fp32 atomics: order only
     assert _rel(gb16.cpu().numpy(), gb32.cpu().numpy()) <= 1e-5
 
