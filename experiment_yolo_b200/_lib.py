@@ -65,6 +65,7 @@ SIGNATURES = {
     "ldconv_conv1x1_bn_act_maxup_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i] + [_i] * 7 + [_vp]),
     "ldconv_conv1x1_bn_act_packed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "ldconv_upsample_nearest": (_i, [_vp, _i, _vp, _i] + [_i] * 6 + [_vp]),
+    "ldconv_upsample_nearest_bwd": (_i, [_vp, _i, _vp, _i] + [_i] * 6 + [_vp]),
     "ldconv_add_nhwc": (_i, [_vp, _vp, _i, _vp, _i, _ll, _i, _i, _vp]),
     "ldconv_scalseq_tail": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 9 + [_vp]),
     "ldconv_image_u8_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),

@@ -31,6 +31,30 @@ upsample_nearest_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, i
         for (int dj = 0; dj < f; ++dj) *reinterpret_cast<uint4*>(o + (di * Wo + dj) * ldo) = v;
 }
 
+// backward of the nearest up-sampling (training graph): grad_x[b, i, j, :] = sum of the f x f block of grad_out it was copied to,
+// fp32 sum, one rounding.  Same thread mapping: one 16-byte vector of a source pixel, f x f loads, one store.  `ldg` lets grad_out
+// be a channel slice of a wider NHWC tensor (the gradient of the Concat that follows the Upsample rows of the YAML).
+__global__ void __launch_bounds__(256)
+upsample_nearest_bwd_kernel(const T* __restrict__ gout, int ldg, T* __restrict__ gx, int ldx, int H, int W, int CV, int f, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    const long long pix = t / CV;
+    const int j = (int)(pix % W);
+    const long long bi = pix / W;
+    const long long Wo = (long long)W * f;
+    const T* g = gout + ((bi * f) * Wo + (long long)j * f) * ldg + cv * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, v[8];
+    for (int di = 0; di < f; ++di)
+        for (int dj = 0; dj < f; ++dj) {
+            Vec16<T>::load(g + (di * Wo + dj) * ldg, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        }
+    Vec16<T>::store(gx + pix * ldx + cv * 8, acc);
+}
+
 // `Add` rows of the YAML (nn/extra_modules/block.py:3479-3484: torch.sum(torch.stack(x), 0)) for up to four NHWC inputs /
 // channel slices: fp32 accumulation, one rounding -- what torch's reduction does for bf16 tensors
 struct AddArgs { const T* src[4]; int ld[4]; int n; };
@@ -309,6 +333,20 @@ LDC_API int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, 
     upsample_nearest_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, ldo, H, W, C / 8,
                                                                                factor, total);
     LDC_LAUNCH_CHECK("upsample_nearest_kernel");
+    return LDCONV_OK;
+}
+
+LDC_API int ldconv_upsample_nearest_bwd(const void* grad_out, int ldg, void* grad_x, int ldx, int B, int H, int W, int C, int factor,
+                                        int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_upsample_nearest_bwd: bf16 only");
+    LDC_REQUIRE(grad_out && grad_x && C % 8 == 0 && ldg % 8 == 0 && ldx % 8 == 0 && factor >= 1 && aligned16(grad_out) && aligned16(grad_x),
+                "ldconv_upsample_nearest_bwd: needs C, ldg, ldx multiples of 8 and 16-byte aligned pointers");
+    const long long total = (long long)B * H * W * (C / 8);     // (H, W): the SOURCE (low-resolution) size
+    if (total == 0) return LDCONV_OK;
+    upsample_nearest_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)grad_out, ldg, (T*)grad_x, ldx, H, W, C / 8,
+                                                                                   factor, total);
+    LDC_LAUNCH_CHECK("upsample_nearest_bwd_kernel");
     return LDCONV_OK;
 }
 

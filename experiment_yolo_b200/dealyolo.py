@@ -102,6 +102,33 @@ class SPPF(nn.Module):
         return self.cv2(torch.cat((x, p1, p2, self.m(p2)), 1))
 
 
+class Upsample(nn.Upsample):
+    """nn.Upsample whose nearest / integer-factor case on a CUDA bf16 tensor runs through the library (train_ops.upsample_nearest:
+    bf16 in, bf16 out, one kernel each way); everything else is torch's op.  Same constructor and state (none) as nn.Upsample,
+    so the YAML row `nn.Upsample [None, 2, nearest]` (yolov8-LD-P2.yaml:26,33) builds it unchanged."""
+
+    def forward(self, x):
+        if self.mode == "nearest" and self.scale_factor is not None and float(self.scale_factor).is_integer():
+            if torch.is_autocast_enabled("cuda") and x.is_cuda and x.dtype == torch.float32 and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+                x = x.to(torch.bfloat16)
+            from .train_ops import upsample_nearest
+            y = upsample_nearest(x, int(self.scale_factor))
+            if y is not None:
+                return y
+        return super().forward(x)
+
+
+def _nearest_to(x, size):
+    """F.interpolate(x, size, mode="nearest") -- through the library when `size` is an integer multiple of x's size"""
+    H, W = x.shape[2:]
+    if size[0] % H == 0 and size[1] % W == 0 and size[0] // H == size[1] // W:
+        from .train_ops import upsample_nearest
+        y = upsample_nearest(x, size[0] // H)
+        if y is not None:
+            return y
+    return F.interpolate(x, size, mode="nearest")
+
+
 class Concat(nn.Module):
     def __init__(self, dimension=1):
         super().__init__()
@@ -139,8 +166,8 @@ class ScalSeq(nn.Module):
         if hasattr(self, "conv0"):
             fine = self.conv0(fine)
         size = fine.shape[2:]
-        mid = F.interpolate(self.conv1(mid), size, mode="nearest")
-        coarse = F.interpolate(self.conv2(coarse), size, mode="nearest")
+        mid = _nearest_to(self.conv1(mid), size)
+        coarse = _nearest_to(self.conv2(coarse), size)
         vol = torch.stack([fine, mid, coarse], dim=2)                # (B, C, 3, H, W)
         vol = self.act(self.bn(self.conv3d(vol)))
         return self.pool_3d(vol).squeeze(2)
@@ -227,7 +254,7 @@ class DealYolo(nn.Module):
             spec["nc"] = nc
         self.yaml = spec
         modules = {"LDConv": ldconv_cls, "C2f": C2f, "SPPF": SPPF, "Conv": Conv, "Concat": Concat, "Add": Add,
-                   "ScalSeq": ScalSeq, "Detect": Detect, "nn.Upsample": nn.Upsample}
+                   "ScalSeq": ScalSeq, "Detect": Detect, "nn.Upsample": Upsample}
         depth, width, max_ch = spec["scales"][spec.get("scale") or next(iter(spec["scales"]))]
         chans, layers, save = [ch], [], set()
         for i, (f, n, name, args) in enumerate(spec["backbone"] + spec["head"]):

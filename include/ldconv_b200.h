@@ -307,6 +307,10 @@ int ldconv_head_decode_rows(const void* x, const float* anc, float* boxes, float
  * :3479-3484); SPPF's three chained k x k max-pools (nn/modules/block.py:166-171) as the k, 2k-1, 3k-2 window maxima. */
 int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, int H, int W, int C, int factor, int dtype,
                             void* stream);
+/* backward of ldconv_upsample_nearest for the training graph: grad_x (B,H,W,C) = sum over each factor x factor block of grad_out
+ * (B,H*factor,W*factor,C); fp32 sum, one rounding; ldg / ldx = pixel strides (grad_out may be a channel slice of the Concat's gradient). */
+int ldconv_upsample_nearest_bwd(const void* grad_out, int ldg, void* grad_x, int ldx, int B, int H, int W, int C, int factor,
+                                int dtype, void* stream);
 /* `Add` rows (nn/extra_modules/block.py:3479-3484, torch.sum(torch.stack(x), 0)): out = sum of n <= 4 NHWC tensors / channel
  * slices (host arrays of device pointers and pixel strides), fp32 accumulation, one rounding. */
 int ldconv_add_nhwc(const void* const* srcs, const int* lds, int n, void* out, int ldo, long long pixels, int C, int dtype,

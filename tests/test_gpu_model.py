@@ -249,3 +249,29 @@ def test_fused_engine_on_a_model_whose_conv_blocks_were_fused_like_model_fuse():
 def copy_model(model):
     import copy
     return copy.deepcopy(model)
+
+
+@pytest.mark.parametrize("B,C,H,W,f,sliced", [(2, 32, 20, 12, 2, False), (1, 64, 7, 9, 2, True), (2, 16, 5, 6, 4, True), (1, 8, 3, 3, 1, False)])
+def test_library_upsample_nearest_forward_backward_vs_torch(B, C, H, W, f, sliced):
+    """dealyolo.Upsample (the YAML's nn.Upsample [None, f, nearest] rows) on CUDA bf16: forward bit-equal to torch's nearest
+    interpolation, backward = the f x f block sums of the gradient (fp32 sum, one bf16 rounding), also when the gradient arrives as
+    a channel slice of a wider channels_last tensor (what the Concat behind the row hands back)."""
+    from experiment_yolo_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(B * 100 + C + f)
+    x = torch.randn((B, C, H, W), device=DEV, generator=g).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    up = dealyolo.Upsample(None, f, "nearest")
+    _lib.call_counts.clear()
+    y = up(x)
+    assert "ldconv_upsample_nearest" in _lib.call_counts
+    ref = torch.nn.functional.interpolate(x.detach().float(), scale_factor=f, mode="nearest")
+    assert torch.equal(y.float(), ref)
+    if sliced:
+        wide = torch.randn((B, C + 24, H * f, W * f), device=DEV, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+        gout = wide[:, 8:8 + C]
+    else:
+        gout = torch.randn((B, C, H * f, W * f), device=DEV, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    y.backward(gout)
+    xr = x.detach().float().requires_grad_(True)
+    torch.nn.functional.interpolate(xr, scale_factor=f, mode="nearest").backward(gout.float())
+    assert "ldconv_upsample_nearest_bwd" in _lib.call_counts
+    assert torch.equal(x.grad.float(), xr.grad.bfloat16().float())
