@@ -59,3 +59,44 @@ def upsample_nearest(x: torch.Tensor, factor: int):
     if not (x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and factor >= 1 and x.numel() > 0):
         return None
     return _UpsampleNearestFunction.apply(x, int(factor))
+
+
+class _AddFunction(torch.autograd.Function):
+    """`Add` row of the YAML (nn/extra_modules/block.py:3479-3484: torch.sum(torch.stack(x), 0)) for bf16 NHWC tensors: one
+    ldconv_add_nhwc launch per four inputs (fp32 sum, one rounding) instead of stack -> sum -> layout / dtype copies; the gradient
+    of a sum is the incoming gradient for every input."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        import ctypes
+        B, C, H, W = xs[0].shape
+        pending = [nhwc_view(t) for t in xs]
+        L = _lib.load()
+        while True:
+            part, pending = pending[:4], pending[4:]
+            srcs = (ctypes.c_void_p * len(part))(*[v.data_ptr() for v, _ in part])
+            lds = (ctypes.c_int * len(part))(*[ld for _, ld in part])
+            out = torch.empty((B, H, W, C), device=xs[0].device, dtype=torch.bfloat16)
+            _lib.check(L.ldconv_add_nhwc(srcs, lds, len(part), out.data_ptr(), C, B * H * W, C, _lib.BF16, _stream()), "ldconv_add_nhwc")
+            if not pending:
+                break
+            pending.insert(0, (out, C))
+        ctx.n = len(xs)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        return (grad_out,) * ctx.n
+
+
+def add_maps(xs):
+    """Sum of same-shape CUDA maps through the library, or None when the case is not covered: bf16 4-D tensors with C % 8 == 0
+    (fp32 inputs are accepted under bf16 autocast and rounded to bf16 first -- the convs behind the row would do that anyway)."""
+    xs = list(xs)
+    if not xs or not all(t.is_cuda and t.dim() == 4 and t.shape == xs[0].shape for t in xs) or xs[0].shape[1] % 8 != 0 or xs[0].numel() == 0:
+        return None
+    ac = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+    if not all(t.dtype == torch.bfloat16 or (ac and t.dtype == torch.float32) for t in xs):
+        return None
+    return _AddFunction.apply(*[t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16) for t in xs])

@@ -275,3 +275,22 @@ def test_library_upsample_nearest_forward_backward_vs_torch(B, C, H, W, f, slice
     torch.nn.functional.interpolate(xr, scale_factor=f, mode="nearest").backward(gout.float())
     assert "ldconv_upsample_nearest_bwd" in _lib.call_counts
     assert torch.equal(x.grad.float(), xr.grad.bfloat16().float())
+
+
+def test_library_add_row_with_autograd_vs_torch():
+    """dealyolo.Add on CUDA bf16 maps (one dense, one a channel slice): the library sum equals torch's fp32 sum rounded once, and the
+    gradient reaches every input unchanged."""
+    from experiment_yolo_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(5)
+    a = torch.randn((2, 32, 12, 20), device=DEV, generator=g).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wide = torch.randn((2, 48, 12, 20), device=DEV, generator=g).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    c = torch.randn((2, 32, 12, 20), device=DEV, generator=g).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    _lib.call_counts.clear()
+    y = dealyolo.Add()([a, wide[:, 16:48], c])
+    assert "ldconv_add_nhwc" in _lib.call_counts
+    ref = (a.detach().float() + wide.detach()[:, 16:48].float() + c.detach().float()).bfloat16()
+    assert torch.equal(y, ref)
+    gout = torch.randn_like(y)
+    y.backward(gout)
+    assert torch.equal(a.grad, gout) and torch.equal(c.grad, gout)
+    assert torch.equal(wide.grad[:, 16:48], gout) and float(wide.grad[:, :16].abs().max()) == 0.0
