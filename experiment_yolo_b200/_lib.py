@@ -73,6 +73,8 @@ SIGNATURES = {
     "ldconv_gather_gemm_supported": (_i, [_i] * 9),
     "ldconv_gather_gemm_fwd": (_i, [_vp] * 7 + [_i] * 10 + [_vp]),
     "ldconv_debug_onepass_trace": (_i, [_vp]),
+    "ldconv_debug_l0_variant": (_i, [_i]),
+    "ldconv_debug_l0_trace": (_i, [_vp]),
     "ldconv_onepass_supported": (_i, [_i] * 9),
     "ldconv_onepass_fwd": (_i, [_vp] * 8 + [_i, _vp] + [_i] * 9 + [_vp]),
     "ldconv_fused_supported": (_i, [_i] * 8),

@@ -573,6 +573,379 @@ static int launch_l0_rows(const __nv_bfloat16* x, const float* w_off, const floa
     return LDCONV_OK;
 }
 
+// =====================================================================================================================
+// first-layer kernel on the tensor cores (bf16, C = 3 -> O = 16, num_param = 3, stride 2, even H and W).
+// l0_rows_kernel above is issue-bound (73 % of the slots, 832 warp instructions per 32 pixels, profiles/r1_ncu_l0rows_v2_constbank.txt):
+// 164 packed FMAs, 92 uniform weight loads and ~50 bf16 unpacks per pixel belong to the two small contractions (offset conv:
+// 27 window elements -> 6 offsets; (N,1) conv: 9 samples -> 16 channels).  Both are MMAs with the pixel as the M row:
+//   * a thread owns one output pixel = one row of the CTA's 128-row operand tiles = one TMEM lane of the accumulators;
+//   * offset conv: the 3 x 3 x 3 window is read as five aligned 4-byte words per input row exactly as above; words 1..4 of the
+//     three rows ARE already eight consecutive bf16 of the operand row (K = 8 tr + e - 1), the three leading half words are
+//     packed into K = 24..26: four 16-byte shared-memory stores build the 64-byte row (SWIZZLE_64B, K = 32), no unpacking;
+//     two tcgen05.mma (M 128, N 16, K 16) against the pre-arranged bf16 weights leave the six offsets in TMEM;
+//   * sampling arithmetic and the 36 two-byte corner loads are unchanged (make_point_grid / bilinear, operand rounded to bf16);
+//   * (N,1) conv: the nine bf16 samples are the 32-byte operand row (SWIZZLE_32B, K = 16), one tcgen05.mma, 16 accumulators per
+//     thread back through tcgen05.ld, folded BatchNorm + SiLU, two 16-byte stores.
+// A tile is 64 columns x 2 rows of output pixels (w = 320 = 5 x 64); CTAs are persistent over tiles; 4 warps = the 4 TMEM lane
+// quarters.  The offset conv's weights reach the MMA as bf16 (the module's are bf16 already: exact), its bias is added in fp32.
+// =====================================================================================================================
+__device__ __forceinline__ uint64_t l0_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;                       // 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+    return d;
+}
+__device__ __forceinline__ uint32_t l0_swz(uint32_t lin, uint32_t mask) { return lin ^ (((lin >> 7) & mask) << 4); }
+
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
+template <int OFS> __device__ __forceinline__ uint32_t lds_u16_at(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFS));
+    return v;
+}
+template <int OFS> __device__ __forceinline__ uint32_t lds_u32_at(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFS));
+    return v;
+}
+
+constexpr int L0T_THREADS = 128, L0T_COLS = 64;
+// staged input tile of a 64 x 2 output tile: 10 input rows (2 i0 - 3 ...) x 216 four-byte words = 144 pixels (2 j0 - 8 ...); the image
+// rows are mapped as rows of 4-byte words (W * 3 / 2 per row, box dims are limited to 256 elements), out-of-image parts are
+// zero-filled by the TMA unit = the offset conv's zero padding.  The box must START on a 16-byte boundary of the row (a start at
+// 8 mod 16 bytes raised "illegal instruction"): the column halo is 8 pixels = 48 bytes.
+constexpr int L0T_TROWS = 10, L0T_TWORDS = 216, L0T_TPIX = 144, L0T_RHALO = 3, L0T_KHALO = 8;
+static int g_l0_variant = 0;
+static long long* g_l0_trace = nullptr;          // debug: clock64 stamps of CTA 0 / thread 0 (benchmarks/l0_ab.py --trace)
+
+template <bool TRACE>
+__global__ void __launch_bounds__(L0T_THREADS, 8)
+l0_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ x, const float* __restrict__ w_off, const float* __restrict__ b_off,
+             const int* __restrict__ pn, const __nv_bfloat16* __restrict__ wt, const float* __restrict__ scale,
+             const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, float* __restrict__ off_out, int rows, int H, int W,
+             int h, int w, int act, int tiles_x, int num_tiles, long long* trace)
+{
+    constexpr int C = 3, N = 3, O = 16, O2 = 6;
+    int tn = 0;
+    auto stamp = [&](int it) {
+        if constexpr (TRACE) {
+            if (trace && blockIdx.x == 0 && threadIdx.x == 0 && it >= 2 && it < 6 && tn < 63) trace[tn++] = clock64();
+        }
+    };
+    // shared memory: operand tiles (swizzle atoms: 512 B / 256 B; the arrays are 1024-byte aligned), weights, constants
+    __shared__ __align__(1024) uint8_t s_a1[128 * 64];       // offset-conv operand: 128 pixels x K = 32 bf16, SWIZZLE_64B
+    __shared__ __align__(1024) uint8_t s_a2[128 * 32];       // (N,1)-conv operand: 128 pixels x K = 16 bf16, SWIZZLE_32B
+    __shared__ __align__(1024) uint8_t s_w1[16 * 64];        // offset-conv weights: 16 rows (6 used) x K = 32
+    __shared__ __align__(1024) uint8_t s_w2[16 * 32];        // (N,1)-conv weights: 16 rows x K = 16
+    __shared__ __align__(128) uint32_t s_x[L0T_TROWS * L0T_TWORDS];      // TMA-staged input tile
+    __shared__ __align__(16) float s_sc[2 * O];              // scale | shift (halved for SiLU)
+    __shared__ float s_b[8];
+    __shared__ int s_pn[8];
+    __shared__ __align__(8) uint64_t bar[3];                 // offsets ready, accumulator ready, input tile landed
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- one-time setup ------------------------------------------------------------------------------------------------
+    for (int t = tid; t < 16 * 32; t += L0T_THREADS) {        // W1[n][k]
+        const int n = t >> 5, k = t & 31;
+        float v = 0.f;
+        if (n < O2) {
+            int tr = -1, e = 0;
+            if (k < 24) { tr = k >> 3; e = (k & 7) + 1; }
+            else if (k < 27) { tr = k - 24; e = 0; }
+            if (tr >= 0) v = w_off[(tr * 9 + e) * O2 + n];
+        }
+        *reinterpret_cast<__nv_bfloat16*>(s_w1 + l0_swz((uint32_t)(n * 64 + k * 2), 3u)) = __float2bfloat16_rn(v);
+    }
+    for (int t = tid; t < 16 * 16; t += L0T_THREADS) {        // W2[o][k]
+        const int o = t >> 4, k = t & 15;
+        *reinterpret_cast<__nv_bfloat16*>(s_w2 + l0_swz((uint32_t)(o * 32 + k * 2), 1u)) = k < N * C ? wt[o * (N * C) + k] : __float2bfloat16_rn(0.f);
+    }
+    {
+        const float half = act == LDCONV_ACT_SILU ? 0.5f : 1.f;
+        if (tid < O) {
+            s_sc[tid] = half * (scale ? scale[tid] : 1.f);
+            s_sc[O + tid] = half * (shift ? shift[tid] : 0.f);
+        }
+        if (tid < 8) {
+            s_b[tid] = (tid < O2 && b_off) ? b_off[tid] : 0.f;
+            s_pn[tid] = tid < 2 * N ? pn[tid] : 0;
+        }
+    }
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 32);
+    fence_proxy_async_smem();                                  // the weight tiles are read by the tensor core (async proxy)
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t idesc = make_idesc_bf16(128, 16);
+    const uint64_t dA1 = l0_desc(smem_u32(s_a1), 512, 4), dW1 = l0_desc(smem_u32(s_w1), 512, 4);
+    const uint64_t dA2 = l0_desc(smem_u32(s_a2), 256, 6), dW2 = l0_desc(smem_u32(s_w2), 256, 6);
+    const uint32_t a1_row = smem_u32(s_a1) + (uint32_t)tid * 64u, a2_row = smem_u32(s_a2) + (uint32_t)tid * 32u;
+    const uint32_t sw1 = ((uint32_t)(tid >> 1) & 3u) << 4, sw2 = ((uint32_t)(tid >> 2) & 1u) << 4;     // XOR of this row's chunks
+    const float hm = (float)(H - 1), wm = (float)(W - 1);
+    const unsigned short* xs0 = reinterpret_cast<const unsigned short*>(x);
+    const bool leader = warp == 0 && elect_one();
+    const uint32_t tile_s = smem_u32(s_x);
+    constexpr uint32_t kTileBytes = L0T_TROWS * L0T_TWORDS * 4, kRowB = L0T_TWORDS * 4;
+    // tile -> (column segment, image, first output row of the pair); h is even (host), so a pair of output rows lies in one image.
+    // The decomposition is kept incrementally (tile advances by gridDim.x): no division per tile.
+    struct TilePos { int seg, b, i0; };
+    const int step_pairs = (int)gridDim.x / tiles_x, step_segs = (int)gridDim.x - step_pairs * tiles_x;
+    auto advance = [&](TilePos t) {
+        t.seg += step_segs;
+        t.i0 += 2 * step_pairs;
+        if (t.seg >= tiles_x) { t.seg -= tiles_x; t.i0 += 2; }
+        while (t.i0 >= h) { t.i0 -= h; ++t.b; }
+        return t;
+    };
+    auto issue_tile = [&](const TilePos& t) {
+        mbar_arrive_expect_tx(&bar[2], kTileBytes);
+        tma_load_4d(s_x, &tmX, &bar[2], (t.seg * L0T_COLS * 2 - L0T_KHALO) * 3 / 2, 2 * t.i0 - L0T_RHALO, t.b, 0);
+    };
+    TilePos cur;
+    {
+        const int pair = (int)blockIdx.x / tiles_x;
+        cur.seg = (int)blockIdx.x - pair * tiles_x;
+        cur.b = (2 * pair) / h;
+        cur.i0 = 2 * pair - cur.b * h;
+    }
+    if (leader && (int)blockIdx.x < num_tiles) issue_tile(cur);
+
+    if (TRACE && trace && blockIdx.x == 0 && threadIdx.x == 0) trace[63] = gridDim.x;
+    uint32_t ph = 0;
+    int it = 0;
+    const int jl = tid & (L0T_COLS - 1), rsel = tid >> 6;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ph ^= 1, ++it) {
+        stamp(it);
+        const TilePos nxt = advance(cur);
+        const int j = cur.seg * L0T_COLS + jl;
+        const int b = cur.b, i = cur.i0 + rsel;
+        const int row = b * h + i;
+        const bool valid = j < w && row < rows;
+        const int r_org = 2 * cur.i0 - L0T_RHALO, k_org = cur.seg * L0T_COLS * 2 - L0T_KHALO;
+        mbar_wait(&bar[2], ph);
+        // ---- offset-conv operand row: the window's five words per input row from the staged tile (zero fill = padding) ----
+        {
+            // pixel 2 j - 1 starts at byte 6 (2 jl + L0T_KHALO - 1) of the tile row = 2 mod 4: the words start 2 bytes earlier
+            const uint32_t wbase = tile_s + (uint32_t)(2 * rsel - 1 + L0T_RHALO) * kRowB + (uint32_t)(6 * (2 * jl + L0T_KHALO - 1) - 2);
+            uint32_t e0[3];
+#define L0T_WINDOW_ROW(TR)                                                                                                        \
+    {                                                                                                                             \
+        constexpr int RB_ = TR * (int)kRowB;                                                                                      \
+        e0[TR] = lds_u32_at<RB_>(wbase);                                                                                          \
+        const uint32_t w1_ = lds_u32_at<RB_ + 4>(wbase), w2_ = lds_u32_at<RB_ + 8>(wbase), w3_ = lds_u32_at<RB_ + 12>(wbase),     \
+                       w4_ = lds_u32_at<RB_ + 16>(wbase);                                                                         \
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1_row + (((uint32_t)TR << 4) ^ sw1)), "r"(w1_), "r"(w2_),  \
+                     "r"(w3_), "r"(w4_) : "memory");                                                                              \
+    }
+            L0T_WINDOW_ROW(0)
+            L0T_WINDOW_ROW(1)
+            L0T_WINDOW_ROW(2)
+#undef L0T_WINDOW_ROW
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a1_row + ((3u << 4) ^ sw1)), "r"(__byte_perm(e0[0], e0[1], 0x7632)),
+                         "r"(e0[2] >> 16), "r"(0u), "r"(0u) : "memory");
+        }
+        stamp(it);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        stamp(it);
+        if (leader) {
+            tc_fence_after_sync();
+            mma_bf16_ss(tmem_base, dA1, dW1, idesc, 0u);
+            mma_bf16_ss(tmem_base, dA1 + 2, dW1 + 2, idesc, 1u);          // K 16..31: +32 bytes inside the swizzled rows
+            mma_commit(&bar[0]);
+        }
+        __syncwarp();
+        mbar_wait(&bar[0], ph);
+        stamp(it);
+        tc_fence_after_sync();
+        float offv[O2];
+        {
+            uint32_t v[8];
+            tmem_ld_32x32b_x8(lane_addr, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int o = 0; o < O2; ++o) offv[o] = __uint_as_float(v[o]) + s_b[o];
+        }
+        stamp(it);
+        const size_t m = (size_t)row * w + j;
+        // ---- sampling -> (N,1)-conv operand row --------------------------------------------------------------------------
+        if (valid) {
+            if (off_out) {
+                float2* op = reinterpret_cast<float2*>(off_out + m * O2);
+                op[0] = make_float2(offv[0], offv[1]);
+                op[1] = make_float2(offv[2], offv[3]);
+                op[2] = make_float2(offv[4], offv[5]);
+            }
+            const unsigned short* xs = xs0 + (size_t)b * ((size_t)H * W * C);
+            float sv[N * C + 1];
+            sv[N * C] = 0.f;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const SamplePoint q = make_point_grid(2 * i + s_pn[n], 2 * j + s_pn[N + n], offv[n], offv[N + n], hm, wm);
+                const float g_lt = __fmul_rn(q.ar0, q.ak0), g_rb = __fmul_rn(q.ar1, q.ak1);
+                const float g_lb = __fmul_rn(q.ar0, q.ak1), g_rt = __fmul_rn(q.ar1, q.ak0);
+                const int t0 = q.r0 - r_org, t1 = q.r1 - r_org, u0 = q.k0 - k_org, u1 = q.k1 - k_org;
+                const bool inside = (unsigned)t0 < (unsigned)L0T_TROWS && (unsigned)t1 < (unsigned)L0T_TROWS &&
+                                    (unsigned)u0 < (unsigned)L0T_TPIX && (unsigned)u1 < (unsigned)L0T_TPIX;
+                if (inside) {          // the four corners from the staged tile (two-byte shared-memory loads)
+                    const uint32_t a0 = tile_s + (uint32_t)t0 * kRowB, a1 = tile_s + (uint32_t)t1 * kRowB;
+                    const uint32_t b0 = (uint32_t)u0 * 6u, b1 = (uint32_t)u1 * 6u;
+                    const uint32_t p00 = a0 + b0, p11 = a1 + b1, p01 = a0 + b1, p10 = a1 + b0;
+                    // a pixel = 6 bytes at 0 or 2 mod 4: always inside two aligned words (two loads per corner instead of three
+                    // two-byte ones: a third fewer shared-memory wavefronts, the stride-12-byte lanes cost three per instruction)
+                    float c00[3], c11[3], c01[3], c10[3];
+                    auto corner = [&](uint32_t p, float (&e)[3]) {
+                        const uint32_t pa = p & ~3u, sh = (p & 2u) << 3;
+                        const uint32_t w0 = lds_u32_at<0>(pa), w1 = lds_u32_at<4>(pa);
+                        const uint32_t xw = __funnelshift_r(w0, w1, sh), yw = w1 >> sh;
+                        e[0] = __uint_as_float(xw << 16);
+                        e[1] = __uint_as_float(xw & 0xffff0000u);
+                        e[2] = __uint_as_float(yw << 16);
+                    };
+                    corner(p00, c00);
+                    corner(p11, c11);
+                    corner(p01, c01);
+                    corner(p10, c10);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) sv[n * C + c] = bilinear(g_lt, g_rb, g_lb, g_rt, c00[c], c11[c], c01[c], c10[c]);
+                } else {               // offset beyond the halo: from the image (L2), as in l0_rows_kernel
+                    const uint32_t ra = (uint32_t)q.r0 * (uint32_t)(W * C), rb = (uint32_t)q.r1 * (uint32_t)(W * C);
+                    const uint32_t ka = (uint32_t)q.k0 * C, kb = (uint32_t)q.k1 * C;
+                    const unsigned short* p00 = xs + (ra + ka);
+                    const unsigned short* p11 = xs + (rb + kb);
+                    const unsigned short* p01 = xs + (ra + kb);
+                    const unsigned short* p10 = xs + (rb + ka);
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        sv[n * C + c] = bilinear(g_lt, g_rb, g_lb, g_rt, bf16_lo(p00[c]), bf16_lo(p11[c]), bf16_lo(p01[c]), bf16_lo(p10[c]));
+                }
+            }
+            uint32_t pk[5];
+#pragma unroll
+            for (int q2 = 0; q2 < 5; ++q2) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[q2]) : "f"(sv[2 * q2 + 1]), "f"(sv[2 * q2]));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a2_row + (0u ^ sw2)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a2_row + (16u ^ sw2)), "r"(pk[4]), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        }
+        stamp(it);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        stamp(it);
+        if (leader) {
+            tc_fence_after_sync();
+            mma_bf16_ss(tmem_base + 16, dA2, dW2, idesc, 0u);
+            mma_commit(&bar[1]);
+            // every thread is past its last read of the staged tile: fetch the next one under the MMA and the epilogue
+            if (tile + (int)gridDim.x < num_tiles) issue_tile(nxt);
+        }
+        __syncwarp();
+        mbar_wait(&bar[1], ph);
+        stamp(it);
+        tc_fence_after_sync();
+        {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(lane_addr + 16, v);
+            tmem_ld_wait();
+            if (valid) {
+                uint32_t pk[O / 2];
+#pragma unroll
+                for (int o4 = 0; o4 < O / 4; ++o4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_sc + o4 * 4);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_sc + O + o4 * 4);
+                    float z[4];
+                    z[0] = fmaf(__uint_as_float(v[o4 * 4 + 0]), sc.x, sh.x);
+                    z[1] = fmaf(__uint_as_float(v[o4 * 4 + 1]), sc.y, sh.y);
+                    z[2] = fmaf(__uint_as_float(v[o4 * 4 + 2]), sc.z, sh.z);
+                    z[3] = fmaf(__uint_as_float(v[o4 * 4 + 3]), sc.w, sh.w);
+                    if (act == LDCONV_ACT_SILU) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {                  // z holds 0.5 (scale acc + shift): y = z tanh(z) + z
+                            float t;
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z[e]));
+                            z[e] = fmaf(z[e], t, z[e]);
+                        }
+                    }
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[o4 * 2 + 0]) : "f"(z[1]), "f"(z[0]));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[o4 * 2 + 1]) : "f"(z[3]), "f"(z[2]));
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out + m * O);
+                dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+        }
+        cur = nxt;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 32);
+}
+
+static int launch_l0_tc(const __nv_bfloat16* x, const float* w_off, const float* b_off, const int* pn, const __nv_bfloat16* wt,
+                        const float* scale, const float* shift, __nv_bfloat16* out, float* off_out, int B, int H, int W, int act,
+                        cudaStream_t st)
+{
+    const int h = H / 2, w = W / 2, rows = B * h;
+    const int tiles_x = (w + L0T_COLS - 1) / L0T_COLS;
+    const long long nt = (long long)tiles_x * ((rows + 1) / 2);
+    if (nt > 0x7fffffffll) return fail(LDCONV_E_ARG, "first-layer kernel: too many tiles");
+    static int sms = 0, per_sm = 0;
+    if (!sms) {
+        int dev = 0;
+        LDC_CUDA(cudaGetDevice(&dev));
+        LDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // CTAs per SM from the kernel's own resource counts: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel
+        // (23 KB of static shared memory against the default carveout) although eight CTAs do run side by side -- measured: 861 us
+        // with 148 CTAs, 489 / 293 / 213 us with 2 / 4 / 8 CTAs per SM (benchmarks/l0_ab.py)
+        cudaFuncAttributes fa;
+        LDC_CUDA(cudaFuncGetAttributes(&fa, l0_tc_kernel<false>));
+        LDC_CUDA(cudaFuncSetAttribute(l0_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LDC_CUDA(cudaFuncSetAttribute(l0_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const int by_regs = 65536 / ((fa.numRegs > 0 ? fa.numRegs : 64) * L0T_THREADS);
+        const int by_smem = (int)((220u * 1024u) / (fa.sharedSizeBytes + 1024u));
+        per_sm = by_regs < by_smem ? by_regs : by_smem;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 16) per_sm = 16;                      // 32 TMEM columns per CTA: 16 CTAs own the SM's 512
+    }
+    long long grid = (long long)sms * per_sm;
+    if (grid > nt) grid = nt;
+    CUtensorMap tm;
+    {   // the image as rows of 4-byte words: (W * 3 / 2, H, B, 1)
+        cuuint64_t gdim[4] = {(cuuint64_t)W * 3 / 2, (cuuint64_t)H, (cuuint64_t)B, 1};
+        cuuint64_t gstr[3] = {(cuuint64_t)W * 6, (cuuint64_t)H * W * 6, (cuuint64_t)B * H * W * 6};
+        cuuint32_t box[4] = {(cuuint32_t)L0T_TWORDS, (cuuint32_t)L0T_TROWS, 1, 1};
+        if (int e = encode_map(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, x, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    }
+    auto kern = g_l0_trace ? l0_tc_kernel<true> : l0_tc_kernel<false>;
+    kern<<<(unsigned)grid, L0T_THREADS, 0, st>>>(tm, x, w_off, b_off, pn, wt, scale, shift, out, off_out, rows, H, W, h, w, act,
+                                                        tiles_x, (int)nt, g_l0_trace);
+    LDC_LAUNCH_CHECK("l0_tc_kernel");
+    set_impl(LDCONV_IMPL_TCGEN05);
+    return LDCONV_OK;
+}
+
 template <typename T, int C>
 static int launch_smallc(const T* x, const float* w_off, const float* b_off, const int* pn, const T* wt, const float* scale,
                          const float* shift, T* out, float* off_out, int B, int H, int W, int N, int s, int O, int act,
@@ -634,6 +1007,11 @@ static int dispatch_smallc(const void* x, const float* w_off, const float* b_off
 
 using namespace ldc;
 
+// debug / A-B: 0 = first layer on the tensor cores (l0_tc_kernel), 1 = the CUDA-core rows kernel
+LDC_API int ldconv_debug_l0_variant(int v) { ldc::g_l0_variant = v; return LDCONV_OK; }
+// device buffer of 64 long long (zero-filled by the caller) that the next first-layer launches stamp, or NULL to stop
+LDC_API int ldconv_debug_l0_trace(void* device_buf) { ldc::g_l0_trace = (long long*)device_buf; return LDCONV_OK; }
+
 LDC_API int ldconv_fused_supported(int B, int C, int H, int W, int N, int s, int O, int dtype)
 {
     if (B < 0 || C < 1 || H < 1 || W < 1 || N < 1 || s < 1 || O < 1) return 0;
@@ -656,9 +1034,15 @@ LDC_API int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_o
     if (B == 0) return LDCONV_OK;
     LDC_REQUIRE(aligned16(out), "ldconv_fused_fwd: out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == LDCONV_BF16 && l0_rows_applicable(x, B, C, H, W, N, s, O))
-        return launch_l0_rows((const __nv_bfloat16*)x, w_off, b_off, p_n, (const __nv_bfloat16*)wt, scale, shift,
-                              (__nv_bfloat16*)out, off_out, B, H, W, act, st);
+    if (dtype == LDCONV_BF16 && l0_rows_applicable(x, B, C, H, W, N, s, O)) {
+        // tensor-core kernel: row pairs inside one image (H % 4 == 0), image rows that are whole 16-byte units for the tensor map
+        const bool tc_ok = H % 4 == 0 && W % 8 == 0 && ((uintptr_t)x & 15) == 0 && B <= 65535;
+        if (g_l0_variant == 1 || !tc_ok)
+            return launch_l0_rows((const __nv_bfloat16*)x, w_off, b_off, p_n, (const __nv_bfloat16*)wt, scale, shift,
+                                  (__nv_bfloat16*)out, off_out, B, H, W, act, st);
+        return launch_l0_tc((const __nv_bfloat16*)x, w_off, b_off, p_n, (const __nv_bfloat16*)wt, scale, shift,
+                            (__nv_bfloat16*)out, off_out, B, H, W, act, st);
+    }
     if (dtype == LDCONV_BF16)
         return dispatch_smallc<__nv_bfloat16>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);
     return dispatch_smallc<float>(x, w_off, b_off, p_n, wt, scale, shift, out, off_out, B, C, H, W, N, s, O, act, st);

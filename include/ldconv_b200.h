@@ -205,6 +205,8 @@ int ldconv_fused_fwd(const void* x, const float* w_off, const float* b_off, cons
  *   offsets the kernel used, bit-identical to ldconv_offset_conv_{tc,s2d}_fwd).
  * Covered: the yolov8-LD-P2 shapes (num_param 1 / stride 1 / C in {32,64,128}; num_param 3 / stride 2 / C in {16,32,64},
  * even H and W), O % 16 == 0, O <= 256; ldconv_onepass_supported returns 1 for them, else use the entry points below. */
+int ldconv_debug_l0_variant(int v);                     /* A/B of the first-layer kernel: 0 = tensor cores (default), 1 = CUDA-core rows kernel */
+int ldconv_debug_l0_trace(void* device_buf);            /* clock64 stamps of CTA 0 of the next first-layer launches (benchmarks/l0_ab.py --trace) */
 int ldconv_debug_onepass_trace(void* device_buf);      /* debug timeline of the next ldconv_onepass_fwd call (benchmarks/trace_onepass.py) */
 int ldconv_onepass_supported(int B, int C, int H, int W, int N, int s, int O, int ldo, int dtype);
 int ldconv_onepass_fwd(const void* x, const void* w_offconv, const float* b_off, const int32_t* p_n, const void* wt,
