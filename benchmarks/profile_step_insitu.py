@@ -22,7 +22,10 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--per-launch", action="store_true")
+    ap.add_argument("--l0-variant", type=int, default=0, help="first-layer kernel: 0 = tensor cores, 1 = CUDA-core rows kernel")
     args = ap.parse_args()
+    from experiment_yolo_b200 import _lib as _l
+    _l.load().ldconv_debug_l0_variant(args.l0_variant)
     dev = torch.device("cuda", 0)
     model = dealyolo.DealYolo(nc=6)
     model.load_state_dict(dealyolo.seeded_state(model, 0))

@@ -6,7 +6,6 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <cstdio>
 
 namespace ldc {
 namespace umma {
@@ -70,11 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     const uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-            printf("mbar_wait timeout: barrier at shared 0x%x, parity %u, block %d, thread %d\n", smem_u32(bar), parity, (int)blockIdx.x,
-                   (int)threadIdx.x);
-            __trap();
-        }
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
     }
 }
 
