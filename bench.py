@@ -10,7 +10,8 @@ channels_last; the batch is sharded over ranks with no collective (every LDConv 
   value     images/s with the batch already resident in HBM (CUDA-graph replay of the forward), max over ranks
   e2e       images/s through the public call `engine.PipelinedPredictor.submit()/result()` with HOST buffers: every step copies its
             uint8 batch from pinned host memory, normalises on the device, runs the forward and reads the result back to the host
-  roofline  the LDConv gather+GEMM kernel at its largest launch of the step (and `roofline_gather`: the stand-alone gather
+  roofline  the LDConv gather+GEMM kernel at its largest launch of the step (`roofline_scatter`: the backward scatter of the training
+            path with the bf16 accumulator at the same shapes; and `roofline_gather`: the stand-alone gather
             kernel): algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the eager CPU port of the reference path (oracle/ldconv_torch_port.py inside the same
             graph), all host threads, on a bounded sample (batch 8) of the same workload
@@ -288,7 +289,7 @@ def ldconv_roofline(model, x, peaks, iters: int):
         ms = sorted(a.elapsed_time(b) for a, b in ev[1:])
         return ms[len(ms) // 2]
 
-    per_layer, tot = [], {"one": [0.0, 0.0], "two": [0.0, 0.0], "gather": [0.0, 0.0]}
+    per_layer, tot = [], {"one": [0.0, 0.0], "two": [0.0, 0.0], "gather": [0.0, 0.0], "scatter": [0.0, 0.0]}
     for m in model.ldconv_layers():
         xin = feats[m.i]
         B, C, H, W = xin.shape
@@ -311,6 +312,20 @@ def ldconv_roofline(model, x, peaks, iters: int):
         if C >= 8:          # layer 0 (C = 3) runs the one-kernel small-C path in the step, not these kernels
             tot["gather"][0] += nbytes
             tot["gather"][1] += ms
+        if dt == _lib.BF16 and L.ldconv_bwd_acc16_supported(B, C, H, W, N, s):
+            # backward scatter of the training path (autograd of the four gathers): grad_operand + x + offsets in, grad_x (bf16
+            # accumulator) + grad_offset out
+            gop = torch.randn((B * h * w, N * C), device=xin.device, dtype=torch.float32).to(xin.dtype)
+            gx = torch.zeros((B, H, W, C), device=xin.device, dtype=xin.dtype)
+            goff = torch.empty_like(off)
+            ms = timed(lambda: _lib.check(L.ldconv_gather_bwd_acc16(gop.data_ptr(), xh.data_ptr(), off.data_ptr(), pr.pn.data_ptr(),
+                                                                    gx.data_ptr(), goff.data_ptr(), B, C, H, W, N, s, sv),
+                                          "ldconv_gather_bwd_acc16"))
+            nb = e * B * h * w * N * C + x_bytes + off_bytes + e * B * C * H * W + off_bytes
+            row.update({"scatter_MB": round(nb / 1e6, 1), "scatter_us": round(ms * 1e3, 1), "scatter_GBps": round(nb / ms / 1e6, 1)})
+            tot["scatter"][0] += nb
+            tot["scatter"][1] += ms
+            del gop, gx, goff
         out = torch.empty((B, h, w, O), device=xin.device, dtype=xin.dtype)
         w_conv = pr.w_off_tc if s == 1 else pr.w_off_s2d
         if w_conv is not None and L.ldconv_onepass_supported(B, C, H, W, N, s, O, O, dt):
@@ -358,7 +373,19 @@ def ldconv_roofline(model, x, peaks, iters: int):
                    "frac": round(g_ach / peak, 4), "frac_of_8TBs_nominal": round(g_ach / 8000.0, 4),
                    "traffic": traffic.get("gather_kernel_bytes"),
                    "us_per_step": round(tot["gather"][1] * 1e3, 1)}
-    return roof, roof_gather
+    roof_scatter = None
+    if tot["scatter"][1] > 0:
+        s_ach = tot["scatter"][0] / tot["scatter"][1] / 1e6
+        big_s = max((r for r in per_layer if "scatter_us" in r), key=lambda r: r["scatter_MB"])
+        roof_scatter = {"bound": "hbm", "kernel": "scatter_bwd_tiled2_kernel / gather_bwd_kernel (LDConv backward scatter of grad_x and "
+                        "grad_offset, bf16 grad_x accumulator: ldconv_gather_bwd_acc16; the 9 launches with C >= 16 of one training step "
+                        "at this batch)", "achieved": round(s_ach, 1), "peak": peak, "peak_source": src, "unit": "GB/s",
+                        "frac": round(s_ach / peak, 4), "frac_of_8TBs_nominal": round(s_ach / 8000.0, 4), "traffic": None,
+                        "algorithmic_bytes": "e*M*K (grad_operand) + e*B*C*H*W (x) + 4*B*2N*h*w (offsets) + e*B*C*H*W (grad_x) + 4*B*2N*h*w "
+                        "(grad_offset)", "us_per_step": round(tot["scatter"][1] * 1e3, 1),
+                        "largest_launch": {"layer": big_s["layer"], "us": big_s["scatter_us"], "GBps": big_s["scatter_GBps"],
+                                           "frac": round(big_s["scatter_GBps"] / peak, 4)}}
+    return roof, roof_gather, roof_scatter
 
 
 def run_gpu_arm(args):
@@ -532,7 +559,7 @@ def run_gpu_arm(args):
 
     line = None
     if rank == 0:
-        roof, roof_gather = ldconv_roofline(model, host_u8[0].to(dev).float().div_(255.0).bfloat16().contiguous(memory_format=torch.channels_last),
+        roof, roof_gather, roof_scatter = ldconv_roofline(model, host_u8[0].to(dev).float().div_(255.0).bfloat16().contiguous(memory_format=torch.channels_last),
                                             peaks, iters=7)
         cpu_best, cpu_mean, cpu_sec, cores = cpu_port_images_per_s(CPU_SAMPLE_BATCH, 3, 1) if world == 1 else (None,) * 4
         eager = gpu_eager_images_per_s(local, B) if world == 1 else None
@@ -550,7 +577,7 @@ def run_gpu_arm(args):
                                   "memory" if args.engine == "fused" else "decoded head output (B,10,33600) bf16 copied to pinned host memory",
                         **e2e_extra},
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "clocks": clk.summary(), "roofline": roof, "roofline_gather": roof_gather}
+                "clocks": clk.summary(), "roofline": roof, "roofline_gather": roof_gather, "roofline_scatter": roof_scatter}
         if step_bytes and B == PER_GPU_BATCH:
             # whole-step roofline: DRAM bytes of one step (sum over the ncu launch list of this library build) / step time
             line["step_roofline"] = {"bound": "hbm", "dram_bytes_per_step": step_bytes, "achieved": round(step_bytes / ms_per_step / 1e6, 1),

@@ -65,6 +65,8 @@ SIGNATURES = {
     "ldconv_conv1x1_bn_act_maxup_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, _i] + [_i] * 7 + [_vp]),
     "ldconv_conv1x1_bn_act_packed_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
     "ldconv_upsample_nearest": (_i, [_vp, _i, _vp, _i] + [_i] * 6 + [_vp]),
+    "ldconv_ssff_max_fwd": (_i, [_vp] * 4 + [ctypes.c_longlong, _i, _i, _vp]),
+    "ldconv_ssff_max_bwd": (_i, [_vp] * 5 + [ctypes.c_longlong, _i, _i, _vp]),
     "ldconv_upsample_nearest_bwd": (_i, [_vp, _i, _vp, _i] + [_i] * 6 + [_vp]),
     "ldconv_add_nhwc": (_i, [_vp, _vp, _i, _vp, _i, _ll, _i, _i, _vp]),
     "ldconv_scalseq_tail": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 9 + [_vp]),

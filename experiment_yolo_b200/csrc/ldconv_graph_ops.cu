@@ -55,6 +55,62 @@ upsample_nearest_bwd_kernel(const T* __restrict__ gout, int ldg, T* __restrict__
     Vec16<T>::store(gx + pix * ldx + cv * 8, acc);
 }
 
+// SSFF tail of the TRAINING graph (nn/extra_modules/block.py:3438-3443: BatchNorm3d -> LeakyReLU(0.1) -> MaxPool3d((3,1,1)) over the
+// depth axis of the stacked volume).  `pre` holds the three depth slices as (3 M, C) rows (slice d = rows d M ... d M + M - 1), scale /
+// shift = the batch-statistics BatchNorm folded per channel.  Forward: out[m] = max_d leaky(pre[d M + m] * scale + shift).  Backward
+// routing: dz[d M + m] = grad_out[m] * leaky'(z_d) for the FIRST slice that attains the maximum (torch's max_pool3d keeps the first
+// index on ties), 0 for the other two -- the gradient w.r.t. the BatchNorm output, which the generic bn_act_bwd passes then take
+// with act = none.
+__device__ __forceinline__ float leaky01(float z) { return z > 0.f ? z : 0.1f * z; }
+
+__global__ void __launch_bounds__(256)
+ssff_max_fwd_kernel(const T* __restrict__ pre, const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ out,
+                    long long M, int CV, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    float sc[8], sh[8], a[8], b[8], c[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = scale[cv * 8 + e]; sh[e] = shift[cv * 8 + e]; }
+    Vec16<T>::load(pre + t * 8, a);
+    Vec16<T>::load(pre + (t + M * CV) * 8, b);
+    Vec16<T>::load(pre + (t + 2 * M * CV) * 8, c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        a[e] = fmaxf(fmaxf(leaky01(fmaf(a[e], sc[e], sh[e])), leaky01(fmaf(b[e], sc[e], sh[e]))), leaky01(fmaf(c[e], sc[e], sh[e])));
+    Vec16<T>::store(out + t * 8, a);
+}
+
+__global__ void __launch_bounds__(256)
+ssff_max_bwd_kernel(const T* __restrict__ pre, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const T* __restrict__ gout, T* __restrict__ dz, long long M, int CV, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int cv = (int)(t % CV);
+    float sc[8], sh[8], z[3][8], g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = scale[cv * 8 + e]; sh[e] = shift[cv * 8 + e]; }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Vec16<T>::load(pre + (t + d * M * CV) * 8, z[d]);
+    Vec16<T>::load(gout + t * 8, g);
+    float o[3][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        float zz[3], y[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { zz[d] = fmaf(z[d][e], sc[e], sh[e]); y[d] = leaky01(zz[d]); }
+        int arg = 0;
+        if (y[1] > y[arg]) arg = 1;
+        if (y[2] > y[arg]) arg = 2;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) o[d][e] = d == arg ? g[e] * (zz[d] > 0.f ? 1.f : 0.1f) : 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Vec16<T>::store(dz + (t + d * M * CV) * 8, o[d]);
+}
+
 // `Add` rows of the YAML (nn/extra_modules/block.py:3479-3484: torch.sum(torch.stack(x), 0)) for up to four NHWC inputs /
 // channel slices: fp32 accumulation, one rounding -- what torch's reduction does for bf16 tensors
 struct AddArgs { const T* src[4]; int ld[4]; int n; };
@@ -333,6 +389,33 @@ LDC_API int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, 
     upsample_nearest_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)out, ldo, H, W, C / 8,
                                                                                factor, total);
     LDC_LAUNCH_CHECK("upsample_nearest_kernel");
+    return LDCONV_OK;
+}
+
+LDC_API int ldconv_ssff_max_fwd(const void* pre, const float* scale, const float* shift, void* out, long long M, int C, int dtype,
+                                void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_ssff_max_fwd: bf16 only");
+    LDC_REQUIRE(pre && scale && shift && out && M >= 0 && C >= 8 && C % 8 == 0 && aligned16(pre) && aligned16(out),
+                "ldconv_ssff_max_fwd: needs C %% 8 == 0 and 16-byte aligned pointers");
+    const long long total = M * (C / 8);
+    if (total == 0) return LDCONV_OK;
+    ssff_max_fwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)pre, scale, shift, (T*)out, M, C / 8, total);
+    LDC_LAUNCH_CHECK("ssff_max_fwd_kernel");
+    return LDCONV_OK;
+}
+
+LDC_API int ldconv_ssff_max_bwd(const void* pre, const float* scale, const float* shift, const void* grad_out, void* dz, long long M,
+                                int C, int dtype, void* stream)
+{
+    LDC_REQUIRE(dtype == LDCONV_BF16, "ldconv_ssff_max_bwd: bf16 only");
+    LDC_REQUIRE(pre && scale && shift && grad_out && dz && M >= 0 && C >= 8 && C % 8 == 0 && aligned16(pre) && aligned16(grad_out) &&
+                    aligned16(dz), "ldconv_ssff_max_bwd: needs C %% 8 == 0 and 16-byte aligned pointers");
+    const long long total = M * (C / 8);
+    if (total == 0) return LDCONV_OK;
+    ssff_max_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)pre, scale, shift, (const T*)grad_out, (T*)dz, M,
+                                                                           C / 8, total);
+    LDC_LAUNCH_CHECK("ssff_max_bwd_kernel");
     return LDCONV_OK;
 }
 

@@ -155,6 +155,10 @@ class ScalSeq(nn.Module):
     three maps are stacked along a depth axis, Conv3d(1x1x1)+BatchNorm3d+LeakyReLU(0.1), then max over the depth axis
     (reference nn/extra_modules/block.py:3414-3443)."""
 
+    # training on the GPU under bf16 autocast: the tail after the three 1x1 Convs through the library (train_ops.scalseq_tail);
+    # class switch for A/B and tests
+    fused_train_tail = True
+
     def __init__(self, inc, channel):
         super().__init__()
         if channel != inc[0]:
@@ -171,8 +175,17 @@ class ScalSeq(nn.Module):
         if hasattr(self, "conv0"):
             fine = self.conv0(fine)
         size = fine.shape[2:]
-        mid = _nearest_to(self.conv1(mid), size)
-        coarse = _nearest_to(self.conv2(coarse), size)
+        mid, coarse = self.conv1(mid), self.conv2(coarse)
+        if self.training and self.fused_train_tail and fine.is_cuda and mid.dtype == torch.bfloat16 and torch.is_grad_enabled() \
+                and isinstance(self.act, nn.LeakyReLU) and abs(self.act.negative_slope - 0.1) < 1e-12:
+            from .train_ops import scalseq_tail
+            # an fp32 finest map under bf16 autocast (no conv0 in front of it): the Conv3d would round it to bf16 anyway
+            f16 = fine.to(torch.bfloat16) if fine.dtype == torch.float32 and torch.is_autocast_enabled("cuda") else fine
+            y = scalseq_tail(f16, mid, coarse, self.conv3d, self.bn)
+            if y is not None:
+                return y
+        mid = _nearest_to(mid, size)
+        coarse = _nearest_to(coarse, size)
         vol = torch.stack([fine, mid, coarse], dim=2)                # (B, C, 3, H, W)
         vol = self.act(self.bn(self.conv3d(vol)))
         return self.pool_3d(vol).squeeze(2)

@@ -311,6 +311,13 @@ int ldconv_upsample_nearest(const void* x, int ldx, void* out, int ldo, int B, i
                             void* stream);
 /* backward of ldconv_upsample_nearest for the training graph: grad_x (B,H,W,C) = sum over each factor x factor block of grad_out
  * (B,H*factor,W*factor,C); fp32 sum, one rounding; ldg / ldx = pixel strides (grad_out may be a channel slice of the Concat's gradient). */
+/* SSFF tail of the training graph (nn/extra_modules/block.py:3438-3443): `pre` (3 M, C) = the three depth slices of the Conv3d
+ * output as rows, scale / shift (C) fp32 = the batch-statistics BatchNorm3d folded.  fwd: out (M, C) = max over the slices of
+ * LeakyReLU(0.1)(pre * scale + shift).  bwd: dz (3 M, C) = the gradient w.r.t. the BatchNorm output: grad_out (M, C) * LeakyReLU'
+ * on the first slice attaining the maximum (MaxPool3d's tie rule), zero on the others; feed it to ldconv_bn_act_bwd_* with act NONE. */
+int ldconv_ssff_max_fwd(const void* pre, const float* scale, const float* shift, void* out, long long M, int C, int dtype, void* stream);
+int ldconv_ssff_max_bwd(const void* pre, const float* scale, const float* shift, const void* grad_out, void* dz, long long M, int C,
+                        int dtype, void* stream);
 int ldconv_upsample_nearest_bwd(const void* grad_out, int ldg, void* grad_x, int ldx, int B, int H, int W, int C, int factor,
                                 int dtype, void* stream);
 /* `Add` rows (nn/extra_modules/block.py:3479-3484, torch.sum(torch.stack(x), 0)): out = sum of n <= 4 NHWC tensors / channel

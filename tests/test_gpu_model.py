@@ -294,3 +294,42 @@ def test_library_add_row_with_autograd_vs_torch():
     y.backward(gout)
     assert torch.equal(a.grad, gout) and torch.equal(c.grad, gout)
     assert torch.equal(wide.grad[:, 16:48], gout) and float(wide.grad[:, :16].abs().max()) == 0.0
+
+
+def test_scalseq_training_tail_through_the_library_vs_torch():
+    """dealyolo.ScalSeq in training mode under bf16 autocast: the tail after the three 1x1 Convs (up-sampling, stack, Conv3d 1x1x1,
+    BatchNorm3d with batch statistics, LeakyReLU(0.1), MaxPool3d over the depth axis; nn/extra_modules/block.py:3432-3443) through
+    train_ops.scalseq_tail against torch's own ops on the same module: output, input / parameter gradients and running statistics."""
+    import copy
+    from experiment_yolo_b200 import _lib
+    torch.manual_seed(11)
+    ref = dealyolo.ScalSeq([32, 64, 128], 32).to(DEV).train()
+    with torch.no_grad():
+        ref.bn.weight.uniform_(0.5, 1.5)
+        ref.bn.bias.normal_(0, 0.2)
+        ref.conv3d.bias.normal_(0, 0.5)
+    lib = copy.deepcopy(ref)
+    xs = [torch.randn(2, c, h, w, device=DEV).contiguous(memory_format=torch.channels_last) for c, h, w in ((32, 16, 24), (64, 8, 12), (128, 4, 6))]
+    outs, grads = {}, {}
+    for name, mod, fused in (("ref", ref, False), ("lib", lib, True)):
+        dealyolo.ScalSeq.fused_train_tail = fused
+        try:
+            ins = [t.clone().requires_grad_(True) for t in xs]
+            _lib.call_counts.clear()
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                y = mod(ins)
+            assert ("ldconv_ssff_max_fwd" in _lib.call_counts) == fused
+            g = torch.randn(y.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+            y.float().backward(g)
+            outs[name] = y.float().detach()
+            grads[name] = [t.grad.float() for t in ins] + [mod.conv3d.weight.grad.float(), mod.bn.weight.grad.float(), mod.bn.bias.grad.float(),
+                                                            mod.conv1.conv.weight.grad.float()]
+        finally:
+            dealyolo.ScalSeq.fused_train_tail = True
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-12))
+    assert rel(outs["lib"], outs["ref"]) <= 1e-2
+    for a, b in zip(grads["lib"], grads["ref"]):
+        assert rel(a, b) <= 4e-2, (a.shape, rel(a, b))
+    assert rel(lib.bn.running_mean, ref.bn.running_mean) <= 2e-3 and rel(lib.bn.running_var, ref.bn.running_var) <= 2e-3
+    assert float(lib.conv3d.bias.grad.abs().max()) <= 1e-2 * max(1.0, float(ref.conv3d.bias.grad.abs().max()) * 100)
+    assert int(lib.bn.num_batches_tracked) == int(ref.bn.num_batches_tracked) == 1
