@@ -235,3 +235,27 @@ def test_install_against_the_real_reference_parse_model(tmp_path):
     assert out["kinds"] == ["ldconv", "ldconv", "c2f", "ldconv", "c2f", "ldconv", "c2f", "sppf", "ldconv", "up", "ldconv", "cat",
                             "c2f", "ldconv", "up", "ldconv", "cat", "c2f", "ldconv", "cat", "c2f", "ldconv", "cat", "c2f",
                             "scalseq", "add", "detect"]
+
+
+def test_train_ops_host_logic_on_cpu():
+    """train_ops: the NHWC view helper takes dense channels_last tensors and channel slices without a copy and copies anything else;
+    the library-backed training ops decline CPU tensors (None -> the caller runs torch's op), so the CPU graph is unchanged."""
+    import torch
+    from experiment_yolo_b200 import dealyolo, train_ops
+    x = torch.randn(2, 32, 6, 5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    v, ld = train_ops.nhwc_view(x)
+    assert ld == 32 and v.data_ptr() == x.data_ptr() and v.shape == (2, 6, 5, 32)
+    wide = torch.randn(2, 48, 6, 5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    v, ld = train_ops.nhwc_view(wide[:, 8:40])
+    assert ld == 48 and v.data_ptr() == wide.data_ptr() + 8 * 2
+    v, ld = train_ops.nhwc_view(torch.randn(2, 32, 6, 5).to(torch.bfloat16))          # NCHW-contiguous: copied
+    assert ld == 32 and v.is_contiguous()
+    v, ld = train_ops.nhwc_view(wide[:, 3:35])                                        # slice start not 16-byte aligned: copied
+    assert ld == 32 and v.is_contiguous()
+    assert train_ops.upsample_nearest(x, 2) is None and train_ops.add_maps([x, x]) is None
+    up = dealyolo.Upsample(None, 2, "nearest")
+    assert torch.equal(up(x.float()), torch.nn.functional.interpolate(x.float(), scale_factor=2, mode="nearest"))
+    assert torch.equal(dealyolo.Add()([x.float(), x.float()]), 2 * x.float())
+    seq = dealyolo.ScalSeq([32, 64, 128], 32).train()
+    y = seq([torch.randn(2, 32, 8, 8), torch.randn(2, 64, 4, 4), torch.randn(2, 128, 2, 2)])
+    assert y.shape == (2, 32, 8, 8)
