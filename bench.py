@@ -196,10 +196,21 @@ def gpu_eager_images_per_s(local: int, batch: int, iters: int = 3):
 
 
 def lib_sha16() -> str:
+    """Identity of the library build: sha256 over its SOURCES (csrc/*.cu, *.cuh, Makefile, include/*.h, in name order).  The binary
+    itself is not reproducible bit for bit (a clean rebuild of the same sources hashes differently), so the stamp that ties an ncu
+    capture to the library being timed is taken over what the binary is built from."""
+    import glob
     import hashlib
-    from experiment_yolo_b200 import _lib
-    with open(_lib.LIB_PATH, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()[:16]
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "experiment_yolo_b200", "csrc", "*.cu")) +
+                   glob.glob(os.path.join(ROOT, "experiment_yolo_b200", "csrc", "*.cuh")) +
+                   glob.glob(os.path.join(ROOT, "experiment_yolo_b200", "csrc", "Makefile")) +
+                   glob.glob(os.path.join(ROOT, "include", "*.h")))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def committed_traffic():

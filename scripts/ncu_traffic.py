@@ -18,8 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def main():
-    lib = os.path.join(ROOT, "experiment_yolo_b200", "libldconv_b200.so")
-    sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    sha = bench.lib_sha16()            # sha256 over the library's sources (the binary is not reproducible bit for bit)
     stamp_file = os.path.join(ROOT, "gpurun_out", "r2_capture_lib_sha16.txt")
     captured = open(stamp_file).read().strip() if os.path.exists(stamp_file) else None
     out = {"lib_sha16": captured or sha, "lib_sha16_now": sha}

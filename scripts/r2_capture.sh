@@ -4,7 +4,7 @@
 # scripts/ncu_summary.py turn them into profiles/r2_ncu_traffic.json / profiles/r2_ncu_onepassL1.txt.
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-sha256sum experiment_yolo_b200/libldconv_b200.so | cut -c1-16 > $OUT/r2_capture_lib_sha16.txt
+python -c "import bench; print(bench.lib_sha16())" > $OUT/r2_capture_lib_sha16.txt      # source hash of the library (bench.lib_sha16)
 timeout 300 python benchmarks/profile_step.py > $OUT/profstep_plain.log 2>&1 &&
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file $OUT/r2_step_launches.csv python benchmarks/profile_step.py > $OUT/profstep_ncu.log 2>&1

@@ -32,8 +32,11 @@ def main():
         if re.search(r"/\*[0-9a-f]{4}\*/", line):
             counts[name]["instructions"] += 1
     import hashlib
-    sha = hashlib.sha256(open(LIB, "rb").read()).hexdigest()[:16]
-    print(f"libldconv_b200.so sha256[:16] = {sha}; SASS op counts per kernel (static instruction counts, not executions)")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    sha = bench.lib_sha16()
+    print(f"library source sha256[:16] (bench.lib_sha16) = {sha}; SASS op counts per kernel (static instruction counts, not executions)")
     print("%-96s %7s " % ("kernel", "instr") + " ".join("%9s" % o for o in OPS))
     agg = collections.OrderedDict()
     for k, c in counts.items():
