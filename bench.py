@@ -230,13 +230,14 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    best, mean, sec, cores = cpu_port_images_per_s(CPU_SAMPLE_BATCH, max(1, args.steps), max(1, min(args.warmup, 2)))
-    sample = f"batch {CPU_SAMPLE_BATCH} of 640x640 fp32 images per step, eager CPU port of the reference graph"
+    cpu_batch = args.cpu_batch or CPU_SAMPLE_BATCH       # --cpu-batch 1: BASELINE.json config 1 (benchmarks/config1.py)
+    best, mean, sec, cores = cpu_port_images_per_s(cpu_batch, max(1, args.steps), max(1, min(args.warmup, 2)))
+    sample = f"batch {cpu_batch} of 640x640 fp32 images per step, eager CPU port of the reference graph"
     line = {"impl": "reference", "metric": "images_per_sec", "value": round(mean, 3), "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args.gpus), timed_batch=CPU_SAMPLE_BATCH, engine="eager CPU port",
-                           note=f"each step times a bounded sample of the workload: batch {CPU_SAMPLE_BATCH} of the "
+            "config": dict(workload_config(args.gpus), timed_batch=cpu_batch, engine="eager CPU port",
+                           note=f"each step times a bounded sample of the workload: batch {cpu_batch} of the "
                                 f"{PER_GPU_BATCH}-image batch (the CPU port's images/s at batch 64 and batch 8 agree, DESIGN.md 6)"),
             "cpu_baseline": {"value": round(mean, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(mean, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -633,6 +634,7 @@ def main():
                     help="weak: 64 images per GPU; strong: one 64-image batch split over the ranks (SURVEY.md 8d config 3)")
     ap.add_argument("--micro-batch", type=int, default=0, help="images per pass of the fused executor (0 = its default)")
     ap.add_argument("--train-steps", type=int, default=6, help="timed steps of the config-4 training leg (0 = skip)")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="--impl reference: images per timed step (default 8; 1 = BASELINE config 1)")
     ap.add_argument("--eager-leg", default=None, help=argparse.SUPPRESS)      # internal: one dtype of gpu_eager_baseline
     ap.add_argument("--eager-batch", type=int, default=PER_GPU_BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--eager-iters", type=int, default=3, help=argparse.SUPPRESS)

@@ -119,7 +119,7 @@ __global__ void dw_scatter_kernel(const float* __restrict__ dW, float* __restric
 template <int NMAX, int S, typename ACC>
 __global__ void __launch_bounds__(256)
 offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict__ w, ACC* __restrict__ grad_x, int C, int H, int W,
-                        int h, int wo, int N, int s_rt, int rows)
+                        int h, int wo, int N, int s_rt, int rows, int segs, int chunks, int items)
 {
     constexpr bool V16 = sizeof(ACC) == 2;
     constexpr int CG = V16 ? 8 : 4;                         // channels per thread: one 16-byte reduction
@@ -132,10 +132,13 @@ offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict_
         s_w[t] = c < C ? w[((size_t)tap * C + c) * O2 + o] : 0.f;
     }
     __syncthreads();
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (unsigned)(W * CGn)) return;
+    // work item = (image, row chunk, column segment); a CTA stages the weights once and walks its items (grid = a few CTAs per SM:
+    // with num_param 9 the weights are 20 KB, re-staging them for every chunk of a small map cost more than the chunk itself)
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int seg = item % segs, chunk = (item / segs) % chunks, b = item / (segs * chunks);
+    const unsigned t = (unsigned)seg * blockDim.x + threadIdx.x;
+    if (t >= (unsigned)(W * CGn)) continue;
     const int k = (int)(t / (unsigned)CGn), cg = (int)(t - (unsigned)k * (unsigned)CGn);
-    const int b = blockIdx.z;
     // the (at most three) taps of this column: kx valid iff k + 1 - kx = s * j with 0 <= j < wo
     int jx[3];
 #pragma unroll
@@ -145,7 +148,7 @@ offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict_
         const int j = S == 2 ? (kj >> 1) : (S == 1 ? kj : kj / s);
         jx[kx] = (ok && j < wo) ? j : -1;
     }
-    const int r_begin = blockIdx.y * rows, r_end = min(H, r_begin + rows);
+    const int r_begin = chunk * rows, r_end = min(H, r_begin + rows);
     for (int r = r_begin; r < r_end; ++r) {
         float acc[CG];
 #pragma unroll
@@ -196,6 +199,7 @@ offconv_bwd_data_kernel(const float* __restrict__ goff, const float* __restrict_
                 if (cg * 4 + e < C) atomicAdd(dst + e, acc[e]);
         }
     }
+    }
 }
 
 // returns 1 when launched, 0 when the shape is outside the kernel's range (caller uses the generic kernel)
@@ -206,18 +210,20 @@ static int offconv_bwd_data_fast_t(const float* goff, const float* w, ACC* grad_
     constexpr int CG = sizeof(ACC) == 2 ? 8 : 4;
     const int CGn = (C + CG - 1) / CG;
     const size_t smem = (size_t)9 * 2 * N * CGn * CG * sizeof(float);
-    if (smem > 96 * 1024 || N > 16 || B > 65535 || (long long)W * CGn > 0x7fffffffll) return 0;
+    if (smem > 96 * 1024 || N > 16 || (long long)W * CGn > 0x7fffffffll) return 0;
     if (sizeof(ACC) == 2 && C % 8 != 0) return 0;
     const int h = out_size(H, s), wo = out_size(W, s);
-    const unsigned gx = (unsigned)(((long long)W * CGn + 255) / 256);
-    // rows per CTA: enough CTAs to fill the machine a few times over, at most 16 rows (the weights are re-staged per CTA)
+    const long long segs = ((long long)W * CGn + 255) / 256;
+    // rows per item: enough items to fill the machine a few times over, at most 16 rows
     int rows = 16;
-    while (rows > 1 && (long long)gx * ((H + rows - 1) / rows) * B < (long long)num_sms() * 16) rows >>= 1;
-    const unsigned gy = (unsigned)((H + rows - 1) / rows);
-    if (gy > 65535) return 0;
+    while (rows > 1 && segs * ((H + rows - 1) / rows) * B < (long long)num_sms() * 16) rows >>= 1;
+    const long long chunks = (H + rows - 1) / rows;
+    const long long items = segs * chunks * B;
+    if (items > 0x7fffffffll) return 0;
+    const unsigned grid = (unsigned)min(items, (long long)num_sms() * 8);
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3(gx, gy, (unsigned)B), 256, smem, st>>>(goff, w, grad_x, C, H, W, h, wo, N, s, rows);
+        kern<<<grid, 256, smem, st>>>(goff, w, grad_x, C, H, W, h, wo, N, s, rows, (int)segs, (int)chunks, (int)items);
     };
 #define LDC_BWD_DATA(NM)                                                          \
     do {                                                                          \
