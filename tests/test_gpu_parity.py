@@ -1059,3 +1059,47 @@ def test_cuda_graph_capture_of_inference_forward():
         g.replay()
         torch.cuda.synchronize()
     assert torch.equal(y, ref)
+
+
+def test_first_layer_rows_kernel_constant_bank_follows_the_weights_at_a_reused_address():
+    """The CUDA-core first-layer kernel keeps its weights in a constant-bank slot keyed on the argument POINTERS.  The slot's content
+    is rewritten in stream order before every launch, so a second module whose (freshly allocated) parameters land on the addresses a
+    freed module used must get ITS weights: run module A, free it, build module B with other values, compare B with the oracle-checked
+    tensor-core kernel on the same input."""
+    L = _lib.load()
+    C, O, N, s, H, W, B = 3, 16, 3, 2, 16, 320, 2
+    x = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+
+    def build(seed):
+        torch.manual_seed(seed)
+        m = E.LDConv(C, O, N, s)
+        with torch.no_grad():
+            m.p_conv.weight.normal_(0, 0.1)
+            m.p_conv.bias.normal_(0, 0.5)
+            m.conv[0].weight.normal_(0, 0.5)
+        return m.to(DEV).bfloat16().eval()
+
+    try:
+        L.ldconv_debug_l0_variant(1)
+        a = build(1)
+        with torch.no_grad():
+            ya = a(x).float()
+        pa = a._prepared(torch.bfloat16, False)
+        ptrs_a = {t.data_ptr() for t in (pa.w_off, pa.b_off, pa.wt, pa.pn)}
+        del pa
+        del a
+        b = build(2)
+        with torch.no_grad():
+            yb_rows = b(x).float()
+        pb = b._prepared(torch.bfloat16, False)
+        ptrs_b = {t.data_ptr() for t in (pb.w_off, pb.b_off, pb.wt, pb.pn)}
+        L.ldconv_debug_l0_variant(0)
+        with torch.no_grad():
+            yb_tc = b(x).float()
+    finally:
+        L.ldconv_debug_l0_variant(0)
+    torch.cuda.synchronize()
+    assert float((yb_rows - yb_tc).norm() / yb_tc.norm()) <= 2e-3            # B's weights, whichever addresses they landed on
+    assert float((ya - yb_tc).norm() / yb_tc.norm()) > 0.1                   # and the two modules do differ
+    # informational: the caching allocator usually hands B the blocks A freed (the case the slot table has to survive)
+    print("reused parameter addresses:", len(ptrs_a & ptrs_b))
