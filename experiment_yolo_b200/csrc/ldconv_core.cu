@@ -608,7 +608,10 @@ int col_stats_bf16(const __nv_bfloat16* pre, long long M, int O, double* sum, do
     const int tile = pow2_at_least(cvn < 256 ? cvn : 256);
     const int phases = 256 / tile;
     long long want = (M + (long long)phases * 8 - 1) / ((long long)phases * 8);
-    const long long cap = (long long)num_sms() * 8;
+    // two CTAs per SM: every CTA ends with one fp64 atomic per column and quantity on the SAME addresses, which the L2 serialises;
+    // measured at layer 1, batch 64 (105 MB): 49.6 us with 8 CTAs per SM, 37.0 with 4, 33.3 with 2 (the unrolled loop keeps
+    // four 16-byte loads in flight per thread, so two CTAs per SM still cover the memory latency)
+    const long long cap = (long long)num_sms() * 2;
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
     const int vper = vec ? V : 1;
     for (int col0 = 0; col0 < O; col0 += tile * vper) {
@@ -1234,7 +1237,7 @@ static int bn_act_bwd_reduce_t(const T* pre, const T* gout, const float* scale, 
     const int tile = pow2_at_least(cvn < 256 ? cvn : 256);
     const int phases = 256 / tile;
     long long want = (M + (long long)phases * 8 - 1) / ((long long)phases * 8);
-    const long long cap = (long long)num_sms() * 8;
+    const long long cap = (long long)num_sms() * 2;
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
     const int vper = vec ? V : 1;
     for (int col0 = 0; col0 < O; col0 += tile * vper) {
