@@ -6,7 +6,7 @@ set -u
 OUT=gpurun_out; mkdir -p $OUT
 python -c "import bench; print(bench.lib_sha16())" > $OUT/r2_capture_lib_sha16.txt      # source hash of the library (bench.lib_sha16)
 timeout 300 python benchmarks/profile_step.py > $OUT/profstep_plain.log 2>&1 &&
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active \
     --clock-control none --csv --log-file $OUT/r2_step_launches.csv python benchmarks/profile_step.py > $OUT/profstep_ncu.log 2>&1
 echo "launch list exit $?"
 timeout 300 python benchmarks/onepass_ab.py --layers 1 --iters 2 > $OUT/onepass_plain.log 2>&1 &&
